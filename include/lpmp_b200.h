@@ -1,0 +1,158 @@
+/*
+ * lpmp_b200.h -- C ABI of the B200-native LP_MP message-passing hot path.
+ *
+ * Drop-in boundary: this is the surface a reference-style driver binds instead of LP<FMC>
+ * (the LP_TYPE consumed by Solver<LP_TYPE,VISITOR>, /root/reference/include/solver.hxx:29-30).
+ * Each entry point cites the reference interface it replaces.  Plain pointers and sizes only;
+ * no C++/torch types cross the boundary; errors are integer status codes (0 = ok) with a
+ * per-handle message (the reference throws std::runtime_error / asserts).
+ *
+ * The same header is implemented twice:
+ *   - lp_mp_b200/csrc (CUDA, sm_100a)       symbols  lpmp_<name>          -> liblpmp_b200.so
+ *   - oracle/lpmp_oracle.cpp (CPU, checker) symbols  lpmp_oracle_<name>   -> oracle/liblpmp_oracle.so
+ * so that one test body can drive both.  The product never loads the oracle.
+ *
+ * Model.  Node i has theta_i in R^L.  Edge e=(i,j) has parameters c_e and two
+ * vectors a_e ("msg1", on i's variable) and b_e ("msg2", on j's variable);
+ * theta_e(x,y) = c_e(x,y) + a_e(x) + b_e(y).  Messages are implicit: only these reparametrised
+ * potentials are stored (include/factors_messages.hxx:432).
+ */
+#ifndef LPMP_B200_H
+#define LPMP_B200_H
+
+#include <stdint.h>
+
+#ifndef LPMP_FN
+#define LPMP_FN(name) lpmp_##name
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lpmp_solver lpmp_solver; /* opaque; owns all host + device memory of one LP */
+
+enum { LPMP_OK = 0, LPMP_ERR_INVALID = 1, LPMP_ERR_STATE = 2, LPMP_ERR_CUDA = 3, LPMP_ERR_NOT_DAG = 4, LPMP_ERR_UNSUPPORTED = 5 };
+
+/* storage / arithmetic type of theta, a, b, c on the device.  F64 = parity mode (REAL = double,
+ * include/config.hxx:28); F32 = throughput mode (REAL = float is the commented alternative, :23-26). */
+enum { LPMP_F32 = 0, LPMP_F64 = 1 };
+
+/* LPReparametrizationMode, include/config.hxx:72 (Anisotropic2 / Mixed: out of scope) */
+enum { LPMP_REPAM_ANISOTROPIC = 0, LPMP_REPAM_UNIFORM = 1, LPMP_REPAM_DAMPED_UNIFORM = 2 };
+
+/* pairwise factor family: PairwiseSimplexFactor / pairwise_potts_factor (test/potts_factor.cpp:21-71) /
+ * truncated linear min(slope*|x-y|, trunc) (new, BASELINE.json config 2) */
+enum { LPMP_PAIRWISE_DENSE = 0, LPMP_PAIRWISE_POTTS = 1, LPMP_PAIRWISE_TRUNCLIN = 2 };
+
+/* how the update order of LP::SortFactors (include/LP_MP.h:730-797) is realised on the device */
+enum {
+  LPMP_SCHEDULE_LEVELS = 0,    /* general graphs: level sets of the factor-relation DAG given by the node ranks */
+  LPMP_SCHEDULE_WAVEFRONT = 1, /* grids only: persistent anti-diagonal row-band pipeline */
+};
+
+/* iteration order of a factor's messages of one type (include/factors_messages.hxx:2005-2077 LIFO
+ * intrusive list -- the storage the SRMP configuration selects -- vs :1772-1930 chunked FIFO) */
+enum { LPMP_EDGE_ORDER_LIFO = 0, LPMP_EDGE_ORDER_FIFO = 1 };
+
+typedef struct lpmp_stats {
+  uint64_t num_nodes, num_edges, num_labels;
+  uint64_t num_levels;            /* sequential steps per pass of the active schedule */
+  uint64_t kernel_launches;       /* CUDA kernels launched by this handle so far */
+  uint64_t message_updates;       /* receives + sends performed so far (SURVEY.md 8d unit of work) */
+  uint64_t device_bytes;          /* bytes of device memory owned */
+  double   algorithmic_bytes_per_pass; /* s*[2NL + E(P+5L)], BASELINE.md section 4 */
+} lpmp_stats;
+
+/* ---- lifetime: LP<FMC>::LP(cmd) / ~LP, include/LP_MP.h:212,596-600 ------------------------------- */
+int LPMP_FN(create)(int dtype, int device, lpmp_solver** out);
+int LPMP_FN(destroy)(lpmp_solver* h);
+const char* LPMP_FN(last_error)(const lpmp_solver* h);
+
+/* ---- problem construction ------------------------------------------------------------------------
+ * General graphs.  add_unaries == n x LP::add_factor<UnaryFactor> (include/LP_MP.h:238-253);
+ * add_pairwise_* == per edge add_factor<PairwiseFactor> + 2 x add_message + AddFactorRelation(u_i,p),
+ * AddFactorRelation(p,u_j) (include/LP_MP.h:266-285,697-702), as mrf.AddUnaryFactor / AddPairwiseFactor do
+ * (test/graphical_model.cpp:98-108).  One label count L and one pairwise family per LP.  Inputs are host
+ * buffers of doubles and are copied. */
+int LPMP_FN(add_unaries)(lpmp_solver* h, uint64_t n, uint32_t L, const double* theta /* [n][L] */);
+int LPMP_FN(add_pairwise_dense)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* tables /* [m][L][L], x_i major */);
+int LPMP_FN(add_pairwise_potts)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* lambda /* [m] */);
+int LPMP_FN(add_pairwise_trunclin)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* slope, const double* trunc /* [m] each */);
+/* Orientation of the factor-relation DAG: every edge is directed from its lower-rank to its higher-rank
+ * endpoint (default rank = node index, i.e. the reference's u_i -> p -> u_j with i<j).  A proper colouring
+ * passed as rank = colour*N + index gives the graph-colouring schedule. */
+int LPMP_FN(set_node_ranks)(lpmp_solver* h, const uint64_t* rank /* [N], distinct */);
+int LPMP_FN(set_edge_order)(lpmp_solver* h, int edge_order);
+int LPMP_FN(set_schedule)(lpmp_solver* h, int schedule);
+/* Deterministic greedy colouring in node order (host utility, no handle state): colour[i] = smallest colour
+ * not used by an already coloured neighbour.  Returns the number of colours through *num_colours. */
+int LPMP_FN(greedy_colouring)(uint64_t n, uint64_t m, const uint64_t* i, const uint64_t* j, uint32_t* colour, uint32_t* num_colours);
+
+/* Grids (4-connected, nodes row-major r*W+c, edges oriented low -> high index, per node the horizontal edge
+ * is inserted before the vertical one: SURVEY.md 8d).  Storage is allocated on the device and zeroed.
+ * src_dtype is the element type of the HOST buffers (LPMP_F32 / LPMP_F64). */
+int LPMP_FN(grid_create)(lpmp_solver* h, uint32_t H, uint32_t W, uint32_t L, int pairwise_type);
+int LPMP_FN(grid_set_unaries)(lpmp_solver* h, const void* theta /* [H][W][L] */, int src_dtype);
+/* P = L*L (dense), 1 (Potts: lambda), 2 (truncated linear: slope, trunc) parameters per edge */
+int LPMP_FN(grid_set_pairwise)(lpmp_solver* h, const void* horizontal /* [H][W-1][P] */, const void* vertical /* [H-1][W][P] */, int src_dtype);
+/* Counter-based synthetic potentials generated in place on the device (no host copy): theta ~ U[0,1),
+ * pairwise parameters ~ U[p_lo, p_hi) (dense: every table entry; Potts: lambda; truncated linear: p_lo = slope,
+ * p_hi = trunc, constant).  The generator is specified in DESIGN.md so that the oracle reproduces it. */
+int LPMP_FN(grid_fill_synthetic)(lpmp_solver* h, uint64_t seed, double p_lo, double p_hi);
+
+/* Row-stripe partition (multi-GPU): declare that this grid is rows [r0, r0+H) of a taller
+ * grid with H_total rows.  Stripe-boundary vertical edges get their parameters and this side's message
+ * vector here, plus a halo buffer for the other side's vector. */
+int LPMP_FN(grid_set_stripe)(lpmp_solver* h, uint32_t row0, uint32_t H_total);
+int LPMP_FN(grid_set_boundary_pairwise)(lpmp_solver* h, const void* top /* [W][P] or NULL */, const void* bottom /* [W][P] or NULL */, int src_dtype);
+/* device pointers (storage dtype) to the W*L boundary vectors: what this stripe owns and sends (out) and the
+ * halo it receives (in).  which: 0 = top boundary, 1 = bottom boundary. */
+int LPMP_FN(grid_boundary_ptrs)(lpmp_solver* h, int which, void** owned_out, void** halo_in, uint64_t* bytes);
+
+/* finish construction: build schedule + weights (SortFactors / ComputeAnisotropicWeights / ComputeUniformWeights,
+ * include/LP_MP.h:730-797,1230-1449) and upload.  Mutating the problem afterwards is an error. */
+int LPMP_FN(finalize)(lpmp_solver* h);
+
+/* ---- the LP_TYPE surface used by Solver / visitors (include/solver.hxx:185,233,248,263,269,274,281,306,323,390-392) */
+int LPMP_FN(begin)(lpmp_solver* h);                                  /* LP::Begin, include/LP_MP.h:704-728 */
+int LPMP_FN(end)(lpmp_solver* h);                                    /* LP::End */
+int LPMP_FN(set_reparametrization)(lpmp_solver* h, int mode);        /* LP::set_reparametrization */
+int LPMP_FN(compute_pass)(lpmp_solver* h, uint64_t iteration);       /* LP::ComputePass, include/LP_MP.h:869-887 */
+int LPMP_FN(compute_forward_pass)(lpmp_solver* h);                   /* :889-900 */
+int LPMP_FN(compute_backward_pass)(lpmp_solver* h);                  /* :902-911 */
+int LPMP_FN(compute_forward_pass_and_primal)(lpmp_solver* h, uint64_t iteration);  /* :913-922 */
+int LPMP_FN(compute_backward_pass_and_primal)(lpmp_solver* h, uint64_t iteration); /* :924-933 */
+int LPMP_FN(lower_bound)(lpmp_solver* h, double* out);               /* LP::LowerBound, :1507-1518 */
+int LPMP_FN(evaluate_primal)(lpmp_solver* h, double* out);           /* LP::EvaluatePrimal, :1520-1536 (+inf if inconsistent) */
+int LPMP_FN(check_primal_consistency)(lpmp_solver* h, int* out);     /* LP::CheckPrimalConsistency, :1066-1082 */
+int LPMP_FN(add_to_constant)(lpmp_solver* h, double x);              /* LP::add_to_constant, :462 */
+int LPMP_FN(num_factors)(const lpmp_solver* h, uint64_t* out);       /* LP::GetNumberOfFactors (N + E) */
+int LPMP_FN(num_messages)(const lpmp_solver* h, uint64_t* out);      /* LP::GetNumberOfMessages (2E) */
+
+/* ---- state access (serialize_dual / serialize_primal equivalents, include/serialization.hxx:228-426) -- */
+int LPMP_FN(get_labeling)(lpmp_solver* h, uint32_t* out /* [N] */);
+int LPMP_FN(get_unaries)(lpmp_solver* h, double* theta /* [N][L] */);
+int LPMP_FN(get_messages)(lpmp_solver* h, double* a /* [E][L] */, double* b /* [E][L] */); /* edge insertion order */
+int LPMP_FN(set_messages)(lpmp_solver* h, const double* a, const double* b);
+int LPMP_FN(set_unaries)(lpmp_solver* h, const double* theta);
+int LPMP_FN(stats)(lpmp_solver* h, lpmp_stats* out);
+int LPMP_FN(synchronize)(lpmp_solver* h);
+/* the CUDA stream (cudaStream_t) all work of this handle is enqueued on, for event timing by the caller */
+int LPMP_FN(stream)(lpmp_solver* h, void** out);
+
+/* ---- single-factor entry points used by the parity tests (SURVEY.md 8b last row) -----------------------
+ * n independent pairwise factors with L1 x L2 labels; side 0: out[x1] = msg1(x1) + min_x2 [c + msg2],
+ * side 1: out[x2] = msg2(x2) + min_x1 [c + msg1]   (min_marginal_1/2, test/potts_factor.cpp:27-31;
+ * arithmetic of matrix::min1(v)/min2(v), include/vector.hxx:850-859,889-913).  Host buffers of doubles;
+ * computed on the device in `dtype`.  lb (optional) receives PairwiseSimplexFactor::LowerBound per factor. */
+int LPMP_FN(minmarginal_dense)(int dtype, uint64_t n, uint32_t L1, uint32_t L2, const double* tables, const double* msg1, const double* msg2, int side, double* out, double* lb);
+int LPMP_FN(minmarginal_potts)(int dtype, uint64_t n, uint32_t L, const double* lambda, const double* msg1, const double* msg2, int side, double* out, double* lb);
+int LPMP_FN(minmarginal_trunclin)(int dtype, uint64_t n, uint32_t L, const double* slope, const double* trunc, const double* msg1, const double* msg2, int side, double* out, double* lb);
+/* n unary factors: lb[k] = min theta_k (vector::min, include/vector.hxx:289-313), arg[k] = first minimiser */
+int LPMP_FN(unary_min)(int dtype, uint64_t n, uint32_t L, const double* theta, double* lb, uint32_t* arg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPMP_B200_H */

@@ -1,0 +1,258 @@
+"""Host-side mirror of the reference's ``LP<FMC>`` (the LP_TYPE consumed by ``Solver<LP_TYPE,VISITOR>``,
+/root/reference/include/solver.hxx:29-30) for the SRMP simplex configuration.
+
+Method names, argument meaning and error behaviour follow the reference (include/LP_MP.h:200-585) so that the
+parity tests read like the reference's own tests (test/graphical_model.cpp:98-136).  Every method is one call
+into the C ABI (include/lpmp_b200.h); nothing is computed in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as K
+
+
+def _pd(x):
+    return None if x is None else x.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _pu64(x):
+    return x.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def _f64(x, shape=None):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    return x if shape is None else x.reshape(shape)
+
+
+class LP:
+    """LP<FMC_SRMP>: unary + pairwise simplex factors tied by marginalisation messages."""
+
+    def __init__(self, dtype="f64", device=0, capi=None):
+        if capi is None:
+            from . import load_library
+            capi = load_library()
+        self.api = capi
+        self.dtype = {"f32": K.F32, "f64": K.F64, K.F32: K.F32, K.F64: K.F64}[dtype]
+        h = C.c_void_p()
+        capi.check(capi.create(self.dtype, int(device), C.byref(h)))
+        self.h = h
+        self.N = self.E = self.L = 0
+        self._pending_unaries, self._pending_pairwise = [], []
+        self.grid_shape = None
+        self.finalized = False
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            self.api.destroy(h)
+
+    def _ck(self, status):
+        self.api.check(status, self.h)
+
+    # ---- problem construction ---------------------------------------------------------------------------
+    def add_unaries(self, theta):
+        theta = _f64(theta)
+        n, L = theta.shape
+        self._ck(self.api.add_unaries(self.h, n, L, _pd(theta)))
+        self.N += n
+        self.L = L
+
+    def _edges(self, i, j):
+        i = np.ascontiguousarray(i, dtype=np.uint64)
+        j = np.ascontiguousarray(j, dtype=np.uint64)
+        assert i.shape == j.shape and i.ndim == 1
+        return i, j
+
+    def add_pairwise_dense(self, i, j, tables):
+        i, j = self._edges(i, j)
+        tables = _f64(tables, (len(i), self.L, self.L))
+        self._ck(self.api.add_pairwise_dense(self.h, len(i), _pu64(i), _pu64(j), _pd(tables)))
+        self.E += len(i)
+
+    def add_pairwise_potts(self, i, j, lam):
+        i, j = self._edges(i, j)
+        lam = _f64(lam, (len(i),))
+        self._ck(self.api.add_pairwise_potts(self.h, len(i), _pu64(i), _pu64(j), _pd(lam)))
+        self.E += len(i)
+
+    def add_pairwise_trunclin(self, i, j, slope, trunc):
+        i, j = self._edges(i, j)
+        slope = _f64(np.broadcast_to(slope, (len(i),)))
+        trunc = _f64(np.broadcast_to(trunc, (len(i),)))
+        self._ck(self.api.add_pairwise_trunclin(self.h, len(i), _pu64(i), _pu64(j), _pd(slope), _pd(trunc)))
+        self.E += len(i)
+
+    # mrf.AddUnaryFactor / mrf.AddPairwiseFactor of the MRF problem constructor (test/graphical_model.cpp:98-108)
+    def AddUnaryFactor(self, cost):
+        assert not self._pending_pairwise, "add all unary factors first"
+        self._pending_unaries.append(np.asarray(cost, dtype=np.float64))
+        return len(self._pending_unaries) - 1
+
+    def AddPairwiseFactor(self, i, j, cost):
+        self._pending_pairwise.append((int(i), int(j), np.asarray(cost, dtype=np.float64)))
+        return len(self._pending_pairwise) - 1
+
+    def _flush_pending(self):
+        if self._pending_unaries:
+            self.add_unaries(np.stack(self._pending_unaries))
+            self._pending_unaries = []
+        if self._pending_pairwise:
+            i, j, t = zip(*self._pending_pairwise)
+            self.add_pairwise_dense(np.array(i), np.array(j), np.stack(t))
+            self._pending_pairwise = []
+
+    def set_node_ranks(self, rank):
+        self._flush_pending()
+        rank = np.ascontiguousarray(rank, dtype=np.uint64)
+        assert rank.shape == (self.N,)
+        self._ck(self.api.set_node_ranks(self.h, _pu64(rank)))
+
+    def set_edge_order(self, order):
+        self._ck(self.api.set_edge_order(self.h, K.EDGE_ORDER[order]))
+
+    def set_schedule(self, schedule):
+        self._ck(self.api.set_schedule(self.h, K.SCHEDULE[schedule]))
+
+    def greedy_colouring(self, i, j):
+        i, j = self._edges(i, j)
+        colour = np.zeros(self.N + len(self._pending_unaries), dtype=np.uint32)
+        nc = C.c_uint32()
+        self._ck(self.api.greedy_colouring(len(colour), len(i), _pu64(i), _pu64(j),
+                                           colour.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(nc)))
+        return colour, nc.value
+
+    # ---- grids ------------------------------------------------------------------------------------------
+    def grid_create(self, H, W, L, pairwise):
+        self._ck(self.api.grid_create(self.h, H, W, L, K.PAIRWISE[pairwise]))
+        self.grid_shape = (H, W)
+        self.N, self.L = H * W, L
+        self.E = H * (W - 1) + (H - 1) * W
+        self.pairwise = pairwise
+        return self
+
+    def _src(self, x):
+        x = np.ascontiguousarray(x)
+        if x.dtype not in (np.float32, np.float64):
+            x = x.astype(np.float64)
+        return x, (K.F32 if x.dtype == np.float32 else K.F64)
+
+    def grid_set_unaries(self, theta):
+        H, W = self.grid_shape
+        theta, src = self._src(theta)
+        assert theta.size == H * W * self.L
+        self._ck(self.api.grid_set_unaries(self.h, theta.ctypes.data, src))
+
+    def grid_set_pairwise(self, horizontal, vertical):
+        H, W = self.grid_shape
+        P = {"dense": self.L * self.L, "potts": 1, "trunclin": 2}[self.pairwise]
+        horizontal, s0 = self._src(horizontal)
+        vertical, s1 = self._src(vertical)
+        if s0 != s1:
+            horizontal, vertical, s0 = horizontal.astype(np.float64), vertical.astype(np.float64), K.F64
+        assert horizontal.size == H * (W - 1) * P and vertical.size == (H - 1) * W * P
+        self._ck(self.api.grid_set_pairwise(self.h, horizontal.ctypes.data, vertical.ctypes.data, s0))
+
+    def grid_fill_synthetic(self, seed, p_lo, p_hi):
+        self._ck(self.api.grid_fill_synthetic(self.h, int(seed), float(p_lo), float(p_hi)))
+
+    def finalize(self):
+        self._flush_pending()
+        self._ck(self.api.finalize(self.h))
+        self.finalized = True
+        return self
+
+    # ---- the LP_TYPE surface (include/LP_MP.h) ------------------------------------------------------------
+    def Begin(self):
+        if not self.finalized:
+            self.finalize()
+        self._ck(self.api.begin(self.h))
+
+    def End(self):
+        self._ck(self.api.end(self.h))
+
+    def set_reparametrization(self, mode):
+        self._ck(self.api.set_reparametrization(self.h, K.REPAM[mode] if isinstance(mode, str) else int(mode)))
+
+    def ComputePass(self, iteration=0):
+        self._ck(self.api.compute_pass(self.h, int(iteration)))
+
+    def ComputeForwardPass(self):
+        self._ck(self.api.compute_forward_pass(self.h))
+
+    def ComputeBackwardPass(self):
+        self._ck(self.api.compute_backward_pass(self.h))
+
+    def ComputeForwardPassAndPrimal(self, iteration):
+        self._ck(self.api.compute_forward_pass_and_primal(self.h, int(iteration)))
+
+    def ComputeBackwardPassAndPrimal(self, iteration):
+        self._ck(self.api.compute_backward_pass_and_primal(self.h, int(iteration)))
+
+    def LowerBound(self) -> float:
+        out = C.c_double()
+        self._ck(self.api.lower_bound(self.h, C.byref(out)))
+        return out.value
+
+    def EvaluatePrimal(self) -> float:
+        out = C.c_double()
+        self._ck(self.api.evaluate_primal(self.h, C.byref(out)))
+        return out.value
+
+    def CheckPrimalConsistency(self) -> bool:
+        out = C.c_int()
+        self._ck(self.api.check_primal_consistency(self.h, C.byref(out)))
+        return bool(out.value)
+
+    def add_to_constant(self, x):
+        self._ck(self.api.add_to_constant(self.h, float(x)))
+
+    def GetNumberOfFactors(self) -> int:
+        out = C.c_uint64()
+        self._ck(self.api.num_factors(self.h, C.byref(out)))
+        return out.value
+
+    def GetNumberOfMessages(self) -> int:
+        out = C.c_uint64()
+        self._ck(self.api.num_messages(self.h, C.byref(out)))
+        return out.value
+
+    # ---- state ------------------------------------------------------------------------------------------
+    def labeling(self):
+        out = np.zeros(self.N, dtype=np.uint32)
+        self._ck(self.api.get_labeling(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def unaries(self):
+        out = np.zeros((self.N, self.L), dtype=np.float64)
+        self._ck(self.api.get_unaries(self.h, _pd(out)))
+        return out
+
+    def messages(self):
+        a = np.zeros((self.E, self.L), dtype=np.float64)
+        b = np.zeros((self.E, self.L), dtype=np.float64)
+        self._ck(self.api.get_messages(self.h, _pd(a), _pd(b)))
+        return a, b
+
+    def set_messages(self, a, b):
+        a, b = _f64(a, (self.E, self.L)), _f64(b, (self.E, self.L))
+        self._ck(self.api.set_messages(self.h, _pd(a), _pd(b)))
+
+    def set_unaries(self, theta):
+        theta = _f64(theta, (self.N, self.L))
+        self._ck(self.api.set_unaries(self.h, _pd(theta)))
+
+    def stats(self):
+        s = K.Stats()
+        self._ck(self.api.stats(self.h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in K.Stats._fields_}
+
+    def synchronize(self):
+        self._ck(self.api.synchronize(self.h))
+
+    def stream(self) -> int:
+        out = C.c_void_p()
+        self._ck(self.api.stream(self.h, C.byref(out)))
+        return out.value or 0

@@ -1,0 +1,575 @@
+// TEST INFRASTRUCTURE ONLY (oracle/).  Never linked into, imported by or called from the product path
+// (lp_mp_b200/).  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may use it.
+//
+// Standalone CPU restatement of the LP_MP message-passing hot path for simplex (unary/pairwise) factors in
+// the SRMP configuration, behind the same C ABI as the CUDA library
+// (include/lpmp_b200.h, symbols prefixed lpmp_oracle_).  Dependency-free C++17, strictly sequential like the
+// reference.  Compile with -ffp-contract=off: bit-parity statements assume one rounding per + and *.
+//
+// Parity status: PINNED.  (1) every golden vector the reference's tests hold for this path
+// (test/simplex.cpp, test/simplex_marginalization.cpp, test/potts_factor.cpp, test/vector.cpp,
+// test/test_model.cpp, test/graphical_model.cpp:98-136) is checked in tests/test_oracle_goldens.py;
+// (2) on random instances it is compared bit-for-bit (theta, a, b, labels) with oracle/_ref -- the
+// reference's own scheduler/containers/solver/visitor compiled unmodified (oracle/ref_driver.cpp).
+//
+// What follows which reference lines:
+//   node update (receive, argmin, snapshot, send)   include/factors_messages.hxx:2256-2261,2332-2373,2440-2471,
+//                                                   2698-2744,2787-2814; sign conventions :486-510
+//   per-node message order (types, LIFO/FIFO)       include/factors_messages.hxx:2005-2077,1772-1930,3402-3419
+//   weights / receive masks                         include/LP_MP.h:1230-1415 (anisotropic), 1420-1449 (uniform),
+//                                                   1037-1063,1487-1505 (damped, full receive mask)
+//   pass / iteration                                include/LP_MP.h:869-911,981-1005,1592-1602
+//   lower bound, primal cost                        include/LP_MP.h:1507-1536
+//   min-marginal arithmetic                         include/vector.hxx:289-443,850-859,889-944
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#define LPMP_FN(name) lpmp_oracle_##name
+#include "../include/lpmp_b200.h"
+#include "../include/lpmp_synthetic.h"
+
+namespace {
+
+constexpr uint32_t NO_LABEL = 0xffffffffu;
+
+struct Incidence {
+  uint64_t edge;
+  uint32_t side;   // 0: node is the first variable (owns a_e), 1: second variable (owns b_e)
+  uint32_t later;  // other endpoint has higher rank (is processed later in the forward pass)
+};
+
+struct OracleBase {
+  virtual ~OracleBase() {}
+  std::string err;
+};
+
+template <typename Real>
+struct Oracle : OracleBase {
+  uint64_t N = 0, E = 0;
+  uint32_t L = 0;
+  int pw = -1;
+  bool finalized = false, force_dense = false;
+  int repam = -1, edge_order = LPMP_EDGE_ORDER_LIFO;
+  double constant = 0.0;
+  bool labels_valid = false;
+  uint32_t gridH = 0, gridW = 0;
+  std::vector<Real> theta, a, b, params;  // params: [E][P]
+  std::vector<uint64_t> ei, ej, rank, order, inc_off;
+  std::vector<Incidence> inc;
+  std::vector<uint32_t> n_in, n_out, labels;
+  std::vector<Real> h_, t_;  // scratch
+  uint64_t message_updates = 0;
+
+  uint32_t P() const { return pw == LPMP_PAIRWISE_DENSE ? L * L : (pw == LPMP_PAIRWISE_POTTS ? 1u : 2u); }
+
+  // c_e(x,y) of the materialised table (defines Potts / truncated linear: test/potts_factor.cpp:8-19)
+  Real cost(uint64_t e, uint32_t x, uint32_t y) const {
+    const Real* p = &params[e * P()];
+    if (pw == LPMP_PAIRWISE_DENSE) return p[x * L + y];
+    if (pw == LPMP_PAIRWISE_POTTS) return x == y ? Real(0) : p[0];
+    const uint32_t d = x > y ? x - y : y - x;
+    return std::min(Real(p[0] * Real(d)), p[1]);
+  }
+
+  // h(x) = min_y [ c_e(.,.) + other_side(y) ], x on `side`.  matrix::min1(v)/min2(v): include/vector.hxx:850-859,889-913
+  void min_plus(uint64_t e, uint32_t side, Real* h) const {
+    const Real* other = side == 0 ? &b[e * L] : &a[e * L];
+    const Real INF = std::numeric_limits<Real>::infinity();
+    const bool tl_fast_ok = pw != LPMP_PAIRWISE_TRUNCLIN || (params[2 * e] >= Real(0) && params[2 * e + 1] >= Real(0));
+    if (pw == LPMP_PAIRWISE_DENSE || force_dense || !tl_fast_ok) {
+      for (uint32_t x = 0; x < L; ++x) {
+        Real m = INF;
+        for (uint32_t y = 0; y < L; ++y) {
+          const Real c = side == 0 ? cost(e, x, y) : cost(e, y, x);
+          m = std::min(m, Real(c + other[y]));
+        }
+        h[x] = m;
+      }
+    } else if (pw == LPMP_PAIRWISE_POTTS) {
+      // two smallest entries: vector::two_min / min_except, include/vector.hxx:315-323,348-443
+      Real m1 = INF, m2 = INF;
+      uint32_t i1 = 0;
+      for (uint32_t y = 0; y < L; ++y) {
+        const Real v = other[y];
+        if (v < m1) { m2 = m1; m1 = v; i1 = y; } else if (v < m2) { m2 = v; }
+      }
+      const Real lambda = params[e];
+      for (uint32_t x = 0; x < L; ++x) h[x] = std::min(other[x], Real(lambda + (x == i1 ? m2 : m1)));
+    } else {
+      // truncated linear: terms with slope*d >= trunc collapse to trunc + global min (rounding is monotone)
+      const Real slope = params[2 * e], trunc = params[2 * e + 1];
+      Real gmin = INF;
+      for (uint32_t y = 0; y < L; ++y) gmin = std::min(gmin, other[y]);
+      const Real far = trunc + gmin;
+      for (uint32_t x = 0; x < L; ++x) {
+        Real m = std::min(far, other[x]);  // d = 0: c = min(0, trunc) = 0
+        for (uint32_t d = 1; d < L; ++d) {
+          const Real cd = slope * Real(d);
+          if (!(cd < trunc)) break;
+          if (x >= d) m = std::min(m, Real(cd + other[x - d]));
+          if (x + d < L) m = std::min(m, Real(cd + other[x + d]));
+        }
+        h[x] = m;
+      }
+    }
+  }
+
+  Real omega(uint64_t i) const {
+    const uint32_t deg = n_in[i] + n_out[i];
+    double w;
+    if (repam == LPMP_REPAM_ANISOTROPIC) w = 1.0 / double(std::max(n_in[i], n_out[i]));  // include/LP_MP.h:1397
+    else if (repam == LPMP_REPAM_UNIFORM) w = 1.0 / double(deg);                            // :1437 leave_weight 0
+    else w = 1.0 / double(deg + 1);                                                          // :1437 leave_weight 1
+    return Real(w);
+  }
+
+  // FactorContainer::UpdateFactor / UpdateFactorPrimal, include/factors_messages.hxx:2256-2261,2332-2373
+  void update_node(uint64_t i, bool forward, bool primal) {
+    const uint64_t k0 = inc_off[i], k1 = inc_off[i + 1];
+    if (k0 == k1 && !primal) return;
+    Real* th = &theta[i * L];
+    Real* h = h_.data();
+    const bool aniso = repam == LPMP_REPAM_ANISOTROPIC;
+    for (uint64_t k = k0; k < k1; ++k) {  // ReceiveMessages, :2440-2471
+      const Incidence& c = inc[k];
+      const bool earlier = forward ? !c.later : c.later;
+      if (aniso && !earlier) continue;
+      min_plus(c.edge, c.side, h);
+      Real* own = c.side == 0 ? &a[c.edge * L] : &b[c.edge * L];
+      for (uint32_t x = 0; x < L; ++x) {
+        const Real m = h[x] + own[x];
+        th[x] += m;   // RepamLeft(+)  :498-500
+        own[x] -= m;  // RepamRight(-)
+      }
+      ++message_updates;
+    }
+    if (primal) {  // MaximizePotentialAndComputePrimal: first minimum
+      uint32_t arg = 0;
+      for (uint32_t x = 1; x < L; ++x) if (th[x] < th[arg]) arg = x;
+      labels[i] = arg;
+    }
+    if (k0 == k1) return;
+    const Real w = omega(i);
+    Real* t = t_.data();
+    for (uint32_t x = 0; x < L; ++x) t[x] = th[x];  // tmp_factor snapshot, :2801-2805
+    for (uint64_t k = k0; k < k1; ++k) {             // CallSendMessages, :2698-2744
+      const Incidence& c = inc[k];
+      const bool later = forward ? c.later : !c.later;
+      if (aniso && !later) continue;
+      Real* own = c.side == 0 ? &a[c.edge * L] : &b[c.edge * L];
+      for (uint32_t x = 0; x < L; ++x) {
+        const Real d = w * t[x];
+        own[x] += d;  // RepamRight(+) first, :501-503
+        th[x] -= d;   // RepamLeft(-)
+      }
+      ++message_updates;
+    }
+  }
+
+  void pass(bool forward, bool primal) {
+    if (forward) for (uint64_t k = 0; k < N; ++k) update_node(order[k], true, primal);
+    else for (uint64_t k = N; k-- > 0;) update_node(order[k], false, primal);
+    if (primal) labels_valid = true;
+  }
+
+  double lower_bound() {  // LP::LowerBound, include/LP_MP.h:1507-1518: unaries first, then pairwise, in double
+    double lb = constant;
+    for (uint64_t i = 0; i < N; ++i) {
+      Real m = theta[i * L];
+      for (uint32_t x = 1; x < L; ++x) m = std::min(m, theta[i * L + x]);
+      lb += double(m);
+    }
+    Real* h = h_.data();
+    for (uint64_t e = 0; e < E; ++e) {
+      min_plus(e, 0, h);
+      Real m = std::numeric_limits<Real>::infinity();
+      for (uint32_t x = 0; x < L; ++x) m = std::min(m, Real(h[x] + a[e * L + x]));
+      lb += double(m);
+    }
+    return lb;
+  }
+
+  double evaluate_primal() const {  // LP::EvaluatePrimal, include/LP_MP.h:1520-1536
+    if (!labels_valid) return std::numeric_limits<double>::infinity();
+    double cost_sum = constant;
+    for (uint64_t i = 0; i < N; ++i) cost_sum += double(theta[i * L + labels[i]]);
+    for (uint64_t e = 0; e < E; ++e) {
+      const uint32_t x = labels[ei[e]], y = labels[ej[e]];
+      cost_sum += double(Real(Real(cost(e, x, y) + a[e * L + x]) + b[e * L + y]));
+    }
+    return cost_sum;
+  }
+
+  int add_unaries(uint64_t n, uint32_t L_, const double* th) {
+    if (finalized) { err = "add_unaries after finalize"; return LPMP_ERR_STATE; }
+    if (L_ == 0 || (L != 0 && L != L_)) { err = "one label count per LP"; return LPMP_ERR_UNSUPPORTED; }
+    L = L_;
+    theta.reserve((N + n) * L);
+    for (uint64_t k = 0; k < n * L; ++k) theta.push_back(Real(th[k]));
+    N += n;
+    return LPMP_OK;
+  }
+
+  int add_pairwise(int type, uint64_t m, const uint64_t* i, const uint64_t* j, const double* p0, const double* p1) {
+    if (finalized) { err = "add_pairwise after finalize"; return LPMP_ERR_STATE; }
+    if (pw != -1 && pw != type) { err = "one pairwise family per LP"; return LPMP_ERR_UNSUPPORTED; }
+    pw = type;
+    const uint32_t Pn = P();
+    for (uint64_t k = 0; k < m; ++k) {
+      if (i[k] >= N || j[k] >= N || i[k] == j[k]) { err = "edge endpoint out of range"; return LPMP_ERR_INVALID; }
+      ei.push_back(i[k]);
+      ej.push_back(j[k]);
+      if (type == LPMP_PAIRWISE_DENSE) for (uint32_t q = 0; q < Pn; ++q) params.push_back(Real(p0[k * Pn + q]));
+      else if (type == LPMP_PAIRWISE_POTTS) params.push_back(Real(p0[k]));
+      else { params.push_back(Real(p0[k])); params.push_back(Real(p1[k])); }
+    }
+    E += m;
+    return LPMP_OK;
+  }
+
+  int finalize() {
+    if (finalized) { err = "finalize called twice"; return LPMP_ERR_STATE; }
+    if (N == 0) { err = "no factors"; return LPMP_ERR_STATE; }
+    if (pw == -1) pw = LPMP_PAIRWISE_POTTS;
+    if (rank.empty()) { rank.resize(N); std::iota(rank.begin(), rank.end(), uint64_t(0)); }
+    a.assign(E * L, Real(0));
+    b.assign(E * L, Real(0));
+    labels.assign(N, NO_LABEL);
+    h_.resize(L);
+    t_.resize(L);
+    order.resize(N);
+    std::iota(order.begin(), order.end(), uint64_t(0));
+    std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return rank[x] < rank[y]; });
+    for (uint64_t k = 1; k < N; ++k) if (rank[order[k]] == rank[order[k - 1]]) { err = "node ranks must be distinct"; return LPMP_ERR_INVALID; }
+    // per-node message order: first-variable message type, then second-variable type (dispatcher list order,
+    // include/factors_messages.hxx:3402-3419); inside a type LIFO (:2030-2041) or FIFO (:1772-1930)
+    std::vector<std::vector<uint64_t>> first(N), second(N);
+    for (uint64_t e = 0; e < E; ++e) { first[ei[e]].push_back(e); second[ej[e]].push_back(e); }
+    inc_off.assign(N + 1, 0);
+    inc.clear();
+    n_in.assign(N, 0);
+    n_out.assign(N, 0);
+    for (uint64_t i = 0; i < N; ++i) {
+      for (int s = 0; s < 2; ++s) {
+        std::vector<uint64_t>& v = s == 0 ? first[i] : second[i];
+        if (edge_order == LPMP_EDGE_ORDER_LIFO) std::reverse(v.begin(), v.end());
+        for (uint64_t e : v) {
+          const uint64_t other = s == 0 ? ej[e] : ei[e];
+          const uint32_t later = rank[other] > rank[i] ? 1u : 0u;
+          inc.push_back({e, uint32_t(s), later});
+          if (later) ++n_out[i]; else ++n_in[i];
+        }
+      }
+      inc_off[i + 1] = inc.size();
+    }
+    finalized = true;
+    return LPMP_OK;
+  }
+};
+
+struct Handle {
+  int dtype;
+  Oracle<float>* f = nullptr;
+  Oracle<double>* d = nullptr;
+  std::string err;
+  ~Handle() { delete f; delete d; }
+};
+
+#define DISPATCH(h, expr) ((h)->dtype == LPMP_F32 ? ([&](auto& o) { return expr; })(*(h)->f) : ([&](auto& o) { return expr; })(*(h)->d))
+#define GET_ERR(h) ((h)->dtype == LPMP_F32 ? (h)->f->err : (h)->d->err)
+
+inline Handle* H(lpmp_solver* h) { return reinterpret_cast<Handle*>(h); }
+inline const Handle* H(const lpmp_solver* h) { return reinterpret_cast<const Handle*>(h); }
+
+template <typename O>
+int need_final(O& o) {
+  if (!o.finalized) { o.err = "finalize() has not been called"; return LPMP_ERR_STATE; }
+  return LPMP_OK;
+}
+template <typename O>
+int need_repam(O& o) {
+  if (int r = need_final(o)) return r;
+  if (o.repam < 0) { o.err = "no reparametrization mode set"; return LPMP_ERR_STATE; }  // include/LP_MP.h:458
+  return LPMP_OK;
+}
+
+template <typename O>
+int grid_create(O& o, uint32_t Hh, uint32_t W, uint32_t L, int type) {
+  if (o.N != 0 || o.finalized) { o.err = "grid_create on a non-empty LP"; return LPMP_ERR_STATE; }
+  if (Hh == 0 || W == 0 || L == 0 || type < 0 || type > 2) { o.err = "bad grid shape"; return LPMP_ERR_INVALID; }
+  o.gridH = Hh; o.gridW = W; o.L = L; o.pw = type;
+  o.N = uint64_t(Hh) * W;
+  o.theta.assign(o.N * L, 0);
+  // per node: horizontal edge before vertical edge
+  for (uint32_t r = 0; r < Hh; ++r)
+    for (uint32_t c = 0; c < W; ++c) {
+      const uint64_t i = uint64_t(r) * W + c;
+      if (c + 1 < W) { o.ei.push_back(i); o.ej.push_back(i + 1); }
+      if (r + 1 < Hh) { o.ei.push_back(i); o.ej.push_back(i + W); }
+    }
+  o.E = o.ei.size();
+  o.params.assign(o.E * o.P(), 0);
+  return LPMP_OK;
+}
+
+// edge index (insertion order) of the horizontal / vertical edge leaving node (r,c)
+template <typename O>
+uint64_t grid_edge(const O& o, uint32_t r, uint32_t c, bool vertical) {
+  // edges before row r: r rows x (W-1) horizontal + r*W vertical (all rows < r have a row below, since r < H)
+  const uint64_t W = o.gridW, Hh = o.gridH;
+  uint64_t base = uint64_t(r) * (W - 1) + uint64_t(r) * W;
+  const bool has_v = r + 1 < Hh;
+  // inside row r: nodes 0..c-1 each contribute (c'<W-1) + has_v
+  base += uint64_t(c) * (1 + (has_v ? 1 : 0));  // all c' < c satisfy c' < W-1
+  if (!vertical) return base;
+  return base + (c + 1 < W ? 1 : 0);
+}
+
+template <typename O, typename Src>
+void grid_set_pairwise_t(O& o, const Src* hz, const Src* vt) {
+  using Real = typename std::remove_reference<decltype(o.params[0])>::type;
+  const uint32_t P = o.P();
+  for (uint32_t r = 0; r < o.gridH; ++r)
+    for (uint32_t c = 0; c < o.gridW; ++c) {
+      if (c + 1 < o.gridW && hz) {
+        const uint64_t e = grid_edge(o, r, c, false), s = uint64_t(r) * (o.gridW - 1) + c;
+        for (uint32_t q = 0; q < P; ++q) o.params[e * P + q] = Real(hz[s * P + q]);
+      }
+      if (r + 1 < o.gridH && vt) {
+        const uint64_t e = grid_edge(o, r, c, true), s = uint64_t(r) * o.gridW + c;
+        for (uint32_t q = 0; q < P; ++q) o.params[e * P + q] = Real(vt[s * P + q]);
+      }
+    }
+}
+
+template <typename O>
+int grid_fill_synthetic(O& o, uint64_t seed, double p_lo, double p_hi) {
+  using Real = typename std::remove_reference<decltype(o.params[0])>::type;
+  if (o.gridH == 0) { o.err = "not a grid"; return LPMP_ERR_STATE; }
+  const uint32_t P = o.P(), L = o.L;
+  const uint64_t W = o.gridW;
+  for (uint64_t k = 0; k < o.N * L; ++k) o.theta[k] = Real(lpmp_synth_u01(seed, LPMP_SYNTH_STREAM_UNARY, k));
+  for (uint32_t r = 0; r < o.gridH; ++r)
+    for (uint32_t c = 0; c < o.gridW; ++c)
+      for (int v = 0; v < 2; ++v) {
+        if (v == 0 ? c + 1 >= o.gridW : r + 1 >= o.gridH) continue;
+        const uint64_t e = grid_edge(o, r, c, v == 1);
+        const uint64_t slot = uint64_t(r) * W + c;  // device plane slot (pitch W for both planes)
+        for (uint32_t q = 0; q < P; ++q) {
+          double val;
+          if (o.pw == LPMP_PAIRWISE_TRUNCLIN) val = q == 0 ? p_lo : p_hi;
+          else val = lpmp_synth_param(seed, v == 0 ? LPMP_SYNTH_STREAM_HORIZONTAL : LPMP_SYNTH_STREAM_VERTICAL, slot * P + q, p_lo, p_hi);
+          o.params[e * P + q] = Real(val);
+        }
+      }
+  return LPMP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int LPMP_FN(create)(int dtype, int device, lpmp_solver** out) {
+  (void)device;
+  if (!out || (dtype != LPMP_F32 && dtype != LPMP_F64)) return LPMP_ERR_INVALID;
+  Handle* h = new Handle();
+  h->dtype = dtype;
+  if (dtype == LPMP_F32) h->f = new Oracle<float>(); else h->d = new Oracle<double>();
+  *out = reinterpret_cast<lpmp_solver*>(h);
+  return LPMP_OK;
+}
+int LPMP_FN(destroy)(lpmp_solver* h) { delete H(h); return LPMP_OK; }
+const char* LPMP_FN(last_error)(const lpmp_solver* h) { return h ? GET_ERR(H(h)).c_str() : "null handle"; }
+
+int LPMP_FN(add_unaries)(lpmp_solver* h, uint64_t n, uint32_t L, const double* theta) { return DISPATCH(H(h), o.add_unaries(n, L, theta)); }
+int LPMP_FN(add_pairwise_dense)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* t) { return DISPATCH(H(h), o.add_pairwise(LPMP_PAIRWISE_DENSE, m, i, j, t, nullptr)); }
+int LPMP_FN(add_pairwise_potts)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* l) { return DISPATCH(H(h), o.add_pairwise(LPMP_PAIRWISE_POTTS, m, i, j, l, nullptr)); }
+int LPMP_FN(add_pairwise_trunclin)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* s, const double* t) { return DISPATCH(H(h), o.add_pairwise(LPMP_PAIRWISE_TRUNCLIN, m, i, j, s, t)); }
+
+int LPMP_FN(set_node_ranks)(lpmp_solver* h, const uint64_t* rank) {
+  return DISPATCH(H(h), ([&] {
+    if (o.finalized) { o.err = "set_node_ranks after finalize"; return int(LPMP_ERR_STATE); }
+    o.rank.assign(rank, rank + o.N);
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(set_edge_order)(lpmp_solver* h, int eo) {
+  return DISPATCH(H(h), ([&] {
+    if (o.finalized) { o.err = "set_edge_order after finalize"; return int(LPMP_ERR_STATE); }
+    if (eo != LPMP_EDGE_ORDER_LIFO && eo != LPMP_EDGE_ORDER_FIFO) { o.err = "bad edge order"; return int(LPMP_ERR_INVALID); }
+    o.edge_order = eo;
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(set_schedule)(lpmp_solver* h, int) { (void)h; return LPMP_OK; }  // the oracle is always sequential
+
+int LPMP_FN(greedy_colouring)(uint64_t n, uint64_t m, const uint64_t* i, const uint64_t* j, uint32_t* colour, uint32_t* num_colours) {
+  std::vector<std::vector<uint64_t>> adj(n);
+  for (uint64_t e = 0; e < m; ++e) {
+    if (i[e] >= n || j[e] >= n) return LPMP_ERR_INVALID;
+    adj[i[e]].push_back(j[e]);
+    adj[j[e]].push_back(i[e]);
+  }
+  uint32_t nc = 0;
+  std::vector<uint32_t> used;
+  for (uint64_t v = 0; v < n; ++v) {
+    used.clear();
+    for (uint64_t u : adj[v]) if (u < v) used.push_back(colour[u]);
+    std::sort(used.begin(), used.end());
+    uint32_t c = 0;
+    for (uint32_t x : used) { if (x == c) ++c; else if (x > c) break; }
+    colour[v] = c;
+    nc = std::max(nc, c + 1);
+  }
+  if (num_colours) *num_colours = nc;
+  return LPMP_OK;
+}
+
+int LPMP_FN(grid_create)(lpmp_solver* h, uint32_t Hh, uint32_t W, uint32_t L, int type) { return DISPATCH(H(h), grid_create(o, Hh, W, L, type)); }
+int LPMP_FN(grid_set_unaries)(lpmp_solver* h, const void* theta, int src) {
+  return DISPATCH(H(h), ([&] {
+    if (o.gridH == 0) { o.err = "not a grid"; return int(LPMP_ERR_STATE); }
+    using Real = typename std::remove_reference<decltype(o.theta[0])>::type;
+    for (uint64_t k = 0; k < o.N * o.L; ++k) o.theta[k] = src == LPMP_F32 ? Real(static_cast<const float*>(theta)[k]) : Real(static_cast<const double*>(theta)[k]);
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(grid_set_pairwise)(lpmp_solver* h, const void* hz, const void* vt, int src) {
+  return DISPATCH(H(h), ([&] {
+    if (o.gridH == 0) { o.err = "not a grid"; return int(LPMP_ERR_STATE); }
+    if (src == LPMP_F32) grid_set_pairwise_t(o, static_cast<const float*>(hz), static_cast<const float*>(vt));
+    else grid_set_pairwise_t(o, static_cast<const double*>(hz), static_cast<const double*>(vt));
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(grid_fill_synthetic)(lpmp_solver* h, uint64_t seed, double lo, double hi) { return DISPATCH(H(h), grid_fill_synthetic(o, seed, lo, hi)); }
+int LPMP_FN(grid_set_stripe)(lpmp_solver* h, uint32_t, uint32_t) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
+int LPMP_FN(grid_set_boundary_pairwise)(lpmp_solver* h, const void*, const void*, int) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
+int LPMP_FN(grid_boundary_ptrs)(lpmp_solver* h, int, void**, void**, uint64_t*) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
+
+int LPMP_FN(finalize)(lpmp_solver* h) { return DISPATCH(H(h), o.finalize()); }
+int LPMP_FN(begin)(lpmp_solver* h) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; o.repam = -1; return int(LPMP_OK); })()); }
+int LPMP_FN(end)(lpmp_solver* h) { return DISPATCH(H(h), need_final(o)); }
+int LPMP_FN(set_reparametrization)(lpmp_solver* h, int mode) {
+  return DISPATCH(H(h), ([&] {
+    if (mode < 0 || mode > 2) { o.err = "reparametrization mode unknown"; return int(LPMP_ERR_INVALID); }
+    o.repam = mode;
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(compute_pass)(lpmp_solver* h, uint64_t) {
+  return DISPATCH(H(h), ([&] { if (int r = need_repam(o)) return r; o.pass(true, false); o.pass(false, false); return int(LPMP_OK); })());
+}
+int LPMP_FN(compute_forward_pass)(lpmp_solver* h) { return DISPATCH(H(h), ([&] { if (int r = need_repam(o)) return r; o.pass(true, false); return int(LPMP_OK); })()); }
+int LPMP_FN(compute_backward_pass)(lpmp_solver* h) { return DISPATCH(H(h), ([&] { if (int r = need_repam(o)) return r; o.pass(false, false); return int(LPMP_OK); })()); }
+int LPMP_FN(compute_forward_pass_and_primal)(lpmp_solver* h, uint64_t) { return DISPATCH(H(h), ([&] { if (int r = need_repam(o)) return r; o.pass(true, true); return int(LPMP_OK); })()); }
+int LPMP_FN(compute_backward_pass_and_primal)(lpmp_solver* h, uint64_t) { return DISPATCH(H(h), ([&] { if (int r = need_repam(o)) return r; o.pass(false, true); return int(LPMP_OK); })()); }
+int LPMP_FN(lower_bound)(lpmp_solver* h, double* out) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; *out = o.lower_bound(); return int(LPMP_OK); })()); }
+int LPMP_FN(evaluate_primal)(lpmp_solver* h, double* out) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; *out = o.evaluate_primal(); return int(LPMP_OK); })()); }
+int LPMP_FN(check_primal_consistency)(lpmp_solver* h, int* out) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; *out = 1; return int(LPMP_OK); })()); }
+int LPMP_FN(add_to_constant)(lpmp_solver* h, double x) { return DISPATCH(H(h), ([&] { o.constant += x; return int(LPMP_OK); })()); }
+int LPMP_FN(num_factors)(const lpmp_solver* h, uint64_t* out) { return DISPATCH(H(h), ([&] { *out = o.N + o.E; return int(LPMP_OK); })()); }
+int LPMP_FN(num_messages)(const lpmp_solver* h, uint64_t* out) { return DISPATCH(H(h), ([&] { *out = 2 * o.E; return int(LPMP_OK); })()); }
+
+int LPMP_FN(get_labeling)(lpmp_solver* h, uint32_t* out) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; std::copy(o.labels.begin(), o.labels.end(), out); return int(LPMP_OK); })()); }
+int LPMP_FN(get_unaries)(lpmp_solver* h, double* th) { return DISPATCH(H(h), ([&] { for (uint64_t k = 0; k < o.N * o.L; ++k) th[k] = double(o.theta[k]); return int(LPMP_OK); })()); }
+int LPMP_FN(get_messages)(lpmp_solver* h, double* a, double* b) {
+  return DISPATCH(H(h), ([&] {
+    if (int r = need_final(o)) return r;
+    for (uint64_t k = 0; k < o.E * o.L; ++k) { if (a) a[k] = double(o.a[k]); if (b) b[k] = double(o.b[k]); }
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(set_messages)(lpmp_solver* h, const double* a, const double* b) {
+  return DISPATCH(H(h), ([&] {
+    if (int r = need_final(o)) return r;
+    using Real = typename std::remove_reference<decltype(o.a[0])>::type;
+    for (uint64_t k = 0; k < o.E * o.L; ++k) { if (a) o.a[k] = Real(a[k]); if (b) o.b[k] = Real(b[k]); }
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(set_unaries)(lpmp_solver* h, const double* th) {
+  return DISPATCH(H(h), ([&] {
+    using Real = typename std::remove_reference<decltype(o.theta[0])>::type;
+    for (uint64_t k = 0; k < o.N * o.L; ++k) o.theta[k] = Real(th[k]);
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(stats)(lpmp_solver* h, lpmp_stats* out) {
+  return DISPATCH(H(h), ([&] {
+    std::memset(out, 0, sizeof(*out));
+    out->num_nodes = o.N; out->num_edges = o.E; out->num_labels = o.L; out->num_levels = o.N;
+    out->message_updates = o.message_updates;
+    const double s = sizeof(o.theta[0]);
+    out->algorithmic_bytes_per_pass = s * (2.0 * o.N * o.L + double(o.E) * (o.P() + 5.0 * o.L));
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(synchronize)(lpmp_solver*) { return LPMP_OK; }
+int LPMP_FN(stream)(lpmp_solver*, void** out) { if (out) *out = nullptr; return LPMP_OK; }
+
+// oracle-only switch: evaluate Potts / truncated-linear min-marginals through the materialised dense table
+int lpmp_oracle_force_dense(lpmp_solver* h, int on) { return DISPATCH(H(h), ([&] { o.force_dense = on != 0; return int(LPMP_OK); })()); }
+
+}  // extern "C"
+
+namespace {
+template <typename Real>
+int minmarginal(int type, uint64_t n, uint32_t L1, uint32_t L2, const double* p0, const double* p1, const double* msg1, const double* msg2, int side, double* out, double* lb) {
+  if (type != LPMP_PAIRWISE_DENSE && L1 != L2) return LPMP_ERR_INVALID;
+  const Real INF = std::numeric_limits<Real>::infinity();
+  for (uint64_t k = 0; k < n; ++k) {
+    auto c = [&](uint32_t x, uint32_t y) -> Real {
+      if (type == LPMP_PAIRWISE_DENSE) return Real(p0[(k * L1 + x) * L2 + y]);
+      if (type == LPMP_PAIRWISE_POTTS) return x == y ? Real(0) : Real(p0[k]);
+      const uint32_t d = x > y ? x - y : y - x;
+      return std::min(Real(Real(p0[k]) * Real(d)), Real(p1[k]));
+    };
+    auto m1 = [&](uint32_t x) { return msg1 ? Real(msg1[k * L1 + x]) : Real(0); };
+    auto m2 = [&](uint32_t y) { return msg2 ? Real(msg2[k * L2 + y]) : Real(0); };
+    if (side == 0) {
+      for (uint32_t x = 0; x < L1; ++x) { Real m = INF; for (uint32_t y = 0; y < L2; ++y) m = std::min(m, Real(c(x, y) + m2(y))); out[k * L1 + x] = double(Real(m + m1(x))); }
+    } else {
+      for (uint32_t y = 0; y < L2; ++y) { Real m = INF; for (uint32_t x = 0; x < L1; ++x) m = std::min(m, Real(c(x, y) + m1(x))); out[k * L2 + y] = double(Real(m + m2(y))); }
+    }
+    if (lb) {
+      Real best = INF;
+      for (uint32_t x = 0; x < L1; ++x) { Real m = INF; for (uint32_t y = 0; y < L2; ++y) m = std::min(m, Real(c(x, y) + m2(y))); best = std::min(best, Real(m + m1(x))); }
+      lb[k] = double(best);
+    }
+  }
+  return LPMP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int LPMP_FN(minmarginal_dense)(int dtype, uint64_t n, uint32_t L1, uint32_t L2, const double* t, const double* msg1, const double* msg2, int side, double* out, double* lb) {
+  return dtype == LPMP_F32 ? minmarginal<float>(LPMP_PAIRWISE_DENSE, n, L1, L2, t, nullptr, msg1, msg2, side, out, lb) : minmarginal<double>(LPMP_PAIRWISE_DENSE, n, L1, L2, t, nullptr, msg1, msg2, side, out, lb);
+}
+int LPMP_FN(minmarginal_potts)(int dtype, uint64_t n, uint32_t L, const double* lambda, const double* msg1, const double* msg2, int side, double* out, double* lb) {
+  return dtype == LPMP_F32 ? minmarginal<float>(LPMP_PAIRWISE_POTTS, n, L, L, lambda, nullptr, msg1, msg2, side, out, lb) : minmarginal<double>(LPMP_PAIRWISE_POTTS, n, L, L, lambda, nullptr, msg1, msg2, side, out, lb);
+}
+int LPMP_FN(minmarginal_trunclin)(int dtype, uint64_t n, uint32_t L, const double* slope, const double* trunc, const double* msg1, const double* msg2, int side, double* out, double* lb) {
+  return dtype == LPMP_F32 ? minmarginal<float>(LPMP_PAIRWISE_TRUNCLIN, n, L, L, slope, trunc, msg1, msg2, side, out, lb) : minmarginal<double>(LPMP_PAIRWISE_TRUNCLIN, n, L, L, slope, trunc, msg1, msg2, side, out, lb);
+}
+int LPMP_FN(unary_min)(int dtype, uint64_t n, uint32_t L, const double* theta, double* lb, uint32_t* arg) {
+  for (uint64_t k = 0; k < n; ++k) {
+    uint32_t best = 0;
+    for (uint32_t x = 1; x < L; ++x) {
+      const bool less = dtype == LPMP_F32 ? float(theta[k * L + x]) < float(theta[k * L + best]) : theta[k * L + x] < theta[k * L + best];
+      if (less) best = x;
+    }
+    if (lb) lb[k] = dtype == LPMP_F32 ? double(float(theta[k * L + best])) : theta[k * L + best];
+    if (arg) arg[k] = best;
+  }
+  return LPMP_OK;
+}
+
+}  // extern "C"
