@@ -80,7 +80,10 @@ class StandardVisitor:
             self.remainingIter_ = min(1, self.remainingIter_)
         if (c.computeLowerBound and self.curIter_ >= self.minDualImprovementInterval
                 and self.minDualImprovement is not None):
-            prev = self.lowerBound_[len(self.lowerBound_) - 1 - self.minDualImprovementInterval]
+            # the reference indexes lowerBound_[size-1-interval]; at the first eligible visit that is index -1 (an
+            # out-of-bounds read, standard_visitor.hxx:166-167) -- we skip that one visit instead of reading garbage
+            k = len(self.lowerBound_) - 1 - self.minDualImprovementInterval
+            prev = self.lowerBound_[k] if k >= 0 else -math.inf
             if self.minDualImprovement > 0 and lowerBound - prev < self.minDualImprovement:
                 self._say(f"Dual improvement smaller than {self.minDualImprovement} after "
                           f"{self.minDualImprovementInterval} iterations, terminating optimization")

@@ -110,7 +110,7 @@ public:
   void assign(const std::string& text) override {
     T v = detail::convert<T>(text);
     if (constraint_ != nullptr && !constraint_->check(v))
-      throw ArgException("value violates " + constraint_->description(), name_);
+      throw ArgException("value violates " + constraint_->description() + " (value text '" + text + "', arg " + name_ + ")", name_);
     value_ = v;
     set_ = true;
   }
