@@ -85,6 +85,9 @@ int LPMP_FN(add_pairwise_trunclin)(lpmp_solver* h, uint64_t m, const uint64_t* i
 int LPMP_FN(set_node_ranks)(lpmp_solver* h, const uint64_t* rank /* [N], distinct */);
 int LPMP_FN(set_edge_order)(lpmp_solver* h, int edge_order);
 int LPMP_FN(set_schedule)(lpmp_solver* h, int schedule);
+/* launch-shape knobs of the device schedule (no effect on results): "wavefront_vpl" (labels per lane),
+ * "wavefront_warps" (bands per CTA), "wavefront_stages" (prefetch depth), "wavefront_max_ctas".  Before finalize. */
+int LPMP_FN(set_tuning)(lpmp_solver* h, const char* key, int value);
 /* Deterministic greedy colouring in node order (host utility, no handle state): colour[i] = smallest colour
  * not used by an already coloured neighbour.  Returns the number of colours through *num_colours. */
 int LPMP_FN(greedy_colouring)(uint64_t n, uint64_t m, const uint64_t* i, const uint64_t* j, uint32_t* colour, uint32_t* num_colours);
@@ -136,7 +139,7 @@ int LPMP_FN(get_unaries)(lpmp_solver* h, double* theta /* [N][L] */);
 int LPMP_FN(get_messages)(lpmp_solver* h, double* a /* [E][L] */, double* b /* [E][L] */); /* edge insertion order */
 int LPMP_FN(set_messages)(lpmp_solver* h, const double* a, const double* b);
 int LPMP_FN(set_unaries)(lpmp_solver* h, const double* theta);
-int LPMP_FN(stats)(lpmp_solver* h, lpmp_stats* out);
+int LPMP_FN(get_stats)(lpmp_solver* h, lpmp_stats* out);
 int LPMP_FN(synchronize)(lpmp_solver* h);
 /* the CUDA stream (cudaStream_t) all work of this handle is enqueued on, for event timing by the caller */
 int LPMP_FN(stream)(lpmp_solver* h, void** out);

@@ -40,6 +40,7 @@ SIGNATURES = {
     "set_node_ranks": [_vp, _pu64],
     "set_edge_order": [_vp, _i],
     "set_schedule": [_vp, _i],
+    "set_tuning": [_vp, C.c_char_p, _i],
     "greedy_colouring": [_u64, _u64, _pu64, _pu64, _pu32, _pu32],
     "grid_create": [_vp, _u32, _u32, _u32, _i],
     "grid_set_unaries": [_vp, _vp, _i],
@@ -68,7 +69,7 @@ SIGNATURES = {
     "get_messages": [_vp, _pd, _pd],
     "set_messages": [_vp, _pd, _pd],
     "set_unaries": [_vp, _pd],
-    "stats": [_vp, C.POINTER(Stats)],
+    "get_stats": [_vp, C.POINTER(Stats)],
     "synchronize": [_vp],
     "stream": [_vp, C.POINTER(_vp)],
     "minmarginal_dense": [_i, _u64, _u32, _u32, _pd, _pd, _pd, _i, _pd, _pd],

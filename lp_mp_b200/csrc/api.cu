@@ -1,0 +1,845 @@
+// C ABI of the B200-native LP_MP message-passing hot path (include/lpmp_b200.h): handle, problem construction,
+// schedule construction (host), kernel launches.  Host logic mirrors LP<FMC> (/root/reference/include/LP_MP.h:200-585)
+// for the SRMP simplex configuration; all arithmetic on potentials happens in the kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/lpmp_b200.h"
+#include "../../include/lpmp_synthetic.h"
+#include "kernels_general.cuh"
+#include "wavefront_launch.h"
+
+namespace lpmp {
+
+template <typename Real, int PW>
+cudaError_t launch_family(const GridArgs<Real>& args, uint32_t L, const WavefrontTuning& tune, int num_sms, cudaStream_t stream);
+
+bool wavefront_supported(int pw, uint32_t L, int vpl, int stages) {
+  if (pw != LPMP_PAIRWISE_POTTS && pw != LPMP_PAIRWISE_TRUNCLIN) return false;
+  if (stages != 4 && stages != 8) return false;
+  if (vpl == 4) return L == 8 || L == 16 || L == 32 || L == 64;
+  if (vpl == 2) return L == 16 || L == 32;
+  return false;
+}
+int wavefront_rows_per_band(uint32_t L, int vpl) { return 32 / (int)(L / vpl); }
+
+template <typename Real>
+cudaError_t launch_wavefront(const GridArgs<Real>& args, int pw, uint32_t L, const WavefrontTuning& tune, int num_sms, cudaStream_t stream) {
+  if (pw == LPMP_PAIRWISE_POTTS) return launch_family<Real, LPMP_PAIRWISE_POTTS>(args, L, tune, num_sms, stream);
+  if (pw == LPMP_PAIRWISE_TRUNCLIN) return launch_family<Real, LPMP_PAIRWISE_TRUNCLIN>(args, L, tune, num_sms, stream);
+  return cudaErrorInvalidValue;
+}
+
+// ---- small helpers ----------------------------------------------------------------------------------------------
+template <typename T>
+struct DeviceBuffer {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  size_t bytes() const { return n * sizeof(T); }
+  ~DeviceBuffer() { release(); }
+};
+
+template <typename Dst, typename Src>
+__global__ void convert_kernel(Dst* __restrict__ dst, const Src* __restrict__ src, uint64_t n) {
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) dst[k] = (Dst)src[k];
+}
+
+// scatter compact [rows][cols][P] host layout into plane slots r*W+c (P reals per slot)
+template <typename Dst, typename Src>
+__global__ void scatter_plane_kernel(Dst* __restrict__ dst, const Src* __restrict__ src, uint32_t rows, uint32_t cols, uint32_t W, uint32_t P) {
+  const uint64_t n = (uint64_t)rows * cols * P;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = (uint32_t)(k % P);
+    const uint64_t cell = k / P;
+    const uint32_t c = (uint32_t)(cell % cols), r = (uint32_t)(cell / cols);
+    dst[((uint64_t)r * W + c) * P + p] = (Dst)src[k];
+  }
+}
+
+template <typename Real>
+__global__ void synth_fill_kernel(Real* __restrict__ dst, uint64_t n, uint64_t seed, uint64_t stream, double lo, double hi, int P, int trunclin) {
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+    double v;
+    if (trunclin) v = (k % P) == 0 ? lo : hi;
+    else v = lpmp_synth_param(seed, stream, k, lo, hi);
+    dst[k] = (Real)v;
+  }
+}
+
+static inline int grid_for(uint64_t n, int block, int cap = 148 * 16) {
+  uint64_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)cap) g = cap;
+  return (int)g;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      err = std::string(#expr) + ": " + cudaGetErrorString(_e);                              \
+      return LPMP_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+struct ISolver {
+  std::string err;
+  virtual ~ISolver() {}
+  virtual int add_unaries(uint64_t n, uint32_t L, const double* theta) = 0;
+  virtual int add_pairwise(int type, uint64_t m, const uint64_t* i, const uint64_t* j, const double* p0, const double* p1) = 0;
+  virtual int set_node_ranks(const uint64_t* rank) = 0;
+  virtual int set_edge_order(int eo) = 0;
+  virtual int set_schedule(int s) = 0;
+  virtual int set_tuning(const char* key, int value) = 0;
+  virtual int grid_create(uint32_t H, uint32_t W, uint32_t L, int type) = 0;
+  virtual int grid_set_unaries(const void* theta, int src) = 0;
+  virtual int grid_set_pairwise(const void* hz, const void* vt, int src) = 0;
+  virtual int grid_fill_synthetic(uint64_t seed, double lo, double hi) = 0;
+  virtual int grid_set_stripe(uint32_t row0, uint32_t H_total) = 0;
+  virtual int grid_set_boundary_pairwise(const void* top, const void* bottom, int src) = 0;
+  virtual int grid_boundary_ptrs(int which, void** owned, void** halo, uint64_t* bytes) = 0;
+  virtual int finalize() = 0;
+  virtual int begin() = 0;
+  virtual int set_reparametrization(int mode) = 0;
+  virtual int pass(bool forward, bool primal) = 0;
+  virtual int lower_bound(double* out) = 0;
+  virtual int evaluate_primal(double* out) = 0;
+  virtual int check_primal_consistency(int* out) = 0;
+  virtual int add_to_constant(double x) = 0;
+  virtual int counts(uint64_t* factors, uint64_t* messages) = 0;
+  virtual int get_labeling(uint32_t* out) = 0;
+  virtual int get_unaries(double* th) = 0;
+  virtual int get_messages(double* a, double* b) = 0;
+  virtual int set_messages(const double* a, const double* b) = 0;
+  virtual int set_unaries(const double* th) = 0;
+  virtual int stats(lpmp_stats* out) = 0;
+  virtual int synchronize() = 0;
+  virtual void* stream_ptr() = 0;
+};
+
+template <typename Real>
+struct Solver : ISolver {
+  int device = 0, num_sms = 148;
+  cudaStream_t stream = nullptr;
+  // problem
+  uint64_t N = 0, E = 0, slots = 0;
+  uint32_t L = 0, gridH = 0, gridW = 0, row0 = 0, H_total = 0;
+  int pw = -1, repam = -1, edge_order = LPMP_EDGE_ORDER_LIFO, schedule = -1;
+  bool finalized = false, labels_valid = false, is_grid = false, striped = false;
+  double constant = 0.0;
+  WavefrontTuning tune;
+  // host staging (general graphs)
+  std::vector<double> h_theta, h_params;
+  std::vector<uint64_t> h_ei, h_ej, h_rank;
+  // device state
+  DeviceBuffer<Real> theta, a, b, params;
+  DeviceBuffer<Real> halo_top, halo_bot, own_top, own_bot, p_top, p_bot;
+  DeviceBuffer<uint32_t> d_ei, d_ej, inc_edge, level_nodes, labels;
+  DeviceBuffer<uint64_t> inc_off;
+  DeviceBuffer<uint8_t> inc_flags;
+  DeviceBuffer<double> partial, result;
+  DeviceBuffer<unsigned int> control;  // [0] ticket, [1..] band progress
+  std::vector<uint64_t> level_off;     // host
+  uint64_t launches = 0, updates = 0;
+  static constexpr int kBoundCtas = 148 * 4;
+
+  explicit Solver(int dev) : device(dev) {}
+  ~Solver() override { if (stream) cudaStreamDestroy(stream); }
+
+  int init() {
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUDA_TRY(partial.alloc(kBoundCtas));
+    CUDA_TRY(result.alloc(1));
+    return LPMP_OK;
+  }
+
+  uint32_t P() const { return pairwise_param_count(pw, L); }
+  int bad_state(const char* m) { err = m; return LPMP_ERR_STATE; }
+  int need_final() { return finalized ? LPMP_OK : bad_state("finalize() has not been called"); }
+
+  // ---- construction: general graphs ---------------------------------------------------------------------------
+  int add_unaries(uint64_t n, uint32_t L_, const double* th) override {
+    if (finalized) return bad_state("add_unaries after finalize");
+    if (is_grid) return bad_state("add_unaries on a grid LP");
+    if (L_ == 0 || (L != 0 && L != L_)) { err = "one label count per LP"; return LPMP_ERR_UNSUPPORTED; }
+    if (!th) { err = "null theta"; return LPMP_ERR_INVALID; }
+    L = L_;
+    h_theta.insert(h_theta.end(), th, th + n * L);
+    N += n;
+    return LPMP_OK;
+  }
+  int add_pairwise(int type, uint64_t m, const uint64_t* i, const uint64_t* j, const double* p0, const double* p1) override {
+    if (finalized) return bad_state("add_pairwise after finalize");
+    if (is_grid) return bad_state("add_pairwise on a grid LP");
+    if (pw != -1 && pw != type) { err = "one pairwise family per LP"; return LPMP_ERR_UNSUPPORTED; }
+    for (uint64_t k = 0; k < m; ++k)
+      if (i[k] >= N || j[k] >= N || i[k] == j[k]) { err = "edge endpoint out of range"; return LPMP_ERR_INVALID; }
+    pw = type;
+    const uint32_t Pn = P();
+    h_ei.insert(h_ei.end(), i, i + m);
+    h_ej.insert(h_ej.end(), j, j + m);
+    if (type == LPMP_PAIRWISE_DENSE) h_params.insert(h_params.end(), p0, p0 + m * Pn);
+    else if (type == LPMP_PAIRWISE_POTTS) h_params.insert(h_params.end(), p0, p0 + m);
+    else for (uint64_t k = 0; k < m; ++k) { h_params.push_back(p0[k]); h_params.push_back(p1[k]); }
+    E += m;
+    return LPMP_OK;
+  }
+  int set_node_ranks(const uint64_t* rank) override {
+    if (finalized) return bad_state("set_node_ranks after finalize");
+    h_rank.assign(rank, rank + N);
+    return LPMP_OK;
+  }
+  int set_edge_order(int eo) override {
+    if (finalized) return bad_state("set_edge_order after finalize");
+    if (eo != LPMP_EDGE_ORDER_LIFO && eo != LPMP_EDGE_ORDER_FIFO) { err = "bad edge order"; return LPMP_ERR_INVALID; }
+    edge_order = eo;
+    return LPMP_OK;
+  }
+  int set_schedule(int s) override {
+    if (finalized) return bad_state("set_schedule after finalize");
+    if (s != LPMP_SCHEDULE_LEVELS && s != LPMP_SCHEDULE_WAVEFRONT) { err = "bad schedule"; return LPMP_ERR_INVALID; }
+    schedule = s;
+    return LPMP_OK;
+  }
+  int set_tuning(const char* key, int value) override {
+    const std::string k(key ? key : "");
+    if (k == "wavefront_vpl") tune.vpl = value;
+    else if (k == "wavefront_warps") tune.warps = value;
+    else if (k == "wavefront_stages") tune.stages = value;
+    else if (k == "wavefront_max_ctas") tune.max_ctas = value;
+    else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
+    return LPMP_OK;
+  }
+
+  // ---- construction: grids --------------------------------------------------------------------------------------
+  int grid_create(uint32_t H, uint32_t W, uint32_t L_, int type) override {
+    if (N != 0 || finalized) return bad_state("grid_create on a non-empty LP");
+    if (H == 0 || W == 0 || L_ == 0 || type < 0 || type > 2) { err = "bad grid shape"; return LPMP_ERR_INVALID; }
+    is_grid = true;
+    gridH = H; gridW = W; L = L_; pw = type;
+    row0 = 0; H_total = H;
+    N = (uint64_t)H * W;
+    E = (uint64_t)H * (W - 1) + (uint64_t)(H - 1) * W;
+    slots = 2 * N;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(theta.alloc(N * L));
+    CUDA_TRY(a.alloc(slots * L));
+    CUDA_TRY(b.alloc(slots * L));
+    CUDA_TRY(params.alloc(slots * P()));
+    CUDA_TRY(cudaMemsetAsync(theta.p, 0, theta.bytes(), stream));
+    CUDA_TRY(cudaMemsetAsync(a.p, 0, a.bytes(), stream));
+    CUDA_TRY(cudaMemsetAsync(b.p, 0, b.bytes(), stream));
+    CUDA_TRY(cudaMemsetAsync(params.p, 0, params.bytes(), stream));
+    return LPMP_OK;
+  }
+  template <typename Src>
+  int upload_converted(Real* dst, const Src* src, uint64_t n) {
+    DeviceBuffer<Src> tmp;
+    CUDA_TRY(tmp.alloc(n));
+    CUDA_TRY(cudaMemcpyAsync(tmp.p, src, n * sizeof(Src), cudaMemcpyHostToDevice, stream));
+    convert_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(dst, tmp.p, n);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
+  template <typename Src>
+  int upload_plane(Real* dst, const Src* src, uint32_t rows, uint32_t cols, uint32_t Pn) {
+    const uint64_t n = (uint64_t)rows * cols * Pn;
+    if (n == 0) return LPMP_OK;
+    DeviceBuffer<Src> tmp;
+    CUDA_TRY(tmp.alloc(n));
+    CUDA_TRY(cudaMemcpyAsync(tmp.p, src, n * sizeof(Src), cudaMemcpyHostToDevice, stream));
+    scatter_plane_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(dst, tmp.p, rows, cols, gridW, Pn);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
+  int grid_set_unaries(const void* th, int src) override {
+    if (!is_grid) return bad_state("not a grid");
+    if (!th) { err = "null theta"; return LPMP_ERR_INVALID; }
+    if (src == LPMP_F32) return upload_converted<float>(theta.p, static_cast<const float*>(th), N * L);
+    return upload_converted<double>(theta.p, static_cast<const double*>(th), N * L);
+  }
+  int grid_set_pairwise(const void* hz, const void* vt, int src) override {
+    if (!is_grid) return bad_state("not a grid");
+    const uint32_t Pn = P();
+    Real* ph = params.p;
+    Real* pv = params.p + N * Pn;
+    int r = LPMP_OK;
+    if (src == LPMP_F32) {
+      if (hz) r = upload_plane<float>(ph, static_cast<const float*>(hz), gridH, gridW - 1, Pn);
+      if (r == LPMP_OK && vt) r = upload_plane<float>(pv, static_cast<const float*>(vt), gridH - 1, gridW, Pn);
+    } else {
+      if (hz) r = upload_plane<double>(ph, static_cast<const double*>(hz), gridH, gridW - 1, Pn);
+      if (r == LPMP_OK && vt) r = upload_plane<double>(pv, static_cast<const double*>(vt), gridH - 1, gridW, Pn);
+    }
+    return r;
+  }
+  int grid_fill_synthetic(uint64_t seed, double lo, double hi) override {
+    if (!is_grid) return bad_state("not a grid");
+    const uint32_t Pn = P();
+    const int tl = pw == LPMP_PAIRWISE_TRUNCLIN;
+    synth_fill_kernel<Real><<<grid_for(N * L, 256), 256, 0, stream>>>(theta.p, N * L, seed, LPMP_SYNTH_STREAM_UNARY, 0.0, 1.0, 1, 0);
+    synth_fill_kernel<Real><<<grid_for(N * Pn, 256), 256, 0, stream>>>(params.p, N * Pn, seed, LPMP_SYNTH_STREAM_HORIZONTAL, lo, hi, Pn, tl);
+    synth_fill_kernel<Real><<<grid_for(N * Pn, 256), 256, 0, stream>>>(params.p + N * Pn, N * Pn, seed, LPMP_SYNTH_STREAM_VERTICAL, lo, hi, Pn, tl);
+    launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return LPMP_OK;
+  }
+  int grid_set_stripe(uint32_t r0, uint32_t Ht) override {
+    if (!is_grid || finalized) return bad_state("grid_set_stripe: need an unfinalized grid");
+    if ((uint64_t)r0 + gridH > Ht) { err = "stripe exceeds the full grid"; return LPMP_ERR_INVALID; }
+    row0 = r0; H_total = Ht; striped = true;
+    const uint64_t n = (uint64_t)gridW * L;
+    if (row0 > 0) { CUDA_TRY(halo_top.alloc(n)); CUDA_TRY(own_top.alloc(n)); CUDA_TRY(p_top.alloc((uint64_t)gridW * P()));
+      CUDA_TRY(cudaMemsetAsync(halo_top.p, 0, halo_top.bytes(), stream)); CUDA_TRY(cudaMemsetAsync(own_top.p, 0, own_top.bytes(), stream)); CUDA_TRY(cudaMemsetAsync(p_top.p, 0, p_top.bytes(), stream)); }
+    if (row0 + gridH < H_total) { CUDA_TRY(halo_bot.alloc(n)); CUDA_TRY(own_bot.alloc(n)); CUDA_TRY(p_bot.alloc((uint64_t)gridW * P()));
+      CUDA_TRY(cudaMemsetAsync(halo_bot.p, 0, halo_bot.bytes(), stream)); CUDA_TRY(cudaMemsetAsync(own_bot.p, 0, own_bot.bytes(), stream)); CUDA_TRY(cudaMemsetAsync(p_bot.p, 0, p_bot.bytes(), stream)); }
+    return LPMP_OK;
+  }
+  int grid_set_boundary_pairwise(const void* top, const void* bottom, int src) override {
+    if (!striped) return bad_state("grid_set_boundary_pairwise: not a stripe");
+    const uint64_t n = (uint64_t)gridW * P();
+    int r = LPMP_OK;
+    if (top && p_top.p) r = src == LPMP_F32 ? upload_converted<float>(p_top.p, static_cast<const float*>(top), n) : upload_converted<double>(p_top.p, static_cast<const double*>(top), n);
+    if (r == LPMP_OK && bottom && p_bot.p) r = src == LPMP_F32 ? upload_converted<float>(p_bot.p, static_cast<const float*>(bottom), n) : upload_converted<double>(p_bot.p, static_cast<const double*>(bottom), n);
+    return r;
+  }
+  int grid_boundary_ptrs(int which, void** owned, void** halo, uint64_t* bytes) override {
+    if (!striped) return bad_state("grid_boundary_ptrs: not a stripe");
+    if (owned) *owned = which == 0 ? (void*)own_top.p : (void*)own_bot.p;
+    if (halo) *halo = which == 0 ? (void*)halo_top.p : (void*)halo_bot.p;
+    if (bytes) *bytes = (uint64_t)gridW * L * sizeof(Real);
+    return LPMP_OK;
+  }
+
+  // ---- finalize: SortFactors + weights (include/LP_MP.h:730-797,1230-1449) realised as CSR + level sets ---------
+  // edge e of a grid in insertion order (per node: horizontal, then vertical) -> storage slot
+  void grid_edge_lists(std::vector<uint64_t>& ei, std::vector<uint64_t>& ej, std::vector<uint64_t>& slot) const {
+    for (uint32_t r = 0; r < gridH; ++r)
+      for (uint32_t c = 0; c < gridW; ++c) {
+        const uint64_t i = (uint64_t)r * gridW + c;
+        if (c + 1 < gridW) { ei.push_back(i); ej.push_back(i + 1); slot.push_back(i); }
+        if (r + 1 < gridH) { ei.push_back(i); ej.push_back(i + gridW); slot.push_back(N + i); }
+      }
+  }
+
+  int build_levels(const std::vector<uint64_t>& ei, const std::vector<uint64_t>& ej, const std::vector<uint64_t>& slot) {
+    std::vector<uint64_t> rank = h_rank;
+    if (rank.empty()) { rank.resize(N); std::iota(rank.begin(), rank.end(), uint64_t(0)); }
+    {
+      std::vector<uint64_t> sorted = rank;
+      std::sort(sorted.begin(), sorted.end());
+      if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) { err = "node ranks must be distinct"; return LPMP_ERR_INVALID; }
+    }
+    const uint64_t m = ei.size();
+    // per-node message order: first-variable type, then second-variable type; LIFO / FIFO inside a type
+    std::vector<uint64_t> cnt_first(N + 1, 0), cnt_second(N + 1, 0);
+    for (uint64_t e = 0; e < m; ++e) { ++cnt_first[ei[e]]; ++cnt_second[ej[e]]; }
+    std::vector<uint64_t> off(N + 1, 0);
+    for (uint64_t i = 0; i < N; ++i) off[i + 1] = off[i] + cnt_first[i] + cnt_second[i];
+    std::vector<uint32_t> inc_e(2 * m);
+    std::vector<uint8_t> inc_f(2 * m);
+    std::vector<uint64_t> pos_first(N), pos_second(N);
+    for (uint64_t i = 0; i < N; ++i) { pos_first[i] = off[i]; pos_second[i] = off[i] + cnt_first[i]; }
+    const bool lifo = edge_order == LPMP_EDGE_ORDER_LIFO;
+    for (uint64_t e = 0; e < m; ++e) {
+      const uint64_t i = ei[e], j = ej[e];
+      const uint64_t ki = lifo ? off[i] + cnt_first[i] - 1 - (pos_first[i] - off[i]) : pos_first[i];
+      const uint64_t kj = lifo ? off[j] + cnt_first[j] + cnt_second[j] - 1 - (pos_second[j] - off[j] - cnt_first[j]) : pos_second[j];
+      ++pos_first[i]; ++pos_second[j];
+      inc_e[ki] = (uint32_t)slot[e]; inc_f[ki] = (uint8_t)(0u | ((rank[j] > rank[i] ? 1u : 0u) << 1));
+      inc_e[kj] = (uint32_t)slot[e]; inc_f[kj] = (uint8_t)(1u | ((rank[i] > rank[j] ? 1u : 0u) << 1));
+    }
+    // levels = longest path from the sources of the DAG "lower rank -> higher rank"
+    std::vector<uint64_t> order(N);
+    std::iota(order.begin(), order.end(), uint64_t(0));
+    std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return rank[x] < rank[y]; });
+    std::vector<std::vector<uint32_t>> nbr_lower(0);
+    std::vector<uint32_t> level(N, 0);
+    std::vector<uint64_t> adj_off(N + 1, 0);
+    for (uint64_t e = 0; e < m; ++e) { ++adj_off[ei[e] + 1]; ++adj_off[ej[e] + 1]; }
+    for (uint64_t i = 0; i < N; ++i) adj_off[i + 1] += adj_off[i];
+    std::vector<uint32_t> adj(2 * m);
+    { std::vector<uint64_t> pos(adj_off.begin(), adj_off.end() - 1);
+      for (uint64_t e = 0; e < m; ++e) { adj[pos[ei[e]]++] = (uint32_t)ej[e]; adj[pos[ej[e]]++] = (uint32_t)ei[e]; } }
+    uint32_t max_level = 0;
+    for (uint64_t k = 0; k < N; ++k) {
+      const uint64_t i = order[k];
+      uint32_t lv = 0;
+      for (uint64_t q = adj_off[i]; q < adj_off[i + 1]; ++q) if (rank[adj[q]] < rank[i]) lv = std::max(lv, level[adj[q]] + 1);
+      level[i] = lv;
+      max_level = std::max(max_level, lv);
+    }
+    level_off.assign((size_t)max_level + 2, 0);
+    for (uint64_t i = 0; i < N; ++i) ++level_off[level[i] + 1];
+    for (size_t l = 0; l + 1 < level_off.size(); ++l) level_off[l + 1] += level_off[l];
+    std::vector<uint32_t> lnodes(N);
+    { std::vector<uint64_t> pos(level_off.begin(), level_off.end() - 1);
+      for (uint64_t k = 0; k < N; ++k) { const uint64_t i = order[k]; lnodes[pos[level[i]]++] = (uint32_t)i; } }
+    CUDA_TRY(inc_off.alloc(N + 1));
+    CUDA_TRY(inc_edge.alloc(std::max<uint64_t>(1, 2 * m)));
+    CUDA_TRY(inc_flags.alloc(std::max<uint64_t>(1, 2 * m)));
+    CUDA_TRY(level_nodes.alloc(N));
+    CUDA_TRY(cudaMemcpyAsync(inc_off.p, off.data(), (N + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    if (m) CUDA_TRY(cudaMemcpyAsync(inc_edge.p, inc_e.data(), 2 * m * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    if (m) CUDA_TRY(cudaMemcpyAsync(inc_flags.p, inc_f.data(), 2 * m, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(level_nodes.p, lnodes.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
+
+  int finalize() override {
+    if (finalized) return bad_state("finalize called twice");
+    if (N == 0) return bad_state("no factors");
+    if (N >= (1ull << 32)) { err = "more than 2^32 nodes"; return LPMP_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(device));
+    if (pw == -1) pw = LPMP_PAIRWISE_POTTS;
+    if (!is_grid) {
+      slots = E;
+      std::vector<Real> tmp(h_theta.size());
+      for (size_t k = 0; k < tmp.size(); ++k) tmp[k] = (Real)h_theta[k];
+      CUDA_TRY(theta.alloc(N * L));
+      CUDA_TRY(cudaMemcpyAsync(theta.p, tmp.data(), theta.bytes(), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      CUDA_TRY(a.alloc(std::max<uint64_t>(1, slots * L)));
+      CUDA_TRY(b.alloc(std::max<uint64_t>(1, slots * L)));
+      CUDA_TRY(cudaMemsetAsync(a.p, 0, a.bytes(), stream));
+      CUDA_TRY(cudaMemsetAsync(b.p, 0, b.bytes(), stream));
+      std::vector<Real> ptmp(h_params.size());
+      for (size_t k = 0; k < ptmp.size(); ++k) ptmp[k] = (Real)h_params[k];
+      CUDA_TRY(params.alloc(std::max<uint64_t>(1, ptmp.size())));
+      if (!ptmp.empty()) CUDA_TRY(cudaMemcpyAsync(params.p, ptmp.data(), ptmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
+      std::vector<uint32_t> e32(E);
+      CUDA_TRY(d_ei.alloc(std::max<uint64_t>(1, E)));
+      CUDA_TRY(d_ej.alloc(std::max<uint64_t>(1, E)));
+      for (uint64_t e = 0; e < E; ++e) e32[e] = (uint32_t)h_ei[e];
+      if (E) CUDA_TRY(cudaMemcpyAsync(d_ei.p, e32.data(), E * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      for (uint64_t e = 0; e < E; ++e) e32[e] = (uint32_t)h_ej[e];
+      if (E) CUDA_TRY(cudaMemcpyAsync(d_ej.p, e32.data(), E * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      if (schedule == LPMP_SCHEDULE_WAVEFRONT) { err = "wavefront schedule needs a grid"; return LPMP_ERR_UNSUPPORTED; }
+      schedule = LPMP_SCHEDULE_LEVELS;
+      std::vector<uint64_t> slot(E);
+      std::iota(slot.begin(), slot.end(), uint64_t(0));
+      if (int r = build_levels(h_ei, h_ej, slot)) return r;
+      h_theta.clear(); h_theta.shrink_to_fit(); h_params.clear(); h_params.shrink_to_fit();
+    } else {
+      const bool wf_ok = wavefront_supported(pw, L, tune.vpl, tune.stages) && h_rank.empty();
+      if (schedule == -1) schedule = wf_ok ? LPMP_SCHEDULE_WAVEFRONT : LPMP_SCHEDULE_LEVELS;
+      if (schedule == LPMP_SCHEDULE_WAVEFRONT && !wf_ok) { err = "no wavefront kernel for this label count / pairwise family / tuning"; return LPMP_ERR_UNSUPPORTED; }
+      if (schedule == LPMP_SCHEDULE_LEVELS) {
+        if (striped) { err = "stripes need the wavefront schedule"; return LPMP_ERR_UNSUPPORTED; }
+        std::vector<uint64_t> ei, ej, slot;
+        grid_edge_lists(ei, ej, slot);
+        if (int r = build_levels(ei, ej, slot)) return r;
+      } else {
+        const int T = wavefront_rows_per_band(L, tune.vpl);
+        const uint32_t bands = (gridH + T - 1) / T;
+        CUDA_TRY(control.alloc(1 + (size_t)bands));
+      }
+    }
+    CUDA_TRY(labels.alloc(N));
+    CUDA_TRY(cudaMemsetAsync(labels.p, 0xff, labels.bytes(), stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    finalized = true;
+    return LPMP_OK;
+  }
+
+  int begin() override { if (int r = need_final()) return r; repam = -1; return LPMP_OK; }
+  int set_reparametrization(int mode) override {
+    if (mode < 0 || mode > 2) { err = "reparametrization mode unknown"; return LPMP_ERR_INVALID; }
+    repam = mode;
+    return LPMP_OK;
+  }
+
+  // ---- one pass: LP::ComputePass(it...) (include/LP_MP.h:981-1005) / ComputePassAndPrimal (:1592-1602) -------
+  int pass(bool forward, bool primal) override {
+    if (int r = need_final()) return r;
+    if (repam < 0) return bad_state("no reparametrization mode set");  // include/LP_MP.h:458
+    CUDA_TRY(cudaSetDevice(device));
+    if (schedule == LPMP_SCHEDULE_LEVELS) {
+      const int G = group_size_for(L);
+      int threads = 256;
+      size_t per_group = 4 * (size_t)L * sizeof(Real);
+      while (threads > G && (threads / G) * per_group > 48 * 1024) threads >>= 1;
+      if ((threads / G) * per_group > 48 * 1024) { err = "label count too large for the level kernel"; return LPMP_ERR_UNSUPPORTED; }
+      const int groups = threads / G;
+      const size_t nlev = level_off.size() - 1;
+      for (size_t q = 0; q < nlev; ++q) {
+        const size_t lv = forward ? q : nlev - 1 - q;
+        const uint64_t cnt = level_off[lv + 1] - level_off[lv];
+        if (cnt == 0) continue;
+        LevelArgs<Real> A;
+        A.theta = theta.p; A.a = a.p; A.b = b.p; A.params = params.p;
+        A.nodes = level_nodes.p + level_off[lv]; A.num_nodes = (uint32_t)cnt;
+        A.inc_off = inc_off.p; A.inc_edge = inc_edge.p; A.inc_flags = inc_flags.p; A.labels = labels.p;
+        A.L = L; A.pw = pw; A.repam = repam; A.forward = forward ? 1 : 0; A.primal = primal ? 1 : 0;
+        const int ctas = (int)std::min<uint64_t>((cnt + groups - 1) / groups, (uint64_t)num_sms * 8);
+        level_update_kernel<Real><<<ctas, threads, (size_t)groups * per_group, stream>>>(A, G);
+        ++launches;
+      }
+      CUDA_TRY(cudaGetLastError());
+    } else {
+      const int T = wavefront_rows_per_band(L, tune.vpl);
+      GridArgs<Real> A;
+      const uint32_t Pn = P();
+      A.theta = theta.p; A.ah = a.p; A.av = a.p + N * L; A.bh = b.p; A.bv = b.p + N * L;
+      A.ph = params.p; A.pv = params.p + N * Pn; A.labels = labels.p;
+      A.H = gridH; A.W = gridW; A.row0 = row0; A.H_total = H_total;
+      A.halo_top = halo_top.p; A.halo_bot = halo_bot.p; A.own_top = own_top.p; A.own_bot = own_bot.p;
+      A.p_top = p_top.p; A.p_bot = p_bot.p;
+      A.num_bands = (gridH + T - 1) / T;
+      A.ticket = control.p; A.progress = control.p + 1;
+      A.forward = forward ? 1 : 0; A.primal = primal ? 1 : 0; A.fifo = edge_order == LPMP_EDGE_ORDER_FIFO; A.repam = repam;
+      CUDA_TRY(cudaMemsetAsync(control.p, 0, control.bytes(), stream));
+      CUDA_TRY(launch_wavefront<Real>(A, pw, L, tune, num_sms, stream));
+      ++launches;
+    }
+    updates += (repam == LPMP_REPAM_ANISOTROPIC ? 2 : 4) * E;
+    if (primal) labels_valid = true;
+    return LPMP_OK;
+  }
+
+  template <typename Topo>
+  BoundArgs<Real, Topo> bound_args(Topo topo) {
+    BoundArgs<Real, Topo> A;
+    A.theta = theta.p; A.a = a.p; A.b = b.p; A.params = params.p; A.topo = topo;
+    A.num_nodes = N; A.L = L; A.pw = pw; A.partial = partial.p;
+    return A;
+  }
+
+  int reduce_to_host(int ctas, double* out) {
+    final_sum_kernel<<<1, 32, 0, stream>>>(partial.p, ctas, constant, result.p);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, result.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
+
+  int lower_bound(double* out) override {
+    if (int r = need_final()) return r;
+    if (striped) { err = "lower_bound of a stripe: use the partial bound entry point"; return LPMP_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(device));
+    const int G = group_size_for(L);
+    int threads = 256;
+    const size_t per_group = 2 * (size_t)L * sizeof(Real);
+    while (threads > G && (threads / G) * per_group > 48 * 1024) threads >>= 1;
+    const int groups = threads / G;
+    const uint64_t total = N + slots;
+    const int ctas = (int)std::min<uint64_t>((total + groups - 1) / groups, (uint64_t)kBoundCtas);
+    if (is_grid) {
+      GridTopo topo{gridH, gridW, slots};
+      lower_bound_kernel<Real, GridTopo><<<ctas, threads, (size_t)groups * per_group, stream>>>(bound_args(topo), G);
+    } else {
+      GraphTopo topo{d_ei.p, d_ej.p, slots};
+      lower_bound_kernel<Real, GraphTopo><<<ctas, threads, (size_t)groups * per_group, stream>>>(bound_args(topo), G);
+    }
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    return reduce_to_host(ctas, out);
+  }
+
+  int evaluate_primal(double* out) override {
+    if (int r = need_final()) return r;
+    if (!labels_valid) { *out = std::numeric_limits<double>::infinity(); return LPMP_OK; }
+    if (striped) { err = "evaluate_primal of a stripe is not supported"; return LPMP_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(device));
+    const uint64_t total = N + slots;
+    const int ctas = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)kBoundCtas);
+    if (is_grid) {
+      GridTopo topo{gridH, gridW, slots};
+      primal_cost_kernel<Real, GridTopo><<<ctas, 256, 0, stream>>>(bound_args(topo), labels.p);
+    } else {
+      GraphTopo topo{d_ei.p, d_ej.p, slots};
+      primal_cost_kernel<Real, GraphTopo><<<ctas, 256, 0, stream>>>(bound_args(topo), labels.p);
+    }
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    return reduce_to_host(ctas, out);
+  }
+
+  int check_primal_consistency(int* out) override {
+    if (int r = need_final()) return r;
+    // pairwise factors hold copies of the unary labels written in the same pass (ComputeRightFromLeftPrimal),
+    // so a completed rounding pass is always consistent; before any rounding pass nothing is labelled.
+    *out = 1;
+    return LPMP_OK;
+  }
+  int add_to_constant(double x) override { constant += x; return LPMP_OK; }
+  int counts(uint64_t* factors, uint64_t* messages) override {
+    if (factors) *factors = N + E;
+    if (messages) *messages = 2 * E;
+    return LPMP_OK;
+  }
+
+  int get_labeling(uint32_t* out) override {
+    if (int r = need_final()) return r;
+    CUDA_TRY(cudaMemcpyAsync(out, labels.p, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
+  int download(std::vector<Real>& tmp, const Real* src, uint64_t n) {
+    tmp.resize(n);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), src, n * sizeof(Real), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
+  int get_unaries(double* th) override {
+    if (!is_grid && !finalized) { for (size_t k = 0; k < h_theta.size(); ++k) th[k] = (double)(Real)h_theta[k]; return LPMP_OK; }
+    std::vector<Real> tmp;
+    if (int r = download(tmp, theta.p, N * L)) return r;
+    for (uint64_t k = 0; k < N * L; ++k) th[k] = (double)tmp[k];
+    return LPMP_OK;
+  }
+  // storage slot of edge e (insertion order)
+  void edge_slots(std::vector<uint64_t>& slot) const {
+    if (!is_grid) { slot.resize(E); std::iota(slot.begin(), slot.end(), uint64_t(0)); return; }
+    std::vector<uint64_t> ei, ej;
+    grid_edge_lists(ei, ej, slot);
+  }
+  int get_messages(double* pa, double* pb) override {
+    if (int r = need_final()) return r;
+    std::vector<uint64_t> slot;
+    edge_slots(slot);
+    std::vector<Real> tmp;
+    for (int which = 0; which < 2; ++which) {
+      double* dst = which == 0 ? pa : pb;
+      if (!dst) continue;
+      if (int r = download(tmp, which == 0 ? a.p : b.p, slots * L)) return r;
+      for (uint64_t e = 0; e < E; ++e)
+        for (uint32_t x = 0; x < L; ++x) dst[e * L + x] = (double)tmp[slot[e] * L + x];
+    }
+    return LPMP_OK;
+  }
+  int set_messages(const double* pa, const double* pb) override {
+    if (int r = need_final()) return r;
+    std::vector<uint64_t> slot;
+    edge_slots(slot);
+    for (int which = 0; which < 2; ++which) {
+      const double* src = which == 0 ? pa : pb;
+      if (!src) continue;
+      std::vector<Real> tmp(slots * L, Real(0));
+      for (uint64_t e = 0; e < E; ++e)
+        for (uint32_t x = 0; x < L; ++x) tmp[slot[e] * L + x] = (Real)src[e * L + x];
+      CUDA_TRY(cudaMemcpyAsync(which == 0 ? a.p : b.p, tmp.data(), tmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return LPMP_OK;
+  }
+  int set_unaries(const double* th) override {
+    if (int r = need_final()) return r;
+    std::vector<Real> tmp(N * L);
+    for (uint64_t k = 0; k < N * L; ++k) tmp[k] = (Real)th[k];
+    CUDA_TRY(cudaMemcpyAsync(theta.p, tmp.data(), tmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
+  int stats(lpmp_stats* out) override {
+    std::memset(out, 0, sizeof(*out));
+    out->num_nodes = N; out->num_edges = E; out->num_labels = L;
+    if (schedule == LPMP_SCHEDULE_WAVEFRONT) out->num_levels = (uint64_t)gridW + gridH - 1;
+    else out->num_levels = level_off.empty() ? 0 : level_off.size() - 1;
+    out->kernel_launches = launches;
+    out->message_updates = updates;
+    out->device_bytes = theta.bytes() + a.bytes() + b.bytes() + params.bytes() + labels.bytes() + inc_off.bytes() + inc_edge.bytes() +
+                        inc_flags.bytes() + level_nodes.bytes() + d_ei.bytes() + d_ej.bytes() + control.bytes();
+    out->algorithmic_bytes_per_pass = (double)sizeof(Real) * (2.0 * (double)N * L + (double)E * ((double)P() + 5.0 * L));
+    return LPMP_OK;
+  }
+  int synchronize() override { CUDA_TRY(cudaStreamSynchronize(stream)); return LPMP_OK; }
+  void* stream_ptr() override { return (void*)stream; }
+};
+
+struct Handle {
+  ISolver* s = nullptr;
+  ~Handle() { delete s; }
+};
+
+static inline ISolver* S(lpmp_solver* h) { return reinterpret_cast<Handle*>(h)->s; }
+static inline const ISolver* S(const lpmp_solver* h) { return reinterpret_cast<const Handle*>(h)->s; }
+
+// one-shot single-factor helpers (parity test entry points)
+template <typename Real>
+static int run_minmarginal(int pw, uint64_t n, uint32_t L1, uint32_t L2, const double* p0, const double* p1, const double* msg1,
+                           const double* msg2, int side, double* out, double* lb) {
+  if (pw != LPMP_PAIRWISE_DENSE && L1 != L2) return LPMP_ERR_INVALID;
+  if (n == 0) return LPMP_OK;
+  const uint64_t np0 = pw == LPMP_PAIRWISE_DENSE ? n * L1 * L2 : n;
+  auto up = [&](DeviceBuffer<Real>& d, const double* src, uint64_t cnt) -> cudaError_t {
+    if (!src) return cudaSuccess;
+    std::vector<Real> tmp(cnt);
+    for (uint64_t k = 0; k < cnt; ++k) tmp[k] = (Real)src[k];
+    cudaError_t e = d.alloc(cnt);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(d.p, tmp.data(), cnt * sizeof(Real), cudaMemcpyHostToDevice);
+  };
+  DeviceBuffer<Real> dp0, dp1, dm1, dm2, dout, dmm, dlb;
+  if (up(dp0, p0, np0) != cudaSuccess || up(dp1, p1, n) != cudaSuccess || up(dm1, msg1, n * L1) != cudaSuccess || up(dm2, msg2, n * L2) != cudaSuccess) return LPMP_ERR_CUDA;
+  auto run = [&](int sd, std::vector<Real>& host) -> int {
+    const uint32_t Lo = sd == 0 ? L1 : L2;
+    if (dout.alloc(n * Lo) != cudaSuccess) return LPMP_ERR_CUDA;
+    minmarginal_kernel<Real><<<grid_for(n * Lo, 128, 1 << 20), 128>>>(pw, n, L1, L2, dp0.p, dp1.p, dm1.p, dm2.p, sd, dout.p);
+    host.resize(n * Lo);
+    if (cudaMemcpy(host.data(), dout.p, host.size() * sizeof(Real), cudaMemcpyDeviceToHost) != cudaSuccess) return LPMP_ERR_CUDA;
+    return LPMP_OK;
+  };
+  std::vector<Real> host;
+  if (int r = run(side, host)) return r;
+  for (size_t k = 0; k < host.size(); ++k) out[k] = (double)host[k];
+  if (lb) {  // PairwiseSimplexFactor::LowerBound = min over min_marginal_1
+    if (side != 0) { if (int r = run(0, host)) return r; }
+    if (dlb.alloc(n) != cudaSuccess) return LPMP_ERR_CUDA;
+    row_min_kernel<Real><<<grid_for(n, 128, 1 << 20), 128>>>(n, L1, dout.p, dlb.p, nullptr);
+    std::vector<Real> hl(n);
+    if (cudaMemcpy(hl.data(), dlb.p, n * sizeof(Real), cudaMemcpyDeviceToHost) != cudaSuccess) return LPMP_ERR_CUDA;
+    for (uint64_t k = 0; k < n; ++k) lb[k] = (double)hl[k];
+  }
+  return cudaGetLastError() == cudaSuccess ? LPMP_OK : LPMP_ERR_CUDA;
+}
+
+template <typename Real>
+static int run_unary_min(uint64_t n, uint32_t L, const double* theta, double* lb, uint32_t* arg) {
+  if (n == 0) return LPMP_OK;
+  std::vector<Real> tmp(n * L);
+  for (uint64_t k = 0; k < n * L; ++k) tmp[k] = (Real)theta[k];
+  DeviceBuffer<Real> dth, dmn;
+  DeviceBuffer<uint32_t> darg;
+  if (dth.alloc(n * L) != cudaSuccess || dmn.alloc(n) != cudaSuccess || darg.alloc(n) != cudaSuccess) return LPMP_ERR_CUDA;
+  if (cudaMemcpy(dth.p, tmp.data(), tmp.size() * sizeof(Real), cudaMemcpyHostToDevice) != cudaSuccess) return LPMP_ERR_CUDA;
+  row_min_kernel<Real><<<grid_for(n, 128, 1 << 20), 128>>>(n, L, dth.p, dmn.p, darg.p);
+  std::vector<Real> hm(n);
+  if (cudaMemcpy(hm.data(), dmn.p, n * sizeof(Real), cudaMemcpyDeviceToHost) != cudaSuccess) return LPMP_ERR_CUDA;
+  if (lb) for (uint64_t k = 0; k < n; ++k) lb[k] = (double)hm[k];
+  if (arg && cudaMemcpy(arg, darg.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return LPMP_ERR_CUDA;
+  return LPMP_OK;
+}
+
+}  // namespace lpmp
+
+using namespace lpmp;
+
+extern "C" {
+
+int lpmp_create(int dtype, int device, lpmp_solver** out) {
+  if (!out || (dtype != LPMP_F32 && dtype != LPMP_F64)) return LPMP_ERR_INVALID;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    std::fprintf(stderr, "lpmp_create: no CUDA device available (there is no CPU fallback)\n");
+    return LPMP_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) return LPMP_ERR_INVALID;
+  Handle* h = new Handle();
+  int r;
+  if (dtype == LPMP_F32) { auto* s = new Solver<float>(device); h->s = s; r = s->init(); }
+  else { auto* s = new Solver<double>(device); h->s = s; r = s->init(); }
+  if (r != LPMP_OK) { std::fprintf(stderr, "lpmp_create: %s\n", h->s->err.c_str()); delete h; return r; }
+  *out = reinterpret_cast<lpmp_solver*>(h);
+  return LPMP_OK;
+}
+int lpmp_destroy(lpmp_solver* h) { delete reinterpret_cast<Handle*>(h); return LPMP_OK; }
+const char* lpmp_last_error(const lpmp_solver* h) { return h ? S(h)->err.c_str() : "null handle"; }
+
+int lpmp_add_unaries(lpmp_solver* h, uint64_t n, uint32_t L, const double* theta) { return S(h)->add_unaries(n, L, theta); }
+int lpmp_add_pairwise_dense(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* t) { return S(h)->add_pairwise(LPMP_PAIRWISE_DENSE, m, i, j, t, nullptr); }
+int lpmp_add_pairwise_potts(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* l) { return S(h)->add_pairwise(LPMP_PAIRWISE_POTTS, m, i, j, l, nullptr); }
+int lpmp_add_pairwise_trunclin(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* s, const double* t) { return S(h)->add_pairwise(LPMP_PAIRWISE_TRUNCLIN, m, i, j, s, t); }
+int lpmp_set_node_ranks(lpmp_solver* h, const uint64_t* rank) { return S(h)->set_node_ranks(rank); }
+int lpmp_set_edge_order(lpmp_solver* h, int eo) { return S(h)->set_edge_order(eo); }
+int lpmp_set_schedule(lpmp_solver* h, int s) { return S(h)->set_schedule(s); }
+int lpmp_set_tuning(lpmp_solver* h, const char* key, int value) { return S(h)->set_tuning(key, value); }
+
+int lpmp_greedy_colouring(uint64_t n, uint64_t m, const uint64_t* i, const uint64_t* j, uint32_t* colour, uint32_t* num_colours) {
+  std::vector<uint64_t> off(n + 1, 0);
+  for (uint64_t e = 0; e < m; ++e) {
+    if (i[e] >= n || j[e] >= n) return LPMP_ERR_INVALID;
+    ++off[i[e] + 1]; ++off[j[e] + 1];
+  }
+  for (uint64_t v = 0; v < n; ++v) off[v + 1] += off[v];
+  std::vector<uint64_t> adj(2 * m), pos(off.begin(), off.end() - 1);
+  for (uint64_t e = 0; e < m; ++e) { adj[pos[i[e]]++] = j[e]; adj[pos[j[e]]++] = i[e]; }
+  uint32_t nc = 0;
+  std::vector<uint32_t> used;
+  for (uint64_t v = 0; v < n; ++v) {
+    used.clear();
+    for (uint64_t q = off[v]; q < off[v + 1]; ++q) if (adj[q] < v) used.push_back(colour[adj[q]]);
+    std::sort(used.begin(), used.end());
+    uint32_t c = 0;
+    for (uint32_t x : used) { if (x == c) ++c; else if (x > c) break; }
+    colour[v] = c;
+    nc = std::max(nc, c + 1);
+  }
+  if (num_colours) *num_colours = nc;
+  return LPMP_OK;
+}
+
+int lpmp_grid_create(lpmp_solver* h, uint32_t H, uint32_t W, uint32_t L, int type) { return S(h)->grid_create(H, W, L, type); }
+int lpmp_grid_set_unaries(lpmp_solver* h, const void* theta, int src) { return S(h)->grid_set_unaries(theta, src); }
+int lpmp_grid_set_pairwise(lpmp_solver* h, const void* hz, const void* vt, int src) { return S(h)->grid_set_pairwise(hz, vt, src); }
+int lpmp_grid_fill_synthetic(lpmp_solver* h, uint64_t seed, double lo, double hi) { return S(h)->grid_fill_synthetic(seed, lo, hi); }
+int lpmp_grid_set_stripe(lpmp_solver* h, uint32_t row0, uint32_t H_total) { return S(h)->grid_set_stripe(row0, H_total); }
+int lpmp_grid_set_boundary_pairwise(lpmp_solver* h, const void* top, const void* bottom, int src) { return S(h)->grid_set_boundary_pairwise(top, bottom, src); }
+int lpmp_grid_boundary_ptrs(lpmp_solver* h, int which, void** owned, void** halo, uint64_t* bytes) { return S(h)->grid_boundary_ptrs(which, owned, halo, bytes); }
+
+int lpmp_finalize(lpmp_solver* h) { return S(h)->finalize(); }
+int lpmp_begin(lpmp_solver* h) { return S(h)->begin(); }
+int lpmp_end(lpmp_solver* h) { return S(h)->synchronize(); }
+int lpmp_set_reparametrization(lpmp_solver* h, int mode) { return S(h)->set_reparametrization(mode); }
+int lpmp_compute_pass(lpmp_solver* h, uint64_t) { if (int r = S(h)->pass(true, false)) return r; return S(h)->pass(false, false); }
+int lpmp_compute_forward_pass(lpmp_solver* h) { return S(h)->pass(true, false); }
+int lpmp_compute_backward_pass(lpmp_solver* h) { return S(h)->pass(false, false); }
+int lpmp_compute_forward_pass_and_primal(lpmp_solver* h, uint64_t) { return S(h)->pass(true, true); }
+int lpmp_compute_backward_pass_and_primal(lpmp_solver* h, uint64_t) { return S(h)->pass(false, true); }
+int lpmp_lower_bound(lpmp_solver* h, double* out) { return S(h)->lower_bound(out); }
+int lpmp_evaluate_primal(lpmp_solver* h, double* out) { return S(h)->evaluate_primal(out); }
+int lpmp_check_primal_consistency(lpmp_solver* h, int* out) { return S(h)->check_primal_consistency(out); }
+int lpmp_add_to_constant(lpmp_solver* h, double x) { return S(h)->add_to_constant(x); }
+int lpmp_num_factors(const lpmp_solver* h, uint64_t* out) { return const_cast<ISolver*>(S(h))->counts(out, nullptr); }
+int lpmp_num_messages(const lpmp_solver* h, uint64_t* out) { return const_cast<ISolver*>(S(h))->counts(nullptr, out); }
+int lpmp_get_labeling(lpmp_solver* h, uint32_t* out) { return S(h)->get_labeling(out); }
+int lpmp_get_unaries(lpmp_solver* h, double* th) { return S(h)->get_unaries(th); }
+int lpmp_get_messages(lpmp_solver* h, double* a, double* b) { return S(h)->get_messages(a, b); }
+int lpmp_set_messages(lpmp_solver* h, const double* a, const double* b) { return S(h)->set_messages(a, b); }
+int lpmp_set_unaries(lpmp_solver* h, const double* th) { return S(h)->set_unaries(th); }
+int lpmp_get_stats(lpmp_solver* h, lpmp_stats* out) { return S(h)->stats(out); }
+int lpmp_synchronize(lpmp_solver* h) { return S(h)->synchronize(); }
+int lpmp_stream(lpmp_solver* h, void** out) { if (out) *out = S(h)->stream_ptr(); return LPMP_OK; }
+
+int lpmp_minmarginal_dense(int dtype, uint64_t n, uint32_t L1, uint32_t L2, const double* t, const double* msg1, const double* msg2, int side, double* out, double* lb) {
+  return dtype == LPMP_F32 ? run_minmarginal<float>(LPMP_PAIRWISE_DENSE, n, L1, L2, t, nullptr, msg1, msg2, side, out, lb)
+                           : run_minmarginal<double>(LPMP_PAIRWISE_DENSE, n, L1, L2, t, nullptr, msg1, msg2, side, out, lb);
+}
+int lpmp_minmarginal_potts(int dtype, uint64_t n, uint32_t L, const double* lambda, const double* msg1, const double* msg2, int side, double* out, double* lb) {
+  return dtype == LPMP_F32 ? run_minmarginal<float>(LPMP_PAIRWISE_POTTS, n, L, L, lambda, nullptr, msg1, msg2, side, out, lb)
+                           : run_minmarginal<double>(LPMP_PAIRWISE_POTTS, n, L, L, lambda, nullptr, msg1, msg2, side, out, lb);
+}
+int lpmp_minmarginal_trunclin(int dtype, uint64_t n, uint32_t L, const double* slope, const double* trunc, const double* msg1, const double* msg2, int side, double* out, double* lb) {
+  return dtype == LPMP_F32 ? run_minmarginal<float>(LPMP_PAIRWISE_TRUNCLIN, n, L, L, slope, trunc, msg1, msg2, side, out, lb)
+                           : run_minmarginal<double>(LPMP_PAIRWISE_TRUNCLIN, n, L, L, slope, trunc, msg1, msg2, side, out, lb);
+}
+int lpmp_unary_min(int dtype, uint64_t n, uint32_t L, const double* theta, double* lb, uint32_t* arg) {
+  return dtype == LPMP_F32 ? run_unary_min<float>(n, L, theta, lb, arg) : run_unary_min<double>(n, L, theta, lb, arg);
+}
+
+}  // extern "C"

@@ -116,6 +116,10 @@ class LP:
     def set_schedule(self, schedule):
         self._ck(self.api.set_schedule(self.h, K.SCHEDULE[schedule]))
 
+    def set_tuning(self, **kw):
+        for k, v in kw.items():
+            self._ck(self.api.set_tuning(self.h, k.encode(), int(v)))
+
     def greedy_colouring(self, i, j):
         i, j = self._edges(i, j)
         colour = np.zeros(self.N + len(self._pending_unaries), dtype=np.uint32)
@@ -157,6 +161,21 @@ class LP:
 
     def grid_fill_synthetic(self, seed, p_lo, p_hi):
         self._ck(self.api.grid_fill_synthetic(self.h, int(seed), float(p_lo), float(p_hi)))
+
+    # ---- row stripes (multi-GPU) -------------------------------------------------------------------------
+    def grid_set_stripe(self, row0, H_total):
+        self._ck(self.api.grid_set_stripe(self.h, int(row0), int(H_total)))
+
+    def grid_set_boundary_pairwise(self, top, bottom):
+        top = None if top is None else np.ascontiguousarray(top, dtype=np.float64)
+        bottom = None if bottom is None else np.ascontiguousarray(bottom, dtype=np.float64)
+        self._ck(self.api.grid_set_boundary_pairwise(self.h, None if top is None else top.ctypes.data,
+                                                     None if bottom is None else bottom.ctypes.data, K.F64))
+
+    def grid_boundary_ptrs(self, which):
+        owned, halo, nbytes = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._ck(self.api.grid_boundary_ptrs(self.h, int(which), C.byref(owned), C.byref(halo), C.byref(nbytes)))
+        return owned.value, halo.value, nbytes.value
 
     def finalize(self):
         self._flush_pending()
@@ -246,7 +265,7 @@ class LP:
 
     def stats(self):
         s = K.Stats()
-        self._ck(self.api.stats(self.h, C.byref(s)))
+        self._ck(self.api.get_stats(self.h, C.byref(s)))
         return {f: getattr(s, f) for f, _ in K.Stats._fields_}
 
     def synchronize(self):

@@ -408,6 +408,7 @@ int LPMP_FN(set_edge_order)(lpmp_solver* h, int eo) {
   })());
 }
 int LPMP_FN(set_schedule)(lpmp_solver* h, int) { (void)h; return LPMP_OK; }  // the oracle is always sequential
+int LPMP_FN(set_tuning)(lpmp_solver* h, const char*, int) { (void)h; return LPMP_OK; }
 
 int LPMP_FN(greedy_colouring)(uint64_t n, uint64_t m, const uint64_t* i, const uint64_t* j, uint32_t* colour, uint32_t* num_colours) {
   std::vector<std::vector<uint64_t>> adj(n);
@@ -501,7 +502,7 @@ int LPMP_FN(set_unaries)(lpmp_solver* h, const double* th) {
     return int(LPMP_OK);
   })());
 }
-int LPMP_FN(stats)(lpmp_solver* h, lpmp_stats* out) {
+int LPMP_FN(get_stats)(lpmp_solver* h, lpmp_stats* out) {
   return DISPATCH(H(h), ([&] {
     std::memset(out, 0, sizeof(*out));
     out->num_nodes = o.N; out->num_edges = o.E; out->num_labels = o.L; out->num_levels = o.N;

@@ -1,0 +1,404 @@
+"""GPU parity tests: the CUDA library, called through the C ABI (include/lpmp_b200.h), against
+  (1) the committed fixtures recorded from the reference's own scheduler (tests/golden),
+  (2) the CPU oracle on the same seeded inputs -- bit-exact state (theta, a, b, labels) in f64 AND f32,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances: state and labelings bit-exact; lower bound / primal cost relative 1e-12 (f64) resp. 1e-6 (f32) because the
+global sums are accumulated in a different (deterministic tree) order than the reference's sequential sum.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from checkers import grid_edges, oracle_lp, potts_table, trunclin_table
+from common import GOLDEN_CASES, build_from_golden, check_against_golden, load_golden, run_lockstep, same_state
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["anisotropic", "uniform", "damped_uniform"]
+LB_RTOL = {"f64": 1e-12, "f32": 1e-6}
+
+
+def cuda_lp(dtype="f64"):
+    import lp_mp_b200
+    return lp_mp_b200.LP(dtype=dtype, device=0)
+
+
+def _pd(x):
+    return None if x is None else x.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# ---- (1) committed fixtures from the reference core ------------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("native", [True, False])
+def test_cuda_reproduces_reference_fixture(name, native):
+    g = load_golden(name)
+    check_against_golden(build_from_golden(cuda_lp("f64"), g, native=native), g, exact=True)
+
+
+@pytest.mark.parametrize("name", ["grid_potts", "grid_trunclin"])
+@pytest.mark.parametrize("schedule", ["levels", "wavefront"])
+def test_cuda_grid_api_reproduces_reference_fixture(name, schedule):
+    g = load_golden(name)
+    lp = build_from_golden(cuda_lp("f64"), g, use_grid_api=True)
+    lp.set_schedule(schedule)
+    check_against_golden(lp, g, exact=True)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cuda_f32_tracks_reference_fixture(name):
+    g = load_golden(name)
+    check_against_golden(build_from_golden(cuda_lp("f32"), g), g, exact=False, rtol=1e-5)
+
+
+# ---- single-factor kernels (north_star: 1e-5 relative; we get bit-exact) -----------------------------------------
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_single_factor_kernels(cuda_api, oracle_api, dtype):
+    rng = np.random.default_rng(1)
+    n, L1, L2 = 37, 5, 7
+    t, m1, m2 = rng.normal(size=(n, L1, L2)), rng.normal(size=(n, L1)), rng.normal(size=(n, L2))
+    for side in (0, 1):
+        outs = []
+        for api in (cuda_api, oracle_api):
+            out, lb = np.zeros((n, L1 if side == 0 else L2)), np.zeros(n)
+            api.check(api.minmarginal_dense(dtype, n, L1, L2, _pd(t), _pd(m1), _pd(m2), side, _pd(out), _pd(lb)))
+            outs.append((out, lb))
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    L = 9
+    lam, slope, trunc = rng.uniform(-1, 1, size=n), rng.uniform(0, 0.5, size=n), rng.uniform(0.2, 2.0, size=n)
+    m1, m2 = rng.normal(size=(n, L)), rng.normal(size=(n, L))
+    for side in (0, 1):
+        res = []
+        for api in (cuda_api, oracle_api):
+            o1, l1, o2, l2 = np.zeros((n, L)), np.zeros(n), np.zeros((n, L)), np.zeros(n)
+            api.check(api.minmarginal_potts(dtype, n, L, _pd(lam), _pd(m1), _pd(m2), side, _pd(o1), _pd(l1)))
+            api.check(api.minmarginal_trunclin(dtype, n, L, _pd(slope), _pd(trunc), _pd(m1), _pd(m2), side, _pd(o2), _pd(l2)))
+            res.append((o1, l1, o2, l2))
+        for x, y in zip(*res):
+            assert np.array_equal(x, y)
+    theta = rng.normal(size=(n, 11))
+    theta[3, 4] = theta[3, 9] = theta[3].min() - 1.0  # tie: first minimum wins
+    res = []
+    for api in (cuda_api, oracle_api):
+        lb, arg = np.zeros(n), np.zeros(n, dtype=np.uint32)
+        api.check(api.unary_min(dtype, n, 11, _pd(theta), _pd(lb), arg.ctypes.data_as(C.POINTER(C.c_uint32))))
+        res.append((lb, arg))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and res[0][1][3] == 4
+
+
+def test_reference_goldens_on_device(cuda_api):
+    """test/simplex.cpp:8-11,52-64 and test/simplex_marginalization.cpp:9-41 through the CUDA kernels"""
+    theta = np.array([[0.1, 0.2, 0.05, 1.0]])
+    lb, arg = np.zeros(1), np.zeros(1, dtype=np.uint32)
+    cuda_api.check(cuda_api.unary_min(1, 1, 4, _pd(theta), _pd(lb), arg.ctypes.data_as(C.POINTER(C.c_uint32))))
+    assert lb[0] == 0.05
+    t = np.zeros((3, 3))
+    for x in range(3):
+        t[x, x] = -float(x) - 1.0
+    out, lb = np.zeros(3), np.zeros(1)
+    cuda_api.check(cuda_api.minmarginal_dense(1, 1, 3, 3, _pd(t), None, None, 0, _pd(out), _pd(lb)))
+    assert lb[0] == -3.0
+    cost = np.array([[0.1, 0.2, 0.05], [0.3, 0.001, 0.2], [-0.3, -0.001, -0.2], [0.3, 0.001, 0.2]])
+    out = np.zeros(4)
+    cuda_api.check(cuda_api.minmarginal_dense(1, 1, 4, 3, _pd(cost), None, None, 0, _pd(out), None))
+    assert list(-out) == [-0.05, -0.001, 0.3, -0.001]
+    out = np.zeros(3)
+    cuda_api.check(cuda_api.minmarginal_dense(1, 1, 4, 3, _pd(cost), None, None, 1, _pd(out), None))
+    assert list(-out) == [0.3, 0.001, 0.2]
+    for lam in (1.0, -1.0):  # test/potts_factor.cpp:34-66
+        m1, m2 = np.array([[-0.1, 0.5, 0.8]]), np.array([[1.5, 1.0, 0.0]])
+        for side in (0, 1):
+            d, p, ld, lp_ = np.zeros(3), np.zeros(3), np.zeros(1), np.zeros(1)
+            cuda_api.check(cuda_api.minmarginal_dense(1, 1, 3, 3, _pd(potts_table(3, lam)), _pd(m1), _pd(m2), side, _pd(d), _pd(ld)))
+            cuda_api.check(cuda_api.minmarginal_potts(1, 1, 3, _pd(np.array([lam])), _pd(m1), _pd(m2), side, _pd(p), _pd(lp_)))
+            assert np.array_equal(d, p) and ld[0] == lp_[0]
+
+
+# ---- (2) general graphs, level schedule ---------------------------------------------------------------------------
+def random_graph(rng, n, m):
+    edges = set()
+    while len(edges) < m:
+        i, j = rng.integers(0, n, size=2)
+        if i != j:
+            edges.add((int(min(i, j)), int(max(i, j))))
+    edges = sorted(edges)
+    rng.shuffle(edges)
+    return np.array([e[0] for e in edges], dtype=np.uint64), np.array([e[1] for e in edges], dtype=np.uint64)
+
+
+def fill(lp, kind, theta, ei, ej, rng_seed, L):
+    rng = np.random.default_rng(rng_seed)
+    lp.add_unaries(theta)
+    if kind == "dense":
+        lp.add_pairwise_dense(ei, ej, rng.random((len(ei), L, L)) - 0.2)
+    elif kind == "potts":
+        lp.add_pairwise_potts(ei, ej, rng.uniform(-0.5, 1.0, size=len(ei)))
+    else:
+        lp.add_pairwise_trunclin(ei, ej, rng.uniform(0.05, 0.5, size=len(ei)), rng.uniform(0.2, 1.5, size=len(ei)))
+    return lp
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("kind,L", [("dense", 2), ("dense", 5), ("dense", 8), ("potts", 3), ("potts", 32), ("potts", 40),
+                                    ("trunclin", 7), ("trunclin", 16), ("dense", 64)])
+def test_general_graph_bit_parity(dtype, mode, kind, L):
+    rng = np.random.default_rng(L * 7 + len(mode))
+    n = 60
+    ei, ej = random_graph(rng, n, 130)
+    theta = rng.random((n, L))
+    lps = [fill(oracle_lp(dtype), kind, theta, ei, ej, 5, L), fill(cuda_lp(dtype), kind, theta, ei, ej, 5, L)]
+    run_lockstep(lps, mode, iters=4, lb_rtol=LB_RTOL[dtype])
+
+
+@pytest.mark.parametrize("edge_order", ["lifo", "fifo"])
+def test_edge_order_parameter(edge_order):
+    rng = np.random.default_rng(9)
+    ei, ej = grid_edges(5, 7)
+    theta = rng.random((35, 6))
+    lps = [fill(oracle_lp("f64"), "dense", theta, ei, ej, 2, 6), fill(cuda_lp("f64"), "dense", theta, ei, ej, 2, 6)]
+    for lp in lps:
+        lp.set_edge_order(edge_order)
+    run_lockstep(lps, "damped_uniform", iters=3)
+
+
+def test_degenerate_graphs():
+    """isolated nodes, a single edge, a star (degree 12), duplicate-free multi-component graph"""
+    rng = np.random.default_rng(2)
+    theta = rng.random((14, 4))
+    ei = np.array([0] * 12 + [12], dtype=np.uint64)          # node 13 stays isolated
+    ej = np.array(list(range(1, 13)) + [1], dtype=np.uint64)
+    ej[12] = 11
+    ei[12] = 12
+    for mode in MODES:
+        lps = [fill(oracle_lp("f64"), "dense", theta, ei, ej, 3, 4), fill(cuda_lp("f64"), "dense", theta, ei, ej, 3, 4)]
+        run_lockstep(lps, mode, iters=3)
+    lp = cuda_lp("f64")          # no edges at all
+    lp.add_unaries(theta)
+    lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+    lp.ComputePass(0)
+    assert np.isclose(lp.LowerBound(), theta.min(axis=1).sum(), rtol=1e-14)
+    lp.ComputeForwardPassAndPrimal(1)
+    assert np.array_equal(lp.labeling(), theta.argmin(axis=1))
+
+
+def test_colouring_schedule():
+    """graph-colouring schedule (BASELINE config 4 shape, small): exact parity with the oracle run on the same
+    colour ranks; final bound within 1e-4 relative of the natural-order run."""
+    rng = np.random.default_rng(17)
+    n, L = 400, 8
+    # random 3-regular-ish graph: union of a ring and a random perfect matching
+    perm = rng.permutation(n)
+    edges = {(min(i, (i + 1) % n), max(i, (i + 1) % n)) for i in range(n)}
+    for k in range(0, n, 2):
+        i, j = int(perm[k]), int(perm[k + 1])
+        edges.add((min(i, j), max(i, j)))
+    edges = sorted(edges)
+    ei, ej = np.array([e[0] for e in edges], dtype=np.uint64), np.array([e[1] for e in edges], dtype=np.uint64)
+    theta = rng.random((n, L))
+    cu = fill(cuda_lp("f64"), "dense", theta, ei, ej, 4, L)
+    colour, nc = cu.greedy_colouring(ei, ej)
+    assert nc <= 4 and all(colour[i] != colour[j] for i, j in zip(ei, ej))
+    rank = colour.astype(np.uint64) * n + np.arange(n, dtype=np.uint64)
+    orc = fill(oracle_lp("f64"), "dense", theta, ei, ej, 4, L)
+    ocol, onc = orc.greedy_colouring(ei, ej)
+    assert np.array_equal(ocol, colour) and onc == nc
+    cu.set_node_ranks(rank); orc.set_node_ranks(rank)
+    run_lockstep([orc, cu], "anisotropic", iters=5)
+    assert cu.stats()["num_levels"] <= nc
+    nat = fill(oracle_lp("f64"), "dense", theta, ei, ej, 4, L)
+    nat.finalize(); nat.Begin(); nat.set_reparametrization("anisotropic")
+    for it in range(5, 200):
+        cu.ComputePass(it)
+    for it in range(200):
+        nat.ComputePass(it)
+    assert abs(cu.LowerBound() - nat.LowerBound()) <= 1e-4 * abs(nat.LowerBound())
+
+
+# ---- grids: wavefront kernel ------------------------------------------------------------------------------------------
+def grid_pair(dtype, H, W, L, kind, seed, schedule="wavefront", edge_order="lifo", **tuning):
+    rng = np.random.default_rng(seed)
+    theta = rng.random((H, W, L))
+    if kind == "potts":
+        hz, vt = rng.uniform(-0.3, 1.0, size=(H, W - 1, 1)), rng.uniform(-0.3, 1.0, size=(H - 1, W, 1))
+    else:
+        hz = np.stack([rng.uniform(0.05, 0.5, size=(H, W - 1)), rng.uniform(0.2, 1.5, size=(H, W - 1))], axis=-1)
+        vt = np.stack([rng.uniform(0.05, 0.5, size=(H - 1, W)), rng.uniform(0.2, 1.5, size=(H - 1, W))], axis=-1)
+    lps = []
+    for make in (oracle_lp, cuda_lp):
+        lp = make(dtype).grid_create(H, W, L, kind)
+        lp.grid_set_unaries(theta)
+        lp.grid_set_pairwise(hz, vt)
+        lp.set_edge_order(edge_order)
+        lps.append(lp)
+    lps[1].set_schedule(schedule)
+    if tuning:
+        lps[1].set_tuning(**tuning)
+    return lps
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("kind,L", [("potts", 8), ("potts", 32), ("trunclin", 16), ("potts", 64), ("trunclin", 8)])
+def test_wavefront_bit_parity(dtype, mode, kind, L):
+    lps = grid_pair(dtype, 37, 29, L, kind, seed=L + len(mode))
+    run_lockstep(lps, mode, iters=3, lb_rtol=LB_RTOL[dtype])
+
+
+@pytest.mark.parametrize("H,W", [(1, 1), (1, 9), (9, 1), (2, 2), (3, 50), (50, 3), (33, 33), (64, 17)])
+def test_wavefront_ragged_shapes(H, W):
+    """bands that do not divide H, grids narrower than a band, single rows / columns"""
+    for kind, L in (("potts", 16), ("trunclin", 32)):
+        lps = grid_pair("f64", H, W, L, kind, seed=H * 100 + W)
+        run_lockstep(lps, "anisotropic", iters=3)
+        lps = grid_pair("f64", H, W, L, kind, seed=H * 100 + W)
+        run_lockstep(lps, "damped_uniform", iters=2)
+
+
+@pytest.mark.parametrize("tuning", [dict(wavefront_vpl=2), dict(wavefront_warps=1), dict(wavefront_warps=2, wavefront_stages=4),
+                                    dict(wavefront_max_ctas=3), dict(wavefront_vpl=2, wavefront_stages=4, wavefront_warps=3)])
+def test_wavefront_launch_shapes_do_not_change_results(tuning):
+    lps = grid_pair("f32", 70, 45, 16, "trunclin", seed=3, **tuning)
+    run_lockstep(lps, "anisotropic", iters=3, lb_rtol=1e-6)
+    lps = grid_pair("f64", 45, 70, 32, "potts", seed=4, **tuning)
+    run_lockstep(lps, "uniform", iters=2)
+
+
+def test_wavefront_fifo_order():
+    lps = grid_pair("f64", 20, 23, 8, "potts", seed=5, edge_order="fifo")
+    run_lockstep(lps, "damped_uniform", iters=3)
+    lps = grid_pair("f64", 20, 23, 8, "potts", seed=5, edge_order="fifo")
+    run_lockstep(lps, "anisotropic", iters=3)
+
+
+def test_wavefront_equals_level_schedule_on_device():
+    """two device schedules of the same DAG must agree bit for bit (order invariance)"""
+    for dtype in ("f32", "f64"):
+        a = grid_pair(dtype, 130, 97, 16, "trunclin", seed=8, schedule="wavefront")[1]
+        b = grid_pair(dtype, 130, 97, 16, "trunclin", seed=8, schedule="levels")[1]
+        run_lockstep([a, b], "anisotropic", iters=3, lb_rtol=1e-13)
+
+
+def test_synthetic_generator_matches_oracle():
+    for kind, lo, hi, L in (("potts", 0.1, 1.0, 8), ("trunclin", 0.25, 1.0, 16)):
+        lps = [oracle_lp("f32").grid_create(19, 21, L, kind), cuda_lp("f32").grid_create(19, 21, L, kind)]
+        for lp in lps:
+            lp.grid_fill_synthetic(0x5EED, lo, hi)
+        run_lockstep(lps, "anisotropic", iters=3, lb_rtol=1e-6)
+
+
+# ---- solver loop: reference control law driving the device ---------------------------------------------------------
+def test_frustrated_cycle_goldens_on_device():
+    """test/graphical_model.cpp:98-136 (lower bounds are goldens; see tests/test_oracle_goldens.py for the primal note)"""
+    from lp_mp_b200 import MpRoundingSolver, StandardVisitor
+    NEG, POS = np.array([[1.0, 0.0], [0.0, 1.0]]), np.array([[0.0, 1.0], [1.0, 0.0]])
+    for n, edges, ub in ((5, [(0, 1, NEG), (1, 2, POS), (2, 3, POS), (3, 4, POS)], 1.0),
+                         (4, [(0, 1, NEG), (1, 2, POS), (2, 3, POS), (0, 3, POS)], 3.0)):
+        lp = cuda_lp("f64")
+        for _ in range(n):
+            lp.AddUnaryFactor(np.zeros(2))
+        for i, j, t in edges:
+            lp.AddPairwiseFactor(i, j, t)
+        s = MpRoundingSolver(lp, StandardVisitor(maxIter=100))
+        s.Solve()
+        assert abs(s.lower_bound()) <= 1e-8 and s.primal_cost() <= ub + 1e-8
+
+
+def test_solve_trajectory_matches_reference_solver():
+    """MpRoundingSolver + StandardVisitor defaults (rounding in damped_uniform every 5th iteration) on the device vs the
+    reference's own Solve() (oracle/_ref) if it travelled to this box, else vs the oracle under the same Python loop."""
+    from checkers import RefLP, ref_library
+    from lp_mp_b200 import MpRoundingSolver, StandardVisitor
+    rng = np.random.default_rng(8)
+    H, W, L = 8, 8, 4
+    ei, ej = grid_edges(H, W)
+    theta, tables = rng.random((H * W, L)), rng.random((len(ei), L, L))
+    lp = cuda_lp("f64")
+    lp.add_unaries(theta); lp.add_pairwise_dense(ei, ej, tables)
+    s = MpRoundingSolver(lp, StandardVisitor(maxIter=13))
+    s.Solve()
+    lib = ref_library()
+    if lib is not None:
+        ref = RefLP(lib, ["-v", "0", "--maxIter", "13"])
+        for t in theta:
+            ref.AddUnaryFactor(t)
+        for e in range(len(ei)):
+            ref.AddPairwiseFactor(int(ei[e]), int(ej[e]), tables[e])
+        r = ref.solve()
+        want_lb, want_ub, flb, fub = r["lb"], r["ub"], r["final_lb"], r["final_ub"]
+    else:
+        o = oracle_lp("f64")
+        o.add_unaries(theta); o.add_pairwise_dense(ei, ej, tables)
+        so = MpRoundingSolver(o, StandardVisitor(maxIter=13))
+        so.Solve()
+        want_lb, want_ub = [h[0] for h in so.history], [h[1] for h in so.history]
+        flb, fub = so.lower_bound(), so.primal_cost()
+    assert len(s.history) == len(want_lb) == 13
+    for k, (lb, ub, c) in enumerate(s.history):
+        assert np.isclose(lb, want_lb[k], rtol=1e-12)
+        assert ub == want_ub[k] or np.isclose(ub, want_ub[k], rtol=1e-12)
+    assert np.isclose(s.lower_bound(), flb, rtol=1e-12) and np.isclose(s.primal_cost(), fub, rtol=1e-12)
+    assert [k for k, h in enumerate(s.history) if h[2].computePrimal] == [1, 6, 11, 12]
+
+
+# ---- (3) properties at BASELINE.json's full sizes -------------------------------------------------------------------
+@pytest.mark.parametrize("H,W,L,kind,lo,hi", [(1024, 1024, 16, "trunclin", 0.25, 1.0), (4096, 4096, 32, "potts", 0.1, 1.0)])
+def test_full_size_properties(H, W, L, kind, lo, hi):
+    """configs 2 and 3: dual ascent is monotone, bound <= primal, reruns are bit-identical (deterministic schedule),
+    and the bound equals the oracle's on a crop-independent checksum: the first pass' bound of the top-left 64x64 crop
+    cannot be compared (the grid couples), so we compare the full-size run with a second run under another launch shape."""
+    lp = cuda_lp("f32").grid_create(H, W, L, kind)
+    lp.grid_fill_synthetic(0x5EED, lo, hi)
+    lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+    prev = lp.LowerBound()
+    lbs = []
+    for it in range(3):
+        lp.ComputePass(it)
+        lb = lp.LowerBound()
+        assert lb >= prev - 1e-6 * abs(prev)
+        prev = lb
+        lbs.append(lb)
+    lp.ComputeForwardPassAndPrimal(3)
+    primal = lp.EvaluatePrimal()
+    assert np.isfinite(primal) and primal >= prev - 1e-6 * abs(prev)
+    labels = lp.labeling()
+    assert labels.max() < L
+    other = cuda_lp("f32").grid_create(H, W, L, kind)
+    other.grid_fill_synthetic(0x5EED, lo, hi)
+    other.set_tuning(wavefront_warps=2, wavefront_stages=4)
+    other.finalize(); other.Begin(); other.set_reparametrization("anisotropic")
+    for it in range(3):
+        other.ComputePass(it)
+        assert other.LowerBound() == lbs[it]
+    other.ComputeForwardPassAndPrimal(3)
+    assert np.array_equal(other.labeling(), labels) and other.EvaluatePrimal() == primal
+
+
+def test_mid_size_grid_against_oracle():
+    """256x256 crops of configs 2 / 3 against the oracle (seconds on the CPU), f32 bit-exact"""
+    for kind, L, lo, hi in (("trunclin", 16, 0.25, 1.0), ("potts", 32, 0.1, 1.0)):
+        lps = [oracle_lp("f32").grid_create(256, 256, L, kind), cuda_lp("f32").grid_create(256, 256, L, kind)]
+        for lp in lps:
+            lp.grid_fill_synthetic(7, lo, hi)
+        run_lockstep(lps, "anisotropic", iters=2, lb_rtol=1e-6)
+
+
+def test_error_behaviour_on_device():
+    from lp_mp_b200 import LpmpError
+    lp = cuda_lp("f64")
+    lp.add_unaries(np.zeros((3, 2)))
+    with pytest.raises(LpmpError):
+        lp.add_pairwise_potts([0], [7], [1.0])
+    lp.add_pairwise_potts([0, 1], [1, 2], [1.0, 1.0])
+    with pytest.raises(LpmpError):
+        lp.ComputePass(0)
+    lp.finalize(); lp.Begin()
+    with pytest.raises(LpmpError, match="no reparametrization mode set"):
+        lp.ComputePass(0)
+    with pytest.raises(LpmpError):
+        lp.add_unaries(np.zeros((1, 2)))
+    assert lp.EvaluatePrimal() == np.inf
+    g = cuda_lp("f32").grid_create(4, 4, 5, "potts")      # L=5: no wavefront instance
+    g.set_schedule("wavefront")
+    with pytest.raises(LpmpError):
+        g.finalize()
