@@ -48,7 +48,7 @@ enum { LPMP_PAIRWISE_DENSE = 0, LPMP_PAIRWISE_POTTS = 1, LPMP_PAIRWISE_TRUNCLIN 
 /* how the update order of LP::SortFactors (include/LP_MP.h:730-797) is realised on the device */
 enum {
   LPMP_SCHEDULE_LEVELS = 0,    /* general graphs: level sets of the factor-relation DAG given by the node ranks */
-  LPMP_SCHEDULE_WAVEFRONT = 1, /* grids only: persistent anti-diagonal row-band pipeline */
+  LPMP_SCHEDULE_WAVEFRONT = 1, /* grids only: persistent anti-diagonal row-band pipeline (Potts / truncated linear, L in {8,16,32,64}) */
 };
 
 /* iteration order of a factor's messages of one type (include/factors_messages.hxx:2005-2077 LIFO
@@ -85,8 +85,8 @@ int LPMP_FN(add_pairwise_trunclin)(lpmp_solver* h, uint64_t m, const uint64_t* i
 int LPMP_FN(set_node_ranks)(lpmp_solver* h, const uint64_t* rank /* [N], distinct */);
 int LPMP_FN(set_edge_order)(lpmp_solver* h, int edge_order);
 int LPMP_FN(set_schedule)(lpmp_solver* h, int schedule);
-/* launch-shape knobs of the device schedule (no effect on results): "wavefront_vpl" (labels per lane),
- * "wavefront_warps" (bands per CTA), "wavefront_stages" (prefetch depth), "wavefront_max_ctas".  Before finalize. */
+/* launch-shape knobs of the device schedule (no effect on results): "wavefront_max_ctas" (cap on resident bands),
+ * "wavefront_ctas_per_sm".  Before finalize. */
 int LPMP_FN(set_tuning)(lpmp_solver* h, const char* key, int value);
 /* Deterministic greedy colouring in node order (host utility, no handle state): colour[i] = smallest colour
  * not used by an already coloured neighbour.  Returns the number of colours through *num_colours. */
@@ -104,14 +104,40 @@ int LPMP_FN(grid_set_pairwise)(lpmp_solver* h, const void* horizontal /* [H][W-1
  * p_hi = trunc, constant).  The generator is specified in DESIGN.md so that the oracle reproduces it. */
 int LPMP_FN(grid_fill_synthetic)(lpmp_solver* h, uint64_t seed, double p_lo, double p_hi);
 
-/* Row-stripe partition (multi-GPU): declare that this grid is rows [r0, r0+H) of a taller
- * grid with H_total rows.  Stripe-boundary vertical edges get their parameters and this side's message
- * vector here, plus a halo buffer for the other side's vector. */
+/* Row-stripe partition (multi-GPU): declare that this grid is rows [row0, row0+H) of a taller grid with
+ * H_total rows (call before grid_fill_synthetic / finalize).  A stripe owns its nodes, its horizontal and inner
+ * vertical edges and, for the vertical edges crossing a stripe boundary, the message vector on ITS side (bU of its
+ * first row, aD of its last row) plus a copy of their parameters.  Stripes run the wavefront schedule in the
+ * anisotropic mode only.
+ *
+ * A pass consumes the neighbouring stripe's outgoing vectors from an "in" buffer of W*L reals (storage dtype) per
+ * boundary: in(0 = top) feeds the forward pass, in(1 = bottom) the backward pass.  Slots carry their own validity (a
+ * slot holds the all-ones NaN until the vector is stored; the pass puts that sentinel back after reading), so the
+ * same kernel serves both couplings:
+ *   - per-pass halo: deposit the neighbour's vectors (lpmp_grid_get_boundary_vectors on the neighbour, then a copy
+ *     or ncclSend/Recv into in_buf) before launching the pass;
+ *   - exact pipelined: lpmp_grid_set_peer_boundary hands the pass kernel the neighbour's in_buf (peer-mapped
+ *     pointer, same node: lpmp_ipc_export / lpmp_ipc_open); the last band of this stripe then stores each
+ *     outgoing vector straight into it over NVLink while the neighbour's first band polls -- results are
+ *     bit-identical to the unstriped LP. */
 int LPMP_FN(grid_set_stripe)(lpmp_solver* h, uint32_t row0, uint32_t H_total);
-int LPMP_FN(grid_set_boundary_pairwise)(lpmp_solver* h, const void* top /* [W][P] or NULL */, const void* bottom /* [W][P] or NULL */, int src_dtype);
-/* device pointers (storage dtype) to the W*L boundary vectors: what this stripe owns and sends (out) and the
- * halo it receives (in).  which: 0 = top boundary, 1 = bottom boundary. */
-int LPMP_FN(grid_boundary_ptrs)(lpmp_solver* h, int which, void** owned_out, void** halo_in, uint64_t* bytes);
+/* parameters of the boundary-crossing vertical edges, [W][P] each (NULL where there is no neighbour) */
+int LPMP_FN(grid_set_boundary_pairwise)(lpmp_solver* h, const void* top, const void* bottom, int src_dtype);
+int LPMP_FN(grid_boundary_ptrs)(lpmp_solver* h, int which, void** in_buf, uint64_t* bytes);
+/* which: 0 = deliver the backward pass's outgoing vectors to the upper neighbour's in(1), 1 = the forward pass's to
+ * the lower neighbour's in(0); NULL = do not deliver */
+int LPMP_FN(grid_set_peer_boundary)(lpmp_solver* h, int which, void* peer_in_buf);
+/* gather this stripe's current side of a boundary (0: bU of the first row, 1: aD of the last row) into a device
+ * buffer of W*L reals, enqueued on the handle's stream */
+int LPMP_FN(grid_get_boundary_vectors)(lpmp_solver* h, int which, void* dst_dev);
+/* stripe share of LP::LowerBound (include/LP_MP.h:1507-1518): own unaries, own edges and the edges to the stripe
+ * below, whose b-side vectors (the lower stripe's lpmp_grid_get_boundary_vectors(0)) are passed as a device
+ * pointer (NULL for the last stripe).  The LP's bound is the sum over stripes (all-reduce). */
+int LPMP_FN(grid_lower_bound_partial)(lpmp_solver* h, const void* below_b, double* out);
+/* cudaIpc wrappers (64-byte handles) so that a host language without CUDA bindings can exchange in_buf pointers */
+int LPMP_FN(ipc_export)(const void* devptr, void* handle64);
+int LPMP_FN(ipc_open)(const void* handle64, void** devptr);
+int LPMP_FN(ipc_close)(void* devptr);
 
 /* finish construction: build schedule + weights (SortFactors / ComputeAnisotropicWeights / ComputeUniformWeights,
  * include/LP_MP.h:730-797,1230-1449) and upload.  Mutating the problem afterwards is an error. */

@@ -48,7 +48,13 @@ SIGNATURES = {
     "grid_fill_synthetic": [_vp, _u64, _d, _d],
     "grid_set_stripe": [_vp, _u32, _u32],
     "grid_set_boundary_pairwise": [_vp, _vp, _vp, _i],
-    "grid_boundary_ptrs": [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), _pu64],
+    "grid_boundary_ptrs": [_vp, _i, C.POINTER(_vp), _pu64],
+    "grid_set_peer_boundary": [_vp, _i, _vp],
+    "grid_get_boundary_vectors": [_vp, _i, _vp],
+    "grid_lower_bound_partial": [_vp, _vp, _pd],
+    "ipc_export": [_vp, _vp],
+    "ipc_open": [_vp, C.POINTER(_vp)],
+    "ipc_close": [_vp],
     "finalize": [_vp],
     "begin": [_vp],
     "end": [_vp],

@@ -17,23 +17,31 @@
 
 namespace lpmp {
 
-template <typename Real, int PW>
-cudaError_t launch_family(const GridArgs<Real>& args, uint32_t L, const WavefrontTuning& tune, int num_sms, cudaStream_t stream);
-
-bool wavefront_supported(int pw, uint32_t L, int vpl, int stages) {
-  if (pw != LPMP_PAIRWISE_POTTS && pw != LPMP_PAIRWISE_TRUNCLIN) return false;
-  if (stages != 4 && stages != 8) return false;
-  if (vpl == 4) return L == 8 || L == 16 || L == 32 || L == 64;
-  if (vpl == 2) return L == 16 || L == 32;
-  return false;
-}
-int wavefront_rows_per_band(uint32_t L, int vpl) { return 32 / (int)(L / vpl); }
-
 template <typename Real>
-cudaError_t launch_wavefront(const GridArgs<Real>& args, int pw, uint32_t L, const WavefrontTuning& tune, int num_sms, cudaStream_t stream) {
-  if (pw == LPMP_PAIRWISE_POTTS) return launch_family<Real, LPMP_PAIRWISE_POTTS>(args, L, tune, num_sms, stream);
-  if (pw == LPMP_PAIRWISE_TRUNCLIN) return launch_family<Real, LPMP_PAIRWISE_TRUNCLIN>(args, L, tune, num_sms, stream);
+cudaError_t launch_wavefront(const CUtensorMap* maps, const GridArgs<Real>& args, int pw, uint32_t L, int hops, const WavefrontTuning& tune, int num_sms,
+                             cudaStream_t stream) {
+  const bool aniso = args.repam == LPMP_REPAM_ANISOTROPIC;
+  if (pw == LPMP_PAIRWISE_POTTS)
+    return aniso ? launch_family<Real, LPMP_PAIRWISE_POTTS, true>(maps, args, L, hops, tune, num_sms, stream)
+                 : launch_family<Real, LPMP_PAIRWISE_POTTS, false>(maps, args, L, hops, tune, num_sms, stream);
+  if (pw == LPMP_PAIRWISE_TRUNCLIN)
+    return aniso ? launch_family<Real, LPMP_PAIRWISE_TRUNCLIN, true>(maps, args, L, hops, tune, num_sms, stream)
+                 : launch_family<Real, LPMP_PAIRWISE_TRUNCLIN, false>(maps, args, L, hops, tune, num_sms, stream);
   return cudaErrorInvalidValue;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
 }
 
 // ---- small helpers ----------------------------------------------------------------------------------------------
@@ -52,30 +60,67 @@ struct DeviceBuffer {
   ~DeviceBuffer() { release(); }
 };
 
+// compact [n][inner] source into records of `dst_stride` elements (and back)
 template <typename Dst, typename Src>
-__global__ void convert_kernel(Dst* __restrict__ dst, const Src* __restrict__ src, uint64_t n) {
-  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) dst[k] = (Dst)src[k];
+__global__ void scatter_strided_kernel(Dst* __restrict__ dst, const Src* __restrict__ src, uint64_t n, uint32_t inner, uint64_t dst_stride) {
+  const uint64_t total = n * inner;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (uint64_t)gridDim.x * blockDim.x)
+    dst[(k / inner) * dst_stride + (k % inner)] = (Dst)src[k];
+}
+template <typename Dst, typename Src>
+__global__ void gather_strided_kernel(Dst* __restrict__ dst, const Src* __restrict__ src, uint64_t n, uint32_t inner, uint64_t src_stride) {
+  const uint64_t total = n * inner;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (uint64_t)gridDim.x * blockDim.x)
+    dst[k] = (Dst)src[(k / inner) * src_stride + (k % inner)];
 }
 
-// scatter compact [rows][cols][P] host layout into plane slots r*W+c (P reals per slot)
+// parameters of a plane of grid edges, compact [rows][cols][P], into the parameter records of BOTH endpoints:
+// edge at cell (r,c) -> node (r,c) field f_first and node (r,c) + second_off field f_second
 template <typename Dst, typename Src>
-__global__ void scatter_plane_kernel(Dst* __restrict__ dst, const Src* __restrict__ src, uint32_t rows, uint32_t cols, uint32_t W, uint32_t P) {
+__global__ void scatter_edge_params_kernel(Dst* __restrict__ par, const Src* __restrict__ src, uint32_t rows, uint32_t cols, uint32_t W, uint32_t P,
+                                           uint32_t second_off, int f_first, int f_second) {
   const uint64_t n = (uint64_t)rows * cols * P;
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t p = (uint32_t)(k % P);
     const uint64_t cell = k / P;
-    const uint32_t c = (uint32_t)(cell % cols), r = (uint32_t)(cell / cols);
-    dst[((uint64_t)r * W + c) * P + p] = (Dst)src[k];
+    const uint64_t node = (cell / cols) * W + (cell % cols);
+    const Dst v = (Dst)src[k];
+    if (f_first >= 0) par[(node * PAR_EDGES + f_first) * P + p] = v;
+    if (f_second >= 0) par[((node + second_off) * PAR_EDGES + f_second) * P + p] = v;
   }
 }
 
+// synthetic potentials (include/lpmp_synthetic.h): counters are indices of the FULL grid so that a stripe holds
+// exactly the values the unstriped LP would hold
 template <typename Real>
-__global__ void synth_fill_kernel(Real* __restrict__ dst, uint64_t n, uint64_t seed, uint64_t stream, double lo, double hi, int P, int trunclin) {
+__global__ void synth_unary_kernel(Real* __restrict__ rec, uint64_t n_nodes, uint32_t L, uint64_t rec_stride, uint64_t node0, uint64_t seed) {
+  const uint64_t total = n_nodes * L;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t node = k / L;
+    rec[node * rec_stride + (k % L)] = (Real)lpmp_synth_param(seed, LPMP_SYNTH_STREAM_UNARY, (node0 + node) * L + (k % L), 0.0, 1.0);
+  }
+}
+// vertical == 0: edges (r,c)-(r,c+1); vertical == 1: edges (r,c)-(r+1,c) for r in [-1, H): r = -1 and r = H-1 are the
+// stripe-boundary edges, of which only the endpoint inside the stripe is written
+template <typename Real>
+__global__ void synth_edge_kernel(Real* __restrict__ par, uint32_t H, uint32_t W, uint32_t P, uint32_t row0, uint32_t H_total, int vertical,
+                                  uint64_t seed, double lo, double hi, int trunclin) {
+  const uint64_t rows = vertical ? (uint64_t)H + 1 : H;
+  const uint64_t n = rows * W * P;
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
-    double v;
-    if (trunclin) v = (k % P) == 0 ? lo : hi;
-    else v = lpmp_synth_param(seed, stream, k, lo, hi);
-    dst[k] = (Real)v;
+    const uint32_t p = (uint32_t)(k % P);
+    const uint64_t cell = k / P;
+    const uint32_t c = (uint32_t)(cell % W);
+    const int64_t r = (int64_t)(cell / W) - (vertical ? 1 : 0);           // row (inside the stripe) of the edge's first endpoint
+    const int64_t gr = (int64_t)row0 + r;                                  // ... and in the full grid
+    if (gr < 0) continue;
+    if (vertical ? gr + 1 >= (int64_t)H_total : c + 1 >= W) continue;       // no such edge
+    const uint64_t slot = (uint64_t)gr * W + c;
+    const double v = trunclin ? (p == 0 ? lo : hi)
+                              : lpmp_synth_param(seed, vertical ? LPMP_SYNTH_STREAM_VERTICAL : LPMP_SYNTH_STREAM_HORIZONTAL, slot * P + p, lo, hi);
+    if (r >= 0) par[(((uint64_t)r * W + c) * PAR_EDGES + (vertical ? PAR_D : PAR_R)) * P + p] = (Real)v;
+    if (vertical) { if (r + 1 < (int64_t)H) par[(((uint64_t)(r + 1) * W + c) * PAR_EDGES + PAR_U) * P + p] = (Real)v; }
+    else par[(((uint64_t)r * W + c + 1) * PAR_EDGES + PAR_L) * P + p] = (Real)v;
   }
 }
 
@@ -110,7 +155,10 @@ struct ISolver {
   virtual int grid_fill_synthetic(uint64_t seed, double lo, double hi) = 0;
   virtual int grid_set_stripe(uint32_t row0, uint32_t H_total) = 0;
   virtual int grid_set_boundary_pairwise(const void* top, const void* bottom, int src) = 0;
-  virtual int grid_boundary_ptrs(int which, void** owned, void** halo, uint64_t* bytes) = 0;
+  virtual int grid_boundary_ptrs(int which, void** in_buf, uint64_t* bytes) = 0;
+  virtual int grid_set_peer_boundary(int which, void* peer_in_buf) = 0;
+  virtual int grid_get_boundary_vectors(int which, void* dst_dev) = 0;
+  virtual int grid_lower_bound_partial(const void* below_b, double* out) = 0;
   virtual int finalize() = 0;
   virtual int begin() = 0;
   virtual int set_reparametrization(int mode) = 0;
@@ -141,17 +189,23 @@ struct Solver : ISolver {
   bool finalized = false, labels_valid = false, is_grid = false, striped = false;
   double constant = 0.0;
   WavefrontTuning tune;
+  WavefrontShape shape{0, 0, 0};
+  int tl_reach = 0;          // truncated linear: max #{d >= 1: slope*d < trunc} over all edges seen so far
+  bool tl_irregular = false; // a negative slope / trunc was seen: only the all-distances kernel is exact
   // host staging (general graphs)
   std::vector<double> h_theta, h_params;
   std::vector<uint64_t> h_ei, h_ej, h_rank;
-  // device state
-  DeviceBuffer<Real> theta, a, b, params;
-  DeviceBuffer<Real> halo_top, halo_bot, own_top, own_bot, p_top, p_bot;
+  // device state.  General graphs: theta[N][L], a[E][L], b[E][L], params[E][P].  Grids: rec[N][5][L], par[N][4][P].
+  DeviceBuffer<Real> theta, a, b, params, rec, par;
+  DeviceBuffer<Real> handoff, in_top, in_bot;   // band-to-band / stripe-to-stripe column vectors (sentinel protocol)
+  Real* peer_top = nullptr;  // upper neighbour's in_bot (delivery target of the backward pass), or null
+  Real* peer_bot = nullptr;  // lower neighbour's in_top (delivery target of the forward pass), or null
   DeviceBuffer<uint32_t> d_ei, d_ej, inc_edge, level_nodes, labels;
   DeviceBuffer<uint64_t> inc_off;
   DeviceBuffer<uint8_t> inc_flags;
   DeviceBuffer<double> partial, result;
-  DeviceBuffer<unsigned int> control;  // [0] ticket, [1..] band progress
+  DeviceBuffer<unsigned int> control;  // [0] band ticket, [1] sticky abort flag (hand-off poll timed out)
+  CUtensorMap maps[3];
   std::vector<uint64_t> level_off;     // host
   uint64_t launches = 0, updates = 0;
   static constexpr int kBoundCtas = 148 * 4;
@@ -171,8 +225,35 @@ struct Solver : ISolver {
   }
 
   uint32_t P() const { return pairwise_param_count(pw, L); }
+  uint64_t REC() const { return (uint64_t)REC_VECS * L; }
+  uint64_t PREC() const { return (uint64_t)PAR_EDGES * P(); }
   int bad_state(const char* m) { err = m; return LPMP_ERR_STATE; }
   int need_final() { return finalized ? LPMP_OK : bad_state("finalize() has not been called"); }
+
+  // truncated-linear window of one edge, evaluated in the storage type exactly like the kernels do
+  void note_trunclin(double slope_d, double trunc_d) {
+    const Real slope = (Real)slope_d, trunc = (Real)trunc_d;
+    if (!(slope >= Real(0)) || !(trunc >= Real(0))) { tl_irregular = true; return; }
+    int reach = 0;
+    while (reach + 1 < (int)L && Real(slope * Real(reach + 1)) < trunc) ++reach;
+    tl_reach = std::max(tl_reach, reach);
+  }
+  template <typename Src>
+  void note_trunclin_array(const Src* p, uint64_t n_edges) {
+    Src ls = 0, lt = 0;
+    bool have = false;
+    for (uint64_t e = 0; e < n_edges; ++e) {
+      if (have && p[2 * e] == ls && p[2 * e + 1] == lt) continue;
+      ls = p[2 * e]; lt = p[2 * e + 1]; have = true;
+      note_trunclin((double)ls, (double)lt);
+    }
+  }
+  int tl_hops() const {
+    if (pw != LPMP_PAIRWISE_TRUNCLIN || tl_irregular) return 0;
+    if (tl_reach <= 4) return 1;
+    if (tl_reach <= 8 && L >= 16) return 2;
+    return 0;
+  }
 
   // ---- construction: general graphs ---------------------------------------------------------------------------
   int add_unaries(uint64_t n, uint32_t L_, const double* th) override {
@@ -220,10 +301,8 @@ struct Solver : ISolver {
   }
   int set_tuning(const char* key, int value) override {
     const std::string k(key ? key : "");
-    if (k == "wavefront_vpl") tune.vpl = value;
-    else if (k == "wavefront_warps") tune.warps = value;
-    else if (k == "wavefront_stages") tune.stages = value;
-    else if (k == "wavefront_max_ctas") tune.max_ctas = value;
+    if (k == "wavefront_max_ctas") tune.max_ctas = value;
+    else if (k == "wavefront_ctas_per_sm") tune.ctas_per_sm = value;
     else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
     return LPMP_OK;
   }
@@ -239,35 +318,23 @@ struct Solver : ISolver {
     E = (uint64_t)H * (W - 1) + (uint64_t)(H - 1) * W;
     slots = 2 * N;
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(theta.alloc(N * L));
-    CUDA_TRY(a.alloc(slots * L));
-    CUDA_TRY(b.alloc(slots * L));
-    CUDA_TRY(params.alloc(slots * P()));
-    CUDA_TRY(cudaMemsetAsync(theta.p, 0, theta.bytes(), stream));
-    CUDA_TRY(cudaMemsetAsync(a.p, 0, a.bytes(), stream));
-    CUDA_TRY(cudaMemsetAsync(b.p, 0, b.bytes(), stream));
-    CUDA_TRY(cudaMemsetAsync(params.p, 0, params.bytes(), stream));
+    CUDA_TRY(rec.alloc(N * REC()));
+    CUDA_TRY(par.alloc(N * PREC()));
+    CUDA_TRY(cudaMemsetAsync(rec.p, 0, rec.bytes(), stream));
+    CUDA_TRY(cudaMemsetAsync(par.p, 0, par.bytes(), stream));
     return LPMP_OK;
   }
   template <typename Src>
-  int upload_converted(Real* dst, const Src* src, uint64_t n) {
-    DeviceBuffer<Src> tmp;
+  int upload(DeviceBuffer<Src>& tmp, const Src* src, uint64_t n) {
     CUDA_TRY(tmp.alloc(n));
     CUDA_TRY(cudaMemcpyAsync(tmp.p, src, n * sizeof(Src), cudaMemcpyHostToDevice, stream));
-    convert_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(dst, tmp.p, n);
-    ++launches;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(stream));
     return LPMP_OK;
   }
   template <typename Src>
-  int upload_plane(Real* dst, const Src* src, uint32_t rows, uint32_t cols, uint32_t Pn) {
-    const uint64_t n = (uint64_t)rows * cols * Pn;
-    if (n == 0) return LPMP_OK;
+  int set_unaries_from(const Src* src) {
     DeviceBuffer<Src> tmp;
-    CUDA_TRY(tmp.alloc(n));
-    CUDA_TRY(cudaMemcpyAsync(tmp.p, src, n * sizeof(Src), cudaMemcpyHostToDevice, stream));
-    scatter_plane_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(dst, tmp.p, rows, cols, gridW, Pn);
+    if (int r = upload(tmp, src, N * L)) return r;
+    scatter_strided_kernel<Real, Src><<<grid_for(N * L, 256), 256, 0, stream>>>(rec.p, tmp.p, N, L, REC());
     ++launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(stream));
@@ -276,31 +343,44 @@ struct Solver : ISolver {
   int grid_set_unaries(const void* th, int src) override {
     if (!is_grid) return bad_state("not a grid");
     if (!th) { err = "null theta"; return LPMP_ERR_INVALID; }
-    if (src == LPMP_F32) return upload_converted<float>(theta.p, static_cast<const float*>(th), N * L);
-    return upload_converted<double>(theta.p, static_cast<const double*>(th), N * L);
+    return src == LPMP_F32 ? set_unaries_from(static_cast<const float*>(th)) : set_unaries_from(static_cast<const double*>(th));
+  }
+  template <typename Src>
+  int set_edge_plane(const Src* src, uint32_t rows, uint32_t cols, uint32_t second_off, int f_first, int f_second) {
+    const uint32_t Pn = P();
+    const uint64_t n = (uint64_t)rows * cols * Pn;
+    if (n == 0 || !src) return LPMP_OK;
+    if (pw == LPMP_PAIRWISE_TRUNCLIN) note_trunclin_array(src, (uint64_t)rows * cols);
+    DeviceBuffer<Src> tmp;
+    if (int r = upload(tmp, src, n)) return r;
+    scatter_edge_params_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(par.p, tmp.p, rows, cols, gridW, Pn, second_off, f_first, f_second);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
   }
   int grid_set_pairwise(const void* hz, const void* vt, int src) override {
     if (!is_grid) return bad_state("not a grid");
-    const uint32_t Pn = P();
-    Real* ph = params.p;
-    Real* pv = params.p + N * Pn;
-    int r = LPMP_OK;
+    if (pw == LPMP_PAIRWISE_DENSE) { err = "dense tables on the grid API are not supported: use add_pairwise_dense"; return LPMP_ERR_UNSUPPORTED; }
+    int r;
     if (src == LPMP_F32) {
-      if (hz) r = upload_plane<float>(ph, static_cast<const float*>(hz), gridH, gridW - 1, Pn);
-      if (r == LPMP_OK && vt) r = upload_plane<float>(pv, static_cast<const float*>(vt), gridH - 1, gridW, Pn);
+      r = set_edge_plane(static_cast<const float*>(hz), gridH, gridW - 1, 1, PAR_R, PAR_L);
+      if (r == LPMP_OK) r = set_edge_plane(static_cast<const float*>(vt), gridH - 1, gridW, gridW, PAR_D, PAR_U);
     } else {
-      if (hz) r = upload_plane<double>(ph, static_cast<const double*>(hz), gridH, gridW - 1, Pn);
-      if (r == LPMP_OK && vt) r = upload_plane<double>(pv, static_cast<const double*>(vt), gridH - 1, gridW, Pn);
+      r = set_edge_plane(static_cast<const double*>(hz), gridH, gridW - 1, 1, PAR_R, PAR_L);
+      if (r == LPMP_OK) r = set_edge_plane(static_cast<const double*>(vt), gridH - 1, gridW, gridW, PAR_D, PAR_U);
     }
     return r;
   }
   int grid_fill_synthetic(uint64_t seed, double lo, double hi) override {
     if (!is_grid) return bad_state("not a grid");
+    if (pw == LPMP_PAIRWISE_DENSE) { err = "dense tables on the grid API are not supported"; return LPMP_ERR_UNSUPPORTED; }
     const uint32_t Pn = P();
     const int tl = pw == LPMP_PAIRWISE_TRUNCLIN;
-    synth_fill_kernel<Real><<<grid_for(N * L, 256), 256, 0, stream>>>(theta.p, N * L, seed, LPMP_SYNTH_STREAM_UNARY, 0.0, 1.0, 1, 0);
-    synth_fill_kernel<Real><<<grid_for(N * Pn, 256), 256, 0, stream>>>(params.p, N * Pn, seed, LPMP_SYNTH_STREAM_HORIZONTAL, lo, hi, Pn, tl);
-    synth_fill_kernel<Real><<<grid_for(N * Pn, 256), 256, 0, stream>>>(params.p + N * Pn, N * Pn, seed, LPMP_SYNTH_STREAM_VERTICAL, lo, hi, Pn, tl);
+    if (tl) note_trunclin(lo, hi);
+    synth_unary_kernel<Real><<<grid_for(N * L, 256), 256, 0, stream>>>(rec.p, N, L, REC(), (uint64_t)row0 * gridW, seed);
+    synth_edge_kernel<Real><<<grid_for(N * Pn, 256), 256, 0, stream>>>(par.p, gridH, gridW, Pn, row0, H_total, 0, seed, lo, hi, tl);
+    synth_edge_kernel<Real><<<grid_for((N + gridW) * Pn, 256), 256, 0, stream>>>(par.p, gridH, gridW, Pn, row0, H_total, 1, seed, lo, hi, tl);
     launches += 3;
     CUDA_TRY(cudaGetLastError());
     return LPMP_OK;
@@ -310,25 +390,55 @@ struct Solver : ISolver {
     if ((uint64_t)r0 + gridH > Ht) { err = "stripe exceeds the full grid"; return LPMP_ERR_INVALID; }
     row0 = r0; H_total = Ht; striped = true;
     const uint64_t n = (uint64_t)gridW * L;
-    if (row0 > 0) { CUDA_TRY(halo_top.alloc(n)); CUDA_TRY(own_top.alloc(n)); CUDA_TRY(p_top.alloc((uint64_t)gridW * P()));
-      CUDA_TRY(cudaMemsetAsync(halo_top.p, 0, halo_top.bytes(), stream)); CUDA_TRY(cudaMemsetAsync(own_top.p, 0, own_top.bytes(), stream)); CUDA_TRY(cudaMemsetAsync(p_top.p, 0, p_top.bytes(), stream)); }
-    if (row0 + gridH < H_total) { CUDA_TRY(halo_bot.alloc(n)); CUDA_TRY(own_bot.alloc(n)); CUDA_TRY(p_bot.alloc((uint64_t)gridW * P()));
-      CUDA_TRY(cudaMemsetAsync(halo_bot.p, 0, halo_bot.bytes(), stream)); CUDA_TRY(cudaMemsetAsync(own_bot.p, 0, own_bot.bytes(), stream)); CUDA_TRY(cudaMemsetAsync(p_bot.p, 0, p_bot.bytes(), stream)); }
+    if (row0 > 0) { CUDA_TRY(in_top.alloc(n)); CUDA_TRY(cudaMemsetAsync(in_top.p, 0xff, in_top.bytes(), stream)); }
+    if (row0 + gridH < H_total) { CUDA_TRY(in_bot.alloc(n)); CUDA_TRY(cudaMemsetAsync(in_bot.p, 0xff, in_bot.bytes(), stream)); }
+    CUDA_TRY(cudaStreamSynchronize(stream));
     return LPMP_OK;
   }
   int grid_set_boundary_pairwise(const void* top, const void* bottom, int src) override {
     if (!striped) return bad_state("grid_set_boundary_pairwise: not a stripe");
-    const uint64_t n = (uint64_t)gridW * P();
     int r = LPMP_OK;
-    if (top && p_top.p) r = src == LPMP_F32 ? upload_converted<float>(p_top.p, static_cast<const float*>(top), n) : upload_converted<double>(p_top.p, static_cast<const double*>(top), n);
-    if (r == LPMP_OK && bottom && p_bot.p) r = src == LPMP_F32 ? upload_converted<float>(p_bot.p, static_cast<const float*>(bottom), n) : upload_converted<double>(p_bot.p, static_cast<const double*>(bottom), n);
+    // top[c]: edge (row0-1, c)-(row0, c): field U of the first row; bottom[c]: edge (last row, c)-(below): field D of the last row
+    if (src == LPMP_F32) {
+      if (top && row0 > 0) r = set_edge_plane(static_cast<const float*>(top), 1, gridW, 0, PAR_U, -1);
+      if (r == LPMP_OK && bottom && row0 + gridH < H_total) r = set_bottom_plane(static_cast<const float*>(bottom));
+    } else {
+      if (top && row0 > 0) r = set_edge_plane(static_cast<const double*>(top), 1, gridW, 0, PAR_U, -1);
+      if (r == LPMP_OK && bottom && row0 + gridH < H_total) r = set_bottom_plane(static_cast<const double*>(bottom));
+    }
     return r;
   }
-  int grid_boundary_ptrs(int which, void** owned, void** halo, uint64_t* bytes) override {
+  template <typename Src>
+  int set_bottom_plane(const Src* bottom) {
+    const uint32_t Pn = P();
+    const uint64_t n = (uint64_t)gridW * Pn;
+    if (pw == LPMP_PAIRWISE_TRUNCLIN) note_trunclin_array(bottom, gridW);
+    DeviceBuffer<Src> tmp;
+    if (int r = upload(tmp, bottom, n)) return r;
+    scatter_edge_params_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(par.p + (uint64_t)(gridH - 1) * gridW * PREC(), tmp.p, 1, gridW, gridW, Pn, 0, PAR_D, -1);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
+  int grid_boundary_ptrs(int which, void** in_buf, uint64_t* bytes) override {
     if (!striped) return bad_state("grid_boundary_ptrs: not a stripe");
-    if (owned) *owned = which == 0 ? (void*)own_top.p : (void*)own_bot.p;
-    if (halo) *halo = which == 0 ? (void*)halo_top.p : (void*)halo_bot.p;
+    if (in_buf) *in_buf = which == 0 ? (void*)in_top.p : (void*)in_bot.p;
     if (bytes) *bytes = (uint64_t)gridW * L * sizeof(Real);
+    return LPMP_OK;
+  }
+  int grid_set_peer_boundary(int which, void* peer_in_buf) override {
+    if (!striped) return bad_state("grid_set_peer_boundary: not a stripe");
+    (which == 0 ? peer_top : peer_bot) = static_cast<Real*>(peer_in_buf);
+    return LPMP_OK;
+  }
+  // own side of the stripe-boundary edges: bU of the first row (which = 0), aD of the last row (which = 1)
+  int grid_get_boundary_vectors(int which, void* dst_dev) override {
+    if (!is_grid) return bad_state("not a grid");
+    const Real* src = which == 0 ? rec.p + (uint64_t)REC_BU * L : rec.p + (uint64_t)(gridH - 1) * gridW * REC() + (uint64_t)REC_AD * L;
+    gather_strided_kernel<Real, Real><<<grid_for((uint64_t)gridW * L, 256), 256, 0, stream>>>(static_cast<Real*>(dst_dev), src, gridW, L, REC());
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
     return LPMP_OK;
   }
 
@@ -341,6 +451,24 @@ struct Solver : ISolver {
         if (c + 1 < gridW) { ei.push_back(i); ej.push_back(i + 1); slot.push_back(i); }
         if (r + 1 < gridH) { ei.push_back(i); ej.push_back(i + gridW); slot.push_back(N + i); }
       }
+  }
+
+  Store<Real> store() const {
+    Store<Real> s;
+    s.L_ = L;
+    if (is_grid) {
+      const uint64_t R = REC(), Pn = P();
+      s.theta = rec.p; s.theta_stride = R;
+      s.a0 = rec.p + (uint64_t)REC_AR * L; s.a1 = rec.p + (uint64_t)REC_AD * L;
+      s.b0 = rec.p + R + (uint64_t)REC_BL * L; s.b1 = rec.p + (uint64_t)gridW * R + (uint64_t)REC_BU * L;
+      s.p0 = par.p + (uint64_t)PAR_R * Pn; s.p1 = par.p + (uint64_t)PAR_D * Pn;
+      s.split = N; s.estride = R; s.pstride = PREC();
+    } else {
+      s.theta = theta.p; s.theta_stride = L;
+      s.a0 = s.a1 = a.p; s.b0 = s.b1 = b.p; s.p0 = s.p1 = params.p;
+      s.split = ~uint64_t(0); s.estride = L; s.pstride = P();
+    }
+    return s;
   }
 
   int build_levels(const std::vector<uint64_t>& ei, const std::vector<uint64_t>& ej, const std::vector<uint64_t>& slot) {
@@ -374,7 +502,6 @@ struct Solver : ISolver {
     std::vector<uint64_t> order(N);
     std::iota(order.begin(), order.end(), uint64_t(0));
     std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return rank[x] < rank[y]; });
-    std::vector<std::vector<uint32_t>> nbr_lower(0);
     std::vector<uint32_t> level(N, 0);
     std::vector<uint64_t> adj_off(N + 1, 0);
     for (uint64_t e = 0; e < m; ++e) { ++adj_off[ei[e] + 1]; ++adj_off[ej[e] + 1]; }
@@ -408,10 +535,35 @@ struct Solver : ISolver {
     return LPMP_OK;
   }
 
+  // TMA descriptors of the record / parameter arrays: tiles of `rows` grid rows x K columns of whole records
+  int encode_map(CUtensorMap* m, Real* base, uint32_t inner, uint32_t vecs, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { err = "cuTensorMapEncodeTiled is not available in this driver"; return LPMP_ERR_CUDA; }
+    const CUtensorMapDataType dt = sizeof(Real) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    CUresult r;
+    if (vecs > 1) {   // (label, vector, column, row)
+      const cuuint64_t dims[4] = {inner, vecs, gridW, gridH};
+      const cuuint64_t strides[3] = {inner * sizeof(Real), (cuuint64_t)inner * vecs * sizeof(Real), (cuuint64_t)gridW * inner * vecs * sizeof(Real)};
+      const cuuint32_t box[4] = {inner, vecs, (cuuint32_t)shape.K, box_rows};
+      const cuuint32_t es[4] = {1, 1, 1, 1};
+      r = fn(m, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {          // (parameter, column, row)
+      const cuuint64_t dims[3] = {inner, gridW, gridH};
+      const cuuint64_t strides[2] = {inner * sizeof(Real), (cuuint64_t)gridW * inner * sizeof(Real)};
+      const cuuint32_t box[3] = {inner, (cuuint32_t)shape.K, box_rows};
+      const cuuint32_t es[3] = {1, 1, 1};
+      r = fn(m, dt, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r); return LPMP_ERR_CUDA; }
+    return LPMP_OK;
+  }
+
   int finalize() override {
     if (finalized) return bad_state("finalize called twice");
     if (N == 0) return bad_state("no factors");
-    if (N >= (1ull << 32)) { err = "more than 2^32 nodes"; return LPMP_ERR_UNSUPPORTED; }
+    if (N >= (1ull << 31)) { err = "more than 2^31 nodes"; return LPMP_ERR_UNSUPPORTED; }
     CUDA_TRY(cudaSetDevice(device));
     if (pw == -1) pw = LPMP_PAIRWISE_POTTS;
     if (!is_grid) {
@@ -445,18 +597,23 @@ struct Solver : ISolver {
       if (int r = build_levels(h_ei, h_ej, slot)) return r;
       h_theta.clear(); h_theta.shrink_to_fit(); h_params.clear(); h_params.shrink_to_fit();
     } else {
-      const bool wf_ok = wavefront_supported(pw, L, tune.vpl, tune.stages) && h_rank.empty();
+      const bool wf_ok = wavefront_shape<Real>(pw, L, shape) && h_rank.empty();
       if (schedule == -1) schedule = wf_ok ? LPMP_SCHEDULE_WAVEFRONT : LPMP_SCHEDULE_LEVELS;
-      if (schedule == LPMP_SCHEDULE_WAVEFRONT && !wf_ok) { err = "no wavefront kernel for this label count / pairwise family / tuning"; return LPMP_ERR_UNSUPPORTED; }
+      if (schedule == LPMP_SCHEDULE_WAVEFRONT && !wf_ok) { err = "no wavefront kernel for this label count / pairwise family"; return LPMP_ERR_UNSUPPORTED; }
       if (schedule == LPMP_SCHEDULE_LEVELS) {
         if (striped) { err = "stripes need the wavefront schedule"; return LPMP_ERR_UNSUPPORTED; }
         std::vector<uint64_t> ei, ej, slot;
         grid_edge_lists(ei, ej, slot);
         if (int r = build_levels(ei, ej, slot)) return r;
       } else {
-        const int T = wavefront_rows_per_band(L, tune.vpl);
-        const uint32_t bands = (gridH + T - 1) / T;
-        CUDA_TRY(control.alloc(1 + (size_t)bands));
+        const uint32_t bands = (gridH + shape.T - 1) / shape.T;
+        CUDA_TRY(control.alloc(2));
+        CUDA_TRY(cudaMemsetAsync(control.p, 0, control.bytes(), stream));
+        CUDA_TRY(handoff.alloc((size_t)bands * gridW * L));
+        CUDA_TRY(cudaMemsetAsync(handoff.p, 0xff, handoff.bytes(), stream));
+        if (int r = encode_map(&maps[0], rec.p, L, REC_VECS, (uint32_t)shape.T)) return r;
+        if (int r = encode_map(&maps[1], rec.p, L, REC_VECS, (uint32_t)shape.T + 1)) return r;
+        if (int r = encode_map(&maps[2], par.p, (uint32_t)PREC(), 1, (uint32_t)shape.T)) return r;
       }
     }
     CUDA_TRY(labels.alloc(N));
@@ -491,7 +648,7 @@ struct Solver : ISolver {
         const uint64_t cnt = level_off[lv + 1] - level_off[lv];
         if (cnt == 0) continue;
         LevelArgs<Real> A;
-        A.theta = theta.p; A.a = a.p; A.b = b.p; A.params = params.p;
+        A.st = store();
         A.nodes = level_nodes.p + level_off[lv]; A.num_nodes = (uint32_t)cnt;
         A.inc_off = inc_off.p; A.inc_edge = inc_edge.p; A.inc_flags = inc_flags.p; A.labels = labels.p;
         A.L = L; A.pw = pw; A.repam = repam; A.forward = forward ? 1 : 0; A.primal = primal ? 1 : 0;
@@ -501,19 +658,21 @@ struct Solver : ISolver {
       }
       CUDA_TRY(cudaGetLastError());
     } else {
-      const int T = wavefront_rows_per_band(L, tune.vpl);
+      if (striped && repam != LPMP_REPAM_ANISOTROPIC) { err = "stripes support the anisotropic reparametrization only"; return LPMP_ERR_UNSUPPORTED; }
       GridArgs<Real> A;
-      const uint32_t Pn = P();
-      A.theta = theta.p; A.ah = a.p; A.av = a.p + N * L; A.bh = b.p; A.bv = b.p + N * L;
-      A.ph = params.p; A.pv = params.p + N * Pn; A.labels = labels.p;
-      A.H = gridH; A.W = gridW; A.row0 = row0; A.H_total = H_total;
-      A.halo_top = halo_top.p; A.halo_bot = halo_bot.p; A.own_top = own_top.p; A.own_bot = own_bot.p;
-      A.p_top = p_top.p; A.p_bot = p_bot.p;
-      A.num_bands = (gridH + T - 1) / T;
-      A.ticket = control.p; A.progress = control.p + 1;
+      A.H = gridH; A.W = gridW;
+      A.num_bands = (gridH + shape.T - 1) / shape.T;
       A.forward = forward ? 1 : 0; A.primal = primal ? 1 : 0; A.fifo = edge_order == LPMP_EDGE_ORDER_FIFO; A.repam = repam;
-      CUDA_TRY(cudaMemsetAsync(control.p, 0, control.bytes(), stream));
-      CUDA_TRY(launch_wavefront<Real>(A, pw, L, tune, num_sms, stream));
+      const bool has_above = row0 > 0, has_below = row0 + gridH < H_total;
+      A.in_halo = forward ? has_above : has_below;
+      A.out_halo = forward ? has_below : has_above;
+      A.tl_reach = tl_reach;
+      A.control = control.p; A.handoff = handoff.p;
+      A.in_boundary = forward ? in_top.p : in_bot.p;
+      A.out_boundary = forward ? peer_bot : peer_top;
+      A.labels = labels.p;
+      CUDA_TRY(cudaMemsetAsync(control.p, 0, sizeof(unsigned int), stream));
+      CUDA_TRY(launch_wavefront<Real>(maps, A, pw, L, tl_hops(), tune, num_sms, stream));
       ++launches;
     }
     updates += (repam == LPMP_REPAM_ANISOTROPIC ? 2 : 4) * E;
@@ -524,23 +683,31 @@ struct Solver : ISolver {
   template <typename Topo>
   BoundArgs<Real, Topo> bound_args(Topo topo) {
     BoundArgs<Real, Topo> A;
-    A.theta = theta.p; A.a = a.p; A.b = b.p; A.params = params.p; A.topo = topo;
+    A.st = store(); A.topo = topo;
     A.num_nodes = N; A.L = L; A.pw = pw; A.partial = partial.p;
     return A;
   }
 
-  int reduce_to_host(int ctas, double* out) {
-    final_sum_kernel<<<1, 32, 0, stream>>>(partial.p, ctas, constant, result.p);
+  // the wavefront kernel bounds its hand-off polls; a timeout leaves a sticky flag and an unusable state
+  int check_abort() {
+    if (!control.p) return LPMP_OK;
+    unsigned int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, control.p + 1, sizeof(flag), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (flag) { err = "wavefront pass aborted: a band waited too long for its predecessor (state is invalid)"; return LPMP_ERR_CUDA; }
+    return LPMP_OK;
+  }
+
+  int reduce_to_host(int ctas, double add, double* out) {
+    final_sum_kernel<<<1, 32, 0, stream>>>(partial.p, ctas, add, result.p);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, result.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    return LPMP_OK;
+    return check_abort();
   }
 
-  int lower_bound(double* out) override {
-    if (int r = need_final()) return r;
-    if (striped) { err = "lower_bound of a stripe: use the partial bound entry point"; return LPMP_ERR_UNSUPPORTED; }
+  int bound_launch(const Real* below_b, double add, double* out) {
     CUDA_TRY(cudaSetDevice(device));
     const int G = group_size_for(L);
     int threads = 256;
@@ -550,15 +717,29 @@ struct Solver : ISolver {
     const uint64_t total = N + slots;
     const int ctas = (int)std::min<uint64_t>((total + groups - 1) / groups, (uint64_t)kBoundCtas);
     if (is_grid) {
-      GridTopo topo{gridH, gridW, slots};
-      lower_bound_kernel<Real, GridTopo><<<ctas, threads, (size_t)groups * per_group, stream>>>(bound_args(topo), G);
+      GridTopo<Real> topo{gridH, gridW, slots, below_b};
+      lower_bound_kernel<Real, GridTopo<Real>><<<ctas, threads, (size_t)groups * per_group, stream>>>(bound_args(topo), G);
     } else {
       GraphTopo topo{d_ei.p, d_ej.p, slots};
       lower_bound_kernel<Real, GraphTopo><<<ctas, threads, (size_t)groups * per_group, stream>>>(bound_args(topo), G);
     }
     ++launches;
     CUDA_TRY(cudaGetLastError());
-    return reduce_to_host(ctas, out);
+    return reduce_to_host(ctas, add, out);
+  }
+
+  int lower_bound(double* out) override {
+    if (int r = need_final()) return r;
+    if (striped) { err = "lower_bound of a stripe: use lpmp_grid_lower_bound_partial"; return LPMP_ERR_UNSUPPORTED; }
+    return bound_launch(nullptr, constant, out);
+  }
+  // stripe share of LP::LowerBound: own unaries, horizontal and inner vertical edges, and the edges to the stripe
+  // below (their a side is this stripe's aD, their b side arrives in `below_b`)
+  int grid_lower_bound_partial(const void* below_b, double* out) override {
+    if (int r = need_final()) return r;
+    if (!is_grid) return bad_state("not a grid");
+    if (row0 + gridH < H_total && !below_b) { err = "the b-side vectors of the stripe below are required"; return LPMP_ERR_INVALID; }
+    return bound_launch(row0 + gridH < H_total ? static_cast<const Real*>(below_b) : nullptr, row0 == 0 ? constant : 0.0, out);
   }
 
   int evaluate_primal(double* out) override {
@@ -569,15 +750,15 @@ struct Solver : ISolver {
     const uint64_t total = N + slots;
     const int ctas = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)kBoundCtas);
     if (is_grid) {
-      GridTopo topo{gridH, gridW, slots};
-      primal_cost_kernel<Real, GridTopo><<<ctas, 256, 0, stream>>>(bound_args(topo), labels.p);
+      GridTopo<Real> topo{gridH, gridW, slots, nullptr};
+      primal_cost_kernel<Real, GridTopo<Real>><<<ctas, 256, 0, stream>>>(bound_args(topo), labels.p);
     } else {
       GraphTopo topo{d_ei.p, d_ej.p, slots};
       primal_cost_kernel<Real, GraphTopo><<<ctas, 256, 0, stream>>>(bound_args(topo), labels.p);
     }
     ++launches;
     CUDA_TRY(cudaGetLastError());
-    return reduce_to_host(ctas, out);
+    return reduce_to_host(ctas, constant, out);
   }
 
   int check_primal_consistency(int* out) override {
@@ -598,7 +779,7 @@ struct Solver : ISolver {
     if (int r = need_final()) return r;
     CUDA_TRY(cudaMemcpyAsync(out, labels.p, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    return LPMP_OK;
+    return check_abort();
   }
   int download(std::vector<Real>& tmp, const Real* src, uint64_t n) {
     tmp.resize(n);
@@ -609,40 +790,69 @@ struct Solver : ISolver {
   int get_unaries(double* th) override {
     if (!is_grid && !finalized) { for (size_t k = 0; k < h_theta.size(); ++k) th[k] = (double)(Real)h_theta[k]; return LPMP_OK; }
     std::vector<Real> tmp;
+    if (is_grid) {
+      if (int r = download(tmp, rec.p, N * REC())) return r;
+      for (uint64_t i = 0; i < N; ++i)
+        for (uint32_t x = 0; x < L; ++x) th[i * L + x] = (double)tmp[i * REC() + x];
+      return LPMP_OK;
+    }
     if (int r = download(tmp, theta.p, N * L)) return r;
     for (uint64_t k = 0; k < N * L; ++k) th[k] = (double)tmp[k];
     return LPMP_OK;
   }
-  // storage slot of edge e (insertion order)
-  void edge_slots(std::vector<uint64_t>& slot) const {
-    if (!is_grid) { slot.resize(E); std::iota(slot.begin(), slot.end(), uint64_t(0)); return; }
-    std::vector<uint64_t> ei, ej;
-    grid_edge_lists(ei, ej, slot);
+  // position of edge e's two vectors inside the host copy of the state (insertion order of the edges)
+  void grid_edge_vector_offsets(std::vector<uint64_t>& oa, std::vector<uint64_t>& ob) const {
+    const uint64_t R = REC();
+    for (uint32_t r = 0; r < gridH; ++r)
+      for (uint32_t c = 0; c < gridW; ++c) {
+        const uint64_t i = (uint64_t)r * gridW + c;
+        if (c + 1 < gridW) { oa.push_back(i * R + (uint64_t)REC_AR * L); ob.push_back((i + 1) * R + (uint64_t)REC_BL * L); }
+        if (r + 1 < gridH) { oa.push_back(i * R + (uint64_t)REC_AD * L); ob.push_back((i + gridW) * R + (uint64_t)REC_BU * L); }
+      }
   }
   int get_messages(double* pa, double* pb) override {
     if (int r = need_final()) return r;
-    std::vector<uint64_t> slot;
-    edge_slots(slot);
     std::vector<Real> tmp;
+    if (is_grid) {
+      std::vector<uint64_t> oa, ob;
+      grid_edge_vector_offsets(oa, ob);
+      if (int r = download(tmp, rec.p, N * REC())) return r;
+      for (uint64_t e = 0; e < E; ++e)
+        for (uint32_t x = 0; x < L; ++x) {
+          if (pa) pa[e * L + x] = (double)tmp[oa[e] + x];
+          if (pb) pb[e * L + x] = (double)tmp[ob[e] + x];
+        }
+      return LPMP_OK;
+    }
     for (int which = 0; which < 2; ++which) {
       double* dst = which == 0 ? pa : pb;
       if (!dst) continue;
       if (int r = download(tmp, which == 0 ? a.p : b.p, slots * L)) return r;
-      for (uint64_t e = 0; e < E; ++e)
-        for (uint32_t x = 0; x < L; ++x) dst[e * L + x] = (double)tmp[slot[e] * L + x];
+      for (uint64_t k = 0; k < E * L; ++k) dst[k] = (double)tmp[k];
     }
     return LPMP_OK;
   }
   int set_messages(const double* pa, const double* pb) override {
     if (int r = need_final()) return r;
-    std::vector<uint64_t> slot;
-    edge_slots(slot);
+    if (is_grid) {
+      std::vector<uint64_t> oa, ob;
+      grid_edge_vector_offsets(oa, ob);
+      std::vector<Real> tmp;
+      if (int r = download(tmp, rec.p, N * REC())) return r;
+      for (uint64_t e = 0; e < E; ++e)
+        for (uint32_t x = 0; x < L; ++x) {
+          if (pa) tmp[oa[e] + x] = (Real)pa[e * L + x];
+          if (pb) tmp[ob[e] + x] = (Real)pb[e * L + x];
+        }
+      CUDA_TRY(cudaMemcpyAsync(rec.p, tmp.data(), tmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      return LPMP_OK;
+    }
     for (int which = 0; which < 2; ++which) {
       const double* src = which == 0 ? pa : pb;
       if (!src) continue;
       std::vector<Real> tmp(slots * L, Real(0));
-      for (uint64_t e = 0; e < E; ++e)
-        for (uint32_t x = 0; x < L; ++x) tmp[slot[e] * L + x] = (Real)src[e * L + x];
+      for (uint64_t k = 0; k < E * L; ++k) tmp[k] = (Real)src[k];
       CUDA_TRY(cudaMemcpyAsync(which == 0 ? a.p : b.p, tmp.data(), tmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
       CUDA_TRY(cudaStreamSynchronize(stream));
     }
@@ -650,6 +860,7 @@ struct Solver : ISolver {
   }
   int set_unaries(const double* th) override {
     if (int r = need_final()) return r;
+    if (is_grid) return set_unaries_from(th);
     std::vector<Real> tmp(N * L);
     for (uint64_t k = 0; k < N * L; ++k) tmp[k] = (Real)th[k];
     CUDA_TRY(cudaMemcpyAsync(theta.p, tmp.data(), tmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
@@ -663,12 +874,13 @@ struct Solver : ISolver {
     else out->num_levels = level_off.empty() ? 0 : level_off.size() - 1;
     out->kernel_launches = launches;
     out->message_updates = updates;
-    out->device_bytes = theta.bytes() + a.bytes() + b.bytes() + params.bytes() + labels.bytes() + inc_off.bytes() + inc_edge.bytes() +
-                        inc_flags.bytes() + level_nodes.bytes() + d_ei.bytes() + d_ej.bytes() + control.bytes();
+    out->device_bytes = theta.bytes() + a.bytes() + b.bytes() + params.bytes() + rec.bytes() + par.bytes() + labels.bytes() + inc_off.bytes() +
+                        inc_edge.bytes() + inc_flags.bytes() + level_nodes.bytes() + d_ei.bytes() + d_ej.bytes() + control.bytes() + handoff.bytes() +
+                        in_top.bytes() + in_bot.bytes();
     out->algorithmic_bytes_per_pass = (double)sizeof(Real) * (2.0 * (double)N * L + (double)E * ((double)P() + 5.0 * L));
     return LPMP_OK;
   }
-  int synchronize() override { CUDA_TRY(cudaStreamSynchronize(stream)); return LPMP_OK; }
+  int synchronize() override { CUDA_TRY(cudaStreamSynchronize(stream)); return check_abort(); }
   void* stream_ptr() override { return (void*)stream; }
 };
 
@@ -800,7 +1012,25 @@ int lpmp_grid_set_pairwise(lpmp_solver* h, const void* hz, const void* vt, int s
 int lpmp_grid_fill_synthetic(lpmp_solver* h, uint64_t seed, double lo, double hi) { return S(h)->grid_fill_synthetic(seed, lo, hi); }
 int lpmp_grid_set_stripe(lpmp_solver* h, uint32_t row0, uint32_t H_total) { return S(h)->grid_set_stripe(row0, H_total); }
 int lpmp_grid_set_boundary_pairwise(lpmp_solver* h, const void* top, const void* bottom, int src) { return S(h)->grid_set_boundary_pairwise(top, bottom, src); }
-int lpmp_grid_boundary_ptrs(lpmp_solver* h, int which, void** owned, void** halo, uint64_t* bytes) { return S(h)->grid_boundary_ptrs(which, owned, halo, bytes); }
+int lpmp_grid_boundary_ptrs(lpmp_solver* h, int which, void** in_buf, uint64_t* bytes) { return S(h)->grid_boundary_ptrs(which, in_buf, bytes); }
+int lpmp_grid_set_peer_boundary(lpmp_solver* h, int which, void* peer_in_buf) { return S(h)->grid_set_peer_boundary(which, peer_in_buf); }
+int lpmp_grid_get_boundary_vectors(lpmp_solver* h, int which, void* dst_dev) { return S(h)->grid_get_boundary_vectors(which, dst_dev); }
+int lpmp_grid_lower_bound_partial(lpmp_solver* h, const void* below_b, double* out) { return S(h)->grid_lower_bound_partial(below_b, out); }
+
+int lpmp_ipc_export(const void* devptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are 64 bytes");
+  cudaIpcMemHandle_t hd;
+  if (cudaIpcGetMemHandle(&hd, const_cast<void*>(devptr)) != cudaSuccess) { cudaGetLastError(); return LPMP_ERR_CUDA; }
+  std::memcpy(handle64, &hd, 64);
+  return LPMP_OK;
+}
+int lpmp_ipc_open(const void* handle64, void** devptr) {
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle64, 64);
+  if (cudaIpcOpenMemHandle(devptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return LPMP_ERR_CUDA; }
+  return LPMP_OK;
+}
+int lpmp_ipc_close(void* devptr) { return cudaIpcCloseMemHandle(devptr) == cudaSuccess ? LPMP_OK : LPMP_ERR_CUDA; }
 
 int lpmp_finalize(lpmp_solver* h) { return S(h)->finalize(); }
 int lpmp_begin(lpmp_solver* h) { return S(h)->begin(); }

@@ -19,26 +19,48 @@ struct GraphTopo {
   __device__ __forceinline__ bool valid(uint64_t) const { return true; }
   __device__ __forceinline__ uint32_t first(uint64_t e) const { return ei[e]; }
   __device__ __forceinline__ uint32_t second(uint64_t e) const { return ej[e]; }
+  template <typename St> __device__ __forceinline__ auto b_of(const St& st, uint64_t e) const { return st.b(e); }
 };
-// grid slots: [0, H*W) horizontal edge (r,c)-(r,c+1) at slot r*W+c; [H*W, 2*H*W) vertical edge (r,c)-(r+1,c)
+// grid slots: [0, H*W) horizontal edge (r,c)-(r,c+1) at slot r*W+c; [H*W, 2*H*W) vertical edge (r,c)-(r+1,c).
+// A stripe's last row owns the edges to the stripe below; their b side is passed in `below_b` ([W][L]).
+template <typename Real>
 struct GridTopo {
   uint32_t H, W;
   uint64_t num_slots;
+  const Real* below_b;
   __device__ __forceinline__ bool valid(uint64_t e) const {
     const uint64_t HW = (uint64_t)H * W;
     if (e < HW) return (e % W) + 1 < W;
-    return (e - HW) / W + 1 < H;
+    return (e - HW) / W + 1 < H || below_b != nullptr;
   }
   __device__ __forceinline__ uint32_t first(uint64_t e) const { const uint64_t HW = (uint64_t)H * W; return (uint32_t)(e < HW ? e : e - HW); }
   __device__ __forceinline__ uint32_t second(uint64_t e) const { const uint64_t HW = (uint64_t)H * W; return (uint32_t)(e < HW ? e + 1 : e - HW + W); }
+  template <typename St> __device__ __forceinline__ const Real* b_of(const St& st, uint64_t e) const {
+    const uint64_t HW = (uint64_t)H * W;
+    if (e >= HW && (e - HW) / W + 1 >= H) return below_b + ((e - HW) % W) * (uint64_t)st.L_;
+    return st.b(e);
+  }
+};
+
+// Where the vectors of node i / edge slot e live.  General graphs: theta[N][L], a[E][L], b[E][L], params[E][P].
+// Grids: the node records of kernels_grid.cuh (rec[N][5][L], par[N][4][P]); slots [0, N) are the horizontal edges
+// (first = node e), slots [N, 2N) the vertical ones (first = node e - N).
+template <typename Real>
+struct Store {
+  Real* theta; uint64_t theta_stride;
+  Real* a0; Real* a1; Real* b0; Real* b1;
+  const Real* p0; const Real* p1;
+  uint64_t split, estride, pstride;
+  uint32_t L_;
+  __device__ __forceinline__ Real* th(uint64_t i) const { return theta + i * theta_stride; }
+  __device__ __forceinline__ Real* a(uint64_t e) const { return e < split ? a0 + e * estride : a1 + (e - split) * estride; }
+  __device__ __forceinline__ Real* b(uint64_t e) const { return e < split ? b0 + e * estride : b1 + (e - split) * estride; }
+  __device__ __forceinline__ const Real* par(uint64_t e) const { return e < split ? p0 + e * pstride : p1 + (e - split) * pstride; }
 };
 
 template <typename Real>
 struct LevelArgs {
-  Real* theta;              // [N][L]
-  Real* a;                  // [slots][L]  first-variable side
-  Real* b;                  // [slots][L]  second-variable side
-  const Real* params;       // [slots][P]
+  Store<Real> st;
   const uint32_t* nodes;    // nodes of this level
   uint32_t num_nodes;
   const uint64_t* inc_off;  // [N+1]
@@ -62,13 +84,12 @@ __global__ void __launch_bounds__(256) level_update_kernel(LevelArgs<Real> A, in
   Real* t = th + L;
   Real* oth = t + L;
   Real* hs = oth + L;
-  const uint32_t P = pairwise_param_count(A.pw, L);
   const bool aniso = A.repam == LPMP_REPAM_ANISOTROPIC;
 
   for (uint32_t k = blockIdx.x * groups_per_cta + g; k < A.num_nodes; k += gridDim.x * groups_per_cta) {
     const uint32_t i = A.nodes[k];
     const uint64_t k0 = A.inc_off[i], k1 = A.inc_off[i + 1];
-    Real* theta_i = A.theta + (uint64_t)i * L;
+    Real* theta_i = A.st.th(i);
     for (uint32_t x = gl; x < L; x += G) th[x] = theta_i[x];
     uint32_t n_in = 0, n_out = 0;
     // ReceiveMessages (include/factors_messages.hxx:2440-2471)
@@ -79,12 +100,12 @@ __global__ void __launch_bounds__(256) level_update_kernel(LevelArgs<Real> A, in
       if (later) ++n_out; else ++n_in;
       const bool earlier = A.forward ? !later : later;
       if (aniso && !earlier) continue;
-      Real* own = (side == 0 ? A.a : A.b) + (uint64_t)e * L;
-      const Real* other = (side == 0 ? A.b : A.a) + (uint64_t)e * L;
+      Real* own = side == 0 ? A.st.a(e) : A.st.b(e);
+      const Real* other = side == 0 ? A.st.b(e) : A.st.a(e);
       __syncwarp(mask);
       for (uint32_t x = gl; x < L; x += G) oth[x] = other[x];
       __syncwarp(mask);
-      group_min_plus<Real>(A.pw, A.params + (uint64_t)e * P, L, side, oth, hs, G, gl, mask);
+      group_min_plus<Real>(A.pw, A.st.par(e), L, side, oth, hs, G, gl, mask);
       for (uint32_t x = gl; x < L; x += G) {
         const Real ow = own[x];
         const Real m = hs[x] + ow;
@@ -114,7 +135,7 @@ __global__ void __launch_bounds__(256) level_update_kernel(LevelArgs<Real> A, in
         const uint32_t side = fl & 1u, later = (fl >> 1) & 1u;
         const bool is_later = A.forward ? later : !later;
         if (aniso && !is_later) continue;
-        Real* own = (side == 0 ? A.a : A.b) + (uint64_t)e * L;
+        Real* own = side == 0 ? A.st.a(e) : A.st.b(e);
         for (uint32_t x = gl; x < L; x += G) {
           const Real d = w * t[x];
           own[x] = own[x] + d;  // RepamRight(+) first, :501-503
@@ -130,10 +151,7 @@ __global__ void __launch_bounds__(256) level_update_kernel(LevelArgs<Real> A, in
 // ---- lower bound: partial sums per CTA, deterministic second stage -------------------------------------------
 template <typename Real, typename Topo>
 struct BoundArgs {
-  const Real* theta;
-  const Real* a;
-  const Real* b;
-  const Real* params;
+  Store<Real> st;
   Topo topo;
   uint64_t num_nodes;
   uint32_t L;
@@ -166,23 +184,24 @@ __global__ void __launch_bounds__(256) lower_bound_kernel(BoundArgs<Real, Topo> 
   const uint32_t L = A.L;
   Real* oth = smem + (size_t)g * 2 * L;
   Real* hs = oth + L;
-  const uint32_t P = pairwise_param_count(A.pw, L);
   const Real INF = RealTraits<Real>::inf();
   double acc = 0.0;
   const uint64_t total = A.num_nodes + A.topo.num_slots;
   for (uint64_t k = (uint64_t)blockIdx.x * groups_per_cta + g; k < total; k += (uint64_t)gridDim.x * groups_per_cta) {
     Real m = INF;
     if (k < A.num_nodes) {
-      const Real* th = A.theta + k * L;
+      const Real* th = A.st.th(k);
       for (uint32_t x = gl; x < L; x += G) m = rmin(m, th[x]);
     } else {
       const uint64_t e = k - A.num_nodes;
       if (!A.topo.valid(e)) continue;
       __syncwarp(mask);
-      for (uint32_t x = gl; x < L; x += G) oth[x] = A.b[e * L + x];
+      const Real* eb = A.topo.b_of(A.st, e);
+      const Real* ea = A.st.a(e);
+      for (uint32_t x = gl; x < L; x += G) oth[x] = eb[x];
       __syncwarp(mask);
-      group_min_plus<Real>(A.pw, A.params + e * P, L, 0u, oth, hs, G, gl, mask);
-      for (uint32_t x = gl; x < L; x += G) m = rmin(m, Real(hs[x] + A.a[e * L + x]));
+      group_min_plus<Real>(A.pw, A.st.par(e), L, 0u, oth, hs, G, gl, mask);
+      for (uint32_t x = gl; x < L; x += G) m = rmin(m, Real(hs[x] + ea[x]));
     }
     m = group_min(m, G, mask);
     if (gl == 0) acc += (double)m;
@@ -195,18 +214,17 @@ __global__ void __launch_bounds__(256) lower_bound_kernel(BoundArgs<Real, Topo> 
 template <typename Real, typename Topo>
 __global__ void __launch_bounds__(256) primal_cost_kernel(BoundArgs<Real, Topo> A, const uint32_t* __restrict__ labels) {
   const uint32_t L = A.L;
-  const uint32_t P = pairwise_param_count(A.pw, L);
   double acc = 0.0;
   const uint64_t total = A.num_nodes + A.topo.num_slots;
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (uint64_t)gridDim.x * blockDim.x) {
     if (k < A.num_nodes) {
-      acc += (double)A.theta[k * L + labels[k]];
+      acc += (double)A.st.th(k)[labels[k]];
     } else {
       const uint64_t e = k - A.num_nodes;
       if (!A.topo.valid(e)) continue;
       const uint32_t x = labels[A.topo.first(e)], y = labels[A.topo.second(e)];
-      const Real c = pairwise_cost<Real>(A.pw, A.params + e * P, L, x, y);
-      acc += (double)Real(Real(c + A.a[e * L + x]) + A.b[e * L + y]);
+      const Real c = pairwise_cost<Real>(A.pw, A.st.par(e), L, x, y);
+      acc += (double)Real(Real(c + A.st.a(e)[x]) + A.st.b(e)[y]);
     }
   }
   const double s = block_sum(acc);

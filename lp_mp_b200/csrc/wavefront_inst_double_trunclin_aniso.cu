@@ -1,3 +1,4 @@
 #define LPMP_INST_REAL double
 #define LPMP_INST_PW LPMP_PAIRWISE_TRUNCLIN
+#define LPMP_INST_ANISO true
 #include "wavefront_inst.cuh"

@@ -1,3 +1,4 @@
 #define LPMP_INST_REAL float
 #define LPMP_INST_PW LPMP_PAIRWISE_POTTS
+#define LPMP_INST_ANISO true
 #include "wavefront_inst.cuh"

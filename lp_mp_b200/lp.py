@@ -173,9 +173,21 @@ class LP:
                                                      None if bottom is None else bottom.ctypes.data, K.F64))
 
     def grid_boundary_ptrs(self, which):
-        owned, halo, nbytes = C.c_void_p(), C.c_void_p(), C.c_uint64()
-        self._ck(self.api.grid_boundary_ptrs(self.h, int(which), C.byref(owned), C.byref(halo), C.byref(nbytes)))
-        return owned.value, halo.value, nbytes.value
+        """(device pointer, bytes) of the in-buffer of boundary `which` (0 = top, 1 = bottom)"""
+        buf, nbytes = C.c_void_p(), C.c_uint64()
+        self._ck(self.api.grid_boundary_ptrs(self.h, int(which), C.byref(buf), C.byref(nbytes)))
+        return buf.value, nbytes.value
+
+    def grid_set_peer_boundary(self, which, peer_ptr):
+        self._ck(self.api.grid_set_peer_boundary(self.h, int(which), C.c_void_p(peer_ptr or 0)))
+
+    def grid_get_boundary_vectors(self, which, dst_ptr):
+        self._ck(self.api.grid_get_boundary_vectors(self.h, int(which), C.c_void_p(dst_ptr)))
+
+    def grid_lower_bound_partial(self, below_ptr=None) -> float:
+        out = C.c_double()
+        self._ck(self.api.grid_lower_bound_partial(self.h, C.c_void_p(below_ptr or 0), C.byref(out)))
+        return out.value
 
     def finalize(self):
         self._flush_pending()

@@ -452,7 +452,13 @@ int LPMP_FN(grid_set_pairwise)(lpmp_solver* h, const void* hz, const void* vt, i
 int LPMP_FN(grid_fill_synthetic)(lpmp_solver* h, uint64_t seed, double lo, double hi) { return DISPATCH(H(h), grid_fill_synthetic(o, seed, lo, hi)); }
 int LPMP_FN(grid_set_stripe)(lpmp_solver* h, uint32_t, uint32_t) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
 int LPMP_FN(grid_set_boundary_pairwise)(lpmp_solver* h, const void*, const void*, int) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
-int LPMP_FN(grid_boundary_ptrs)(lpmp_solver* h, int, void**, void**, uint64_t*) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
+int LPMP_FN(grid_boundary_ptrs)(lpmp_solver* h, int, void**, uint64_t*) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
+int LPMP_FN(grid_set_peer_boundary)(lpmp_solver* h, int, void*) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
+int LPMP_FN(grid_get_boundary_vectors)(lpmp_solver* h, int, void*) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
+int LPMP_FN(grid_lower_bound_partial)(lpmp_solver* h, const void*, double*) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
+int LPMP_FN(ipc_export)(const void*, void*) { return LPMP_ERR_UNSUPPORTED; }
+int LPMP_FN(ipc_open)(const void*, void**) { return LPMP_ERR_UNSUPPORTED; }
+int LPMP_FN(ipc_close)(void*) { return LPMP_ERR_UNSUPPORTED; }
 
 int LPMP_FN(finalize)(lpmp_solver* h) { return DISPATCH(H(h), o.finalize()); }
 int LPMP_FN(begin)(lpmp_solver* h) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; o.repam = -1; return int(LPMP_OK); })()); }
