@@ -18,15 +18,15 @@
 namespace lpmp {
 
 template <typename Real>
-cudaError_t launch_wavefront(const CUtensorMap* maps, const GridArgs<Real>& args, int pw, uint32_t L, int hops, const WavefrontTuning& tune, int num_sms,
-                             cudaStream_t stream) {
+cudaError_t launch_wavefront(const CUtensorMap* maps, const GridArgs<Real>& args, int pw, uint32_t L, int hops, int ksel, const WavefrontTuning& tune,
+                             int num_sms, cudaStream_t stream) {
   const bool aniso = args.repam == LPMP_REPAM_ANISOTROPIC;
   if (pw == LPMP_PAIRWISE_POTTS)
-    return aniso ? launch_family<Real, LPMP_PAIRWISE_POTTS, true>(maps, args, L, hops, tune, num_sms, stream)
-                 : launch_family<Real, LPMP_PAIRWISE_POTTS, false>(maps, args, L, hops, tune, num_sms, stream);
+    return aniso ? launch_family<Real, LPMP_PAIRWISE_POTTS, true>(maps, args, L, hops, ksel, tune, num_sms, stream)
+                 : launch_family<Real, LPMP_PAIRWISE_POTTS, false>(maps, args, L, hops, ksel, tune, num_sms, stream);
   if (pw == LPMP_PAIRWISE_TRUNCLIN)
-    return aniso ? launch_family<Real, LPMP_PAIRWISE_TRUNCLIN, true>(maps, args, L, hops, tune, num_sms, stream)
-                 : launch_family<Real, LPMP_PAIRWISE_TRUNCLIN, false>(maps, args, L, hops, tune, num_sms, stream);
+    return aniso ? launch_family<Real, LPMP_PAIRWISE_TRUNCLIN, true>(maps, args, L, hops, ksel, tune, num_sms, stream)
+                 : launch_family<Real, LPMP_PAIRWISE_TRUNCLIN, false>(maps, args, L, hops, ksel, tune, num_sms, stream);
   return cudaErrorInvalidValue;
 }
 
@@ -189,7 +189,7 @@ struct Solver : ISolver {
   bool finalized = false, labels_valid = false, is_grid = false, striped = false;
   double constant = 0.0;
   WavefrontTuning tune;
-  WavefrontShape shape{0, 0, 0};
+  WavefrontShape shape{0, false, false, 0, 0};
   int tl_reach = 0;          // truncated linear: max #{d >= 1: slope*d < trunc} over all edges seen so far
   bool tl_irregular = false; // a negative slope / trunc was seen: only the all-distances kernel is exact
   // host staging (general graphs)
@@ -205,7 +205,7 @@ struct Solver : ISolver {
   DeviceBuffer<uint8_t> inc_flags;
   DeviceBuffer<double> partial, result;
   DeviceBuffer<unsigned int> control;  // [0] band ticket, [1] sticky abort flag (hand-off poll timed out)
-  CUtensorMap maps[3];
+  CUtensorMap maps8[3], maps4[3];   // tile width 8 / 4 columns
   std::vector<uint64_t> level_off;     // host
   uint64_t launches = 0, updates = 0;
   static constexpr int kBoundCtas = 148 * 4;
@@ -303,6 +303,7 @@ struct Solver : ISolver {
     const std::string k(key ? key : "");
     if (k == "wavefront_max_ctas") tune.max_ctas = value;
     else if (k == "wavefront_ctas_per_sm") tune.ctas_per_sm = value;
+    else if (k == "wavefront_tile_cols") tune.tile_cols = value;
     else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
     return LPMP_OK;
   }
@@ -536,7 +537,7 @@ struct Solver : ISolver {
   }
 
   // TMA descriptors of the record / parameter arrays: tiles of `rows` grid rows x K columns of whole records
-  int encode_map(CUtensorMap* m, Real* base, uint32_t inner, uint32_t vecs, uint32_t box_rows) {
+  int encode_map(CUtensorMap* m, Real* base, uint32_t inner, uint32_t vecs, uint32_t box_rows, uint32_t box_cols) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) { err = "cuTensorMapEncodeTiled is not available in this driver"; return LPMP_ERR_CUDA; }
     const CUtensorMapDataType dt = sizeof(Real) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
@@ -544,14 +545,14 @@ struct Solver : ISolver {
     if (vecs > 1) {   // (label, vector, column, row)
       const cuuint64_t dims[4] = {inner, vecs, gridW, gridH};
       const cuuint64_t strides[3] = {inner * sizeof(Real), (cuuint64_t)inner * vecs * sizeof(Real), (cuuint64_t)gridW * inner * vecs * sizeof(Real)};
-      const cuuint32_t box[4] = {inner, vecs, (cuuint32_t)shape.K, box_rows};
+      const cuuint32_t box[4] = {inner, vecs, box_cols, box_rows};
       const cuuint32_t es[4] = {1, 1, 1, 1};
       r = fn(m, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {          // (parameter, column, row)
       const cuuint64_t dims[3] = {inner, gridW, gridH};
       const cuuint64_t strides[2] = {inner * sizeof(Real), (cuuint64_t)gridW * inner * sizeof(Real)};
-      const cuuint32_t box[3] = {inner, (cuuint32_t)shape.K, box_rows};
+      const cuuint32_t box[3] = {inner, box_cols, box_rows};
       const cuuint32_t es[3] = {1, 1, 1};
       r = fn(m, dt, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -611,9 +612,13 @@ struct Solver : ISolver {
         CUDA_TRY(cudaMemsetAsync(control.p, 0, control.bytes(), stream));
         CUDA_TRY(handoff.alloc((size_t)bands * gridW * L));
         CUDA_TRY(cudaMemsetAsync(handoff.p, 0xff, handoff.bytes(), stream));
-        if (int r = encode_map(&maps[0], rec.p, L, REC_VECS, (uint32_t)shape.T)) return r;
-        if (int r = encode_map(&maps[1], rec.p, L, REC_VECS, (uint32_t)shape.T + 1)) return r;
-        if (int r = encode_map(&maps[2], par.p, (uint32_t)PREC(), 1, (uint32_t)shape.T)) return r;
+        for (int ks = 4; ks <= 8; ks += 4) {
+          if (!(ks == 8 ? shape.fits8 : shape.fits4)) continue;
+          CUtensorMap* m = ks == 8 ? maps8 : maps4;
+          if (int r = encode_map(&m[0], rec.p, L, REC_VECS, (uint32_t)shape.T, (uint32_t)ks)) return r;
+          if (int r = encode_map(&m[1], rec.p, L, REC_VECS, (uint32_t)shape.T + 1, (uint32_t)ks)) return r;
+          if (int r = encode_map(&m[2], par.p, (uint32_t)PREC(), 1, (uint32_t)shape.T, (uint32_t)ks)) return r;
+        }
       }
     }
     CUDA_TRY(labels.alloc(N));
@@ -672,7 +677,14 @@ struct Solver : ISolver {
       A.out_boundary = forward ? peer_bot : peer_top;
       A.labels = labels.p;
       CUDA_TRY(cudaMemsetAsync(control.p, 0, sizeof(unsigned int), stream));
-      CUDA_TRY(launch_wavefront<Real>(maps, A, pw, L, tl_hops(), tune, num_sms, stream));
+      // tile width: 8 columns unless the bands outnumber the resident warps and the narrow tile doubles residency
+      int ksel = shape.default_k();
+      if (repam == LPMP_REPAM_ANISOTROPIC && shape.fits8 && shape.fits4) {
+        const uint64_t resident8 = (uint64_t)num_sms * std::max<size_t>(1, (227 * 1024) / (shape.smem8 + 1024));
+        if (A.num_bands > resident8) ksel = 4;
+        if (tune.tile_cols == 4 || tune.tile_cols == 8) ksel = tune.tile_cols;
+      }
+      CUDA_TRY(launch_wavefront<Real>(ksel == 8 ? maps8 : maps4, A, pw, L, tl_hops(), ksel, tune, num_sms, stream));
       ++launches;
     }
     updates += (repam == LPMP_REPAM_ANISOTROPIC ? 2 : 4) * E;

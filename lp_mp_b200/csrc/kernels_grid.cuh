@@ -86,21 +86,6 @@ template <int BYTES> __device__ __forceinline__ void st_relaxed(void* dst, const
                  : "memory");
 }
 
-// ---- shared-memory vector access: 4 labels per lane ----------------------------------------------------------------
-__device__ __forceinline__ void lds4(float (&v)[4], const float* p) {
-  const float4 x = *reinterpret_cast<const float4*>(p);
-  v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-}
-__device__ __forceinline__ void lds4(double (&v)[4], const double* p) {
-  const double2 x = *reinterpret_cast<const double2*>(p), y = *reinterpret_cast<const double2*>(p + 2);
-  v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
-}
-__device__ __forceinline__ void sts4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
-__device__ __forceinline__ void sts4(double* p, const double (&v)[4]) {
-  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-  *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
-}
-
 // ---- TMA / mbarrier primitives (inline PTX) -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -134,105 +119,172 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 template <int PW> struct ParamCount { static constexpr int value = PW == LPMP_PAIRWISE_POTTS ? 1 : 2; };
 
-// compile-time shape of one kernel instance; the host launcher uses the same struct for tensor maps and smem size
-template <typename Real, int PW, int L>
+// compile-time shape of one kernel instance; the host launcher uses the same struct for tensor maps and smem size.
+// KSEL = columns per tile: 8 (fewer TMA operations; latency-bound grids) or 4 (half the shared memory per band, twice
+// the resident bands per SM; bandwidth-bound grids).
+template <typename Real, int PW, int L, int KSEL>
 struct WavefrontCfg {
   static constexpr int G = L / 4;                        // lanes per node (4 labels per lane)
-  static constexpr int T = (32 / G) < 8 ? (32 / G) : 8;  // rows per band (lanes beyond T*G idle for tiny L)
+  static constexpr int TG = 32 / G;                      // lane groups per warp
+  static constexpr int T = TG < 8 ? TG : 8;              // rows per band (lanes beyond T*G idle for tiny L)
   static constexpr int P = ParamCount<PW>::value;
   static constexpr int REC = REC_VECS * L;               // reals per node record
   static constexpr int PREC = PAR_EDGES * P;             // reals per parameter record
   static constexpr int NSLOT = 4;                        // tiles in the ring
   static constexpr int PDC = 2;                          // tiles of prefetch distance
-  static constexpr size_t slot_bytes(int k) { return (size_t)((T + 1) * k * REC + T * k * PREC) * sizeof(Real); }
-  static constexpr int K = slot_bytes(8) * NSLOT <= 200 * 1024 ? 8 : 4;   // columns per tile
+  static constexpr int K = KSEL;
   static constexpr int LOGK = K == 8 ? 3 : 2;
   static constexpr int SLOT_REC = (T + 1) * K * REC;     // reals
   static constexpr int SLOT_PAR = T * K * PREC;
-  static constexpr int SCRATCH = PW == LPMP_PAIRWISE_TRUNCLIN ? 2 * (32 / G) * 3 * L : 0;   // staging of `other` for the label window
+  static constexpr int SCRATCH = PW == LPMP_PAIRWISE_TRUNCLIN ? 2 * TG * 3 * L : 0;   // staging of `other` for the label window
   static constexpr size_t SMEM_BYTES = 128 + (size_t)(NSLOT * (SLOT_REC + SLOT_PAR) + SCRATCH) * sizeof(Real);
+  static constexpr bool FITS = SMEM_BYTES <= 220 * 1024 && (NSLOT - PDC - 1) * K > T - 2;
+  static_assert(K == 8 || K == 4, "tile width");
   static_assert(L % 4 == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "L/4 must be a power of two <= 32");
-  static_assert((NSLOT - PDC - 1) * K > T - 2, "a ring slot must be stored before it is reloaded");
   static_assert((SLOT_REC * sizeof(Real)) % 128 == 0 && (SLOT_PAR * sizeof(Real)) % 128 == 0, "TMA destination alignment");
 };
 
-// h(x) = min_y [c(x,y) + oth(y)] for the 4 labels x = 4*gl + k of this lane.  oth: registers.
-// Potts: one group minimum (two smallest entries when some lambda < 0).  Truncated linear: every y with
-// slope*|x-y| >= trunc costs trunc, so those terms collapse to trunc + min(oth); the near terms come from a window of
-// 4*HOPS labels either side staged through shared memory (HOPS = 0: all L-1 distances, any parameters).
-template <typename Real, int PW, int L, int HOPS>
-__device__ __forceinline__ void lane_min_plus(const Real* par, const Real (&oth)[4], Real (&h)[4], Real* scratch, int reach, int gl) {
-  constexpr int G = L / 4;
-  constexpr unsigned FULL = 0xffffffffu;
-  Real g = rmin(rmin(oth[0], oth[1]), rmin(oth[2], oth[3]));
-  if constexpr (PW == LPMP_PAIRWISE_POTTS) {
-    const Real lambda = par[0];
-    if (__any_sync(FULL, lambda < Real(0))) {   // repulsive Potts somewhere in the warp: the two smallest entries
-      const Real INF = RealTraits<Real>::inf();
-      TwoMin<Real> t{INF, INF, 0u};
+// ---- shared-memory vector access by 32-bit shared address: 4 labels per lane ----------------------------------------
+// volatile: program order among these accesses is kept (tiles are also written by the TMA and re-read in place)
+__device__ __forceinline__ void lds4(float (&v)[4], uint32_t a) {
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+}
+__device__ __forceinline__ void lds4(double (&v)[4], uint32_t a) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a));
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(v[2]), "=d"(v[3]) : "r"(a));
+}
+__device__ __forceinline__ void sts4(uint32_t a, const float (&v)[4]) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+__device__ __forceinline__ void sts4(uint32_t a, const double (&v)[4]) {
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(v[0]), "d"(v[1]) : "memory");
+  asm volatile("st.shared.v2.f64 [%0+16], {%1,%2};" ::"r"(a), "d"(v[2]), "d"(v[3]) : "memory");
+}
+__device__ __forceinline__ float lds1f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds1d(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+template <typename Real> __device__ __forceinline__ Real lds1(uint32_t a);
+template <> __device__ __forceinline__ float lds1<float>(uint32_t a) { return lds1f(a); }
+template <> __device__ __forceinline__ double lds1<double>(uint32_t a) { return lds1d(a); }
+template <typename Real, int P> __device__ __forceinline__ void lds_par(Real (&v)[P], uint32_t a) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) two_min_insert(t, oth[k], (uint32_t)(gl * 4 + k));
-      group_two_min(t, G, FULL);
+  for (int p = 0; p < P; ++p) v[p] = lds1<Real>(a + p * (uint32_t)sizeof(Real));
+}
+
+// two interleaved butterfly minima over the G lanes of a group (the shuffles of the two chains overlap)
+template <typename Real, int G>
+__device__ __forceinline__ void group_min2(Real& a, Real& b) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) h[k] = rmin(oth[k], Real(lambda + ((uint32_t)(gl * 4 + k) == t.i1 ? t.m2 : t.m1)));
-    } else {
-      // lambda >= 0: at the minimiser min(m1, fl(lambda + m2)) = m1 = min(m1, fl(lambda + m1)) because rounding is
-      // monotone, so one group minimum gives bit-identical results to the two_min formula
-      g = group_min(g, G, FULL);
-      const Real far = lambda + g;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) h[k] = rmin(oth[k], far);
-    }
-  } else {
-    const Real slope = par[0], trunc = par[1];
-    Real* sc = scratch + L + 4 * gl;             // this lane's labels inside the group's [INF pad | L labels | INF pad] staging
-    sts4(sc, oth);
-    g = group_min(g, G, FULL);                   // the shuffles also separate the staging stores from the loads below
-    __syncwarp();
-    const Real far = trunc + g;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) h[k] = rmin(oth[k], far);
-    if constexpr (HOPS > 0) {
-      Real win[4 * (2 * HOPS + 1)];              // labels 4*(gl-HOPS) .. 4*(gl+HOPS)+3
-#pragma unroll
-      for (int hh = 0; hh < 2 * HOPS + 1; ++hh) {
-        Real v[4];
-        lds4(v, sc + 4 * (hh - HOPS));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) win[4 * hh + k] = v[k];
-      }
-#pragma unroll
-      for (int d = 1; d <= 4 * HOPS; ++d) {
-        if (d > reach) break;
-        const Real c = rmin(Real(slope * Real(d)), trunc);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = rmin(h[k], rmin(Real(c + win[4 * HOPS + k - d]), Real(c + win[4 * HOPS + k + d])));
-      }
-    } else {
-      for (int d = 1; d < L; ++d) {
-        const Real c = rmin(Real(slope * Real(d)), trunc);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = rmin(h[k], rmin(Real(c + sc[k - d]), Real(c + sc[k + d])));
-      }
-    }
+  for (int o = G >> 1; o > 0; o >>= 1) {
+    const Real ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+    a = rmin(a, ta);
+    b = rmin(b, tb);
   }
 }
 
-template <typename Real, int PW, int L, int HOPS, bool ANISO>
+// Min-plus of TWO edges at once (independent chains, interleaved so that their latencies overlap):
+//   h(x) = min_y [c(x,y) + oth(y)] for the 4 labels x = 4*gl + k of this lane, oth in registers.
+// Potts: one group minimum (two smallest entries when some lambda < 0).  Truncated linear: every y with
+// slope*|x-y| >= trunc costs trunc, so those terms collapse to trunc + min(oth); the near terms come from a window of
+// 4*HOPS labels either side, staged through shared memory (sa / sb: shared address of this lane's 4 labels inside the
+// group's [INF pad | L labels | INF pad] staging areas).  HOPS = 0: all L-1 distances, any parameters.
+template <typename Real, int PW, int L, int HOPS>
+__device__ __forceinline__ void lane_min_plus2(const Real* pa, const Real (&oa)[4], Real (&ha)[4], const Real* pb, const Real (&ob)[4], Real (&hb)[4],
+                                               uint32_t sa, uint32_t sb, int gl) {
+  constexpr int G = L / 4;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr uint32_t S = (uint32_t)sizeof(Real);
+  Real ga = rmin(rmin(oa[0], oa[1]), rmin(oa[2], oa[3]));
+  Real gb = rmin(rmin(ob[0], ob[1]), rmin(ob[2], ob[3]));
+  if constexpr (PW == LPMP_PAIRWISE_POTTS) {
+    const Real la = pa[0], lb = pb[0];
+    if (__any_sync(FULL, la < Real(0) || lb < Real(0))) {   // repulsive Potts somewhere in the warp: the two smallest entries
+      const Real INF = RealTraits<Real>::inf();
+      TwoMin<Real> ta{INF, INF, 0u}, tb{INF, INF, 0u};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { two_min_insert(ta, oa[k], (uint32_t)(gl * 4 + k)); two_min_insert(tb, ob[k], (uint32_t)(gl * 4 + k)); }
+      group_two_min(ta, G, FULL);
+      group_two_min(tb, G, FULL);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ha[k] = rmin(oa[k], Real(la + ((uint32_t)(gl * 4 + k) == ta.i1 ? ta.m2 : ta.m1)));
+        hb[k] = rmin(ob[k], Real(lb + ((uint32_t)(gl * 4 + k) == tb.i1 ? tb.m2 : tb.m1)));
+      }
+    } else {
+      // lambda >= 0: at the minimiser min(m1, fl(lambda + m2)) = m1 = min(m1, fl(lambda + m1)) because rounding is
+      // monotone, so one group minimum gives bit-identical results to the two_min formula
+      group_min2<Real, G>(ga, gb);
+      const Real fa = la + ga, fb = lb + gb;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ha[k] = rmin(oa[k], fa); hb[k] = rmin(ob[k], fb); }
+    }
+  } else {
+    const Real slope_a = pa[0], trunc_a = pa[1], slope_b = pb[0], trunc_b = pb[1];
+    sts4(sa, oa);
+    sts4(sb, ob);
+    group_min2<Real, G>(ga, gb);
+    __syncwarp();
+    if constexpr (HOPS > 0) {
+      Real wa[4 * (2 * HOPS + 1)], wb[4 * (2 * HOPS + 1)];   // labels 4*(gl-HOPS) .. 4*(gl+HOPS)+3
+#pragma unroll
+      for (int hh = 0; hh < 2 * HOPS + 1; ++hh) {
+        if (hh == HOPS) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { wa[4 * hh + k] = oa[k]; wb[4 * hh + k] = ob[k]; }
+        } else {
+          Real va[4], vb[4];
+          lds4(va, sa + (uint32_t)(4 * (hh - HOPS)) * S);
+          lds4(vb, sb + (uint32_t)(4 * (hh - HOPS)) * S);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { wa[4 * hh + k] = va[k]; wb[4 * hh + k] = vb[k]; }
+        }
+      }
+      const Real fa = trunc_a + ga, fb = trunc_b + gb;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ha[k] = rmin(oa[k], fa); hb[k] = rmin(ob[k], fb); }
+#pragma unroll
+      for (int d = 1; d <= 4 * HOPS; ++d) {
+        const Real ca = rmin(Real(slope_a * Real(d)), trunc_a), cb = rmin(Real(slope_b * Real(d)), trunc_b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ha[k] = rmin(ha[k], rmin(Real(ca + wa[4 * HOPS + k - d]), Real(ca + wa[4 * HOPS + k + d])));
+          hb[k] = rmin(hb[k], rmin(Real(cb + wb[4 * HOPS + k - d]), Real(cb + wb[4 * HOPS + k + d])));
+        }
+      }
+    } else {
+      const Real fa = trunc_a + ga, fb = trunc_b + gb;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ha[k] = rmin(oa[k], fa); hb[k] = rmin(ob[k], fb); }
+      for (int d = 1; d < L; ++d) {
+        const Real ca = rmin(Real(slope_a * Real(d)), trunc_a), cb = rmin(Real(slope_b * Real(d)), trunc_b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ha[k] = rmin(ha[k], rmin(Real(ca + lds1<Real>(sa + (uint32_t)(k - d) * S)), Real(ca + lds1<Real>(sa + (uint32_t)(k + d) * S))));
+          hb[k] = rmin(hb[k], rmin(Real(cb + lds1<Real>(sb + (uint32_t)(k - d) * S)), Real(cb + lds1<Real>(sb + (uint32_t)(k + d) * S))));
+        }
+      }
+    }
+    __syncwarp();   // the staging areas are rewritten by the next call
+  }
+}
+
+template <typename Real, int PW, int L, int HOPS, bool ANISO, int KSEL>
 __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_rec1,
                                                             const __grid_constant__ CUtensorMap tm_par, const GridArgs<Real> A) {
-  using Cfg = WavefrontCfg<Real, PW, L>;
+  using Cfg = WavefrontCfg<Real, PW, L, KSEL>;
   constexpr int G = Cfg::G, T = Cfg::T, P = Cfg::P, K = Cfg::K, LOGK = Cfg::LOGK, REC = Cfg::REC, PREC = Cfg::PREC, NSLOT = Cfg::NSLOT, PDC = Cfg::PDC;
   constexpr int BOXROWS = ANISO ? T : T + 1;           // the uniform modes also read the first row of the next band
   constexpr int HAND_BYTES = 4 * (int)sizeof(Real);
+  constexpr uint32_t S = (uint32_t)sizeof(Real);
   constexpr uint32_t TILE_BYTES = (uint32_t)((BOXROWS * K * REC + T * K * PREC) * sizeof(Real));
+  constexpr uint32_t REC_B = REC * S, PREC_B = PREC * S, SLOT_REC_B = Cfg::SLOT_REC * S, SLOT_PAR_B = Cfg::SLOT_PAR * S, LB = L * S;
   constexpr bool PARTIAL_WARP = T * G < 32;            // tiny L: lanes beyond T groups shadow group T-1 and never store
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  Real* rec_ring = reinterpret_cast<Real*>(smem_raw + 128);
-  Real* par_ring = rec_ring + (size_t)NSLOT * Cfg::SLOT_REC;
-  Real* scratch_all = par_ring + (size_t)NSLOT * Cfg::SLOT_PAR;
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t bars = smem_base;                                     // NSLOT mbarriers
+  const uint32_t rec_ring = smem_base + 128;
+  const uint32_t par_ring = rec_ring + NSLOT * SLOT_REC_B;
+  const uint32_t scratch_all = par_ring + NSLOT * SLOT_PAR_B;
   const int lane = threadIdx.x & 31;
   const bool lane_used = !PARTIAL_WARP || lane / G < T;
   const int t = lane_used ? lane / G : T - 1, gl = lane % G;
@@ -247,31 +299,36 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
   const int roff = fwd ? 0 : nb * T - (int)H;
   const int sp_end = qoff + (int)W + T - 1;
   const CUtensorMap* const tm_load = ANISO ? &tm_rec : &tm_rec1;
-  Real* const scratch0 = scratch_all + (size_t)(2 * (lane / G)) * 3 * L;   // two staging areas per lane group
-  Real* const scratch1 = scratch0 + 3 * L;
+  // two staging areas per lane group: [INF pad L | L labels | INF pad L]
+  const uint32_t stage_a = scratch_all + (uint32_t)((2 * (lane / G)) * 3 * L + L + 4 * gl) * S;
+  const uint32_t stage_b = stage_a + 3 * LB;
 
   if (lane == 0) {
-    for (int i = 0; i < NSLOT; ++i) mbar_init(smem_u32(bars + i), 1);
+    for (int i = 0; i < NSLOT; ++i) mbar_init(bars + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if constexpr (PW == LPMP_PAIRWISE_TRUNCLIN) {
-    for (int i = lane; i < Cfg::SCRATCH; i += 32) scratch_all[i] = RealTraits<Real>::inf();
+    Real* sc = reinterpret_cast<Real*>(smem_raw + 128 + NSLOT * (SLOT_REC_B + SLOT_PAR_B));
+    for (int i = lane; i < Cfg::SCRATCH; i += 32) sc[i] = RealTraits<Real>::inf();
   }
   __syncwarp();
   uint32_t chunk_base = 0;   // tiles loaded by earlier bands of this warp: slot / mbarrier-phase sequence continues
 
-  // record vector / parameter roles in this direction
-  const int v_in_row = fwd ? REC_BL : REC_AR, v_in_col = fwd ? REC_BU : REC_AD;
-  const int v_out_row = fwd ? REC_AR : REC_BL, v_out_col = fwd ? REC_AD : REC_BU;
-  const int p_in_row = fwd ? PAR_L : PAR_R, p_in_col = fwd ? PAR_U : PAR_D;
-  const int p_out_row = fwd ? PAR_R : PAR_L, p_out_col = fwd ? PAR_D : PAR_U;
+  // record vector / parameter roles in this direction (byte offsets inside a record)
+  const uint32_t o_in_row = (fwd ? REC_BL : REC_AR) * LB, o_in_col = (fwd ? REC_BU : REC_AD) * LB;
+  const uint32_t o_out_row = (fwd ? REC_AR : REC_BL) * LB, o_out_col = (fwd ? REC_AD : REC_BU) * LB;
+  const uint32_t p_in_row = (fwd ? PAR_L : PAR_R) * P * S, p_in_col = (fwd ? PAR_U : PAR_D) * P * S;
+  const uint32_t p_out_row = (fwd ? PAR_R : PAR_L) * P * S, p_out_col = (fwd ? PAR_D : PAR_U) * P * S;
   const int kxor = fwd ? 0 : K - 1;
   const int trow = fwd ? t : BOXROWS - 1 - t;            // row of this lane group inside the record tile
   const int trow_par = fwd ? t : T - 1 - t;
-  const int below = fwd ? K * REC : -K * REC;            // smem distance to the same column of virtual row u+1
+  const uint32_t rec_lane = rec_ring + (uint32_t)(trow * K) * REC_B + (uint32_t)(gl * 4) * S;
+  const uint32_t par_lane = par_ring + (uint32_t)(trow_par * K) * PREC_B;
+  const int below = fwd ? (int)(K * REC_B) : -(int)(K * REC_B);   // smem distance to the same column of virtual row u+1
   // receive order of the two processed-side edges: LIFO: (L, U) forward, (D, R) backward
   const bool recv_row_first = fwd ? !A.fifo : (A.fifo != 0);
-  const int reach = A.tl_reach;
+  // weight of the FAST path: (n_in, n_out) = (2, 2), first row (1, 2): 1 / max(n_in, n_out) = 1/2 (include/LP_MP.h:1397)
+  const Real w_fast = (Real)(1.0 / 2.0);
 
   for (;;) {
     unsigned kb = 0;
@@ -285,26 +342,29 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
     const bool last_band = kb + 1 == A.num_bands;
     const bool poll_in = kb > 0 || A.in_halo;              // group t_in takes its column neighbour from the hand-off buffer
     const int t_in = kb == 0 ? roff : 0;                   // first active group of the band
+    const bool poller = poll_in && t == t_in && lane_used;
     const bool hand_out = !last_band || (A.out_halo && A.out_boundary != nullptr);
     const Real* const hand_in = (kb == 0 ? A.in_boundary : A.handoff + (uint64_t)kb * W * L) + gl * 4;
     Real* const hand_dst = (last_band ? A.out_boundary : A.handoff + (uint64_t)(kb + 1) * W * L) + gl * 4;
     const int t_hand = last_band ? (int)H - 1 - (int)kb * T + roff : T - 1;   // group that owns the band's last row
+    const bool hander = hand_out && t == t_hand && lane_used;
     // tile origin rows (actual row of tile row 0); columns follow from the chunk index
     const int row0_own = fwd ? (int)kb * T : (nb - 1 - (int)kb) * T;
     const int row0_rec = fwd ? row0_own : row0_own - (BOXROWS - T);
-    const int store_skip = fwd ? 0 : (BOXROWS - T) * K * REC;   // backward the extra (read-only) tile row comes first
+    const uint32_t store_skip = fwd ? 0u : (uint32_t)(BOXROWS - T) * K * REC_B;   // backward the extra (read-only) tile row comes first
+    const int lane_q0 = (int)(chunk_base << LOGK) - t;   // tile-ring column of this lane group at sp = 0
 
     auto issue_load = [&](int j) {   // lane 0 only
-      const int slot = (int)((chunk_base + (uint32_t)j) & (NSLOT - 1));
+      const uint32_t slot = (chunk_base + (uint32_t)j) & (NSLOT - 1);
       const int col0 = fwd ? j * K : (nchunks - 1 - j) * K;
-      const uint32_t bar = smem_u32(bars + slot);
+      const uint32_t bar = bars + 8 * slot;
       mbar_expect_tx(bar, TILE_BYTES);
-      tma_load_4d(smem_u32(rec_ring + (size_t)slot * Cfg::SLOT_REC), tm_load, col0, row0_rec, bar);
-      tma_load_3d(smem_u32(par_ring + (size_t)slot * Cfg::SLOT_PAR), &tm_par, col0, row0_own, bar);
+      tma_load_4d(rec_ring + slot * SLOT_REC_B, tm_load, col0, row0_rec, bar);
+      tma_load_3d(par_ring + slot * SLOT_PAR_B, &tm_par, col0, row0_own, bar);
     };
     auto wait_chunk = [&](int j) {   // all lanes
       const uint32_t n = chunk_base + (uint32_t)j;
-      const uint32_t bar = smem_u32(bars + (n & (NSLOT - 1)));
+      const uint32_t bar = bars + 8 * (n & (NSLOT - 1));
       const uint32_t parity = (n / NSLOT) & 1u;
       while (!mbar_try_wait(bar, parity)) {}
     };
@@ -312,9 +372,9 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        const int slot = (int)((chunk_base + (uint32_t)j) & (NSLOT - 1));
+        const uint32_t slot = (chunk_base + (uint32_t)j) & (NSLOT - 1);
         const int col0 = fwd ? j * K : (nchunks - 1 - j) * K;
-        tma_store_4d(&tm_rec, col0, row0_own, smem_u32(rec_ring + (size_t)slot * Cfg::SLOT_REC + store_skip));
+        tma_store_4d(&tm_rec, col0, row0_own, rec_ring + slot * SLOT_REC_B + store_skip);
         tma_commit();
       }
     };
@@ -323,31 +383,23 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
       for (int j = 0; j <= PDC && j < nchunks; ++j) issue_load(j);
     }
 
-    // hand-off polls are issued POLL_AHEAD steps before use so that their L2 round trip is off the dependency chain
-    constexpr int POLL_AHEAD = 2;
-    Real poll[POLL_AHEAD][4];
+    // the hand-off slot of column q+1 is polled right after column q has been consumed, one step before its use,
+    // so that the L2 round trip is off the dependency chain
+    Real polled[4];
 #pragma unroll
-    for (int d = 0; d < POLL_AHEAD; ++d) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) poll[d][k] = Real(0);
-    }
-    if (poll_in && t == t_in) {   // column q is consumed at step q + t_in, which uses poll[(q + t_in) & 1]
-      if ((t_in & 1) == 0) { ld_relaxed<HAND_BYTES>(poll[0], hand_in); if (W > 1) ld_relaxed<HAND_BYTES>(poll[1], hand_in + L); }
-      else { ld_relaxed<HAND_BYTES>(poll[1], hand_in); if (W > 1) ld_relaxed<HAND_BYTES>(poll[0], hand_in + L); }
-    }
+    for (int k = 0; k < 4; ++k) polled[k] = Real(0);
+    if (poller) ld_relaxed<HAND_BYTES>(polled, hand_in);
 
     Real carry_row[4], carry_col[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { carry_row[k] = Real(0); carry_col[k] = Real(0); }
-    // weight of the FAST path: (n_in, n_out) = (2, 2), first row (1, 2): 1 / max(n_in, n_out) = 1/2 (include/LP_MP.h:1397)
-    const Real w_fast = (Real)(1.0 / 2.0);
     int next_store = 0;
 
     wait_chunk(0);
     if (!ANISO && nchunks > 1) wait_chunk(1);   // uniform modes: the out_row neighbour may sit in the next tile
 
     // sp = step index shifted by qoff; group t is at tile column q' = sp - t, virtual column q = q' - qoff
-    auto do_step = [&](auto fast_tag, const int sp, Real (&polled)[4]) {
+    auto do_step = [&](auto fast_tag, const int sp) {
       constexpr bool FAST = decltype(fast_tag)::value;
       // ---- tile ring management (warp-uniform) ----
       if ((sp & (K - 1)) == 0 && sp > 0) {
@@ -360,18 +412,28 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
         }
         __syncwarp();
       }
-      const int qp = sp - t;
-      const int q = qp - qoff;
-      const int slot = (int)((chunk_base + (uint32_t)(qp >> LOGK)) & (NSLOT - 1));
-      const int kk = (qp & (K - 1)) ^ kxor;
-      Real* const rec = rec_ring + (size_t)slot * Cfg::SLOT_REC + (size_t)(trow * K + kk) * REC + gl * 4;
-      const Real* const par = par_ring + (size_t)slot * Cfg::SLOT_PAR + (size_t)(trow_par * K + kk) * PREC;
+      const int q = sp - t - qoff;
+      const int qq = sp + lane_q0;               // column in the tile ring (slot sequence continues across bands)
+      const uint32_t slot = ((uint32_t)qq >> LOGK) & (NSLOT - 1);
+      const uint32_t kk = ((uint32_t)qq & (K - 1)) ^ (uint32_t)kxor;
+      const uint32_t rec = rec_lane + slot * SLOT_REC_B + kk * REC_B;
+      const uint32_t par = par_lane + slot * SLOT_PAR_B + kk * PREC_B;
 
-      // ---- the column neighbour's vector: shuffle inside the band, hand-off slot for group 0 ----
+      Real par_ir[P], par_ic[P];
+      lds_par<Real, P>(par_ir, par + p_in_row);
+      lds_par<Real, P>(par_ic, par + p_in_col);
+      Real th[4], own_ir[4], own_ic[4], own_or[4], own_oc[4];
+      lds4(th, rec);
+      lds4(own_ir, rec + o_in_row);
+      lds4(own_ic, rec + o_in_col);
+      lds4(own_or, rec + o_out_row);
+      lds4(own_oc, rec + o_out_col);
+
+      // ---- the column neighbour's vector: shuffle inside the band, hand-off slot for group t_in ----
       Real col_in[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) col_in[k] = carry_col[k];
-      if (poll_in && t == t_in && q >= 0 && q < (int)W) {
+      if (poller && q >= 0 && q < (int)W) {
         const Real* hslot = hand_in + (uint64_t)q * L;
         unsigned spins = 0;
         while (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3])) {
@@ -390,25 +452,14 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
 #pragma unroll
         for (int k = 0; k < 4; ++k) sent[k] = sentinel<Real>();
         st_relaxed<HAND_BYTES>(const_cast<Real*>(hslot), sent);        // the slot is free again for the next pass
-        if (q + POLL_AHEAD < (int)W) ld_relaxed<HAND_BYTES>(polled, hslot + (uint64_t)POLL_AHEAD * L);
+        if (q + 1 < (int)W) ld_relaxed<HAND_BYTES>(polled, hslot + L);
       }
-
-      Real th[4], own_ir[4], own_ic[4], own_or[4], own_oc[4];
-      lds4(th, rec + REC_THETA * L);
-      lds4(own_ir, rec + v_in_row * L);
-      lds4(own_ic, rec + v_in_col * L);
-      lds4(own_or, rec + v_out_row * L);
-      lds4(own_oc, rec + v_out_col * L);
-      Real par_ir[P], par_ic[P];
-#pragma unroll
-      for (int p = 0; p < P; ++p) { par_ir[p] = par[p_in_row * P + p]; par_ic[p] = par[p_in_col * P + p]; }
 
       Real out_col[4];
       if constexpr (FAST) {
         // ---- ReceiveMessages from the two processed neighbours, SendMessages to the two unprocessed ones ----
         Real h_ir[4], h_ic[4];
-        lane_min_plus<Real, PW, L, HOPS>(par_ir, carry_row, h_ir, scratch0, reach, gl);
-        lane_min_plus<Real, PW, L, HOPS>(par_ic, col_in, h_ic, scratch1, reach, gl);
+        lane_min_plus2<Real, PW, L, HOPS>(par_ir, carry_row, h_ir, par_ic, col_in, h_ic, stage_a, stage_b, gl);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const Real m_ir = h_ir[k] + own_ir[k], m_ic = h_ic[k] + own_ic[k];
@@ -434,46 +485,36 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
           out_col[k] = own_oc[k];
         }
         if (lane_used) {
-          sts4(rec + REC_THETA * L, th);
-          sts4(rec + v_in_row * L, own_ir);
-          sts4(rec + v_in_col * L, own_ic);
-          sts4(rec + v_out_row * L, own_or);
-          sts4(rec + v_out_col * L, own_oc);
+          sts4(rec, th);
+          sts4(rec + o_in_row, own_ir);
+          sts4(rec + o_in_col, own_ic);
+          sts4(rec + o_out_row, own_or);
+          sts4(rec + o_out_col, own_oc);
         }
       } else {
         const bool act = row_active && q >= 0 && q < (int)W;
         const bool has_ir = act && q > 0, has_or = act && q + 1 < (int)W;
         const bool has_ic = act && in_col_exists, has_oc = act && out_col_exists;
         const int n_in = (int)has_ir + (int)has_ic, n_out = (int)has_or + (int)has_oc;
-        Real oth_or[4], oth_oc[4], par_or[P], par_oc[P];
-        if constexpr (!ANISO) {
-          // the other side of the edges towards unprocessed neighbours: their in-side vectors, still in the state of
-          // the previous pass, in the neighbouring records of the tile ring
-          const int q1 = qp + 1;
-          const int slot1 = (int)((chunk_base + (uint32_t)(q1 >> LOGK)) & (NSLOT - 1));
-          const Real* rec_q1 = rec_ring + (size_t)slot1 * Cfg::SLOT_REC + (size_t)(trow * K + ((q1 & (K - 1)) ^ kxor)) * REC + gl * 4;
-          lds4(oth_or, rec_q1 + v_in_row * L);
-          lds4(oth_oc, rec + below + v_in_col * L);
+        // min-marginals of a pair of edges (independent of theta): m = h + own, own -= m   (RepamLeft / RepamRight)
+        auto marginal2 = [&](bool on_a, const Real (&pr_a)[P], const Real (&oth_a)[4], Real (&own_a)[4], Real (&m_a)[4],
+                             bool on_b, const Real (&pr_b)[P], const Real (&oth_b)[4], Real (&own_b)[4], Real (&m_b)[4]) {
+          Real pza[P], pzb[P], oza[4], ozb[4], ha[4], hb[4];
 #pragma unroll
-          for (int p = 0; p < P; ++p) { par_or[p] = par[p_out_row * P + p]; par_oc[p] = par[p_out_col * P + p]; }
-        }
-        // min-marginal of one edge (independent of theta): m = h + own, own -= m   (RepamLeft / RepamRight)
-        auto marginal = [&](bool on, const Real (&pr)[P], const Real (&oth)[4], Real (&own)[4], Real (&m)[4], Real* sc) {
-          Real pz[P], oz[4], h[4];
+          for (int p = 0; p < P; ++p) { pza[p] = on_a ? pr_a[p] : Real(0); pzb[p] = on_b ? pr_b[p] : Real(0); }
 #pragma unroll
-          for (int p = 0; p < P; ++p) pz[p] = on ? pr[p] : Real(0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) oz[k] = on ? oth[k] : Real(0);
-          lane_min_plus<Real, PW, L, HOPS>(pz, oz, h, sc, reach, gl);
+          for (int k = 0; k < 4; ++k) { oza[k] = on_a ? oth_a[k] : Real(0); ozb[k] = on_b ? oth_b[k] : Real(0); }
+          lane_min_plus2<Real, PW, L, HOPS>(pza, oza, ha, pzb, ozb, hb, stage_a, stage_b, gl);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            m[k] = on ? Real(h[k] + own[k]) : Real(0);
-            own[k] = on ? Real(own[k] - m[k]) : own[k];
+            m_a[k] = on_a ? Real(ha[k] + own_a[k]) : Real(0);
+            own_a[k] = on_a ? Real(own_a[k] - m_a[k]) : own_a[k];
+            m_b[k] = on_b ? Real(hb[k] + own_b[k]) : Real(0);
+            own_b[k] = on_b ? Real(own_b[k] - m_b[k]) : own_b[k];
           }
         };
         Real m_ir[4], m_ic[4];
-        marginal(has_ir, par_ir, carry_row, own_ir, m_ir, scratch0);
-        marginal(has_ic, par_ic, col_in, own_ic, m_ic, scratch1);
+        marginal2(has_ir, par_ir, carry_row, own_ir, m_ir, has_ic, par_ic, col_in, own_ic, m_ic);
         if constexpr (ANISO) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -483,9 +524,16 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
             th[k] = x;
           }
         } else {
-          Real m_or[4], m_oc[4];
-          marginal(has_or, par_or, oth_or, own_or, m_or, scratch0);
-          marginal(has_oc, par_oc, oth_oc, own_oc, m_oc, scratch1);
+          // the other side of the edges towards unprocessed neighbours: their in-side vectors, still in the state of
+          // the previous pass, in the neighbouring records of the tile ring
+          Real oth_or[4], oth_oc[4], par_or[P], par_oc[P], m_or[4], m_oc[4];
+          const int qq1 = qq + 1;
+          const uint32_t rec_q1 = rec_lane + (((uint32_t)qq1 >> LOGK) & (NSLOT - 1)) * SLOT_REC_B + (((uint32_t)qq1 & (K - 1)) ^ (uint32_t)kxor) * REC_B;
+          lds4(oth_or, rec_q1 + o_in_row);
+          lds4(oth_oc, (uint32_t)((int)rec + below) + o_in_col);
+          lds_par<Real, P>(par_or, par + p_out_row);
+          lds_par<Real, P>(par_oc, par + p_out_col);
+          marginal2(has_or, par_or, oth_or, own_or, m_or, has_oc, par_oc, oth_oc, own_oc, m_oc);
           // actual edges: forward (in_row, in_col, out_row, out_col) = (L, U, R, D); backward = (R, D, L, U)
           const Real* mR = fwd ? m_or : m_ir; const Real* mD = fwd ? m_oc : m_ic;
           const Real* mL = fwd ? m_ir : m_or; const Real* mU = fwd ? m_ic : m_oc;
@@ -527,11 +575,11 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
           out_col[k] = own_oc[k];
         }
         if (act) {
-          sts4(rec + REC_THETA * L, th);
-          sts4(rec + v_in_row * L, own_ir);
-          sts4(rec + v_in_col * L, own_ic);
-          sts4(rec + v_out_row * L, own_or);
-          sts4(rec + v_out_col * L, own_oc);
+          sts4(rec, th);
+          sts4(rec + o_in_row, own_ir);
+          sts4(rec + o_in_col, own_ic);
+          sts4(rec + o_out_row, own_or);
+          sts4(rec + o_out_col, own_oc);
         }
       }
 
@@ -541,7 +589,7 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
         const Real up = __shfl_up_sync(FULL, out_col[k], G);
         carry_col[k] = lane < G ? Real(0) : up;
       }
-      if (hand_out && t == t_hand && lane_used && q >= 0 && q < (int)W) st_relaxed<HAND_BYTES>(hand_dst + (uint64_t)q * L, out_col);
+      if (hander && q >= 0 && q < (int)W) st_relaxed<HAND_BYTES>(hand_dst + (uint64_t)q * L, out_col);
 
       // ---- a tile leaves once its last row has passed its last column ----
       if (((sp - T + 2) & (K - 1)) == 0 && sp >= T + K - 2) {
@@ -552,16 +600,12 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
 
     // FAST path: full bands away from the last grid row, all groups strictly inside the row (1 <= q <= W-2)
     const bool fast_band = ANISO && !last_band && !(kb == 0 && roff > 0) && W >= 3;
-    for (int sp = qoff; sp < sp_end; sp += POLL_AHEAD) {
-      const int s = sp - qoff;
-      if (fast_band && s >= T && s + 1 <= (int)W - 2) {
-        do_step(std::true_type{}, sp, poll[0]);
-        do_step(std::true_type{}, sp + 1, poll[1]);
-      } else {
-        do_step(std::false_type{}, sp, poll[0]);
-        if (sp + 1 < sp_end) do_step(std::false_type{}, sp + 1, poll[1]);
-      }
+    const int sp_fast0 = fast_band ? qoff + T : sp_end, sp_fast1 = fast_band ? qoff + (int)W - 2 : sp_end;   // fast for sp in [fast0, fast1]
+    for (int sp = qoff; sp < sp_end; ++sp) {
+      if (sp >= sp_fast0 && sp <= sp_fast1) do_step(std::true_type{}, sp);
+      else do_step(std::false_type{}, sp);
     }
+
     while (next_store < nchunks) { store_chunk(next_store); ++next_store; }
     if (lane == 0) tma_wait_read<0>();   // every tile of this band has left shared memory before the ring is reused
     __syncwarp();

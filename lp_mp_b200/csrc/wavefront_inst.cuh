@@ -3,52 +3,66 @@
 
 namespace lpmp {
 
-template <typename Real, int PW, int L, int HOPS, bool ANISO>
+template <typename Real, int PW, int L, int HOPS, bool ANISO, int KSEL>
 static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& args, const WavefrontTuning& tune, int num_sms, cudaStream_t stream) {
-  using Cfg = WavefrontCfg<Real, PW, L>;
-  auto kernel = wavefront_pass_kernel<Real, PW, L, HOPS, ANISO>;
-  const size_t smem = Cfg::SMEM_BYTES;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  using Cfg = WavefrontCfg<Real, PW, L, KSEL>;
+  // the narrow tile exists for the anisotropic kernels, and for the uniform ones only where the wide tile does not fit
+  constexpr bool EXISTS = Cfg::FITS && (KSEL == 8 || ANISO || !WavefrontCfg<Real, PW, L, 8>::FITS);
+  if constexpr (!EXISTS) {
+    return cudaErrorInvalidValue;
+  } else {
+    auto kernel = wavefront_pass_kernel<Real, PW, L, HOPS, ANISO, KSEL>;
+    const size_t smem = Cfg::SMEM_BYTES;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    if (tune.ctas_per_sm > 0 && per_sm > tune.ctas_per_sm) per_sm = tune.ctas_per_sm;
+    int ctas = (int)args.num_bands;
+    const int resident = per_sm * num_sms;
+    if (ctas > resident) ctas = resident;   // persistent: the ticket loop covers the remaining bands
+    if (tune.max_ctas > 0 && ctas > tune.max_ctas) ctas = tune.max_ctas;
+    kernel<<<ctas, 32, smem, stream>>>(maps[0], maps[1], maps[2], args);
+    return cudaGetLastError();
   }
-  int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-  if (tune.ctas_per_sm > 0 && per_sm > tune.ctas_per_sm) per_sm = tune.ctas_per_sm;
-  int ctas = (int)args.num_bands;
-  const int resident = per_sm * num_sms;
-  if (ctas > resident) ctas = resident;   // persistent: the ticket loop covers the remaining bands
-  if (tune.max_ctas > 0 && ctas > tune.max_ctas) ctas = tune.max_ctas;
-  kernel<<<ctas, 32, smem, stream>>>(maps[0], maps[1], maps[2], args);
-  return cudaGetLastError();
+}
+
+template <typename Real, int PW, int L, int HOPS, bool ANISO>
+static cudaError_t launch_k(const CUtensorMap* maps, const GridArgs<Real>& args, int ksel, const WavefrontTuning& tune, int num_sms, cudaStream_t stream) {
+  if (ksel == 8) return launch_one<Real, PW, L, HOPS, ANISO, 8>(maps, args, tune, num_sms, stream);
+  if (ksel == 4) return launch_one<Real, PW, L, HOPS, ANISO, 4>(maps, args, tune, num_sms, stream);
+  return cudaErrorInvalidValue;
 }
 
 template <typename Real, int PW, int L, bool ANISO>
-static cudaError_t launch_hops(const CUtensorMap* maps, const GridArgs<Real>& args, int hops, const WavefrontTuning& tune, int num_sms, cudaStream_t stream) {
+static cudaError_t launch_hops(const CUtensorMap* maps, const GridArgs<Real>& args, int hops, int ksel, const WavefrontTuning& tune, int num_sms,
+                               cudaStream_t stream) {
   if constexpr (PW == LPMP_PAIRWISE_TRUNCLIN) {
-    if (hops == 1) return launch_one<Real, PW, L, 1, ANISO>(maps, args, tune, num_sms, stream);
-    if (hops == 2 && L >= 16) return launch_one<Real, PW, L, 2, ANISO>(maps, args, tune, num_sms, stream);
+    if (hops == 1) return launch_k<Real, PW, L, 1, ANISO>(maps, args, ksel, tune, num_sms, stream);
+    if (hops == 2 && L >= 16) return launch_k<Real, PW, L, 2, ANISO>(maps, args, ksel, tune, num_sms, stream);
   }
-  return launch_one<Real, PW, L, 0, ANISO>(maps, args, tune, num_sms, stream);
+  return launch_k<Real, PW, L, 0, ANISO>(maps, args, ksel, tune, num_sms, stream);
 }
 
 template <typename Real, int PW, bool ANISO>
-cudaError_t launch_family(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int hops, const WavefrontTuning& tune, int num_sms,
+cudaError_t launch_family(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int hops, int ksel, const WavefrontTuning& tune, int num_sms,
                           cudaStream_t stream) {
   switch (L) {
-    case 8: return launch_hops<Real, PW, 8, ANISO>(maps, args, hops, tune, num_sms, stream);
-    case 16: return launch_hops<Real, PW, 16, ANISO>(maps, args, hops, tune, num_sms, stream);
-    case 32: return launch_hops<Real, PW, 32, ANISO>(maps, args, hops, tune, num_sms, stream);
-    case 64: return launch_hops<Real, PW, 64, ANISO>(maps, args, hops, tune, num_sms, stream);
+    case 8: return launch_hops<Real, PW, 8, ANISO>(maps, args, hops, ksel, tune, num_sms, stream);
+    case 16: return launch_hops<Real, PW, 16, ANISO>(maps, args, hops, ksel, tune, num_sms, stream);
+    case 32: return launch_hops<Real, PW, 32, ANISO>(maps, args, hops, ksel, tune, num_sms, stream);
+    case 64: return launch_hops<Real, PW, 64, ANISO>(maps, args, hops, ksel, tune, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
-template cudaError_t launch_family<LPMP_INST_REAL, LPMP_INST_PW, LPMP_INST_ANISO>(const CUtensorMap*, const GridArgs<LPMP_INST_REAL>&, uint32_t, int,
+template cudaError_t launch_family<LPMP_INST_REAL, LPMP_INST_PW, LPMP_INST_ANISO>(const CUtensorMap*, const GridArgs<LPMP_INST_REAL>&, uint32_t, int, int,
                                                                                   const WavefrontTuning&, int, cudaStream_t);
 
 }  // namespace lpmp

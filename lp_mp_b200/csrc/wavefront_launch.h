@@ -12,20 +12,34 @@ namespace lpmp {
 struct WavefrontTuning {
   int max_ctas = 0;     // 0 = one CTA (= one warp = one band at a time) per resident slot
   int ctas_per_sm = 0;  // 0 = as many as fit
+  int tile_cols = 0;    // 0 = automatic, else 8 or 4
 };
 
-// tile shape of the kernel instance for (Real, pw, L): rows per band, columns per tile, dynamic shared memory
-struct WavefrontShape { int T, K; size_t smem; };
+// tile shapes of the kernel instances for (Real, pw, L): rows per band; per tile width (8 / 4 columns) whether the
+// instance exists and its dynamic shared memory
+struct WavefrontShape {
+  int T;
+  bool fits8, fits4;
+  size_t smem8, smem4;
+  int default_k() const { return fits8 ? 8 : 4; }
+};
 
+template <typename Real, int PW, int L>
+inline WavefrontShape wavefront_shape_l() {
+  using C8 = WavefrontCfg<Real, PW, L, 8>;
+  using C4 = WavefrontCfg<Real, PW, L, 4>;
+  return WavefrontShape{C8::T, C8::FITS, C4::FITS, C8::SMEM_BYTES, C4::SMEM_BYTES};
+}
 template <typename Real, int PW>
 inline bool wavefront_shape_pw(uint32_t L, WavefrontShape& s) {
   switch (L) {
-    case 8: s = {WavefrontCfg<Real, PW, 8>::T, WavefrontCfg<Real, PW, 8>::K, WavefrontCfg<Real, PW, 8>::SMEM_BYTES}; return true;
-    case 16: s = {WavefrontCfg<Real, PW, 16>::T, WavefrontCfg<Real, PW, 16>::K, WavefrontCfg<Real, PW, 16>::SMEM_BYTES}; return true;
-    case 32: s = {WavefrontCfg<Real, PW, 32>::T, WavefrontCfg<Real, PW, 32>::K, WavefrontCfg<Real, PW, 32>::SMEM_BYTES}; return true;
-    case 64: s = {WavefrontCfg<Real, PW, 64>::T, WavefrontCfg<Real, PW, 64>::K, WavefrontCfg<Real, PW, 64>::SMEM_BYTES}; return true;
+    case 8: s = wavefront_shape_l<Real, PW, 8>(); break;
+    case 16: s = wavefront_shape_l<Real, PW, 16>(); break;
+    case 32: s = wavefront_shape_l<Real, PW, 32>(); break;
+    case 64: s = wavefront_shape_l<Real, PW, 64>(); break;
     default: return false;
   }
+  return s.fits8 || s.fits4;
 }
 // false if no kernel instance exists for this shape (dense tables, other label counts: level schedule instead)
 template <typename Real>
@@ -36,9 +50,11 @@ inline bool wavefront_shape(int pw, uint32_t L, WavefrontShape& s) {
 }
 
 // maps: [0] records, box T rows (tile stores, anisotropic loads); [1] records, box T+1 rows (uniform-mode loads);
-// [2] parameter records, box T rows.  hops: label-window half width / 4 of the truncated-linear kernel (0 = all).
+// [2] parameter records, box T rows -- all with `ksel` columns per box.  hops: label-window half width / 4 of the
+// truncated-linear kernel (0 = all distances).  ksel = 4 exists for the anisotropic kernels (and for the uniform
+// ones where 8 does not fit).
 template <typename Real, int PW, bool ANISO>
-cudaError_t launch_family(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int hops, const WavefrontTuning& tune, int num_sms,
+cudaError_t launch_family(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int hops, int ksel, const WavefrontTuning& tune, int num_sms,
                           cudaStream_t stream);
 
 }  // namespace lpmp
