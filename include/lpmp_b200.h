@@ -86,7 +86,8 @@ int LPMP_FN(set_node_ranks)(lpmp_solver* h, const uint64_t* rank /* [N], distinc
 int LPMP_FN(set_edge_order)(lpmp_solver* h, int edge_order);
 int LPMP_FN(set_schedule)(lpmp_solver* h, int schedule);
 /* launch-shape knobs of the device schedule (no effect on results): "wavefront_max_ctas" (cap on resident bands),
- * "wavefront_ctas_per_sm", "wavefront_tile_cols" (8 or 4 columns per TMA tile).  Before finalize. */
+ * "wavefront_ctas_per_sm", "wavefront_tile_cols" (8 or 4 columns per TMA tile), "wavefront_trace" (see get_trace).
+ * Before finalize. */
 int LPMP_FN(set_tuning)(lpmp_solver* h, const char* key, int value);
 /* Deterministic greedy colouring in node order (host utility, no handle state): colour[i] = smallest colour
  * not used by an already coloured neighbour.  Returns the number of colours through *num_colours. */
@@ -167,6 +168,9 @@ int LPMP_FN(set_messages)(lpmp_solver* h, const double* a, const double* b);
 int LPMP_FN(set_unaries)(lpmp_solver* h, const double* theta);
 int LPMP_FN(get_stats)(lpmp_solver* h, lpmp_stats* out);
 int LPMP_FN(synchronize)(lpmp_solver* h);
+/* debug timeline of the last wavefront pass (after set_tuning "wavefront_trace" = 1): per band 4 globaltimer stamps in ns
+ * {band claimed, first tile in shared memory, first T steps done, band done}; n = number of uint64 the buffer holds */
+int LPMP_FN(get_trace)(lpmp_solver* h, uint64_t* out, uint64_t n);
 /* the CUDA stream (cudaStream_t) all work of this handle is enqueued on, for event timing by the caller */
 int LPMP_FN(stream)(lpmp_solver* h, void** out);
 

@@ -77,6 +77,7 @@ SIGNATURES = {
     "set_unaries": [_vp, _pd],
     "get_stats": [_vp, C.POINTER(Stats)],
     "synchronize": [_vp],
+    "get_trace": [_vp, _pu64, _u64],
     "stream": [_vp, C.POINTER(_vp)],
     "minmarginal_dense": [_i, _u64, _u32, _u32, _pd, _pd, _pd, _i, _pd, _pd],
     "minmarginal_potts": [_i, _u64, _u32, _pd, _pd, _pd, _i, _pd, _pd],

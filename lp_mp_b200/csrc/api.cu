@@ -175,6 +175,7 @@ struct ISolver {
   virtual int set_unaries(const double* th) = 0;
   virtual int stats(lpmp_stats* out) = 0;
   virtual int synchronize() = 0;
+  virtual int get_trace(uint64_t* out, uint64_t n) = 0;
   virtual void* stream_ptr() = 0;
 };
 
@@ -204,6 +205,8 @@ struct Solver : ISolver {
   DeviceBuffer<uint64_t> inc_off;
   DeviceBuffer<uint8_t> inc_flags;
   DeviceBuffer<double> partial, result;
+  DeviceBuffer<unsigned long long> trace;   // debug timeline of the last wavefront pass (set_tuning wavefront_trace=1)
+  bool want_trace = false;
   DeviceBuffer<unsigned int> control;  // [0] band ticket, [1] sticky abort flag (hand-off poll timed out)
   CUtensorMap maps8[3], maps4[3];   // tile width 8 / 4 columns
   std::vector<uint64_t> level_off;     // host
@@ -304,6 +307,7 @@ struct Solver : ISolver {
     if (k == "wavefront_max_ctas") tune.max_ctas = value;
     else if (k == "wavefront_ctas_per_sm") tune.ctas_per_sm = value;
     else if (k == "wavefront_tile_cols") tune.tile_cols = value;
+    else if (k == "wavefront_trace") want_trace = value != 0;
     else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
     return LPMP_OK;
   }
@@ -610,6 +614,7 @@ struct Solver : ISolver {
         const uint32_t bands = (gridH + shape.T - 1) / shape.T;
         CUDA_TRY(control.alloc(2));
         CUDA_TRY(cudaMemsetAsync(control.p, 0, control.bytes(), stream));
+        if (want_trace) { CUDA_TRY(trace.alloc(4 * (size_t)bands)); CUDA_TRY(cudaMemsetAsync(trace.p, 0, trace.bytes(), stream)); }
         CUDA_TRY(handoff.alloc((size_t)bands * gridW * L));
         CUDA_TRY(cudaMemsetAsync(handoff.p, 0xff, handoff.bytes(), stream));
         for (int ks = 4; ks <= 8; ks += 4) {
@@ -676,6 +681,7 @@ struct Solver : ISolver {
       A.in_boundary = forward ? in_top.p : in_bot.p;
       A.out_boundary = forward ? peer_bot : peer_top;
       A.labels = labels.p;
+      A.trace = trace.p;
       CUDA_TRY(cudaMemsetAsync(control.p, 0, sizeof(unsigned int), stream));
       // tile width: 8 columns unless the bands outnumber the resident warps and the narrow tile doubles residency
       int ksel = shape.default_k();
@@ -893,6 +899,12 @@ struct Solver : ISolver {
     return LPMP_OK;
   }
   int synchronize() override { CUDA_TRY(cudaStreamSynchronize(stream)); return check_abort(); }
+  int get_trace(uint64_t* out, uint64_t n) override {
+    if (!trace.p) return bad_state("no trace: set_tuning wavefront_trace=1 before finalize");
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaMemcpy(out, trace.p, std::min<uint64_t>(n, trace.n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return LPMP_OK;
+  }
   void* stream_ptr() override { return (void*)stream; }
 };
 
@@ -1066,6 +1078,7 @@ int lpmp_set_messages(lpmp_solver* h, const double* a, const double* b) { return
 int lpmp_set_unaries(lpmp_solver* h, const double* th) { return S(h)->set_unaries(th); }
 int lpmp_get_stats(lpmp_solver* h, lpmp_stats* out) { return S(h)->stats(out); }
 int lpmp_synchronize(lpmp_solver* h) { return S(h)->synchronize(); }
+int lpmp_get_trace(lpmp_solver* h, uint64_t* out, uint64_t n) { return S(h)->get_trace(out, n); }
 int lpmp_stream(lpmp_solver* h, void** out) { if (out) *out = S(h)->stream_ptr(); return LPMP_OK; }
 
 int lpmp_minmarginal_dense(int dtype, uint64_t n, uint32_t L1, uint32_t L2, const double* t, const double* msg1, const double* msg2, int side, double* out, double* lb) {

@@ -57,6 +57,7 @@ struct GridArgs {
   Real* out_boundary;       // [W][L] where the last band delivers its outgoing vectors when out_halo (the neighbour's
                             // in_boundary, possibly peer memory), or null: not delivered
   uint32_t* labels;         // [H*W]
+  unsigned long long* trace;   // debug: per band {claimed, first tile ready, first hand-off consumed, done} in ns (globaltimer), or null
 };
 
 // ---- hand-off slots: L2-resident, self-validating -------------------------------------------------------------------
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
   const bool recv_row_first = fwd ? !A.fifo : (A.fifo != 0);
   // weight of the FAST path: (n_in, n_out) = (2, 2), first row (1, 2): 1 / max(n_in, n_out) = 1/2 (include/LP_MP.h:1397)
   const Real w_fast = (Real)(1.0 / 2.0);
+  const bool H_total_ge2 = H >= 2 || A.in_halo || A.out_halo;   // a single-row grid has (n_in, n_out) = (1, 1): weight 1
 
   for (;;) {
     unsigned kb = 0;
@@ -382,6 +384,14 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
     if (lane == 0) {
       for (int j = 0; j <= PDC && j < nchunks; ++j) issue_load(j);
     }
+    auto stamp = [&](int which) {
+      if (A.trace != nullptr && lane == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        A.trace[4ull * kb + which] = now;
+      }
+    };
+    stamp(0);
 
     // the hand-off slot of column q+1 is polled right after column q has been consumed, one step before its use,
     // so that the L2 round trip is off the dependency chain
@@ -397,20 +407,26 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
 
     wait_chunk(0);
     if (!ANISO && nchunks > 1) wait_chunk(1);   // uniform modes: the out_row neighbour may sit in the next tile
+    stamp(1);
 
     // sp = step index shifted by qoff; group t is at tile column q' = sp - t, virtual column q = q' - qoff
     auto do_step = [&](auto fast_tag, const int sp) {
       constexpr bool FAST = decltype(fast_tag)::value;
-      // ---- tile ring management (warp-uniform) ----
-      if ((sp & (K - 1)) == 0 && sp > 0) {
-        const int j = sp >> LOGK;
-        const int jw = ANISO ? j : j + 1;
-        if (jw < nchunks) wait_chunk(jw);
-        if (lane == 0 && j + PDC < nchunks) {
-          tma_wait_read<(T < 2 ? 1 : 0)>();     // the tile that last lived in this slot has left shared memory
-          issue_load(j + PDC);
+      // ---- tile ring management (warp-uniform, one branch per step) ----
+      const bool ev_store = ((sp - T + 1) & (K - 1)) == 0 && sp >= T + K - 1;   // the previous step completed a tile
+      const bool ev_load = (sp & (K - 1)) == 0 && sp > 0;                        // group 0 enters a new tile
+      if (ev_store || ev_load) {
+        if (ev_store) { store_chunk(next_store); ++next_store; }
+        if (ev_load) {
+          const int j = sp >> LOGK;
+          const int jw = ANISO ? j : j + 1;
+          if (jw < nchunks) wait_chunk(jw);
+          if (lane == 0 && j + PDC < nchunks) {
+            tma_wait_read<(T < 2 ? 1 : 0)>();     // the tile that last lived in this slot has left shared memory
+            issue_load(j + PDC);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       const int q = sp - t - qoff;
       const int qq = sp + lane_q0;               // column in the tile ring (slot sequence continues across bands)
@@ -430,24 +446,29 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
       lds4(own_oc, rec + o_out_col);
 
       // ---- the column neighbour's vector: shuffle inside the band, hand-off slot for group t_in ----
+      // (the common case -- the slot polled during the previous step is valid -- is branch-free for the warp)
       Real col_in[4];
+      const bool polling = poller && q >= 0 && q < (int)W;
+      const Real* const hslot = hand_in + (int64_t)q * L;
+      if (__any_sync(FULL, polling && (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3])))) {
+        if (polling) {
+          unsigned spins = 0;
+          while (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3])) {
+            ld_relaxed<HAND_BYTES>(polled, hslot);
+            if ((++spins & 0x3ffu) == 0) {      // bounded wait: a lost producer must not hang the device
+              if (spins > (1u << 22)) atomicExch(A.control + 1, 1u);
+              if (*reinterpret_cast<volatile unsigned int*>(A.control + 1) != 0u) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) col_in[k] = carry_col[k];
-      if (poller && q >= 0 && q < (int)W) {
-        const Real* hslot = hand_in + (uint64_t)q * L;
-        unsigned spins = 0;
-        while (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3])) {
-          ld_relaxed<HAND_BYTES>(polled, hslot);
-          if ((++spins & 0x3ffu) == 0) {      // bounded wait: a lost producer must not hang the device
-            if (spins > (1u << 22)) atomicExch(A.control + 1, 1u);
-            if (*reinterpret_cast<volatile unsigned int*>(A.control + 1) != 0u) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) polled[k] = Real(0);
+                for (int k = 0; k < 4; ++k) polled[k] = Real(0);
+              }
             }
           }
         }
+        __syncwarp();
+      }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) col_in[k] = polled[k];
+      for (int k = 0; k < 4; ++k) col_in[k] = polling ? polled[k] : carry_col[k];
+      if (polling) {
         Real sent[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) sent[k] = sentinel<Real>();
@@ -467,24 +488,21 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
           own_ic[k] = own_ic[k] - m_ic;
           th[k] = recv_row_first ? (th[k] + m_ir) + m_ic : (th[k] + m_ic) + m_ir;
         }
-        if (A.primal) {   // MaximizePotentialAndComputePrimal: first minimum
-          Real bv = th[0];
-          uint32_t bi = (uint32_t)(gl * 4);
-#pragma unroll
-          for (int k = 1; k < 4; ++k) if (th[k] < bv) { bv = th[k]; bi = (uint32_t)(gl * 4 + k); }
-          group_argmin(bv, bi, G, FULL);
-          if (gl == 0 && lane_used) A.labels[(uint64_t)r * W + (fwd ? (uint32_t)q : W - 1 - (uint32_t)q)] = bi;
-        }
+        // missing edges: the left column (q = 0) and the first row have all-zero in-side slots and parameters, so their
+        // receives are exact no-ops; the last grid row has no out_col edge (select); groups that have not reached
+        // column 0 yet (q < 0) and rows beyond the grid compute on garbage and neither store nor carry
+        const bool started = q >= 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const Real d = w_fast * th[k];   // every send uses the same snapshot value
-          own_oc[k] = own_oc[k] + d;
+          const Real d_oc = out_col_exists ? d : Real(0);
+          own_oc[k] = own_oc[k] + d_oc;
           own_or[k] = own_or[k] + d;
-          th[k] = (th[k] - d) - d;
-          carry_row[k] = own_or[k];
+          th[k] = (th[k] - d_oc) - d;
+          carry_row[k] = started ? own_or[k] : Real(0);
           out_col[k] = own_oc[k];
         }
-        if (lane_used) {
+        if (row_active && started) {
           sts4(rec, th);
           sts4(rec + o_in_row, own_ir);
           sts4(rec + o_in_col, own_ic);
@@ -587,24 +605,22 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const Real up = __shfl_up_sync(FULL, out_col[k], G);
-        carry_col[k] = lane < G ? Real(0) : up;
+        carry_col[k] = t <= t_in ? Real(0) : up;
       }
       if (hander && q >= 0 && q < (int)W) st_relaxed<HAND_BYTES>(hand_dst + (uint64_t)q * L, out_col);
 
-      // ---- a tile leaves once its last row has passed its last column ----
-      if (((sp - T + 2) & (K - 1)) == 0 && sp >= T + K - 2) {
-        store_chunk(next_store);
-        ++next_store;
-      }
     };
 
-    // FAST path: full bands away from the last grid row, all groups strictly inside the row (1 <= q <= W-2)
-    const bool fast_band = ANISO && !last_band && !(kb == 0 && roff > 0) && W >= 3;
-    const int sp_fast0 = fast_band ? qoff + T : sp_end, sp_fast1 = fast_band ? qoff + (int)W - 2 : sp_end;   // fast for sp in [fast0, fast1]
+    // FAST path: anisotropic non-rounding passes, every group left of the last column (q <= W-2); the last band
+    // (whose last row has (n_in, n_out) = (1, 1) at q = 0, weight 1 instead of 1/2) joins after its left ramp
+    const bool fast_band = ANISO && !A.primal && W >= 3 && H_total_ge2;
+    const int sp_fast0 = fast_band ? (last_band ? qoff + T : qoff) : sp_end, sp_fast1 = fast_band ? qoff + (int)W - 2 : sp_end;   // fast for sp in [fast0, fast1]
     for (int sp = qoff; sp < sp_end; ++sp) {
       if (sp >= sp_fast0 && sp <= sp_fast1) do_step(std::true_type{}, sp);
       else do_step(std::false_type{}, sp);
+      if (sp == qoff + T) stamp(2);
     }
+    stamp(3);
 
     while (next_store < nchunks) { store_chunk(next_store); ++next_store; }
     if (lane == 0) tma_wait_read<0>();   // every tile of this band has left shared memory before the ring is reused

@@ -283,6 +283,11 @@ class LP:
     def synchronize(self):
         self._ck(self.api.synchronize(self.h))
 
+    def trace(self, bands):
+        out = np.zeros((bands, 4), dtype=np.uint64)
+        self._ck(self.api.get_trace(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size))
+        return out
+
     def stream(self) -> int:
         out = C.c_void_p()
         self._ck(self.api.stream(self.h, C.byref(out)))
