@@ -169,7 +169,7 @@ int LPMP_FN(set_unaries)(lpmp_solver* h, const double* theta);
 int LPMP_FN(get_stats)(lpmp_solver* h, lpmp_stats* out);
 int LPMP_FN(synchronize)(lpmp_solver* h);
 /* debug timeline of the last wavefront pass (after set_tuning "wavefront_trace" = 1): per band 4 globaltimer stamps in ns
- * {band claimed, first tile in shared memory, first T steps done, band done}; n = number of uint64 the buffer holds */
+ * {band claimed, first tile in shared memory, first K steps done, band done}; n = number of uint64 the buffer holds */
 int LPMP_FN(get_trace)(lpmp_solver* h, uint64_t* out, uint64_t n);
 /* the CUDA stream (cudaStream_t) all work of this handle is enqueued on, for event timing by the caller */
 int LPMP_FN(stream)(lpmp_solver* h, void** out);

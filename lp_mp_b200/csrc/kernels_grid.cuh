@@ -145,6 +145,26 @@ struct WavefrontCfg {
   static_assert((SLOT_REC * sizeof(Real)) % 128 == 0 && (SLOT_PAR * sizeof(Real)) % 128 == 0, "TMA destination alignment");
 };
 
+// predicated variants (no branch in the instruction stream; a skipped load leaves dst unchanged)
+template <int BYTES> __device__ __forceinline__ void ld_relaxed_if(bool on, void* dst, const void* src) {
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+  for (int o = 0; o < BYTES / 16; ++o)
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4]; }"
+                 : "+r"(d[4 * o]), "+r"(d[4 * o + 1]), "+r"(d[4 * o + 2]), "+r"(d[4 * o + 3])
+                 : "l"(reinterpret_cast<const char*>(src) + 16 * o), "r"((uint32_t)on));
+}
+template <int BYTES> __device__ __forceinline__ void st_relaxed_if(bool on, void* dst, const void* src) {
+  const uint32_t* d = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+  for (int o = 0; o < BYTES / 16; ++o)
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4}; }" ::"l"(reinterpret_cast<char*>(dst) + 16 * o),
+                 "r"(d[4 * o]), "r"(d[4 * o + 1]), "r"(d[4 * o + 2]), "r"(d[4 * o + 3]), "r"((uint32_t)on)
+                 : "memory");
+}
+// pins a kernel parameter in a register (the compiler otherwise re-reads the constant bank inside the step loop)
+__device__ __forceinline__ uint32_t pin(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+
 // ---- shared-memory vector access by 32-bit shared address: 4 labels per lane ----------------------------------------
 // volatile: program order among these accesses is kept (tiles are also written by the TMA and re-read in place)
 __device__ __forceinline__ void lds4(float (&v)[4], uint32_t a) {
@@ -290,7 +310,7 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
   const bool lane_used = !PARTIAL_WARP || lane / G < T;
   const int t = lane_used ? lane / G : T - 1, gl = lane % G;
   const bool fwd = A.forward != 0;
-  const uint32_t H = A.H, W = A.W;
+  const uint32_t H = A.H, W = pin(A.W);
   const int nchunks = ((int)W + K - 1) >> LOGK;
   const int nb = (int)A.num_bands;
   // TMA tile stores must not start at negative coordinates, so tiles are anchored at row 0 / column 0 in BOTH
@@ -418,6 +438,7 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
       if (ev_store || ev_load) {
         if (ev_store) { store_chunk(next_store); ++next_store; }
         if (ev_load) {
+          if (sp == K) stamp(2);
           const int j = sp >> LOGK;
           const int jw = ANISO ? j : j + 1;
           if (jw < nchunks) wait_chunk(jw);
@@ -468,12 +489,12 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) col_in[k] = polling ? polled[k] : carry_col[k];
-      if (polling) {
+      {
         Real sent[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) sent[k] = sentinel<Real>();
-        st_relaxed<HAND_BYTES>(const_cast<Real*>(hslot), sent);        // the slot is free again for the next pass
-        if (q + 1 < (int)W) ld_relaxed<HAND_BYTES>(polled, hslot + L);
+        st_relaxed_if<HAND_BYTES>(polling, const_cast<Real*>(hslot), sent);        // the slot is free again for the next pass
+        ld_relaxed_if<HAND_BYTES>(polling && q + 1 < (int)W, polled, hslot + L);
       }
 
       Real out_col[4];
@@ -607,7 +628,7 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
         const Real up = __shfl_up_sync(FULL, out_col[k], G);
         carry_col[k] = t <= t_in ? Real(0) : up;
       }
-      if (hander && q >= 0 && q < (int)W) st_relaxed<HAND_BYTES>(hand_dst + (uint64_t)q * L, out_col);
+      st_relaxed_if<HAND_BYTES>(hander && q >= 0 && q < (int)W, hand_dst + (int64_t)q * L, out_col);
 
     };
 
@@ -618,7 +639,6 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
     for (int sp = qoff; sp < sp_end; ++sp) {
       if (sp >= sp_fast0 && sp <= sp_fast1) do_step(std::true_type{}, sp);
       else do_step(std::false_type{}, sp);
-      if (sp == qoff + T) stamp(2);
     }
     stamp(3);
 

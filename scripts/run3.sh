@@ -1,4 +1,4 @@
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | grep -E "passed|failed"
 python scripts/trace_c2.py | tail -6
 for wl in C2 C3; do
 echo "== $wl"; timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
