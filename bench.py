@@ -178,7 +178,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--tune", default="", help="comma separated key=value launch-shape knobs, e.g. wavefront_warps=2")
+    ap.add_argument("--coupling", default="halo", choices=["halo", "pipelined"],
+                    help="N > 1: per-pass halo exchange (NCCL send/recv, block-Jacobi across stripes) or exact pipelined "
+                         "stripes (NVLink peer stores from the pass kernel; bit-identical to one GPU)")
+    ap.add_argument("--tune", default="", help="comma separated key=value launch-shape knobs, e.g. wavefront_tile_cols=4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -190,12 +193,13 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps(reference_arm(args, H, W, L, pairwise, lo, hi)))
-        return
+            print(json.dumps(reference_arm(args, H, W, L, pairwise, lo, hi)), flush=True)
+        os._exit(0)   # skip the reference's static destructors (its MemoryPool prints pool statistics to stdout at exit)
 
     import numpy as np
     import torch
     import lp_mp_b200
+    from lp_mp_b200.stripes import StripedLP, StripePlan
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -203,39 +207,23 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     s = 4 if args.dtype == "f32" else 8
-    tune = dict(kv.split("=") for kv in args.tune.split(",") if kv)
+    tune = {k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)}
+    H_total = H * world      # weak scaling: every rank owns a stripe of the single-GPU workload's size
 
-    def make_lp():
-        lp = lp_mp_b200.LP(dtype=args.dtype, device=local_rank).grid_create(H, W, L, pairwise)
-        if tune:
-            lp.set_tuning(**{k: int(v) for k, v in tune.items()})
-        if world > 1:
-            lp.grid_set_stripe(rank * H, world * H)
-        return lp
+    def make():
+        return StripedLP.make(H_total, W, L, pairwise, rank, world, dist=dist, dtype=args.dtype, device=local_rank,
+                              coupling=args.coupling, tuning=tune)
 
     # ---- device-resident arm: inputs generated in HBM, timed with CUDA events on the library's stream ----
-    lp = make_lp()
-    lp.grid_fill_synthetic(SEED + rank, lo, hi)
-    lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+    slp = make()
+    slp.lp.grid_fill_synthetic(SEED, lo, hi)
+    slp.finalize(); slp.Begin(); slp.set_reparametrization("anisotropic")
+    lp = slp.lp
     stream = torch.cuda.ExternalStream(lp.stream(), device=local_rank)
-    halo = None
-    if world > 1:
-        from lp_mp_b200.stripes import HaloExchanger
-        halo = HaloExchanger(lp, rank, world, dist, stream)
-
-    def iteration(it):
-        lp.ComputeForwardPass()
-        if halo:
-            halo.after_forward()
-        lp.ComputeBackwardPass()
-        if halo:
-            halo.after_backward()
-            return halo.lower_bound()
-        return lp.LowerBound()
 
     for it in range(args.warmup):
-        iteration(it)
-    lp.synchronize()
+        slp.ComputePass(it); slp.LowerBound()
+    slp.synchronize()
     launches0 = lp.stats()["kernel_launches"]
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -248,15 +236,18 @@ def main():
     ev[0].record(stream)
     lb = None
     for it in range(args.steps):
-        if world == 1:  # per-launch events for the roofline of the dominant kernel (the wavefront pass)
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            e[0].record(stream); lp.ComputeForwardPass(); e[1].record(stream); lp.ComputeBackwardPass(); e[2].record(stream)
-            pass_ev.append(e)
-            lb = lp.LowerBound()
-        else:
-            lb = iteration(args.warmup + it)
+        # per-launch events for the roofline of the dominant kernel (one wavefront pass = one launch)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        if world > 1 and args.coupling == "halo":
+            slp._exchange(1)
+        e[0].record(stream); lp.ComputeForwardPass(); e[1].record(stream)
+        if world > 1 and args.coupling == "halo":
+            slp._exchange(0)
+        e[2].record(stream); lp.ComputeBackwardPass(); e[3].record(stream)
+        pass_ev.append(e)
+        lb = slp.LowerBound()
     ev[1].record(stream)
-    lp.synchronize()
+    slp.synchronize()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -267,73 +258,84 @@ def main():
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    E = edges_of(H * world, W)
+    E = edges_of(H_total, W)
     value = 4.0 * E * args.steps / (ms * 1e-3)
 
-    roofline = None
-    if world == 1:
-        pass_ms = [e[0].elapsed_time(e[1]) for e in pass_ev] + [e[1].elapsed_time(e[2]) for e in pass_ev]
-        mean_pass_s = 1e-3 * sum(pass_ms) / len(pass_ms)
-        bytes_pass = algorithmic_bytes_per_pass(H, W, L, pairwise, s)
-        peak, peak_src = measured_hbm_peak()
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(f"{args.workload}_{args.dtype}")
-            except Exception:
-                traffic = None
-        achieved = bytes_pass / mean_pass_s / 1e9
-        roofline = {"bound": "hbm", "kernel": "wavefront_pass_kernel (one launch = one pass)", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": bytes_pass, "mean_launch_ms": 1e3 * mean_pass_s,
-                    "critical_path_steps_per_launch": H + W - 1,
-                    "note": "exact reference order: a pass is a dependency chain of H+W-1 node updates (SURVEY.md 7 hard part 1)"}
+    pass_ms = [e[0].elapsed_time(e[1]) for e in pass_ev] + [e[2].elapsed_time(e[3]) for e in pass_ev]
+    mean_pass_s = 1e-3 * sum(pass_ms) / len(pass_ms)
+    rows_here = StripePlan(H_total, world).rows(rank)[1]
+    bytes_pass = algorithmic_bytes_per_pass(rows_here, W, L, pairwise, s)
+    peak, peak_src = measured_hbm_peak()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"{args.workload}_{args.dtype}")
+        except Exception:
+            traffic = None
+    achieved = bytes_pass / mean_pass_s / 1e9
+    roofline = {"bound": "hbm", "kernel": "wavefront_pass_kernel (one launch = one pass over this rank's stripe)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_pass, "mean_launch_ms": 1e3 * mean_pass_s,
+                "critical_path_steps_per_launch": rows_here + W - 1,
+                "note": "exact reference order: a pass is a dependency chain of H+W-1 node updates, so small grids are bound by the "
+                        "per-update latency, not by HBM (DESIGN.md 'Rooflines'; SURVEY.md 7 hard part 1)"}
 
     # ---- end-to-end arm: the call a user makes, from pinned HOST buffers ----
-    # one solve = upload potentials (H2D) + K iterations each with a lower-bound read-back (D2H) + rounding pass +
-    # labeling download; reported per iteration (upload amortised over the K iterations of the solve)
-    Hh = H
-    theta_h = torch.rand((Hh, W, L), dtype=torch.float32).pin_memory()
+    # one solve = upload this rank's potentials (H2D) + K iterations each with a lower-bound read-back (D2H) [+ rounding
+    # pass + labeling download at N = 1]; reported per iteration (upload amortised over the K iterations of the solve)
     P = {"dense": L * L, "potts": 1, "trunclin": 2}[pairwise]
-    if pairwise == "trunclin":
-        hz_h = torch.tensor([lo, hi], dtype=torch.float32).repeat(Hh, W - 1, 1).contiguous().pin_memory()
-        vt_h = torch.tensor([lo, hi], dtype=torch.float32).repeat(Hh - 1, W, 1).contiguous().pin_memory()
-    else:
-        hz_h = (lo + (hi - lo) * torch.rand((Hh, W - 1, P), dtype=torch.float32)).pin_memory()
-        vt_h = (lo + (hi - lo) * torch.rand((Hh - 1, W, P), dtype=torch.float32)).pin_memory()
-    labels_h = np.zeros(Hh * W, dtype=np.uint32)
-    e2e = None
-    if world == 1:
-        def solve():
-            q = make_lp()
-            q._ck(q.api.grid_set_unaries(q.h, theta_h.data_ptr(), 0))
-            q._ck(q.api.grid_set_pairwise(q.h, hz_h.data_ptr(), vt_h.data_ptr(), 0))
-            q.finalize(); q.Begin(); q.set_reparametrization("anisotropic")
-            bound = 0.0
-            for it in range(args.steps):
-                q.ComputePass(it)
-                bound = q.LowerBound()
-            q.ComputeForwardPassAndPrimal(args.steps)
-            cost = q.EvaluatePrimal()
-            lab = q.labeling()
-            return bound, cost, lab
-        solve()  # warm-up (allocator, first-touch)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        bound, cost, lab = solve()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        h2d = theta_h.numel() * 4 + hz_h.numel() * 4 + vt_h.numel() * 4
-        d2h = 8 * args.steps + 8 + lab.nbytes
-        e2e = {"value": 4.0 * edges_of(H, W) * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
-               "d2h_bytes_per_step": d2h / args.steps,
-               "definition": f"one Solve from pinned host buffers: upload + {args.steps} iterations (LB read back every iteration)"
-                             " + rounding pass + labeling download; wall clock; bytes are per iteration",
-               "lower_bound": bound, "primal": cost}
-    else:
-        e2e = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
-               "definition": "multi-GPU run: device-resident stripes, LB all-reduced and read back every iteration"}
+    row0 = StripePlan(H_total, world).rows(rank)[0]
+    g = torch.Generator().manual_seed(SEED + rank)
+    theta_h = torch.rand((rows_here, W, L), dtype=torch.float32, generator=g).pin_memory()
+
+    def edge_params(shape):
+        if pairwise == "trunclin":
+            return torch.tensor([lo, hi], dtype=torch.float32).repeat(*shape, 1).contiguous().pin_memory()
+        return (lo + (hi - lo) * torch.rand((*shape, P), dtype=torch.float32, generator=g)).pin_memory()
+
+    hz_h, vt_h = edge_params((rows_here, W - 1)), edge_params((rows_here - 1, W))
+    top_h = edge_params((W,)) if row0 > 0 else None
+    bot_h = edge_params((W,)) if row0 + rows_here < H_total else None
+
+    def solve():
+        q = make()
+        q.lp._ck(q.lp.api.grid_set_unaries(q.lp.h, theta_h.data_ptr(), 0))
+        q.lp._ck(q.lp.api.grid_set_pairwise(q.lp.h, hz_h.data_ptr(), vt_h.data_ptr(), 0))
+        if world > 1:
+            q.lp._ck(q.lp.api.grid_set_boundary_pairwise(q.lp.h, top_h.data_ptr() if top_h is not None else None,
+                                                         bot_h.data_ptr() if bot_h is not None else None, 0))
+        q.finalize(); q.Begin(); q.set_reparametrization("anisotropic")
+        bound, cost, nlab = 0.0, None, 0
+        for it in range(args.steps):
+            q.ComputePass(it)
+            bound = q.LowerBound()
+        if world == 1:
+            q.lp.ComputeForwardPassAndPrimal(args.steps)
+            cost = q.lp.EvaluatePrimal()
+            nlab = q.lp.labeling().nbytes
+        q.close()
+        return bound, cost, nlab
+
+    solve()  # warm-up (allocator, first touch, IPC mappings)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    bound, cost, nlab = solve()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    h2d = 4 * (theta_h.numel() + hz_h.numel() + vt_h.numel() + (top_h.numel() if top_h is not None else 0) + (bot_h.numel() if bot_h is not None else 0))
+    d2h = 8 * args.steps + (8 + nlab if world == 1 else 0)
+    e2e = {"value": 4.0 * E * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * world / args.steps,
+           "d2h_bytes_per_step": d2h * world / args.steps,
+           "definition": f"one Solve from pinned host buffers: upload + {args.steps} iterations (LB read back every iteration)"
+                         + (" + rounding pass + labeling download" if world == 1 else "") + "; wall clock, max over ranks; bytes are per iteration",
+           "lower_bound": bound, "primal": cost}
 
     if rank != 0:
         if dist:
@@ -346,11 +348,13 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}" + (f"; x{world} row stripes of {H} rows (grid {H * world}x{W})" if world > 1 else ""),
+        "config": {"workload": f"{args.workload}: {desc}" + (f"; x{world} row stripes of {H} rows (grid {H_total}x{W})" if world > 1 else ""),
                    "step": "one iteration = forward pass + backward pass + lower bound", "schedule": "wavefront (exact reference order)",
-                   "reparametrization": "anisotropic (SRMP)", "l2_policy": "working set (theta + 4 message planes, "
-                   f"{(H * W * L * 5 * s) >> 20} MiB) exceeds the 126 MB L2; no flush needed", "tuning": tune,
-                   "lower_bound_after_last_step": lb},
+                   "reparametrization": "anisotropic (SRMP)",
+                   "stripe_coupling": None if world == 1 else ("per-pass halo (NCCL send/recv; block-Jacobi across stripes)" if args.coupling == "halo"
+                                                               else "exact pipelined (NVLink peer stores from the pass kernel)"),
+                   "l2_policy": f"working set per GPU (node records, {(rows_here * W * L * 5 * s) >> 20} MiB) exceeds the 126 MB L2; no flush needed",
+                   "tuning": tune, "lower_bound_after_last_step": lb},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,
     }
     print(json.dumps(out))

@@ -291,6 +291,88 @@ def test_synthetic_generator_matches_oracle():
         run_lockstep(lps, "anisotropic", iters=3, lb_rtol=1e-6)
 
 
+# ---- row stripes (multi-GPU path) exercised with two handles on ONE device ------------------------------------------------
+def _stripe_pair(dtype, H, cut, W, L, kind, lo, hi, seed=0x5EED):
+    """full LP + the two stripes [0, cut), [cut, H) of the same synthetic problem"""
+    full = cuda_lp(dtype).grid_create(H, W, L, kind)
+    full.grid_fill_synthetic(seed, lo, hi)
+    stripes = []
+    for row0, rows in ((0, cut), (cut, H - cut)):
+        lp = cuda_lp(dtype).grid_create(rows, W, L, kind)
+        lp.grid_set_stripe(row0, H)
+        lp.grid_fill_synthetic(seed, lo, hi)
+        stripes.append(lp)
+    for lp in [full] + stripes:
+        lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+    return full, stripes
+
+
+def _striped_bound(stripes):
+    import torch
+    top, bot = stripes
+    W, L = top.grid_shape[1], top.L
+    buf = torch.empty(W * L, dtype=torch.float32 if top.dtype == 0 else torch.float64, device="cuda")
+    bot.grid_get_boundary_vectors(0, buf.data_ptr())
+    bot.synchronize()
+    return top.grid_lower_bound_partial(buf.data_ptr()) + bot.grid_lower_bound_partial(None)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+@pytest.mark.parametrize("kind,L,lo,hi,H,cut,W", [("trunclin", 16, 0.25, 1.0, 70, 30, 45), ("potts", 32, 0.1, 1.0, 41, 17, 39),
+                                                  ("potts", 8, 0.1, 1.0, 33, 16, 20)])
+def test_stripes_pipelined_are_bit_identical_to_the_unstriped_lp(dtype, kind, L, lo, hi, H, cut, W):
+    """exact coupling: the last band of the upper stripe stores its outgoing vectors straight into the lower stripe's
+    in-buffer while that stripe's pass kernel polls them (on multi-GPU boxes the pointer is a cudaIpc mapping)"""
+    full, (top, bot) = _stripe_pair(dtype, H, cut, W, L, kind, lo, hi)
+    top.grid_set_peer_boundary(1, bot.grid_boundary_ptrs(0)[0])   # forward: top's last row -> bot.in(top)
+    bot.grid_set_peer_boundary(0, top.grid_boundary_ptrs(1)[0])   # backward: bot's first row -> top.in(bottom)
+    for it in range(3):
+        full.ComputePass(it)
+        top.ComputeForwardPass(); bot.ComputeForwardPass()        # both kernels in flight, coupled through the buffers
+        bot.ComputeBackwardPass(); top.ComputeBackwardPass()
+        top.synchronize(); bot.synchronize()
+        assert np.array_equal(np.concatenate([top.unaries(), bot.unaries()]), full.unaries()), f"theta differs after pass {it}"
+        assert np.isclose(_striped_bound((top, bot)), full.LowerBound(), rtol=LB_RTOL[dtype])
+    fa, fb = full.messages()
+    ta, tb = top.messages()
+    # edges of the top stripe come first in insertion order, except that its last row has no vertical edges
+    n_top_inner = len(ta)
+    rows_full = []
+    e = 0
+    for r in range(H):
+        for c in range(W):
+            if c + 1 < W:
+                rows_full.append((r, e)); e += 1
+            if r + 1 < H:
+                rows_full.append((r if r + 1 != cut else -1, e)); e += 1
+    keep = [k for (r, k) in rows_full if 0 <= r < cut]
+    assert len(keep) == n_top_inner
+    assert np.array_equal(fa[keep], ta) and np.array_equal(fb[keep], tb)
+
+
+def test_stripes_per_pass_halo_is_monotone_and_close():
+    """block-Jacobi coupling: each stripe sweeps with the neighbour's vectors of the previous pass.  Valid
+    reparametrisation (monotone bound, below the exact one or equal) with a slightly weaker fixed point."""
+    H, cut, W, L = 96, 48, 64, 16
+    full, (top, bot) = _stripe_pair("f64", H, cut, W, L, "trunclin", 0.25, 1.0)
+    prev = _striped_bound((top, bot))
+    assert np.isclose(prev, full.LowerBound(), rtol=1e-12)
+    for it in range(20):
+        full.ComputePass(it)
+        top.grid_get_boundary_vectors(1, bot.grid_boundary_ptrs(0)[0]); top.synchronize()
+        top.ComputeForwardPass(); bot.ComputeForwardPass()
+        top.synchronize(); bot.synchronize()
+        bot.grid_get_boundary_vectors(0, top.grid_boundary_ptrs(1)[0]); bot.synchronize()
+        bot.ComputeBackwardPass(); top.ComputeBackwardPass()
+        top.synchronize(); bot.synchronize()
+        lb = _striped_bound((top, bot))
+        assert lb >= prev - 1e-9 * abs(prev)
+        prev = lb
+    exact = full.LowerBound()
+    assert prev <= exact + 1e-9 * abs(exact)
+    assert abs(prev - exact) <= 5e-3 * abs(exact), (prev, exact)
+
+
 # ---- solver loop: reference control law driving the device ---------------------------------------------------------
 def test_frustrated_cycle_goldens_on_device():
     """test/graphical_model.cpp:98-136 (lower bounds are goldens; see tests/test_oracle_goldens.py for the primal note)"""
