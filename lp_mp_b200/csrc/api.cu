@@ -734,6 +734,16 @@ struct Solver : ISolver {
     const int groups = threads / G;
     const uint64_t total = N + slots;
     const int ctas = (int)std::min<uint64_t>((total + groups - 1) / groups, (uint64_t)kBoundCtas);
+    if (is_grid && schedule == LPMP_SCHEDULE_WAVEFRONT) {
+      // record-streaming sweep (kernels_grid_bound.cuh): every record and parameter is read once
+      GridBoundArgs<Real> B{gridH, gridW, rec.p, par.p, below_b, partial.p};
+      int used = 0;
+      const cudaError_t le = pw == LPMP_PAIRWISE_POTTS ? launch_grid_bound<Real, LPMP_PAIRWISE_POTTS>(B, L, 0, kBoundCtas, &used, stream)
+                                                       : launch_grid_bound<Real, LPMP_PAIRWISE_TRUNCLIN>(B, L, tl_hops(), kBoundCtas, &used, stream);
+      CUDA_TRY(le);
+      ++launches;
+      return reduce_to_host(used, add, out);
+    }
     if (is_grid) {
       GridTopo<Real> topo{gridH, gridW, slots, below_b};
       lower_bound_kernel<Real, GridTopo<Real>><<<ctas, threads, (size_t)groups * per_group, stream>>>(bound_args(topo), G);

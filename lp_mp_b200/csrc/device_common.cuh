@@ -130,6 +130,21 @@ __device__ __forceinline__ void group_min_plus(int pw, const Real* __restrict__ 
   }
 }
 
+// sum over the CTA, valid in thread 0 (fixed tree: deterministic)
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < (int)((blockDim.x + 31) >> 5) ? red[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;  // valid in thread 0
+}
+
 // smallest power of two >= min(L, 32)
 __host__ __device__ inline int group_size_for(uint32_t L) {
   int g = 1;

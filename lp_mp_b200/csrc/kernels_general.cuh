@@ -159,20 +159,6 @@ struct BoundArgs {
   double* partial;  // [gridDim.x]
 };
 
-__device__ __forceinline__ double block_sum(double v) {
-  __shared__ double red[32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if (lane == 0) red[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    v = lane < (int)((blockDim.x + 31) >> 5) ? red[lane] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  }
-  return v;  // valid in thread 0
-}
-
 // LP::LowerBound (include/LP_MP.h:1507-1518): sum_i min theta_i + sum_e min_x [a_e(x) + min_y (c_e(x,y) + b_e(y))]
 template <typename Real, typename Topo>
 __global__ void __launch_bounds__(256) lower_bound_kernel(BoundArgs<Real, Topo> A, int G) {

@@ -21,7 +21,7 @@
 //     column neighbour's vector moves one lane-group up by a warp shuffle -- no memory round trip inside a band;
 //   * bands are claimed in order from an atomic ticket; the last row of band k hands its outgoing column vectors to
 //     band k+1 through a hand-off buffer in L2 whose slots carry their own validity (a slot holds a NaN sentinel
-//     until the producer stores the vector; the consumer polls the slot itself -- two steps ahead -- and puts the
+//     until the producer stores the vector; the consumer polls the slot itself -- PD steps ahead, PD loads in flight -- and puts the
 //     sentinel back after reading).  No flag, no fence: one store and one load per lane and column;
 //   * interior steps of interior bands run a straight-line FAST path without any existence predicate (missing
 //     edges of the first row are exact no-ops because their record slots and parameters are zero); the first /
@@ -134,6 +134,8 @@ struct WavefrontCfg {
   static constexpr int NSLOT = 4;                        // tiles in the ring
   static constexpr int PDC = 2;                          // tiles of prefetch distance
   static constexpr int K = KSEL;
+  static constexpr int PD = KSEL == 4 ? 4 : 2;           // hand-off slots polled ahead (L2 round trips in flight per band):
+                                                         // narrow tiles = bandwidth-bound grids, where the loaded L2 latency is several steps
   static constexpr int LOGK = K == 8 ? 3 : 2;
   static constexpr int SLOT_REC = (T + 1) * K * REC;     // reals
   static constexpr int SLOT_PAR = T * K * PREC;
@@ -292,7 +294,7 @@ template <typename Real, int PW, int L, int HOPS, bool ANISO, int KSEL>
 __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_rec1,
                                                             const __grid_constant__ CUtensorMap tm_par, const GridArgs<Real> A) {
   using Cfg = WavefrontCfg<Real, PW, L, KSEL>;
-  constexpr int G = Cfg::G, T = Cfg::T, P = Cfg::P, K = Cfg::K, LOGK = Cfg::LOGK, REC = Cfg::REC, PREC = Cfg::PREC, NSLOT = Cfg::NSLOT, PDC = Cfg::PDC;
+  constexpr int G = Cfg::G, T = Cfg::T, P = Cfg::P, K = Cfg::K, PD = Cfg::PD, LOGK = Cfg::LOGK, REC = Cfg::REC, PREC = Cfg::PREC, NSLOT = Cfg::NSLOT, PDC = Cfg::PDC;
   constexpr int BOXROWS = ANISO ? T : T + 1;           // the uniform modes also read the first row of the next band
   constexpr int HAND_BYTES = 4 * (int)sizeof(Real);
   constexpr uint32_t S = (uint32_t)sizeof(Real);
@@ -413,12 +415,15 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
     };
     stamp(0);
 
-    // the hand-off slot of column q+1 is polled right after column q has been consumed, one step before its use,
-    // so that the L2 round trip is off the dependency chain
-    Real polled[4];
+    // the hand-off slot of column q+PD is polled right after column q has been consumed, PD steps before its use,
+    // so that the L2 round trip (336 cycles idle, several times that under load) is off the dependency chain
+    Real polled[PD][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) polled[k] = Real(0);
-    if (poller) ld_relaxed<HAND_BYTES>(polled, hand_in);
+    for (int d = 0; d < PD; ++d) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) polled[d][k] = Real(0);
+      ld_relaxed_if<HAND_BYTES>(poller && d < (int)W, polled[d], hand_in + d * L);
+    }
 
     Real carry_row[4], carry_col[4];
 #pragma unroll
@@ -471,16 +476,16 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
       Real col_in[4];
       const bool polling = poller && q >= 0 && q < (int)W;
       const Real* const hslot = hand_in + (int64_t)q * L;
-      if (__any_sync(FULL, polling && (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3])))) {
+      if (__any_sync(FULL, polling && (is_sentinel(polled[0][0]) || is_sentinel(polled[0][1]) || is_sentinel(polled[0][2]) || is_sentinel(polled[0][3])))) {
         if (polling) {
           unsigned spins = 0;
-          while (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3])) {
-            ld_relaxed<HAND_BYTES>(polled, hslot);
+          while (is_sentinel(polled[0][0]) || is_sentinel(polled[0][1]) || is_sentinel(polled[0][2]) || is_sentinel(polled[0][3])) {
+            ld_relaxed<HAND_BYTES>(polled[0], hslot);
             if ((++spins & 0x3ffu) == 0) {      // bounded wait: a lost producer must not hang the device
               if (spins > (1u << 22)) atomicExch(A.control + 1, 1u);
               if (*reinterpret_cast<volatile unsigned int*>(A.control + 1) != 0u) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) polled[k] = Real(0);
+                for (int k = 0; k < 4; ++k) polled[0][k] = Real(0);
               }
             }
           }
@@ -488,13 +493,22 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
         __syncwarp();
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) col_in[k] = polling ? polled[k] : carry_col[k];
+      for (int k = 0; k < 4; ++k) col_in[k] = polling ? polled[0][k] : carry_col[k];
       {
         Real sent[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) sent[k] = sentinel<Real>();
         st_relaxed_if<HAND_BYTES>(polling, const_cast<Real*>(hslot), sent);        // the slot is free again for the next pass
-        ld_relaxed_if<HAND_BYTES>(polling && q + 1 < (int)W, polled, hslot + L);
+        // the poll ring advances once the polling group has entered the grid (warp-uniform); slot q + PD is requested
+        // now and consumed PD steps later, so PD L2 round trips are in flight per band
+        if (sp - t_in - qoff >= 0) {
+#pragma unroll
+          for (int d = 0; d + 1 < PD; ++d) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) polled[d][k] = polled[d + 1][k];
+          }
+        }
+        ld_relaxed_if<HAND_BYTES>(polling && q + PD < (int)W, polled[PD - 1], hslot + PD * L);
       }
 
       Real out_col[4];

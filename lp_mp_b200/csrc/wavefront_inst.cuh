@@ -13,11 +13,13 @@ static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& arg
   } else {
     auto kernel = wavefront_pass_kernel<Real, PW, L, HOPS, ANISO, KSEL>;
     const size_t smem = Cfg::SMEM_BYTES;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};   // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
       cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      configured = true;
+      configured[dev & 63] = true;
     }
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32, smem);
@@ -61,6 +63,49 @@ cudaError_t launch_family(const CUtensorMap* maps, const GridArgs<Real>& args, u
     default: return cudaErrorInvalidValue;
   }
 }
+
+#if LPMP_INST_ANISO
+template <typename Real, int PW, int L, int HOPS>
+static cudaError_t launch_bound_one(const GridBoundArgs<Real>& args, int max_ctas, int* ctas_out, cudaStream_t stream) {
+  auto kernel = grid_bound_kernel<Real, PW, L, HOPS>;
+  constexpr size_t smem = grid_bound_smem<Real, PW, L>();
+  static bool configured[64] = {};   // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63] && smem > 40 * 1024) {   // static shared memory (block_sum) counts towards the 48 KiB default limit
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[dev & 63] = true;
+  }
+  constexpr int nodes_per_cta = kGridBoundWarps * (32 / (L / 4));
+  const uint64_t N = (uint64_t)args.H * args.W;
+  uint64_t ctas = (N + nodes_per_cta - 1) / nodes_per_cta;
+  if (ctas > (uint64_t)max_ctas) ctas = max_ctas;
+  if (ctas < 1) ctas = 1;
+  *ctas_out = (int)ctas;
+  kernel<<<(int)ctas, 32 * kGridBoundWarps, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+template <typename Real, int PW, int L>
+static cudaError_t launch_bound_hops(const GridBoundArgs<Real>& args, int hops, int max_ctas, int* ctas, cudaStream_t stream) {
+  if constexpr (PW == LPMP_PAIRWISE_TRUNCLIN) {
+    if (hops == 1) return launch_bound_one<Real, PW, L, 1>(args, max_ctas, ctas, stream);
+    if (hops == 2 && L >= 16) return launch_bound_one<Real, PW, L, 2>(args, max_ctas, ctas, stream);
+  }
+  return launch_bound_one<Real, PW, L, 0>(args, max_ctas, ctas, stream);
+}
+template <typename Real, int PW>
+cudaError_t launch_grid_bound(const GridBoundArgs<Real>& args, uint32_t L, int hops, int max_ctas, int* ctas, cudaStream_t stream) {
+  switch (L) {
+    case 8: return launch_bound_hops<Real, PW, 8>(args, hops, max_ctas, ctas, stream);
+    case 16: return launch_bound_hops<Real, PW, 16>(args, hops, max_ctas, ctas, stream);
+    case 32: return launch_bound_hops<Real, PW, 32>(args, hops, max_ctas, ctas, stream);
+    case 64: return launch_bound_hops<Real, PW, 64>(args, hops, max_ctas, ctas, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+template cudaError_t launch_grid_bound<LPMP_INST_REAL, LPMP_INST_PW>(const GridBoundArgs<LPMP_INST_REAL>&, uint32_t, int, int, int*, cudaStream_t);
+#endif
 
 template cudaError_t launch_family<LPMP_INST_REAL, LPMP_INST_PW, LPMP_INST_ANISO>(const CUtensorMap*, const GridArgs<LPMP_INST_REAL>&, uint32_t, int, int,
                                                                                   const WavefrontTuning&, int, cudaStream_t);

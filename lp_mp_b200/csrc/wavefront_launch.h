@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "kernels_grid.cuh"
+#include "kernels_grid_bound.cuh"
 
 namespace lpmp {
 
@@ -56,5 +57,10 @@ inline bool wavefront_shape(int pw, uint32_t L, WavefrontShape& s) {
 template <typename Real, int PW, bool ANISO>
 cudaError_t launch_family(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int hops, int ksel, const WavefrontTuning& tune, int num_sms,
                           cudaStream_t stream);
+
+// one streaming sweep over the node records (kernels_grid_bound.cuh); same (pw, L) coverage as the wavefront kernels.
+// Writes one partial sum per CTA into args.partial and returns the number of CTAs through *ctas.
+template <typename Real, int PW>
+cudaError_t launch_grid_bound(const GridBoundArgs<Real>& args, uint32_t L, int hops, int max_ctas, int* ctas, cudaStream_t stream);
 
 }  // namespace lpmp
