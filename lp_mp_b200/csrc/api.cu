@@ -124,6 +124,34 @@ __global__ void synth_edge_kernel(Real* __restrict__ par, uint32_t H, uint32_t W
   }
 }
 
+// dense tables of a plane of grid edges, compact [rows][cols][P], into the padded table plane (pitch W tables per row)
+template <typename Dst, typename Src>
+__global__ void scatter_tables_kernel(Dst* __restrict__ plane, const Src* __restrict__ src, uint32_t rows, uint32_t cols, uint32_t W, uint32_t P) {
+  const uint64_t n = (uint64_t)rows * cols * P;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t cell = k / P;
+    plane[((cell / cols) * W + (cell % cols)) * P + (k % P)] = (Dst)src[k];
+  }
+}
+// synthetic dense tables: plane = tabH (vertical == 0, rows [0, H)) or tabV (vertical == 1, plane rows [0, H] hold the
+// edges leaving grid rows [-1, H-1]); counters are slot indices of the FULL grid, as in synth_edge_kernel
+template <typename Real>
+__global__ void synth_tables_kernel(Real* __restrict__ plane, uint32_t H, uint32_t W, uint32_t P, uint32_t row0, uint32_t H_total, int vertical,
+                                    uint64_t seed, double lo, double hi) {
+  const uint64_t rows = vertical ? (uint64_t)H + 1 : H;
+  const uint64_t n = rows * W * P;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = (uint32_t)(k % P);
+    const uint64_t cell = k / P;
+    const uint32_t c = (uint32_t)(cell % W);
+    const int64_t gr = (int64_t)row0 + (int64_t)(cell / W) - (vertical ? 1 : 0);   // full-grid row of the edge's first endpoint
+    if (gr < 0) continue;
+    if (vertical ? gr + 1 >= (int64_t)H_total : c + 1 >= W) continue;               // no such edge
+    const uint64_t slot = (uint64_t)gr * W + c;
+    plane[k] = (Real)lpmp_synth_param(seed, vertical ? LPMP_SYNTH_STREAM_VERTICAL : LPMP_SYNTH_STREAM_HORIZONTAL, slot * P + p, lo, hi);
+  }
+}
+
 static inline int grid_for(uint64_t n, int block, int cap = 148 * 16) {
   uint64_t g = (n + block - 1) / block;
   if (g < 1) g = 1;
@@ -198,6 +226,8 @@ struct Solver : ISolver {
   std::vector<uint64_t> h_ei, h_ej, h_rank;
   // device state.  General graphs: theta[N][L], a[E][L], b[E][L], params[E][P].  Grids: rec[N][5][L], par[N][4][P].
   DeviceBuffer<Real> theta, a, b, params, rec, par;
+  DeviceBuffer<Real> tab;    // dense grids: table planes tabH [H][W][L*L] then tabV [H+1][W][L*L] (kernels_grid_dense.cuh)
+  bool levels_built = false; // CSR + level sets uploaded (general graphs; grids on demand)
   DeviceBuffer<Real> handoff, in_top, in_bot;   // band-to-band / stripe-to-stripe column vectors (sentinel protocol)
   Real* peer_top = nullptr;  // upper neighbour's in_bot (delivery target of the backward pass), or null
   Real* peer_bot = nullptr;  // lower neighbour's in_top (delivery target of the forward pass), or null
@@ -324,9 +354,14 @@ struct Solver : ISolver {
     slots = 2 * N;
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(rec.alloc(N * REC()));
-    CUDA_TRY(par.alloc(N * PREC()));
     CUDA_TRY(cudaMemsetAsync(rec.p, 0, rec.bytes(), stream));
-    CUDA_TRY(cudaMemsetAsync(par.p, 0, par.bytes(), stream));
+    if (pw == LPMP_PAIRWISE_DENSE) {
+      CUDA_TRY(tab.alloc((2 * N + W) * (uint64_t)P()));
+      CUDA_TRY(cudaMemsetAsync(tab.p, 0, tab.bytes(), stream));
+    } else {
+      CUDA_TRY(par.alloc(N * PREC()));
+      CUDA_TRY(cudaMemsetAsync(par.p, 0, par.bytes(), stream));
+    }
     return LPMP_OK;
   }
   template <typename Src>
@@ -364,10 +399,34 @@ struct Solver : ISolver {
     CUDA_TRY(cudaStreamSynchronize(stream));
     return LPMP_OK;
   }
+  Real* tabH() const { return tab.p; }
+  Real* tabV() const { return tab.p + N * (uint64_t)P(); }   // plane row k = edges leaving grid row k-1
+  template <typename Src>
+  int set_table_plane(const Src* src, uint32_t rows, uint32_t cols, Real* plane) {
+    const uint64_t n = (uint64_t)rows * cols * P();
+    if (n == 0 || !src) return LPMP_OK;
+    DeviceBuffer<Src> tmp;
+    if (int r = upload(tmp, src, n)) return r;
+    scatter_tables_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(plane, tmp.p, rows, cols, gridW, P());
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
   int grid_set_pairwise(const void* hz, const void* vt, int src) override {
     if (!is_grid) return bad_state("not a grid");
-    if (pw == LPMP_PAIRWISE_DENSE) { err = "dense tables on the grid API are not supported: use add_pairwise_dense"; return LPMP_ERR_UNSUPPORTED; }
     int r;
+    if (pw == LPMP_PAIRWISE_DENSE) {
+      Real* const vplane = tabV() + (uint64_t)gridW * P();
+      if (src == LPMP_F32) {
+        r = set_table_plane(static_cast<const float*>(hz), gridH, gridW - 1, tabH());
+        if (r == LPMP_OK) r = set_table_plane(static_cast<const float*>(vt), gridH - 1, gridW, vplane);
+      } else {
+        r = set_table_plane(static_cast<const double*>(hz), gridH, gridW - 1, tabH());
+        if (r == LPMP_OK) r = set_table_plane(static_cast<const double*>(vt), gridH - 1, gridW, vplane);
+      }
+      return r;
+    }
     if (src == LPMP_F32) {
       r = set_edge_plane(static_cast<const float*>(hz), gridH, gridW - 1, 1, PAR_R, PAR_L);
       if (r == LPMP_OK) r = set_edge_plane(static_cast<const float*>(vt), gridH - 1, gridW, gridW, PAR_D, PAR_U);
@@ -379,8 +438,15 @@ struct Solver : ISolver {
   }
   int grid_fill_synthetic(uint64_t seed, double lo, double hi) override {
     if (!is_grid) return bad_state("not a grid");
-    if (pw == LPMP_PAIRWISE_DENSE) { err = "dense tables on the grid API are not supported"; return LPMP_ERR_UNSUPPORTED; }
     const uint32_t Pn = P();
+    if (pw == LPMP_PAIRWISE_DENSE) {
+      synth_unary_kernel<Real><<<grid_for(N * L, 256), 256, 0, stream>>>(rec.p, N, L, REC(), (uint64_t)row0 * gridW, seed);
+      synth_tables_kernel<Real><<<grid_for(N * Pn, 256, 148 * 32), 256, 0, stream>>>(tabH(), gridH, gridW, Pn, row0, H_total, 0, seed, lo, hi);
+      synth_tables_kernel<Real><<<grid_for((N + gridW) * Pn, 256, 148 * 32), 256, 0, stream>>>(tabV(), gridH, gridW, Pn, row0, H_total, 1, seed, lo, hi);
+      launches += 3;
+      CUDA_TRY(cudaGetLastError());
+      return LPMP_OK;
+    }
     const int tl = pw == LPMP_PAIRWISE_TRUNCLIN;
     if (tl) note_trunclin(lo, hi);
     synth_unary_kernel<Real><<<grid_for(N * L, 256), 256, 0, stream>>>(rec.p, N, L, REC(), (uint64_t)row0 * gridW, seed);
@@ -402,6 +468,7 @@ struct Solver : ISolver {
   }
   int grid_set_boundary_pairwise(const void* top, const void* bottom, int src) override {
     if (!striped) return bad_state("grid_set_boundary_pairwise: not a stripe");
+    if (pw == LPMP_PAIRWISE_DENSE) { err = "stripe-boundary tables: only the synthetic fill is supported for dense grids"; return LPMP_ERR_UNSUPPORTED; }
     int r = LPMP_OK;
     // top[c]: edge (row0-1, c)-(row0, c): field U of the first row; bottom[c]: edge (last row, c)-(below): field D of the last row
     if (src == LPMP_F32) {
@@ -466,8 +533,9 @@ struct Solver : ISolver {
       s.theta = rec.p; s.theta_stride = R;
       s.a0 = rec.p + (uint64_t)REC_AR * L; s.a1 = rec.p + (uint64_t)REC_AD * L;
       s.b0 = rec.p + R + (uint64_t)REC_BL * L; s.b1 = rec.p + (uint64_t)gridW * R + (uint64_t)REC_BU * L;
-      s.p0 = par.p + (uint64_t)PAR_R * Pn; s.p1 = par.p + (uint64_t)PAR_D * Pn;
-      s.split = N; s.estride = R; s.pstride = PREC();
+      s.split = N; s.estride = R;
+      if (pw == LPMP_PAIRWISE_DENSE) { s.p0 = tabH(); s.p1 = tabV() + (uint64_t)gridW * Pn; s.pstride = Pn; }
+      else { s.p0 = par.p + (uint64_t)PAR_R * Pn; s.p1 = par.p + (uint64_t)PAR_D * Pn; s.pstride = PREC(); }
     } else {
       s.theta = theta.p; s.theta_stride = L;
       s.a0 = s.a1 = a.p; s.b0 = s.b1 = b.p; s.p0 = s.p1 = params.p;
@@ -537,7 +605,13 @@ struct Solver : ISolver {
     if (m) CUDA_TRY(cudaMemcpyAsync(inc_flags.p, inc_f.data(), 2 * m, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(level_nodes.p, lnodes.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
+    levels_built = true;
     return LPMP_OK;
+  }
+  int build_grid_levels() {
+    std::vector<uint64_t> ei, ej, slot;
+    grid_edge_lists(ei, ej, slot);
+    return build_levels(ei, ej, slot);
   }
 
   // TMA descriptors of the record / parameter arrays: tiles of `rows` grid rows x K columns of whole records
@@ -602,14 +676,18 @@ struct Solver : ISolver {
       if (int r = build_levels(h_ei, h_ej, slot)) return r;
       h_theta.clear(); h_theta.shrink_to_fit(); h_params.clear(); h_params.shrink_to_fit();
     } else {
-      const bool wf_ok = wavefront_shape<Real>(pw, L, shape) && h_rank.empty();
+      const bool dense = pw == LPMP_PAIRWISE_DENSE;
+      const bool wf_ok = (dense ? dense_wavefront_supported<Real>(L) : wavefront_shape<Real>(pw, L, shape)) && h_rank.empty();
       if (schedule == -1) schedule = wf_ok ? LPMP_SCHEDULE_WAVEFRONT : LPMP_SCHEDULE_LEVELS;
       if (schedule == LPMP_SCHEDULE_WAVEFRONT && !wf_ok) { err = "no wavefront kernel for this label count / pairwise family"; return LPMP_ERR_UNSUPPORTED; }
       if (schedule == LPMP_SCHEDULE_LEVELS) {
         if (striped) { err = "stripes need the wavefront schedule"; return LPMP_ERR_UNSUPPORTED; }
-        std::vector<uint64_t> ei, ej, slot;
-        grid_edge_lists(ei, ej, slot);
-        if (int r = build_levels(ei, ej, slot)) return r;
+        if (int r = build_grid_levels()) return r;
+      } else if (dense) {
+        CUDA_TRY(control.alloc(2));
+        CUDA_TRY(cudaMemsetAsync(control.p, 0, control.bytes(), stream));
+        CUDA_TRY(handoff.alloc((size_t)gridH * gridW * L));
+        CUDA_TRY(cudaMemsetAsync(handoff.p, 0xff, handoff.bytes(), stream));
       } else {
         const uint32_t bands = (gridH + shape.T - 1) / shape.T;
         CUDA_TRY(control.alloc(2));
@@ -645,7 +723,14 @@ struct Solver : ISolver {
     if (int r = need_final()) return r;
     if (repam < 0) return bad_state("no reparametrization mode set");  // include/LP_MP.h:458
     CUDA_TRY(cudaSetDevice(device));
-    if (schedule == LPMP_SCHEDULE_LEVELS) {
+    // dense-table grids: the row-dataflow kernel covers the anisotropic mode; the uniform modes of the rounding
+    // iterations (include/visitors/standard_visitor.hxx:44) run on the level schedule, built on first use
+    const bool dense_wf = schedule == LPMP_SCHEDULE_WAVEFRONT && pw == LPMP_PAIRWISE_DENSE;
+    if (dense_wf && repam != LPMP_REPAM_ANISOTROPIC && !levels_built) {
+      if (striped) { err = "stripes support the anisotropic reparametrization only"; return LPMP_ERR_UNSUPPORTED; }
+      if (int r = build_grid_levels()) return r;
+    }
+    if (schedule == LPMP_SCHEDULE_LEVELS || (dense_wf && repam != LPMP_REPAM_ANISOTROPIC)) {
       const int G = group_size_for(L);
       int threads = 256;
       size_t per_group = 4 * (size_t)L * sizeof(Real);
@@ -667,6 +752,20 @@ struct Solver : ISolver {
         ++launches;
       }
       CUDA_TRY(cudaGetLastError());
+    } else if (dense_wf) {
+      DenseGridArgs<Real> A;
+      A.H = gridH; A.W = gridW;
+      A.forward = forward ? 1 : 0; A.primal = primal ? 1 : 0; A.fifo = edge_order == LPMP_EDGE_ORDER_FIFO;
+      const bool has_above = row0 > 0, has_below = row0 + gridH < H_total;
+      A.in_halo = forward ? has_above : has_below;
+      A.out_halo = forward ? has_below : has_above;
+      A.control = control.p; A.rec = rec.p; A.tabH = tabH(); A.tabV = tabV(); A.handoff = handoff.p;
+      A.in_boundary = forward ? in_top.p : in_bot.p;
+      A.out_boundary = forward ? peer_bot : peer_top;
+      A.labels = labels.p;
+      CUDA_TRY(cudaMemsetAsync(control.p, 0, sizeof(unsigned int), stream));
+      CUDA_TRY(launch_dense_pass<Real>(A, L, tune, num_sms, stream));
+      ++launches;
     } else {
       if (striped && repam != LPMP_REPAM_ANISOTROPIC) { err = "stripes support the anisotropic reparametrization only"; return LPMP_ERR_UNSUPPORTED; }
       GridArgs<Real> A;
@@ -734,7 +833,7 @@ struct Solver : ISolver {
     const int groups = threads / G;
     const uint64_t total = N + slots;
     const int ctas = (int)std::min<uint64_t>((total + groups - 1) / groups, (uint64_t)kBoundCtas);
-    if (is_grid && schedule == LPMP_SCHEDULE_WAVEFRONT) {
+    if (is_grid && schedule == LPMP_SCHEDULE_WAVEFRONT && pw != LPMP_PAIRWISE_DENSE) {
       // record-streaming sweep (kernels_grid_bound.cuh): every record and parameter is read once
       GridBoundArgs<Real> B{gridH, gridW, rec.p, par.p, below_b, partial.p};
       int used = 0;
@@ -902,7 +1001,7 @@ struct Solver : ISolver {
     else out->num_levels = level_off.empty() ? 0 : level_off.size() - 1;
     out->kernel_launches = launches;
     out->message_updates = updates;
-    out->device_bytes = theta.bytes() + a.bytes() + b.bytes() + params.bytes() + rec.bytes() + par.bytes() + labels.bytes() + inc_off.bytes() +
+    out->device_bytes = theta.bytes() + a.bytes() + b.bytes() + params.bytes() + rec.bytes() + par.bytes() + tab.bytes() + labels.bytes() + inc_off.bytes() +
                         inc_edge.bytes() + inc_flags.bytes() + level_nodes.bytes() + d_ei.bytes() + d_ej.bytes() + control.bytes() + handoff.bytes() +
                         in_top.bytes() + in_bot.bytes();
     out->algorithmic_bytes_per_pass = (double)sizeof(Real) * (2.0 * (double)N * L + (double)E * ((double)P() + 5.0 * L));

@@ -7,6 +7,7 @@
 
 #include "kernels_grid.cuh"
 #include "kernels_grid_bound.cuh"
+#include "kernels_grid_dense.cuh"
 
 namespace lpmp {
 
@@ -57,6 +58,19 @@ inline bool wavefront_shape(int pw, uint32_t L, WavefrontShape& s) {
 template <typename Real, int PW, bool ANISO>
 cudaError_t launch_family(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int hops, int ksel, const WavefrontTuning& tune, int num_sms,
                           cudaStream_t stream);
+
+// dense-table grids (kernels_grid_dense.cuh): anisotropic passes for L in {16, 32, 64}
+template <typename Real>
+inline bool dense_wavefront_supported(uint32_t L) {
+  switch (L) {
+    case 16: return DenseCfg<Real, 16>::FITS;
+    case 32: return DenseCfg<Real, 32>::FITS;
+    case 64: return DenseCfg<Real, 64>::FITS;
+    default: return false;
+  }
+}
+template <typename Real>
+cudaError_t launch_dense_pass(const DenseGridArgs<Real>& args, uint32_t L, const WavefrontTuning& tune, int num_sms, cudaStream_t stream);
 
 // one streaming sweep over the node records (kernels_grid_bound.cuh); same (pw, L) coverage as the wavefront kernels.
 // Writes one partial sum per CTA into args.partial and returns the number of CTAs through *ctas.

@@ -225,6 +225,8 @@ def grid_pair(dtype, H, W, L, kind, seed, schedule="wavefront", edge_order="lifo
     theta = rng.random((H, W, L))
     if kind == "potts":
         hz, vt = rng.uniform(-0.3, 1.0, size=(H, W - 1, 1)), rng.uniform(-0.3, 1.0, size=(H - 1, W, 1))
+    elif kind == "dense":
+        hz, vt = rng.uniform(-0.5, 1.0, size=(H, W - 1, L * L)), rng.uniform(-0.5, 1.0, size=(H - 1, W, L * L))
     else:
         hz = np.stack([rng.uniform(0.05, 0.5, size=(H, W - 1)), rng.uniform(0.2, 1.5, size=(H, W - 1))], axis=-1)
         vt = np.stack([rng.uniform(0.05, 0.5, size=(H - 1, W)), rng.uniform(0.2, 1.5, size=(H - 1, W))], axis=-1)
@@ -289,6 +291,54 @@ def test_synthetic_generator_matches_oracle():
         for lp in lps:
             lp.grid_fill_synthetic(0x5EED, lo, hi)
         run_lockstep(lps, "anisotropic", iters=3, lb_rtol=1e-6)
+
+
+# ---- grids with dense tables: row-dataflow kernel (BASELINE config 5 shape) --------------------------------------------
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("L", [16, 32, 64])
+def test_dense_grid_bit_parity(dtype, L):
+    lps = grid_pair(dtype, 23, 19, L, "dense", seed=L)
+    run_lockstep(lps, "anisotropic", iters=3, lb_rtol=LB_RTOL[dtype])
+
+
+@pytest.mark.parametrize("H,W", [(1, 1), (1, 7), (7, 1), (2, 2), (3, 40), (40, 3)])
+def test_dense_grid_ragged_shapes(H, W):
+    lps = grid_pair("f64", H, W, 16, "dense", seed=H * 100 + W)
+    run_lockstep(lps, "anisotropic", iters=3)
+
+
+@pytest.mark.parametrize("tuning", [dict(wavefront_max_ctas=1), dict(wavefront_max_ctas=5), dict(wavefront_ctas_per_sm=1)])
+def test_dense_grid_launch_shapes_do_not_change_results(tuning):
+    lps = grid_pair("f32", 31, 45, 64, "dense", seed=9, **tuning)
+    run_lockstep(lps, "anisotropic", iters=2, lb_rtol=1e-6)
+
+
+def test_dense_grid_fifo_and_uniform_modes():
+    """FIFO message order; the uniform modes of the rounding iterations run on the level schedule of the same state"""
+    lps = grid_pair("f64", 12, 14, 32, "dense", seed=6, edge_order="fifo")
+    run_lockstep(lps, "anisotropic", iters=3)
+    lps = grid_pair("f64", 12, 14, 16, "dense", seed=7)
+    run_lockstep(lps, "anisotropic", iters=2)
+    for lp in lps:
+        lp.set_reparametrization("damped_uniform")
+        lp.ComputePass(2)
+    assert np.array_equal(lps[0].unaries(), lps[1].unaries())
+    for lp in lps:
+        lp.set_reparametrization("anisotropic")
+        lp.ComputePass(3)
+    assert np.array_equal(lps[0].unaries(), lps[1].unaries())
+    a0, b0 = lps[0].messages(); a1, b1 = lps[1].messages()
+    assert np.array_equal(a0, a1) and np.array_equal(b0, b1)
+
+
+def test_dense_grid_equals_level_schedule_and_synthetic_generator():
+    for dtype in ("f32", "f64"):
+        lps = [oracle_lp(dtype).grid_create(17, 22, 64, "dense"), cuda_lp(dtype).grid_create(17, 22, 64, "dense"),
+               cuda_lp(dtype).grid_create(17, 22, 64, "dense")]
+        lps[2].set_schedule("levels")
+        for lp in lps:
+            lp.grid_fill_synthetic(0x5EED, 0.0, 1.0)
+        run_lockstep(lps, "anisotropic", iters=3, lb_rtol=LB_RTOL[dtype])
 
 
 # ---- row stripes (multi-GPU path) exercised with two handles on ONE device ------------------------------------------------
