@@ -30,7 +30,15 @@ WORKLOADS = {
     "C1": (64, 64, 8, "potts", 0.1, 1.0, "64x64 Potts grid, 8 labels (BASELINE config 1)"),
     "C2": (1024, 1024, 16, "trunclin", 0.25, 1.0, "1024x1024 truncated-linear grid, 16 labels (BASELINE config 2)"),
     "C3": (4096, 4096, 32, "potts", 0.1, 1.0, "4096x4096 Potts grid, 32 labels (BASELINE config 3)"),
+    "C5": (2048, 2048, 64, "dense", 0.0, 1.0, "2048x2048 grid, dense 64x64 pairwise tables (BASELINE config 5)"),
+    # half of C5's rows: same kernel and per-row behaviour in 72 GB instead of 143 GB of HBM
+    "C5h": (1024, 2048, 64, "dense", 0.0, 1.0, "1024x2048 grid, dense 64x64 pairwise tables (upper half of BASELINE config 5)"),
 }
+GRAPH_WORKLOADS = {
+    # name: (nodes, degree, L, description)
+    "C4": (1_000_000, 3, 8, "random 3-regular graph, 1M nodes, 8 labels, dense tables, graph-colouring schedule (BASELINE config 4)"),
+}
+PASS_KERNEL = {"potts": "wavefront_pass_kernel", "trunclin": "wavefront_pass_kernel", "dense": "dense_row_pass_kernel"}
 SEED = 0x5EED
 METRIC = "pairwise msg updates/s on grid MRF"
 UNIT = "msg_updates/s"
@@ -99,6 +107,8 @@ def cpu_port_baseline(H, W, L, pairwise, lo, hi, budget_s=12.0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from checkers import oracle_lp
     rows = H
+    if pairwise == "dense":
+        W = min(W, 256)    # the oracle holds tables in f64: 32 KiB per edge at L = 64
     probe = oracle_lp("f64").grid_create(min(H, 64), W, L, pairwise)
     probe.grid_fill_synthetic(SEED, lo, hi)
     probe.finalize(); probe.Begin(); probe.set_reparametrization("anisotropic")
@@ -169,6 +179,192 @@ def reference_arm(args, H, W, L, pairwise, lo, hi):
     }
 
 
+# ---- general graphs (BASELINE config 4) ------------------------------------------------------------------------------
+def random_regular_graph(n, d, seed):
+    """Configuration model with local repair of self loops / multi-edges (numpy; n*d even)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    stubs = np.repeat(np.arange(n, dtype=np.int64), d)
+    rng.shuffle(stubs)
+    a, b = stubs[0::2].copy(), stubs[1::2].copy()
+    for _ in range(200):
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        key = lo * n + hi
+        order = np.argsort(key, kind="stable")
+        dup = np.zeros(len(key), dtype=bool)
+        dup[order[1:]] = key[order[1:]] == key[order[:-1]]
+        bad = np.flatnonzero(dup | (a == b))
+        if len(bad) == 0:
+            return lo.astype(np.uint64), hi.astype(np.uint64)
+        # re-pair the stubs of the bad edges with those of as many random good edges
+        pick = np.unique(np.concatenate([bad, rng.integers(0, len(a), size=len(bad) + 1)]))
+        pool = np.concatenate([a[pick], b[pick]])
+        rng.shuffle(pool)
+        a[pick], b[pick] = pool[: len(pick)], pool[len(pick):]
+    raise RuntimeError("could not repair the configuration model")
+
+
+def graph_main(args, rank, world, local_rank):
+    """C4: replicas only (a random 3-regular graph is an expander: no balanced partition with a small cut):
+    every rank solves the same problem, value = sum of the ranks' throughputs."""
+    import numpy as np
+    n, deg, L, desc = GRAPH_WORKLOADS[args.workload]
+    ei, ej = random_regular_graph(n, deg, SEED)
+    E = len(ei)
+    rng = np.random.default_rng(SEED)
+    theta = rng.random((n, L))
+    tables = rng.random((E, L, L))
+
+    if args.impl == "reference":
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from checkers import oracle_lp
+            m = 200_000   # bounded sample: a random 3-regular graph of the same family on m nodes
+            si, sj = random_regular_graph(m, deg, SEED)
+            keep = np.ones(len(si), dtype=bool)
+            lp = oracle_lp("f64")
+            lp.add_unaries(theta[:m]); lp.add_pairwise_dense(si, sj, tables[: len(si)])
+            lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+            for it in range(args.warmup):
+                lp.ComputePass(it); lp.LowerBound()
+            t0 = time.perf_counter()
+            for it in range(args.steps):
+                lp.ComputePass(args.warmup + it); lp.LowerBound()
+            dt = time.perf_counter() - t0
+            value = 4.0 * int(keep.sum()) * args.steps / dt
+            sample = f"random {deg}-regular graph on {m} nodes ({int(keep.sum())} edges) per step, f64, 1 thread, natural order, oracle/lpmp_oracle.cpp"
+            print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                              "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+                              "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload, "sample": sample},
+                              "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+                              "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        os._exit(0)
+
+    import torch
+    import lp_mp_b200
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    s = 4 if args.dtype == "f32" else 8
+
+    def build():
+        lp = lp_mp_b200.LP(dtype=args.dtype, device=local_rank)
+        lp.add_unaries(theta)
+        lp.add_pairwise_dense(ei, ej, tables)
+        colour, nc = lp.greedy_colouring(ei, ej)
+        lp.set_node_ranks(colour.astype(np.uint64) * n + np.arange(n, dtype=np.uint64))
+        lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+        return lp, nc
+
+    lp, nc = build()
+    stream = torch.cuda.ExternalStream(lp.stream(), device=local_rank)
+    for it in range(args.warmup):
+        lp.ComputePass(it); lp.LowerBound()
+    lp.synchronize()
+    launches0 = lp.stats()["kernel_launches"]
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    pass_ev = []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev[0].record(stream)
+    lb = None
+    for it in range(args.steps):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(stream); lp.ComputeForwardPass(); e[1].record(stream); lp.ComputeBackwardPass(); e[2].record(stream)
+        pass_ev.append(e)
+        lb = lp.LowerBound()
+    ev[1].record(stream)
+    lp.synchronize(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    clock_info = clocks.stop() if rank == 0 else None
+    stats = lp.stats()
+    launches = stats["kernel_launches"] - launches0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * 4.0 * E * args.steps / (ms * 1e-3)
+    pass_ms = [e[0].elapsed_time(e[1]) for e in pass_ev] + [e[1].elapsed_time(e[2]) for e in pass_ev]
+    mean_pass_s = 1e-3 * sum(pass_ms) / len(pass_ms)
+    bytes_pass = s * (2.0 * n * L + E * (L * L + 5.0 * L))
+    peak, peak_src = measured_hbm_peak()
+    achieved = bytes_pass / mean_pass_s / 1e9
+    levels = int(stats["num_levels"])
+    roofline = {"bound": "hbm", "kernel": f"level_update_kernel ({levels} launches = one pass: one per colour class)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_pass / levels,
+                "mean_launch_ms": 1e3 * mean_pass_s / levels, "mean_pass_ms": 1e3 * mean_pass_s}
+    del lp
+
+    def solve():
+        q, _ = build()
+        bound = 0.0
+        for it in range(args.steps):
+            q.ComputePass(it)
+            bound = q.LowerBound()
+        q.ComputeForwardPassAndPrimal(args.steps)
+        cost = q.EvaluatePrimal()
+        nlab = q.labeling().nbytes
+        return bound, cost, nlab
+
+    solve()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    bound, cost, nlab = solve()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    h2d = s * (theta.size + tables.size) + 4 * 2 * E + 20 * n
+    e2e = {"value": world * 4.0 * E * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * world / args.steps,
+           "d2h_bytes_per_step": (8 * args.steps + 8 + nlab) * world / args.steps,
+           "definition": f"one Solve from host arrays through the C ABI: add_unaries/add_pairwise_dense + colouring + finalize (upload) + {args.steps} "
+                         "iterations (LB read back every iteration) + rounding pass + labeling download; wall clock, max over ranks",
+           "lower_bound": bound, "primal": cost}
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from checkers import oracle_lp
+        m = 200_000
+        si, sj = random_regular_graph(m, deg, SEED)
+        keep = np.ones(len(si), dtype=bool)
+        o = oracle_lp("f64")
+        o.add_unaries(theta[:m]); o.add_pairwise_dense(si, sj, tables[: len(si)])
+        o.finalize(); o.Begin(); o.set_reparametrization("anisotropic")
+        o.ComputePass(0); o.LowerBound()
+        t0 = time.perf_counter()
+        for it in range(3):
+            o.ComputePass(it + 1); o.LowerBound()
+        cdt = time.perf_counter() - t0
+        cpu = {"value": 4.0 * int(keep.sum()) * 3 / cdt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"random {deg}-regular graph on {m} nodes ({int(keep.sum())} edges), 3 iterations after 1 warm-up, f64, natural order, oracle/lpmp_oracle.cpp"}
+    print(json.dumps({
+        "metric": METRIC.replace("grid MRF", "sparse-graph MRF"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}" + ("; replicas only" if world > 1 else ""), "nodes": n, "edges": E, "colours": int(nc),
+                   "step": "one iteration = forward pass + backward pass + lower bound", "schedule": "graph colouring (level sets of the colour-oriented DAG)",
+                   "reparametrization": "anisotropic (SRMP)", "l2_policy": f"working set {int(bytes_pass / 2) >> 20} MiB exceeds the 126 MB L2; no flush needed",
+                   "lower_bound_after_last_step": lb},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info}))
+    if dist:
+        dist.destroy_process_group()
+
+
 # ---- GPU arm ---------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -176,7 +372,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + sorted(GRAPH_WORKLOADS))
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--coupling", default="halo", choices=["halo", "pipelined"],
                     help="N > 1: per-pass halo exchange (NCCL send/recv, block-Jacobi across stripes) or exact pipelined "
@@ -189,6 +385,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in GRAPH_WORKLOADS:
+        return graph_main(args, rank, world, local_rank)
     H, W, L, pairwise, lo, hi, desc = WORKLOADS[args.workload]
 
     if args.impl == "reference":
@@ -274,7 +472,7 @@ def main():
         except Exception:
             traffic = None
     achieved = bytes_pass / mean_pass_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "wavefront_pass_kernel (one launch = one pass over this rank's stripe)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": f"{PASS_KERNEL[pairwise]} (one launch = one pass over this rank's stripe)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_pass, "mean_launch_ms": 1e3 * mean_pass_s,
                 "critical_path_steps_per_launch": rows_here + W - 1,
@@ -286,6 +484,12 @@ def main():
     # pass + labeling download at N = 1]; reported per iteration (upload amortised over the K iterations of the solve)
     P = {"dense": L * L, "potts": 1, "trunclin": 2}[pairwise]
     row0 = StripePlan(H_total, world).rows(rank)[0]
+    e2e_rows = rows_here
+    if world == 1 and 2 * rows_here * W * P * 4 > 4e9:
+        # the potentials of the full workload do not fit a host upload (C5: 137 GB of tables): the end-to-end arm solves
+        # the top rows that make a 4 GB upload and says so
+        e2e_rows = max(8, int(4e9 / (2 * W * P * 4)))
+    full_rows, rows_here = rows_here, e2e_rows
     g = torch.Generator().manual_seed(SEED + rank)
     theta_h = torch.rand((rows_here, W, L), dtype=torch.float32, generator=g).pin_memory()
 
@@ -298,8 +502,15 @@ def main():
     top_h = edge_params((W,)) if row0 > 0 else None
     bot_h = edge_params((W,)) if row0 + rows_here < H_total else None
 
+    def make_e2e():
+        if e2e_rows == full_rows:
+            return make()
+        return StripedLP.make(e2e_rows, W, L, pairwise, 0, 1, dist=None, dtype=args.dtype, device=local_rank, tuning=tune)
+
+    slp.close(); del slp, lp   # free the device-resident arm's potentials before the end-to-end arm allocates its own
+
     def solve():
-        q = make()
+        q = make_e2e()
         q.lp._ck(q.lp.api.grid_set_unaries(q.lp.h, theta_h.data_ptr(), 0))
         q.lp._ck(q.lp.api.grid_set_pairwise(q.lp.h, hz_h.data_ptr(), vt_h.data_ptr(), 0))
         if world > 1:
@@ -331,10 +542,12 @@ def main():
         dt = float(t.item())
     h2d = 4 * (theta_h.numel() + hz_h.numel() + vt_h.numel() + (top_h.numel() if top_h is not None else 0) + (bot_h.numel() if bot_h is not None else 0))
     d2h = 8 * args.steps + (8 + nlab if world == 1 else 0)
-    e2e = {"value": 4.0 * E * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * world / args.steps,
+    E_e2e = edges_of(e2e_rows * world, W) if e2e_rows != full_rows else E
+    e2e = {"value": 4.0 * E_e2e * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * world / args.steps,
            "d2h_bytes_per_step": d2h * world / args.steps,
            "definition": f"one Solve from pinned host buffers: upload + {args.steps} iterations (LB read back every iteration)"
-                         + (" + rounding pass + labeling download" if world == 1 else "") + "; wall clock, max over ranks; bytes are per iteration",
+                         + (" + rounding pass + labeling download" if world == 1 else "") + "; wall clock, max over ranks; bytes are per iteration"
+                         + (f"; on the top {e2e_rows} rows of the workload (4 GB host upload)" if e2e_rows != full_rows else ""),
            "lower_bound": bound, "primal": cost}
 
     if rank != 0:
@@ -353,7 +566,7 @@ def main():
                    "reparametrization": "anisotropic (SRMP)",
                    "stripe_coupling": None if world == 1 else ("per-pass halo (NCCL send/recv; block-Jacobi across stripes)" if args.coupling == "halo"
                                                                else "exact pipelined (NVLink peer stores from the pass kernel)"),
-                   "l2_policy": f"working set per GPU (node records, {(rows_here * W * L * 5 * s) >> 20} MiB) exceeds the 126 MB L2; no flush needed",
+                   "l2_policy": f"working set per GPU (node records{' + tables' if pairwise == 'dense' else ''}, {int(bytes_pass / 2) >> 20} MiB) exceeds the 126 MB L2; no flush needed",
                    "tuning": tune, "lower_bound_after_last_step": lb},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,
     }

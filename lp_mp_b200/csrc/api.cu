@@ -227,6 +227,8 @@ struct Solver : ISolver {
   // device state.  General graphs: theta[N][L], a[E][L], b[E][L], params[E][P].  Grids: rec[N][5][L], par[N][4][P].
   DeviceBuffer<Real> theta, a, b, params, rec, par;
   DeviceBuffer<Real> tab;    // dense grids: table planes tabH [H][W][L*L] then tabV [H+1][W][L*L] (kernels_grid_dense.cuh)
+  DeviceBuffer<double> lb_rows;   // dense grids: per-row bound terms produced by the last backward pass
+  bool fused_lb_valid = false;    // lb_rows describes the current state (no state change since that pass)
   bool levels_built = false; // CSR + level sets uploaded (general graphs; grids on demand)
   DeviceBuffer<Real> handoff, in_top, in_bot;   // band-to-band / stripe-to-stripe column vectors (sentinel protocol)
   Real* peer_top = nullptr;  // upper neighbour's in_bot (delivery target of the backward pass), or null
@@ -688,6 +690,7 @@ struct Solver : ISolver {
         CUDA_TRY(cudaMemsetAsync(control.p, 0, control.bytes(), stream));
         CUDA_TRY(handoff.alloc((size_t)gridH * gridW * L));
         CUDA_TRY(cudaMemsetAsync(handoff.p, 0xff, handoff.bytes(), stream));
+        CUDA_TRY(lb_rows.alloc(gridH));
       } else {
         const uint32_t bands = (gridH + shape.T - 1) / shape.T;
         CUDA_TRY(control.alloc(2));
@@ -723,6 +726,7 @@ struct Solver : ISolver {
     if (int r = need_final()) return r;
     if (repam < 0) return bad_state("no reparametrization mode set");  // include/LP_MP.h:458
     CUDA_TRY(cudaSetDevice(device));
+    fused_lb_valid = false;
     // dense-table grids: the row-dataflow kernel covers the anisotropic mode; the uniform modes of the rounding
     // iterations (include/visitors/standard_visitor.hxx:44) run on the level schedule, built on first use
     const bool dense_wf = schedule == LPMP_SCHEDULE_WAVEFRONT && pw == LPMP_PAIRWISE_DENSE;
@@ -763,9 +767,11 @@ struct Solver : ISolver {
       A.in_boundary = forward ? in_top.p : in_bot.p;
       A.out_boundary = forward ? peer_bot : peer_top;
       A.labels = labels.p;
+      A.lb_rows = forward ? nullptr : lb_rows.p;   // the backward pass leaves every edge final: LowerBound comes for free
       CUDA_TRY(cudaMemsetAsync(control.p, 0, sizeof(unsigned int), stream));
       CUDA_TRY(launch_dense_pass<Real>(A, L, tune, num_sms, stream));
       ++launches;
+      fused_lb_valid = !forward;
     } else {
       if (striped && repam != LPMP_REPAM_ANISOTROPIC) { err = "stripes support the anisotropic reparametrization only"; return LPMP_ERR_UNSUPPORTED; }
       GridArgs<Real> A;
@@ -815,8 +821,8 @@ struct Solver : ISolver {
     return LPMP_OK;
   }
 
-  int reduce_to_host(int ctas, double add, double* out) {
-    final_sum_kernel<<<1, 32, 0, stream>>>(partial.p, ctas, add, result.p);
+  int reduce_to_host(int ctas, double add, double* out, const double* src = nullptr) {
+    final_sum_kernel<<<1, 32, 0, stream>>>(src ? src : partial.p, ctas, add, result.p);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, result.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -826,6 +832,7 @@ struct Solver : ISolver {
 
   int bound_launch(const Real* below_b, double add, double* out) {
     CUDA_TRY(cudaSetDevice(device));
+    if (fused_lb_valid && !striped) return reduce_to_host((int)gridH, add, out, lb_rows.p);
     const int G = group_size_for(L);
     int threads = 256;
     const size_t per_group = 2 * (size_t)L * sizeof(Real);
@@ -961,6 +968,7 @@ struct Solver : ISolver {
   }
   int set_messages(const double* pa, const double* pb) override {
     if (int r = need_final()) return r;
+    fused_lb_valid = false;
     if (is_grid) {
       std::vector<uint64_t> oa, ob;
       grid_edge_vector_offsets(oa, ob);
@@ -987,6 +995,7 @@ struct Solver : ISolver {
   }
   int set_unaries(const double* th) override {
     if (int r = need_final()) return r;
+    fused_lb_valid = false;
     if (is_grid) return set_unaries_from(th);
     std::vector<Real> tmp(N * L);
     for (uint64_t k = 0; k < N * L; ++k) tmp[k] = (Real)th[k];

@@ -21,7 +21,10 @@
 //     is the second variable (forward pass), rotated row mode when it is the first variable (backward pass)), then
 //     L/4 lanes of warp 0 apply ReceiveMessages / SendMessages on the node record in place;
 //   * the vector for the node below travels through a hand-off buffer in L2 with self-validating slots (NaN sentinel,
-//     same protocol as kernels_grid.cuh); the consumer row requests slots two nodes ahead.
+//     same protocol as kernels_grid.cuh); the consumer row requests slots two nodes ahead;
+//   * the BACKWARD pass also produces LP::LowerBound at no extra traffic: node i is the first variable of its R and D
+//     edges, whose state is final once i has been updated, and h(x) = min_y [c(x,y) + b(y)] is already in registers, so
+//     min theta_i + sum_{e in {R,D}} min_x [a_e(x) + h_e(x)] is accumulated per row in double (fixed order: deterministic).
 #pragma once
 #include "kernels_grid.cuh"
 
@@ -40,6 +43,7 @@ struct DenseGridArgs {
   Real* in_boundary;         // [W][L] slots feeding virtual row 0 when in_halo
   Real* out_boundary;        // [W][L] where the last virtual row delivers when out_halo, or null
   uint32_t* labels;          // [H*W]
+  double* lb_rows;           // backward pass only, or null: [H] row sums of LP::LowerBound's terms (include/LP_MP.h:1507-1518), see below
 };
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(128) dense_row_pass_kernel(const DenseGridArgs
     }
     __syncthreads();
 
+    double row_lb = 0.0;
     for (uint32_t q = 0; q < W; ++q) {
       const uint32_t c = fwd ? q : W - 1 - q;
       const uint32_t n = node_base + q, st = n % NSTAGE;
@@ -225,27 +230,26 @@ __global__ void __launch_bounds__(128) dense_row_pass_kernel(const DenseGridArgs
         const int np = fwd ? NXS : RS;
 #pragma unroll
         for (int k = 0; k < 4; ++k) { m_ir[k] = Real(0); m_ic[k] = Real(0); }
+        Real h_ir[4] = {INF, INF, INF, INF}, h_ic[4] = {INF, INF, INF, INF};
         if (has_ir) {   // ReceiveMessages: m = min-marginal, theta += m (RepamLeft), own -= m (RepamRight)
-          Real h[4] = {INF, INF, INF, INF};
           for (int p = 0; p < np; ++p) {
             Real v[4];
             lds4(v, hpart + (uint32_t)(p * L + 4 * tid) * S);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) h[k] = rmin(h[k], v[k]);
+            for (int k = 0; k < 4; ++k) h_ir[k] = rmin(h_ir[k], v[k]);
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { m_ir[k] = h[k] + own_ir[k]; own_ir[k] = own_ir[k] - m_ir[k]; }
+          for (int k = 0; k < 4; ++k) { m_ir[k] = h_ir[k] + own_ir[k]; own_ir[k] = own_ir[k] - m_ir[k]; }
         }
         if (has_ic) {
-          Real h[4] = {INF, INF, INF, INF};
           for (int p = 0; p < np; ++p) {
             Real v[4];
             lds4(v, hpart + NPART * LB + (uint32_t)(p * L + 4 * tid) * S);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) h[k] = rmin(h[k], v[k]);
+            for (int k = 0; k < 4; ++k) h_ic[k] = rmin(h_ic[k], v[k]);
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { m_ic[k] = h[k] + own_ic[k]; own_ic[k] = own_ic[k] - m_ic[k]; }
+          for (int k = 0; k < 4; ++k) { m_ic[k] = h_ic[k] + own_ic[k]; own_ic[k] = own_ic[k] - m_ic[k]; }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -272,6 +276,19 @@ __global__ void __launch_bounds__(128) dense_row_pass_kernel(const DenseGridArgs
           if (has_oc) { own_oc[k] = own_oc[k] + d; x = x - d; }
           if (has_or) { own_or[k] = own_or[k] + d; x = x - d; }
           th[k] = x;
+        }
+        if (A.lb_rows != nullptr) {   // backward: in_row / in_col are the R / D edges of this node, now final
+          Real mT = rmin(rmin(th[0], th[1]), rmin(th[2], th[3]));
+          Real mR = rmin(rmin(Real(h_ir[0] + own_ir[0]), Real(h_ir[1] + own_ir[1])), rmin(Real(h_ir[2] + own_ir[2]), Real(h_ir[3] + own_ir[3])));
+          Real mD = rmin(rmin(Real(h_ic[0] + own_ic[0]), Real(h_ic[1] + own_ic[1])), rmin(Real(h_ic[2] + own_ic[2]), Real(h_ic[3] + own_ic[3])));
+          constexpr unsigned UM = YQ == 32 ? 0xffffffffu : ((1u << YQ) - 1u);
+#pragma unroll
+          for (int o = YQ >> 1; o > 0; o >>= 1) {
+            mT = rmin(mT, __shfl_xor_sync(UM, mT, o));
+            mR = rmin(mR, __shfl_xor_sync(UM, mR, o));
+            mD = rmin(mD, __shfl_xor_sync(UM, mD, o));
+          }
+          row_lb += (double)mT + (has_ir ? (double)mR : 0.0) + (has_ic ? (double)mD : 0.0);
         }
         sts4(recs, th);
         sts4(recs + o_in_row, own_ir);
@@ -301,6 +318,7 @@ __global__ void __launch_bounds__(128) dense_row_pass_kernel(const DenseGridArgs
         tma_commit();
       }
     }
+    if (A.lb_rows != nullptr && tid == 0) A.lb_rows[r] = row_lb;
     node_base += W;
   }
   if (is_loader) tma_wait_all();   // the global writes of the last records are complete before the CTA exits

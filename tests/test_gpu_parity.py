@@ -331,6 +331,29 @@ def test_dense_grid_fifo_and_uniform_modes():
     assert np.array_equal(a0, a1) and np.array_equal(b0, b1)
 
 
+def test_dense_grid_fused_bound_equals_bound_kernel():
+    """the backward pass accumulates LP::LowerBound on the fly; the stand-alone bound kernel must give the same value"""
+    for dtype in ("f32", "f64"):
+        lp = cuda_lp(dtype).grid_create(21, 33, 32, "dense")
+        lp.grid_fill_synthetic(7, -0.2, 1.0)
+        lp.add_to_constant(3.5)
+        lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+        for it in range(3):
+            lp.ComputePass(it)
+            fused = lp.LowerBound()
+            lp.set_unaries(lp.unaries())          # any state write invalidates the fused rows
+            assert np.isclose(lp.LowerBound(), fused, rtol=1e-13, atol=0)
+        lp.ComputeForwardPass()                    # after a forward pass the bound comes from the bound kernel
+        orc = oracle_lp(dtype).grid_create(21, 33, 32, "dense")
+        orc.grid_fill_synthetic(7, -0.2, 1.0)
+        orc.add_to_constant(3.5)
+        orc.finalize(); orc.Begin(); orc.set_reparametrization("anisotropic")
+        for it in range(3):
+            orc.ComputePass(it)
+        orc.ComputeForwardPass()
+        assert np.isclose(lp.LowerBound(), orc.LowerBound(), rtol=LB_RTOL[dtype])
+
+
 def test_dense_grid_equals_level_schedule_and_synthetic_generator():
     for dtype in ("f32", "f64"):
         lps = [oracle_lp(dtype).grid_create(17, 22, 64, "dense"), cuda_lp(dtype).grid_create(17, 22, 64, "dense"),
