@@ -23,6 +23,10 @@
 //     band k+1 through a hand-off buffer in L2 whose slots carry their own validity (a slot holds a NaN sentinel
 //     until the producer stores the vector; the consumer polls the slot itself -- PD steps ahead, PD loads in flight -- and puts the
 //     sentinel back after reading).  No flag, no fence: one store and one load per lane and column;
+//   * a CTA holds NW warps (1..8, as many as the shared memory allows) that work on NW CONSECUTIVE bands (a "super-band",
+//     claimed together from the ticket): inside the CTA the hand-off goes through a small ring of self-validating slots
+//     in SHARED memory (same sentinel protocol, ~30 cycles instead of an L2 round trip, plus back-pressure: the producer
+//     only writes a slot that holds the sentinel), so only every NW-th band boundary pays the L2 latency;
 //   * interior steps of interior bands run a straight-line FAST path without any existence predicate (missing
 //     edges of the first row are exact no-ops because their record slots and parameters are zero); the first /
 //     last T steps of a band, the last band and the uniform modes run the GENERAL path.
@@ -140,7 +144,12 @@ struct WavefrontCfg {
   static constexpr int SLOT_REC = (T + 1) * K * REC;     // reals
   static constexpr int SLOT_PAR = T * K * PREC;
   static constexpr int SCRATCH = PW == LPMP_PAIRWISE_TRUNCLIN ? 2 * TG * 3 * L : 0;   // staging of `other` for the label window
-  static constexpr size_t SMEM_BYTES = 128 + (size_t)(NSLOT * (SLOT_REC + SLOT_PAR) + SCRATCH) * sizeof(Real);
+  static constexpr size_t SMEM_BYTES = 128 + (size_t)(NSLOT * (SLOT_REC + SLOT_PAR) + SCRATCH) * sizeof(Real);   // per warp
+  static constexpr size_t WARP_SMEM = (SMEM_BYTES + 127) / 128 * 128;
+  static constexpr int RING = 16;                        // columns of an intra-CTA hand-off ring (power of two, > PD)
+  static constexpr int MAX_WARPS = 8;
+  // dynamic shared memory of a CTA of nw warps: nw private regions, the super-band queue (128 B), nw-1 hand-off rings
+  static constexpr size_t cta_smem(int nw) { return (size_t)nw * WARP_SMEM + 128 + (size_t)(nw - 1) * RING * L * sizeof(Real); }
   static constexpr bool FITS = SMEM_BYTES <= 220 * 1024 && (NSLOT - PDC - 1) * K > T - 2;
   static_assert(K == 8 || K == 4, "tile width");
   static_assert(L % 4 == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0, "L/4 must be a power of two <= 32");
@@ -162,6 +171,29 @@ template <int BYTES> __device__ __forceinline__ void st_relaxed_if(bool on, void
   for (int o = 0; o < BYTES / 16; ++o)
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4}; }" ::"l"(reinterpret_cast<char*>(dst) + 16 * o),
                  "r"(d[4 * o]), "r"(d[4 * o + 1]), "r"(d[4 * o + 2]), "r"(d[4 * o + 3]), "r"((uint32_t)on)
+                 : "memory");
+}
+// hand-off slots in shared memory (rings between the warps of a CTA): same protocol, 32-bit shared addresses
+template <int BYTES> __device__ __forceinline__ void lds_hand(void* dst, uint32_t a) {
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+  for (int o = 0; o < BYTES / 16; ++o)
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d[4 * o]), "=r"(d[4 * o + 1]), "=r"(d[4 * o + 2]), "=r"(d[4 * o + 3]) : "r"(a + 16 * o));
+}
+template <int BYTES> __device__ __forceinline__ void lds_hand_if(bool on, void* dst, uint32_t a) {
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+  for (int o = 0; o < BYTES / 16; ++o)
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4]; }"
+                 : "+r"(d[4 * o]), "+r"(d[4 * o + 1]), "+r"(d[4 * o + 2]), "+r"(d[4 * o + 3])
+                 : "r"(a + 16 * o), "r"((uint32_t)on));
+}
+template <int BYTES> __device__ __forceinline__ void sts_hand_if(bool on, uint32_t a, const void* src) {
+  const uint32_t* d = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+  for (int o = 0; o < BYTES / 16; ++o)
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4}; }" ::"r"(a + 16 * o), "r"(d[4 * o]),
+                 "r"(d[4 * o + 1]), "r"(d[4 * o + 2]), "r"(d[4 * o + 3]), "r"((uint32_t)on)
                  : "memory");
 }
 // pins a kernel parameter in a register (the compiler otherwise re-reads the constant bank inside the step loop)
@@ -290,8 +322,8 @@ __device__ __forceinline__ void lane_min_plus2(const Real* pa, const Real (&oa)[
   }
 }
 
-template <typename Real, int PW, int L, int HOPS, bool ANISO, int KSEL>
-__global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_rec1,
+template <typename Real, int PW, int L, int HOPS, bool ANISO, int KSEL, bool RINGS>
+__global__ void __launch_bounds__(RINGS ? 32 * WavefrontCfg<Real, PW, L, KSEL>::MAX_WARPS : 32) wavefront_pass_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_rec1,
                                                             const __grid_constant__ CUtensorMap tm_par, const GridArgs<Real> A) {
   using Cfg = WavefrontCfg<Real, PW, L, KSEL>;
   constexpr int G = Cfg::G, T = Cfg::T, P = Cfg::P, K = Cfg::K, PD = Cfg::PD, LOGK = Cfg::LOGK, REC = Cfg::REC, PREC = Cfg::PREC, NSLOT = Cfg::NSLOT, PDC = Cfg::PDC;
@@ -303,7 +335,13 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
   constexpr bool PARTIAL_WARP = T * G < 32;            // tiny L: lanes beyond T groups shadow group T-1 and never store
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t smem_base = smem_u32(smem_raw);
+  // RINGS: nw > 1 warps per CTA, warp w works on band sb * nw + w; else one warp = one band, no shared-memory hand-off
+  const int wid = RINGS ? (int)(threadIdx.x >> 5) : 0, nw = RINGS ? (int)(blockDim.x >> 5) : 1;
+  unsigned char* const smem_warp = smem_raw + (size_t)wid * Cfg::WARP_SMEM;
+  unsigned char* const smem_cta = smem_raw + (size_t)nw * Cfg::WARP_SMEM;  // super-band queue, then the hand-off rings
+  volatile unsigned long long* const sb_queue = reinterpret_cast<volatile unsigned long long*>(smem_cta);
+  Real* const rings = reinterpret_cast<Real*>(smem_cta + 128);            // [nw-1][RING][L], ring w: warp w -> warp w+1
+  const uint32_t smem_base = smem_u32(smem_warp);
   const uint32_t bars = smem_base;                                     // NSLOT mbarriers
   const uint32_t rec_ring = smem_base + 128;
   const uint32_t par_ring = rec_ring + NSLOT * SLOT_REC_B;
@@ -331,11 +369,18 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if constexpr (PW == LPMP_PAIRWISE_TRUNCLIN) {
-    Real* sc = reinterpret_cast<Real*>(smem_raw + 128 + NSLOT * (SLOT_REC_B + SLOT_PAR_B));
+    Real* sc = reinterpret_cast<Real*>(smem_warp + 128 + NSLOT * (SLOT_REC_B + SLOT_PAR_B));
     for (int i = lane; i < Cfg::SCRATCH; i += 32) sc[i] = RealTraits<Real>::inf();
   }
+  if constexpr (RINGS) {
+    for (int i = (int)threadIdx.x; i < (nw - 1) * Cfg::RING * L; i += (int)blockDim.x) rings[i] = sentinel<Real>();
+    if (threadIdx.x < 16) sb_queue[threadIdx.x] = 0ull;
+    __syncthreads();
+  }
   __syncwarp();
-  uint32_t chunk_base = 0;   // tiles loaded by earlier bands of this warp: slot / mbarrier-phase sequence continues
+  const unsigned num_super = (A.num_bands + (unsigned)nw - 1u) / (unsigned)nw;
+  uint32_t chunk_base = 0;
+  uint32_t ring_in_n = 0, ring_out_n = 0;   // columns through the ring before / after this warp so far: slots are used cyclically   // tiles loaded by earlier bands of this warp: slot / mbarrier-phase sequence continues
 
   // record vector / parameter roles in this direction (byte offsets inside a record)
   const uint32_t o_in_row = (fwd ? REC_BL : REC_AR) * LB, o_in_col = (fwd ? REC_BU : REC_AD) * LB;
@@ -354,11 +399,24 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
   const Real w_fast = (Real)(1.0 / 2.0);
   const bool H_total_ge2 = H >= 2 || A.in_halo || A.out_halo;   // a single-row grid has (n_in, n_out) = (1, 1): weight 1
 
-  for (;;) {
-    unsigned kb = 0;
-    if (lane == 0) kb = atomicAdd(A.control, 1u);
-    kb = __shfl_sync(FULL, kb, 0);
-    if (kb >= A.num_bands) break;
+  for (uint32_t iter = 0;; ++iter) {
+    // warp 0 claims the next super-band and publishes it to the other warps of the CTA ({iteration + 1, index} in a
+    // queue of 16 entries: the rings' back-pressure keeps the warps of a CTA within two iterations of each other)
+    unsigned sb = 0;
+    if (lane == 0) {
+      if (wid == 0) {
+        sb = atomicAdd(A.control, 1u);
+        if (RINGS) sb_queue[iter & 15u] = ((unsigned long long)(iter + 1u) << 32) | sb;
+      } else {
+        unsigned long long v;
+        do { v = sb_queue[iter & 15u]; } while ((uint32_t)(v >> 32) != iter + 1u);
+        sb = (unsigned)v;
+      }
+    }
+    sb = __shfl_sync(FULL, sb, 0);
+    if (sb >= num_super) break;
+    const unsigned kb = sb * (unsigned)nw + (unsigned)wid;
+    if (kb >= A.num_bands) continue;   // the last super-band may be partial
     const int u = (int)kb * T + t - roff;                  // virtual row of this lane group
     const bool row_active = u >= 0 && u < (int)H && lane_used;
     const uint32_t r = fwd ? (uint32_t)u : H - 1 - (uint32_t)u;
@@ -368,6 +426,12 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
     const int t_in = kb == 0 ? roff : 0;                   // first active group of the band
     const bool poller = poll_in && t == t_in && lane_used;
     const bool hand_out = !last_band || (A.out_halo && A.out_boundary != nullptr);
+    // hand-off slots: shared-memory ring between warps of this CTA (column index wraps), else the L2 / peer buffers
+    const bool ring_in = RINGS && wid > 0, ring_out = RINGS && !last_band && wid + 1 < nw;
+    const uint32_t ring_in_s = smem_u32(rings + (size_t)(wid > 0 ? wid - 1 : 0) * Cfg::RING * L + gl * 4);
+    const uint32_t ring_out_s = smem_u32(rings + (size_t)wid * Cfg::RING * L + gl * 4);
+    auto in_slot = [&](int q) { return ring_in_s + ((ring_in_n + (uint32_t)q) & (uint32_t)(Cfg::RING - 1)) * LB; };
+    auto out_slot = [&](int q) { return ring_out_s + ((ring_out_n + (uint32_t)q) & (uint32_t)(Cfg::RING - 1)) * LB; };
     const Real* const hand_in = (kb == 0 ? A.in_boundary : A.handoff + (uint64_t)kb * W * L) + gl * 4;
     Real* const hand_dst = (last_band ? A.out_boundary : A.handoff + (uint64_t)(kb + 1) * W * L) + gl * 4;
     const int t_hand = last_band ? (int)H - 1 - (int)kb * T + roff : T - 1;   // group that owns the band's last row
@@ -422,8 +486,10 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
     for (int d = 0; d < PD; ++d) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) polled[d][k] = Real(0);
-      ld_relaxed_if<HAND_BYTES>(poller && d < (int)W, polled[d], hand_in + d * L);
+      ld_relaxed_if<HAND_BYTES>(poller && !ring_in && d < (int)W, polled[d], hand_in + d * L);
     }
+    // a shared-memory ring answers in ~30 cycles: its slots are read ONE step ahead (into polled[0])
+    if constexpr (RINGS) lds_hand_if<HAND_BYTES>(poller && ring_in, polled[0], in_slot(0));
 
     Real carry_row[4], carry_col[4];
 #pragma unroll
@@ -440,7 +506,30 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
       // ---- tile ring management (warp-uniform, one branch per step) ----
       const bool ev_store = ((sp - T + 1) & (K - 1)) == 0 && sp >= T + K - 1;   // the previous step completed a tile
       const bool ev_load = (sp & (K - 1)) == 0 && sp > 0;                        // group 0 enters a new tile
-      if (ev_store || ev_load) {
+      // back-pressure of the outgoing ring, once per RING/2 columns: slots are written and freed in cyclic order, so when
+      // the slot of the last column of the next half ring holds the sentinel, all slots up to it are free
+      const int q_h = sp - t_hand - qoff;        // column of the band's last row
+      const bool ev_ring = RINGS && ring_out && q_h >= 0 && q_h < (int)W && (q_h == 0 || ((ring_out_n + (uint32_t)q_h) & (uint32_t)(Cfg::RING / 2 - 1)) == 0);
+      if (ev_store || ev_load || ev_ring) {
+        if constexpr (RINGS) {
+          if (ev_ring) {
+            if (hander) {
+              const int rem = Cfg::RING / 2 - 1 - (int)((ring_out_n + (uint32_t)q_h) & (uint32_t)(Cfg::RING / 2 - 1));
+              const int qa = q_h + rem < (int)W ? q_h + rem : (int)W - 1;
+              Real f[4];
+              unsigned spins = 0;
+              for (;;) {
+                lds_hand<HAND_BYTES>(f, out_slot(qa));
+                if (is_sentinel(f[0]) && is_sentinel(f[1]) && is_sentinel(f[2]) && is_sentinel(f[3])) break;
+                if ((++spins & 0x3ffu) == 0) {
+                  if (spins > (1u << 27)) atomicExch(A.control + 1, 1u);
+                  if (*reinterpret_cast<volatile unsigned int*>(A.control + 1) != 0u) break;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
         if (ev_store) { store_chunk(next_store); ++next_store; }
         if (ev_load) {
           if (sp == K) stamp(2);
@@ -480,9 +569,10 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
         if (polling) {
           unsigned spins = 0;
           while (is_sentinel(polled[0][0]) || is_sentinel(polled[0][1]) || is_sentinel(polled[0][2]) || is_sentinel(polled[0][3])) {
-            ld_relaxed<HAND_BYTES>(polled[0], hslot);
+            if (ring_in) lds_hand<HAND_BYTES>(polled[0], in_slot(q));
+            else ld_relaxed<HAND_BYTES>(polled[0], hslot);
             if ((++spins & 0x3ffu) == 0) {      // bounded wait: a lost producer must not hang the device
-              if (spins > (1u << 22)) atomicExch(A.control + 1, 1u);
+              if (spins > (ring_in ? (1u << 27) : (1u << 22))) atomicExch(A.control + 1, 1u);   // ~1 s either way
               if (*reinterpret_cast<volatile unsigned int*>(A.control + 1) != 0u) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) polled[0][k] = Real(0);
@@ -498,7 +588,8 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
         Real sent[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) sent[k] = sentinel<Real>();
-        st_relaxed_if<HAND_BYTES>(polling, const_cast<Real*>(hslot), sent);        // the slot is free again for the next pass
+        st_relaxed_if<HAND_BYTES>(polling && !ring_in, const_cast<Real*>(hslot), sent);        // the slot is free again for the next pass
+        if constexpr (RINGS) sts_hand_if<HAND_BYTES>(polling && ring_in, in_slot(q), sent);
         // the poll ring advances once the polling group has entered the grid (warp-uniform); slot q + PD is requested
         // now and consumed PD steps later, so PD L2 round trips are in flight per band
         if (sp - t_in - qoff >= 0) {
@@ -508,7 +599,8 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
             for (int k = 0; k < 4; ++k) polled[d][k] = polled[d + 1][k];
           }
         }
-        ld_relaxed_if<HAND_BYTES>(polling && q + PD < (int)W, polled[PD - 1], hslot + PD * L);
+        ld_relaxed_if<HAND_BYTES>(polling && !ring_in && q + PD < (int)W, polled[PD - 1], hslot + PD * L);
+        if constexpr (RINGS) lds_hand_if<HAND_BYTES>(polling && ring_in && q + 1 < (int)W, polled[0], in_slot(q + 1));
       }
 
       Real out_col[4];
@@ -642,7 +734,9 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
         const Real up = __shfl_up_sync(FULL, out_col[k], G);
         carry_col[k] = t <= t_in ? Real(0) : up;
       }
-      st_relaxed_if<HAND_BYTES>(hander && q >= 0 && q < (int)W, hand_dst + (int64_t)q * L, out_col);
+      const bool handing = hander && q >= 0 && q < (int)W;
+      st_relaxed_if<HAND_BYTES>(handing && !ring_out, hand_dst + (int64_t)q * L, out_col);
+      if constexpr (RINGS) sts_hand_if<HAND_BYTES>(handing && ring_out, out_slot(q), out_col);
 
     };
 
@@ -660,6 +754,8 @@ __global__ void __launch_bounds__(32) wavefront_pass_kernel(const __grid_constan
     if (lane == 0) tma_wait_read<0>();   // every tile of this band has left shared memory before the ring is reused
     __syncwarp();
     chunk_base += (uint32_t)nchunks;
+    if (ring_in) ring_in_n += W;
+    if (ring_out) ring_out_n += W;
   }
   if (lane == 0) tma_wait_all();   // the global writes of the last tiles are complete before the warp exits
 }

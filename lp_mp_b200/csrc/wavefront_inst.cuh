@@ -11,26 +11,36 @@ static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& arg
   if constexpr (!EXISTS) {
     return cudaErrorInvalidValue;
   } else {
-    auto kernel = wavefront_pass_kernel<Real, PW, L, HOPS, ANISO, KSEL>;
-    const size_t smem = Cfg::SMEM_BYTES;
-    static bool configured[64] = {};   // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int smem_cap = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    // warps (= consecutive bands) per CTA: at most what the shared memory holds and MAX_WARPS; the hand-off between the
+    // bands of a CTA stays in shared memory
+    int nw_max = 1;
+    while (nw_max < Cfg::MAX_WARPS && Cfg::cta_smem(nw_max + 1) <= (size_t)smem_cap) ++nw_max;
+    // measured (profiles/r01b_superbands.txt): the ring kernel's longer step outweighs the cheaper hand-off on C2 / C3,
+    // so one band per CTA stays the default and super-bands are opt-in ("wavefront_warps_per_cta")
+    const int nw = tune.warps_per_cta > 1 ? (tune.warps_per_cta < nw_max ? tune.warps_per_cta : nw_max) : 1;
+    auto kernel = nw > 1 ? wavefront_pass_kernel<Real, PW, L, HOPS, ANISO, KSEL, true> : wavefront_pass_kernel<Real, PW, L, HOPS, ANISO, KSEL, false>;
+    static bool configured[64][2] = {};   // the attribute is per device and kernel
+    if (!configured[dev & 63][nw > 1]) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
       if (e != cudaSuccess) return e;
-      configured[dev & 63] = true;
+      configured[dev & 63][nw > 1] = true;
     }
+    const size_t smem = Cfg::cta_smem(nw);
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * nw, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     if (tune.ctas_per_sm > 0 && per_sm > tune.ctas_per_sm) per_sm = tune.ctas_per_sm;
-    int ctas = (int)args.num_bands;
+    int ctas = (int)((args.num_bands + nw - 1) / nw);
     const int resident = per_sm * num_sms;
-    if (ctas > resident) ctas = resident;   // persistent: the ticket loop covers the remaining bands
+    if (ctas > resident) ctas = resident;   // persistent: the ticket loop covers the remaining super-bands
     if (tune.max_ctas > 0 && ctas > tune.max_ctas) ctas = tune.max_ctas;
-    kernel<<<ctas, 32, smem, stream>>>(maps[0], maps[1], maps[2], args);
+    kernel<<<ctas, 32 * nw, smem, stream>>>(maps[0], maps[1], maps[2], args);
     return cudaGetLastError();
   }
 }

@@ -12,9 +12,10 @@
 namespace lpmp {
 
 struct WavefrontTuning {
-  int max_ctas = 0;     // 0 = one CTA (= one warp = one band at a time) per resident slot
+  int max_ctas = 0;     // 0 = one CTA (= warps_per_cta bands at a time) per resident slot
   int ctas_per_sm = 0;  // 0 = as many as fit
   int tile_cols = 0;    // 0 = automatic, else 8 or 4
+  int warps_per_cta = 0;  // consecutive bands per CTA (<= 8 and what the shared memory holds); 0 or 1 = one band per CTA
 };
 
 // tile shapes of the kernel instances for (Real, pw, L): rows per band; per tile width (8 / 4 columns) whether the

@@ -262,12 +262,26 @@ def test_wavefront_ragged_shapes(H, W):
 
 
 @pytest.mark.parametrize("tuning", [dict(wavefront_max_ctas=1), dict(wavefront_max_ctas=3), dict(wavefront_ctas_per_sm=1),
-                                    dict(wavefront_max_ctas=2, wavefront_ctas_per_sm=1)])
+                                    dict(wavefront_max_ctas=2, wavefront_ctas_per_sm=1), dict(wavefront_warps_per_cta=1),
+                                    dict(wavefront_warps_per_cta=2), dict(wavefront_warps_per_cta=3, wavefront_tile_cols=4),
+                                    dict(wavefront_warps_per_cta=3, wavefront_max_ctas=1),
+                                    dict(wavefront_warps_per_cta=8, wavefront_tile_cols=4, wavefront_max_ctas=2)])
 def test_wavefront_launch_shapes_do_not_change_results(tuning):
     lps = grid_pair("f32", 70, 45, 16, "trunclin", seed=3, **tuning)
     run_lockstep(lps, "anisotropic", iters=3, lb_rtol=1e-6)
     lps = grid_pair("f64", 45, 70, 32, "potts", seed=4, **tuning)
     run_lockstep(lps, "uniform", iters=2)
+
+
+@pytest.mark.parametrize("kind,L,tuning", [("trunclin", 16, dict(wavefront_tile_cols=4, wavefront_warps_per_cta=4)),
+                                           ("trunclin", 16, dict(wavefront_tile_cols=8, wavefront_warps_per_cta=2)),
+                                           ("potts", 32, dict(wavefront_warps_per_cta=8)),
+                                           ("potts", 8, dict(wavefront_max_ctas=3, wavefront_warps_per_cta=3))])
+def test_wavefront_super_bands(kind, L, tuning):
+    """several consecutive bands per CTA: hand-off through the shared-memory rings (they wrap many times: W >> ring),
+    partial last super-band, CTAs that take several super-bands"""
+    lps = grid_pair("f32", 203, 157, L, kind, seed=21, **tuning)
+    run_lockstep(lps, "anisotropic", iters=3, lb_rtol=1e-6)
 
 
 def test_wavefront_fifo_order():
