@@ -1,5 +1,6 @@
 // Included by wavefront_inst_*.cu with LPMP_INST_REAL, LPMP_INST_PW and LPMP_INST_ANISO defined.
 #include "wavefront_launch.h"
+#include "kernels_grid_lean.cuh"
 
 namespace lpmp {
 
@@ -16,6 +17,29 @@ static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& arg
     int smem_cap = 0;
     cudaError_t e = cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
+    if constexpr (ANISO && LeanCfg<Real, PW, L, KSEL>::LEAN_FITS) {
+      if (tune.lean > 0) {
+        // lean variant: compute warp + in-mover + out-mover per band (kernels_grid_lean.cuh)
+        using LCfg = LeanCfg<Real, PW, L, KSEL>;
+        auto lkernel = wavefront_lean_kernel<Real, PW, L, HOPS, KSEL>;
+        static bool lconfigured[64] = {};
+        if (!lconfigured[dev & 63]) {
+          e = cudaFuncSetAttribute(lkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LCfg::LEAN_SMEM);
+          if (e != cudaSuccess) return e;
+          lconfigured[dev & 63] = true;
+        }
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lkernel, 96, LCfg::LEAN_SMEM);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        if (tune.ctas_per_sm > 0 && per_sm > tune.ctas_per_sm) per_sm = tune.ctas_per_sm;
+        int ctas = (int)args.num_bands;
+        if (ctas > per_sm * num_sms) ctas = per_sm * num_sms;   // persistent: the ticket loop covers the remaining bands
+        if (tune.max_ctas > 0 && ctas > tune.max_ctas) ctas = tune.max_ctas;
+        lkernel<<<ctas, 96, LCfg::LEAN_SMEM, stream>>>(maps[0], maps[2], args);
+        return cudaGetLastError();
+      }
+    }
     // warps (= consecutive bands) per CTA: at most what the shared memory holds and MAX_WARPS; the hand-off between the
     // bands of a CTA stays in shared memory
     int nw_max = 1;

@@ -284,6 +284,19 @@ def test_wavefront_super_bands(kind, L, tuning):
     run_lockstep(lps, "anisotropic", iters=3, lb_rtol=1e-6)
 
 
+@pytest.mark.parametrize("kind,L,dtype,tuning", [("trunclin", 16, "f32", dict(wavefront_lean=1)), ("trunclin", 16, "f64", dict(wavefront_lean=1, wavefront_tile_cols=4)),
+                                                 ("potts", 32, "f32", dict(wavefront_lean=1)), ("potts", 8, "f64", dict(wavefront_lean=1, wavefront_max_ctas=3)),
+                                                 ("potts", 64, "f32", dict(wavefront_lean=1, wavefront_max_ctas=1))])
+def test_wavefront_lean_variant(kind, L, dtype, tuning):
+    """compute warp + mover warps per band (kernels_grid_lean.cuh): anisotropic passes and rounding, several bands per CTA
+    in sequence, halo ring wrapping many times, ragged last band / tile"""
+    lps = grid_pair(dtype, 203, 157, L, kind, seed=22, **tuning)
+    run_lockstep(lps, "anisotropic", iters=3, lb_rtol=1e-6 if dtype == "f32" else 1e-12)
+    for H, W in ((1, 40), (40, 1), (3, 3), (9, 2), (17, 70)):
+        lps = grid_pair(dtype, H, W, L, kind, seed=H * 100 + W, **tuning)
+        run_lockstep(lps, "anisotropic", iters=2, lb_rtol=1e-6 if dtype == "f32" else 1e-12)
+
+
 def test_wavefront_fifo_order():
     lps = grid_pair("f64", 20, 23, 8, "potts", seed=5, edge_order="fifo")
     run_lockstep(lps, "damped_uniform", iters=3)
