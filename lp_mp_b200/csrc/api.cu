@@ -219,6 +219,7 @@ struct Solver : ISolver {
   double constant = 0.0;
   WavefrontTuning tune;
   WavefrontShape shape{0, false, false, 0, 0};
+  bool potts_neg = false;    // Potts: a negative lambda has been seen
   int tl_reach = 0;          // truncated linear: max #{d >= 1: slope*d < trunc} over all edges seen so far
   bool tl_irregular = false; // a negative slope / trunc was seen: only the all-distances kernel is exact
   // host staging (general graphs)
@@ -272,6 +273,10 @@ struct Solver : ISolver {
     int reach = 0;
     while (reach + 1 < (int)L && Real(slope * Real(reach + 1)) < trunc) ++reach;
     tl_reach = std::max(tl_reach, reach);
+  }
+  template <typename Src>
+  void note_potts_array(const Src* p, uint64_t n_edges) {
+    for (uint64_t e = 0; e < n_edges && !potts_neg; ++e) potts_neg = !(p[e] >= Src(0));
   }
   template <typename Src>
   void note_trunclin_array(const Src* p, uint64_t n_edges) {
@@ -395,6 +400,7 @@ struct Solver : ISolver {
     const uint64_t n = (uint64_t)rows * cols * Pn;
     if (n == 0 || !src) return LPMP_OK;
     if (pw == LPMP_PAIRWISE_TRUNCLIN) note_trunclin_array(src, (uint64_t)rows * cols);
+    if (pw == LPMP_PAIRWISE_POTTS) note_potts_array(src, (uint64_t)rows * cols);
     DeviceBuffer<Src> tmp;
     if (int r = upload(tmp, src, n)) return r;
     scatter_edge_params_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(par.p, tmp.p, rows, cols, gridW, Pn, second_off, f_first, f_second);
@@ -453,6 +459,7 @@ struct Solver : ISolver {
     }
     const int tl = pw == LPMP_PAIRWISE_TRUNCLIN;
     if (tl) note_trunclin(lo, hi);
+    else if (!(lo >= 0.0)) potts_neg = true;
     synth_unary_kernel<Real><<<grid_for(N * L, 256), 256, 0, stream>>>(rec.p, N, L, REC(), (uint64_t)row0 * gridW, seed);
     synth_edge_kernel<Real><<<grid_for(N * Pn, 256), 256, 0, stream>>>(par.p, gridH, gridW, Pn, row0, H_total, 0, seed, lo, hi, tl);
     synth_edge_kernel<Real><<<grid_for((N + gridW) * Pn, 256), 256, 0, stream>>>(par.p, gridH, gridW, Pn, row0, H_total, 1, seed, lo, hi, tl);
@@ -489,6 +496,7 @@ struct Solver : ISolver {
     const uint32_t Pn = P();
     const uint64_t n = (uint64_t)gridW * Pn;
     if (pw == LPMP_PAIRWISE_TRUNCLIN) note_trunclin_array(bottom, gridW);
+    if (pw == LPMP_PAIRWISE_POTTS) note_potts_array(bottom, gridW);
     DeviceBuffer<Src> tmp;
     if (int r = upload(tmp, bottom, n)) return r;
     scatter_edge_params_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(par.p + (uint64_t)(gridH - 1) * gridW * PREC(), tmp.p, 1, gridW, gridW, Pn, 0, PAR_D, -1);
@@ -784,6 +792,7 @@ struct Solver : ISolver {
       A.in_halo = forward ? has_above : has_below;
       A.out_halo = forward ? has_below : has_above;
       A.tl_reach = tl_reach;
+      A.potts_nonneg = pw == LPMP_PAIRWISE_POTTS && !potts_neg;
       A.control = control.p; A.handoff = handoff.p;
       A.in_boundary = forward ? in_top.p : in_bot.p;
       A.out_boundary = forward ? peer_bot : peer_top;

@@ -53,6 +53,7 @@ struct GridArgs {
   uint32_t num_bands;
   int forward, primal, fifo, repam;
   int in_halo, out_halo;    // striped: the band before virtual band 0 / after the last band lives on another device
+  int potts_nonneg;         // Potts: the host has seen no negative lambda (the kernels then skip the two-smallest-entries test)
   int tl_reach;             // truncated linear: max over edges of #{d >= 1 : slope*d < trunc} (host-computed)
   unsigned int* control;    // [0] band ticket (zeroed before the launch), [1] sticky abort flag (poll timeout)
   Real* handoff;            // [num_bands][W][L]: boundary b (1 <= b < num_bands) sits between virtual band b-1 and band b;
@@ -244,7 +245,7 @@ __device__ __forceinline__ void group_min2(Real& a, Real& b) {
 // group's [INF pad | L labels | INF pad] staging areas).  HOPS = 0: all L-1 distances, any parameters.
 template <typename Real, int PW, int L, int HOPS>
 __device__ __forceinline__ void lane_min_plus2(const Real* pa, const Real (&oa)[4], Real (&ha)[4], const Real* pb, const Real (&ob)[4], Real (&hb)[4],
-                                               uint32_t sa, uint32_t sb, int gl) {
+                                               uint32_t sa, uint32_t sb, int gl, bool potts_nonneg = false) {
   constexpr int G = L / 4;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr uint32_t S = (uint32_t)sizeof(Real);
@@ -252,7 +253,7 @@ __device__ __forceinline__ void lane_min_plus2(const Real* pa, const Real (&oa)[
   Real gb = rmin(rmin(ob[0], ob[1]), rmin(ob[2], ob[3]));
   if constexpr (PW == LPMP_PAIRWISE_POTTS) {
     const Real la = pa[0], lb = pb[0];
-    if (__any_sync(FULL, la < Real(0) || lb < Real(0))) {   // repulsive Potts somewhere in the warp: the two smallest entries
+    if (!potts_nonneg && __any_sync(FULL, la < Real(0) || lb < Real(0))) {   // repulsive Potts somewhere in the warp: the two smallest entries
       const Real INF = RealTraits<Real>::inf();
       TwoMin<Real> ta{INF, INF, 0u}, tb{INF, INF, 0u};
 #pragma unroll
@@ -398,6 +399,7 @@ __global__ void __launch_bounds__(RINGS ? 32 * WavefrontCfg<Real, PW, L, KSEL>::
   // weight of the FAST path: (n_in, n_out) = (2, 2), first row (1, 2): 1 / max(n_in, n_out) = 1/2 (include/LP_MP.h:1397)
   const Real w_fast = (Real)(1.0 / 2.0);
   const bool H_total_ge2 = H >= 2 || A.in_halo || A.out_halo;   // a single-row grid has (n_in, n_out) = (1, 1): weight 1
+  const bool potts_nonneg = A.potts_nonneg != 0;
 
   for (uint32_t iter = 0;; ++iter) {
     // warp 0 claims the next super-band and publishes it to the other warps of the CTA ({iteration + 1, index} in a
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(RINGS ? 32 * WavefrontCfg<Real, PW, L, KSEL>::
       if constexpr (FAST) {
         // ---- ReceiveMessages from the two processed neighbours, SendMessages to the two unprocessed ones ----
         Real h_ir[4], h_ic[4];
-        lane_min_plus2<Real, PW, L, HOPS>(par_ir, carry_row, h_ir, par_ic, col_in, h_ic, stage_a, stage_b, gl);
+        lane_min_plus2<Real, PW, L, HOPS>(par_ir, carry_row, h_ir, par_ic, col_in, h_ic, stage_a, stage_b, gl, potts_nonneg);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const Real m_ir = h_ir[k] + own_ir[k], m_ic = h_ic[k] + own_ic[k];
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(RINGS ? 32 * WavefrontCfg<Real, PW, L, KSEL>::
           for (int p = 0; p < P; ++p) { pza[p] = on_a ? pr_a[p] : Real(0); pzb[p] = on_b ? pr_b[p] : Real(0); }
 #pragma unroll
           for (int k = 0; k < 4; ++k) { oza[k] = on_a ? oth_a[k] : Real(0); ozb[k] = on_b ? oth_b[k] : Real(0); }
-          lane_min_plus2<Real, PW, L, HOPS>(pza, oza, ha, pzb, ozb, hb, stage_a, stage_b, gl);
+          lane_min_plus2<Real, PW, L, HOPS>(pza, oza, ha, pzb, ozb, hb, stage_a, stage_b, gl, potts_nonneg);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             m_a[k] = on_a ? Real(ha[k] + own_a[k]) : Real(0);

@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
   const bool recv_row_first = fwd ? !A.fifo : (A.fifo != 0);
   const Real w_fast = (Real)(1.0 / 2.0);
   const bool H_total_ge2 = H >= 2 || A.in_halo || A.out_halo;
+  const bool potts_nonneg = A.potts_nonneg != 0;
   const int sp_end = qoff + (int)W + T - 1;
 
   for (uint32_t iter = 0;; ++iter) {
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
       if constexpr (FAST) {
         // ---- ReceiveMessages from the two processed neighbours, SendMessages to the two unprocessed ones ----
         Real h_ir[4], h_ic[4];
-        lane_min_plus2<Real, PW, L, HOPS>(par_ir, carry_row, h_ir, par_ic, col_in, h_ic, stage_a, stage_b, gl);
+        lane_min_plus2<Real, PW, L, HOPS>(par_ir, carry_row, h_ir, par_ic, col_in, h_ic, stage_a, stage_b, gl, potts_nonneg);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const Real m_ir = h_ir[k] + own_ir[k], m_ic = h_ic[k] + own_ic[k];
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
           for (int p = 0; p < P; ++p) { pza[p] = on_a ? pr_a[p] : Real(0); pzb[p] = on_b ? pr_b[p] : Real(0); }
 #pragma unroll
           for (int k = 0; k < 4; ++k) { oza[k] = on_a ? oth_a[k] : Real(0); ozb[k] = on_b ? oth_b[k] : Real(0); }
-          lane_min_plus2<Real, PW, L, HOPS>(pza, oza, ha, pzb, ozb, hb, stage_a, stage_b, gl);
+          lane_min_plus2<Real, PW, L, HOPS>(pza, oza, ha, pzb, ozb, hb, stage_a, stage_b, gl, potts_nonneg);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             m_a[k] = on_a ? Real(ha[k] + own_a[k]) : Real(0);
@@ -475,17 +476,20 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
         carry_col[k] = t <= t_in ? Real(0) : up;
       }
       // ---- publish the step: records (and re-armed halo slots) of this step are in shared memory ----
-      if (((sp - T + 2) & (K - 1)) == 0 || sp + 1 == sp_end) fence_proxy_async();   // this step completes a tile: the mover's TMA store reads it
+      // (predicated, no branch: this step completes a tile, the out-mover's TMA store reads it through the async proxy)
+      asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p fence.proxy.async.shared::cta; }" ::"r"((uint32_t)(((sp - T + 2) & (K - 1)) == 0 || sp + 1 == sp_end)) : "memory");
       __syncwarp();
-      if (lane == 0) sts_volatile_u32(ctrl + 16, step_base + (uint32_t)(sp - qoff + 1));
+      asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctrl + 16), "r"(step_base + (uint32_t)(sp - qoff + 1)) : "memory");
     };
 
     const bool fast_band = !A.primal && W >= 3 && H_total_ge2;
     const int sp_fast0 = fast_band ? (last_band ? qoff + T : qoff) : sp_end, sp_fast1 = fast_band ? qoff + (int)W - 2 : sp_end;
-    for (int sp = qoff; sp < sp_end; ++sp) {
-      if (sp >= sp_fast0 && sp <= sp_fast1) do_step(std::true_type{}, sp);
-      else do_step(std::false_type{}, sp);
-    }
+    // three loops, so that the fast steps form one compact loop body (a lone warp pays every far jump with a fetch stall)
+    int sp = qoff;
+    for (; sp < sp_fast0 && sp < sp_end; ++sp) do_step(std::false_type{}, sp);
+#pragma unroll 1
+    for (; sp <= sp_fast1; ++sp) do_step(std::true_type{}, sp);
+    for (; sp < sp_end; ++sp) do_step(std::false_type{}, sp);
     stamp(3);
     chunk_base += (uint32_t)nchunks;
     step_base += (uint32_t)(W + T - 1);

@@ -18,7 +18,7 @@ static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& arg
     cudaError_t e = cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
     if constexpr (ANISO && LeanCfg<Real, PW, L, KSEL>::LEAN_FITS) {
-      if (tune.lean > 0) {
+      if (tune.lean != 0 && tune.warps_per_cta <= 1) {
         // lean variant: compute warp + in-mover + out-mover per band (kernels_grid_lean.cuh)
         using LCfg = LeanCfg<Real, PW, L, KSEL>;
         auto lkernel = wavefront_lean_kernel<Real, PW, L, HOPS, KSEL>;

@@ -15,7 +15,8 @@ struct WavefrontTuning {
   int max_ctas = 0;     // 0 = one CTA (= warps_per_cta bands at a time) per resident slot
   int ctas_per_sm = 0;  // 0 = as many as fit
   int tile_cols = 0;    // 0 = automatic, else 8 or 4
-  int lean = 0;         // 1 = lean variant for the anisotropic passes: compute warp + two mover warps per band
+  int lean = -1;        // lean variant for the anisotropic passes (compute warp + two mover warps per band): 1 on, 0 off,
+                        // -1 automatic (on where it fits; profiles/r01c_lean.txt)
   int warps_per_cta = 0;  // consecutive bands per CTA (<= 8 and what the shared memory holds); 0 or 1 = one band per CTA
 };
 

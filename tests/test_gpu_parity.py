@@ -262,7 +262,8 @@ def test_wavefront_ragged_shapes(H, W):
 
 
 @pytest.mark.parametrize("tuning", [dict(wavefront_max_ctas=1), dict(wavefront_max_ctas=3), dict(wavefront_ctas_per_sm=1),
-                                    dict(wavefront_max_ctas=2, wavefront_ctas_per_sm=1), dict(wavefront_warps_per_cta=1),
+                                    dict(wavefront_max_ctas=2, wavefront_ctas_per_sm=1), dict(wavefront_lean=0), dict(wavefront_lean=0, wavefront_max_ctas=2),
+                                    dict(wavefront_warps_per_cta=1),
                                     dict(wavefront_warps_per_cta=2), dict(wavefront_warps_per_cta=3, wavefront_tile_cols=4),
                                     dict(wavefront_warps_per_cta=3, wavefront_max_ctas=1),
                                     dict(wavefront_warps_per_cta=8, wavefront_tile_cols=4, wavefront_max_ctas=2)])
