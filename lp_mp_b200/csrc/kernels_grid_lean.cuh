@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
     int sp = qoff;
     for (; sp < sp_fast0 && sp < sp_end; ++sp) do_step(std::false_type{}, sp);
 #pragma unroll 1
-    for (; sp <= sp_fast1; ++sp) do_step(std::true_type{}, sp);
+    for (; sp <= sp_fast1 && sp < sp_end; ++sp) do_step(std::true_type{}, sp);
     for (; sp < sp_end; ++sp) do_step(std::false_type{}, sp);
     stamp(3);
     chunk_base += (uint32_t)nchunks;
