@@ -88,7 +88,8 @@ int LPMP_FN(set_schedule)(lpmp_solver* h, int schedule);
 /* launch-shape knobs of the device schedule (no effect on results): "wavefront_max_ctas" (cap on resident bands),
  * "wavefront_ctas_per_sm", "wavefront_tile_cols" (8 or 4 columns per TMA tile), "wavefront_warps_per_cta" (consecutive
  * bands per CTA with the hand-off between them in shared memory; default 1), "wavefront_lean" (anisotropic passes: 1 = compute
- * warp + two data-mover warps per band, 0 = one warp does everything; default automatic), "wavefront_trace" (see get_trace).
+ * warp + two data-mover warps per band, 0 = one warp does everything; default automatic), "wavefront_cluster" (CTAs per
+ * thread-block cluster of the lean variant: consecutive bands hand off through distributed shared memory; 1 = none, default 8), "wavefront_trace" (see get_trace).
  * Before finalize. */
 int LPMP_FN(set_tuning)(lpmp_solver* h, const char* key, int value);
 /* Deterministic greedy colouring in node order (host utility, no handle state): colour[i] = smallest colour

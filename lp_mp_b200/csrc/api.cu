@@ -346,6 +346,7 @@ struct Solver : ISolver {
     else if (k == "wavefront_tile_cols") tune.tile_cols = value;
     else if (k == "wavefront_warps_per_cta") tune.warps_per_cta = value;
     else if (k == "wavefront_lean") tune.lean = value;
+    else if (k == "wavefront_cluster") tune.cluster = value;
     else if (k == "wavefront_trace") want_trace = value != 0;
     else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
     return LPMP_OK;

@@ -33,6 +33,22 @@ struct LeanCfg : WavefrontCfg<Real, PW, L, KSEL> {
 __device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_volatile_u32(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+// ---- thread-block cluster / distributed shared memory primitives ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t a, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+template <int BYTES> __device__ __forceinline__ void st_cluster(uint32_t a, const void* src) {
+  const uint32_t* d = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+  for (int o = 0; o < BYTES / 16; ++o)
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a + 16 * o), "r"(d[4 * o]), "r"(d[4 * o + 1]), "r"(d[4 * o + 2]), "r"(d[4 * o + 3]) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+
 template <typename Real, int PW, int L, int HOPS, int KSEL>
 __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_par,
                                                             const GridArgs<Real> A) {
@@ -52,7 +68,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
   const uint32_t rec_ring = smem_base + 128;
   const uint32_t par_ring = rec_ring + NSLOT * SLOT_REC_B;
   const uint32_t scratch_all = par_ring + NSLOT * SLOT_PAR_B;
-  const uint32_t ctrl = smem_base + (uint32_t)Cfg::WARP_SMEM;          // +0/+8: band queue {iteration + 1, band}, +16: step counter
+  const uint32_t ctrl = smem_base + (uint32_t)Cfg::WARP_SMEM;          // +0..+31: super-band queue {index, iteration + 1} x 4, +64: step counter
   const uint32_t halo = ctrl + 128;                                    // [HALO][L]
   const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5);
   const bool fwd = A.forward != 0;
@@ -80,7 +96,13 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
       for (int i = (int)threadIdx.x; i < Cfg::SCRATCH; i += 96) sc[i] = RealTraits<Real>::inf();
     }
   }
-  __syncthreads();
+  // CTAs of a thread-block cluster work on CONSECUTIVE bands (rank r of the cluster on band sb * csize + r): the vectors
+  // that leave band r go straight into the halo ring of rank r + 1 through distributed shared memory; only the boundary
+  // between two clusters goes through the L2 hand-off slots
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  const unsigned num_super = (A.num_bands + csize - 1u) / csize;
+  if (csize > 1) cluster_sync_all();   // every ring of the cluster is armed before a neighbour may write into it
+  else __syncthreads();
 
   // bounded waits: a lost partner must not hang the device (sticky abort flag, checked by the host after the pass)
   auto timed_out = [&](unsigned& spins, unsigned limit) {
@@ -97,15 +119,31 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
     // ======================================= out-mover: ticket, tiles, hand-out =======================================
     const int g = lane / G, gl = lane % G;              // column slot of this lane group inside a batch, label quad
     for (uint32_t iter = 0;; ++iter) {
-      unsigned kb = 0;
+      unsigned sb = 0;
       if (lane == 0) {
-        kb = atomicAdd(A.control, 1u);
-        asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" ::"r"(ctrl + 8 * (iter & 1u)), "r"(kb), "r"(iter + 1u) : "memory");
+        if (crank == 0) {   // rank 0 claims the super-band and publishes it to every CTA of the cluster
+          sb = atomicAdd(A.control, 1u);
+          for (uint32_t rk = 0; rk < csize; ++rk)
+            asm volatile("st.shared::cluster.v2.u32 [%0], {%1,%2};" ::"r"(mapa_u32(ctrl + 8 * (iter & 3u), rk)), "r"(sb), "r"(iter + 1u) : "memory");
+        } else {
+          unsigned it1, spins = 0;
+          do {
+            asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sb), "=r"(it1) : "r"(ctrl + 8 * (iter & 3u)) : "memory");
+          } while (it1 != iter + 1u && !timed_out(spins, 1u << 27));
+          if (it1 != iter + 1u) sb = 0xffffffffu;
+        }
       }
-      kb = __shfl_sync(FULL, kb, 0);
-      if (kb >= A.num_bands) break;
+      sb = __shfl_sync(FULL, sb, 0);
+      if (sb >= num_super) break;
+      const unsigned kb = sb * csize + crank;
+      if (kb >= A.num_bands) continue;   // the last super-band may be partial
       const bool last_band = kb + 1 == A.num_bands;
       const bool hand_out = !last_band || (A.out_halo && A.out_boundary != nullptr);
+      const bool dsm_out = !last_band && crank + 1 < csize;   // the successor band runs in the next CTA of this cluster
+      const uint32_t r_halo = mapa_u32(halo + (uint32_t)(gl * 4) * S, dsm_out ? crank + 1 : crank);
+      const uint32_t r_ctr = mapa_u32(ctrl + 64, dsm_out ? crank + 1 : crank);
+      const uint32_t col_base = iter * W;   // the successor's running halo column index of this band's column 0 (it polls in every band)
+      uint32_t free_upto = col_base;        // running column index up to which the successor's halo slots are known to be free
       const int t_hand = last_band ? (int)H - 1 - (int)kb * T + roff : T - 1;
       Real* const hand_dst = (last_band ? A.out_boundary : A.handoff + (uint64_t)(kb + 1) * W * L) + gl * 4;
       const int row0_own = fwd ? (int)kb * T : (nb - 1 - (int)kb) * T;
@@ -120,16 +158,32 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
         A.trace[4ull * kb + 0] = now;
       }
       for (;;) {
-        const int c = (int)(lds_volatile_u32(ctrl + 16) - step_base);   // steps of this band the compute warp has completed
+        const int c = (int)(lds_volatile_u32(ctrl + 64) - step_base);   // steps of this band the compute warp has completed
         bool moved = false;
         // ---- 1. vectors leaving through the band's last row: tile ring -> successor's hand-off slots ----
         if (q_out < n_out) {
           int avail = c - t_hand;                       // columns the last row has completed
           if (avail > (int)W) avail = (int)W;
           if (avail < 0) avail = 0;
+          if (dsm_out) {
+            if (q_out < avail && col_base + (uint32_t)q_out >= free_upto) {
+              // steps the successor has completed (all bands) -> columns it has consumed and re-armed
+              const uint32_t p = ld_cluster_u32(r_ctr), ib = p / (uint32_t)nsteps, cl = p - ib * (uint32_t)nsteps;
+              free_upto = ib * W + (cl < W ? cl : W) + (uint32_t)HALO;
+            }
+            const int lim = (int)(free_upto - col_base);
+            if (avail > lim) avail = lim > q_out ? lim : q_out;
+          }
           while (q_out < avail) {
             const int q = q_out + g;
-            if (q < avail) {
+            if (q < avail && dsm_out) {
+              const int qp = q + qoff;
+              const uint32_t slot = (chunk_base + (uint32_t)(qp >> LOGK)) & (NSLOT - 1);
+              const uint32_t kk = ((uint32_t)qp & (K - 1)) ^ (uint32_t)kxor;
+              Real v[4];
+              lds_hand<HAND_BYTES>(v, rec_hand + slot * SLOT_REC_B + kk * REC_B);
+              st_cluster<HAND_BYTES>(r_halo + ((col_base + (uint32_t)q) & (uint32_t)(HALO - 1)) * LB, v);
+            } else if (q < avail) {
               const int qp = q + qoff;
               const uint32_t slot = (chunk_base + (uint32_t)(qp >> LOGK)) & (NSLOT - 1);
               const uint32_t kk = ((uint32_t)qp & (K - 1)) ^ (uint32_t)kxor;
@@ -189,31 +243,32 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
       step_base += (uint32_t)nsteps;
     }
     if (lane == 0) tma_wait_all();   // the global writes of the last tiles are complete before the warp exits
-    return;
-  }
-  if (wid == 1) {
+  } else if (wid == 1) {
     // ============================== in-mover: predecessor's hand-off slots (L2) -> halo ring ==============================
     constexpr int NBATCH = TG >= 16 ? 1 : 16 / TG;      // >= 16 columns polled per L2 round trip
     const int g = lane / G, gl = lane % G;
     for (uint32_t iter = 0;; ++iter) {
-      unsigned kb = 0;
+      unsigned sb = 0;
       if (lane == 0) {
         unsigned it1;
         unsigned spins = 0;
         do {
-          asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(kb), "=r"(it1) : "r"(ctrl + 8 * (iter & 1u)) : "memory");
+          asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sb), "=r"(it1) : "r"(ctrl + 8 * (iter & 3u)) : "memory");
         } while (it1 != iter + 1u && !timed_out(spins, 1u << 27));
-        if (it1 != iter + 1u) kb = 0xffffffffu;
+        if (it1 != iter + 1u) sb = 0xffffffffu;
       }
-      kb = __shfl_sync(FULL, kb, 0);
-      if (kb >= A.num_bands) break;
+      sb = __shfl_sync(FULL, sb, 0);
+      if (sb >= num_super) break;
+      const unsigned kb = sb * csize + crank;
+      if (kb >= A.num_bands) continue;
       const bool poll_in = kb > 0 || A.in_halo;
+      const bool from_l2 = poll_in && crank == 0;   // other ranks: the predecessor's out-mover fills the halo ring directly
       const int t_in = kb == 0 ? roff : 0;
       const Real* const hand_in = (kb == 0 ? A.in_boundary : A.handoff + (uint64_t)kb * W * L) + gl * 4;
       int q_in = 0;
       unsigned spins = 0;
-      while (poll_in && q_in < (int)W) {
-        const int c = (int)(lds_volatile_u32(ctrl + 16) - step_base);
+      while (from_l2 && q_in < (int)W) {
+        const int c = (int)(lds_volatile_u32(ctrl + 64) - step_base);
         int limit = (c - t_in > 0 ? c - t_in : 0) + HALO;   // the compute warp has consumed (and re-armed) c - t_in columns
         if (limit > (int)W) limit = (int)W;
         Real v[NBATCH][4];
@@ -249,9 +304,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
       step_base += (uint32_t)nsteps;
       if (poll_in) halo_n += W;
     }
-    return;
-  }
-
+  } else {
   // =================================================== compute warp ===================================================
   const bool lane_used = !PARTIAL_WARP || lane / G < T;
   const int t = lane_used ? lane / G : T - 1, gl = lane % G;
@@ -269,17 +322,19 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
   const int sp_end = qoff + (int)W + T - 1;
 
   for (uint32_t iter = 0;; ++iter) {
-    unsigned kb = 0;
+    unsigned sb = 0;
     if (lane == 0) {
       unsigned it1;
       unsigned spins = 0;
       do {
-        asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(kb), "=r"(it1) : "r"(ctrl + 8 * (iter & 1u)) : "memory");
+        asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sb), "=r"(it1) : "r"(ctrl + 8 * (iter & 3u)) : "memory");
       } while (it1 != iter + 1u && !timed_out(spins, 1u << 27));
-      if (it1 != iter + 1u) kb = 0xffffffffu;
+      if (it1 != iter + 1u) sb = 0xffffffffu;
     }
-    kb = __shfl_sync(FULL, kb, 0);
-    if (kb >= A.num_bands) break;
+    sb = __shfl_sync(FULL, sb, 0);
+    if (sb >= num_super) break;
+    const unsigned kb = sb * csize + crank;
+    if (kb >= A.num_bands) continue;
     const int u = (int)kb * T + t - roff;                  // virtual row of this lane group
     const bool row_active = u >= 0 && u < (int)H && lane_used;
     const uint32_t r = fwd ? (uint32_t)u : H - 1 - (uint32_t)u;
@@ -479,7 +534,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
       // (predicated, no branch: this step completes a tile, the out-mover's TMA store reads it through the async proxy)
       asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p fence.proxy.async.shared::cta; }" ::"r"((uint32_t)(((sp - T + 2) & (K - 1)) == 0 || sp + 1 == sp_end)) : "memory");
       __syncwarp();
-      asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctrl + 16), "r"(step_base + (uint32_t)(sp - qoff + 1)) : "memory");
+      asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctrl + 64), "r"(step_base + (uint32_t)(sp - qoff + 1)) : "memory");
     };
 
     const bool fast_band = !A.primal && W >= 3 && H_total_ge2;
@@ -495,6 +550,9 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
     step_base += (uint32_t)(W + T - 1);
     if (poll_in) halo_n += W;
   }
+  }
+  // no CTA of the cluster leaves while a neighbour may still read its step counter or write into its halo ring
+  if (csize > 1) cluster_sync_all();
 }
 
 }  // namespace lpmp

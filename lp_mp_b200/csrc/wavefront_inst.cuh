@@ -36,8 +36,38 @@ static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& arg
         int ctas = (int)args.num_bands;
         if (ctas > per_sm * num_sms) ctas = per_sm * num_sms;   // persistent: the ticket loop covers the remaining bands
         if (tune.max_ctas > 0 && ctas > tune.max_ctas) ctas = tune.max_ctas;
-        lkernel<<<ctas, 96, LCfg::LEAN_SMEM, stream>>>(maps[0], maps[2], args);
-        return cudaGetLastError();
+        // thread-block clusters: the CTAs of a cluster take consecutive bands and hand off through distributed shared memory
+        int cs = tune.cluster > 0 ? tune.cluster : 8;
+        if (cs > 8) cs = 8;
+        while (cs > 1 && ((cs & (cs - 1)) != 0 || cs > ctas || (uint32_t)cs > args.num_bands)) --cs;
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        cfg.blockDim = dim3(96);
+        cfg.dynamicSmemBytes = LCfg::LEAN_SMEM;
+        cfg.stream = stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        for (; cs > 1; cs >>= 1) {   // the largest cluster size the device can co-schedule
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          cfg.gridDim = dim3((unsigned)cs);
+          int max_clusters = 0;
+          if (cudaOccupancyMaxActiveClusters(&max_clusters, lkernel, &cfg) == cudaSuccess && max_clusters >= 1) {
+            int clusters = ctas / cs;
+            if (tune.ctas_per_sm > 0 && clusters > per_sm * num_sms / cs) clusters = per_sm * num_sms / cs;
+            if (clusters > max_clusters) clusters = max_clusters;
+            const int want = (int)((args.num_bands + cs - 1) / cs);
+            if (clusters > want) clusters = want;
+            if (clusters >= 1) { ctas = clusters * cs; break; }
+          }
+          (void)cudaGetLastError();
+        }
+        if (cs <= 1) {
+          lkernel<<<ctas, 96, LCfg::LEAN_SMEM, stream>>>(maps[0], maps[2], args);
+          return cudaGetLastError();
+        }
+        cfg.gridDim = dim3((unsigned)ctas);
+        return cudaLaunchKernelEx(&cfg, lkernel, maps[0], maps[2], args);
       }
     }
     // warps (= consecutive bands) per CTA: at most what the shared memory holds and MAX_WARPS; the hand-off between the

@@ -17,6 +17,8 @@ struct WavefrontTuning {
   int tile_cols = 0;    // 0 = automatic, else 8 or 4
   int lean = -1;        // lean variant for the anisotropic passes (compute warp + two mover warps per band): 1 on, 0 off,
                         // -1 automatic (on where it fits; profiles/r01c_lean.txt)
+  int cluster = 0;      // lean variant: CTAs per thread-block cluster (consecutive bands, hand-off through distributed shared
+                        // memory); 0 = automatic (8), 1 = no clusters
   int warps_per_cta = 0;  // consecutive bands per CTA (<= 8 and what the shared memory holds); 0 or 1 = one band per CTA
 };
 

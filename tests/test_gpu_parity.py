@@ -285,7 +285,9 @@ def test_wavefront_super_bands(kind, L, tuning):
     run_lockstep(lps, "anisotropic", iters=3, lb_rtol=1e-6)
 
 
-@pytest.mark.parametrize("kind,L,dtype,tuning", [("trunclin", 16, "f32", dict(wavefront_lean=1)), ("trunclin", 16, "f64", dict(wavefront_lean=1, wavefront_tile_cols=4)),
+@pytest.mark.parametrize("kind,L,dtype,tuning", [("trunclin", 16, "f32", dict(wavefront_lean=1)), ("trunclin", 16, "f32", dict(wavefront_cluster=1)),
+                                                 ("trunclin", 16, "f32", dict(wavefront_cluster=2)), ("potts", 32, "f64", dict(wavefront_cluster=4, wavefront_max_ctas=8)),
+                                                 ("potts", 8, "f32", dict(wavefront_cluster=8, wavefront_max_ctas=8)), ("potts", 16, "f32", dict(wavefront_cluster=4, wavefront_ctas_per_sm=1)), ("trunclin", 16, "f64", dict(wavefront_lean=1, wavefront_tile_cols=4)),
                                                  ("potts", 32, "f32", dict(wavefront_lean=1)), ("potts", 8, "f64", dict(wavefront_lean=1, wavefront_max_ctas=3)),
                                                  ("potts", 64, "f32", dict(wavefront_lean=1, wavefront_max_ctas=1))])
 def test_wavefront_lean_variant(kind, L, dtype, tuning):
