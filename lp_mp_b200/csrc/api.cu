@@ -239,7 +239,7 @@ struct Solver : ISolver {
   DeviceBuffer<uint8_t> inc_flags;
   DeviceBuffer<double> partial, result;
   DeviceBuffer<unsigned long long> trace;   // debug timeline of the last wavefront pass (set_tuning wavefront_trace=1)
-  bool want_trace = false;
+  int want_trace = 0;        // 1: per-band stamps; 2: also per-step stamps of two neighbouring bands (lean variant)
   DeviceBuffer<unsigned int> control;  // [0] band ticket, [1] sticky abort flag (hand-off poll timed out)
   CUtensorMap maps8[3], maps4[3];   // tile width 8 / 4 columns
   std::vector<uint64_t> level_off;     // host
@@ -347,7 +347,7 @@ struct Solver : ISolver {
     else if (k == "wavefront_warps_per_cta") tune.warps_per_cta = value;
     else if (k == "wavefront_lean") tune.lean = value;
     else if (k == "wavefront_cluster") tune.cluster = value;
-    else if (k == "wavefront_trace") want_trace = value != 0;
+    else if (k == "wavefront_trace") want_trace = value;
     else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
     return LPMP_OK;
   }
@@ -706,7 +706,7 @@ struct Solver : ISolver {
         const uint32_t bands = (gridH + shape.T - 1) / shape.T;
         CUDA_TRY(control.alloc(2));
         CUDA_TRY(cudaMemsetAsync(control.p, 0, control.bytes(), stream));
-        if (want_trace) { CUDA_TRY(trace.alloc(4 * (size_t)bands)); CUDA_TRY(cudaMemsetAsync(trace.p, 0, trace.bytes(), stream)); }
+        if (want_trace) { CUDA_TRY(trace.alloc(4 * (size_t)bands + (want_trace >= 2 ? 2 * 8192 : 0))); CUDA_TRY(cudaMemsetAsync(trace.p, 0, trace.bytes(), stream)); }
         CUDA_TRY(handoff.alloc((size_t)bands * gridW * L));
         CUDA_TRY(cudaMemsetAsync(handoff.p, 0xff, handoff.bytes(), stream));
         for (int ks = 4; ks <= 8; ks += 4) {
@@ -799,6 +799,8 @@ struct Solver : ISolver {
       A.out_boundary = forward ? peer_bot : peer_top;
       A.labels = labels.p;
       A.trace = trace.p;
+      A.trace_steps = (trace.p && want_trace >= 2) ? trace.p + 4 * (size_t)A.num_bands : nullptr;
+      A.trace_band = A.num_bands / 2;
       CUDA_TRY(cudaMemsetAsync(control.p, 0, sizeof(unsigned int), stream));
       // tile width: 8 columns unless the bands outnumber the resident warps and the narrow tile doubles residency
       int ksel = shape.default_k();

@@ -63,6 +63,8 @@ struct GridArgs {
                             // in_boundary, possibly peer memory), or null: not delivered
   uint32_t* labels;         // [H*W]
   unsigned long long* trace;   // debug: per band {claimed, first tile ready, first hand-off consumed, done} in ns (globaltimer), or null
+  unsigned long long* trace_steps;   // debug (lean variant): [2][8192] end-of-step stamps of bands trace_band and trace_band + 1, or null
+  uint32_t trace_band;
 };
 
 // ---- hand-off slots: L2-resident, self-validating -------------------------------------------------------------------

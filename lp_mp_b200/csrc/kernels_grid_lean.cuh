@@ -2,7 +2,7 @@
 //
 // Same schedule, storage, tiles and hand-off protocol as wavefront_pass_kernel (kernels_grid.cuh; replaces
 // LP::ComputePass over forward/backwardUpdateOrdering_, /root/reference/include/LP_MP.h:981-1005,1592-1602, and
-// FactorContainer::UpdateFactor, include/factors_messages.hxx:2256-2261) -- but a CTA is a PAIR of warps:
+// FactorContainer::UpdateFactor, include/factors_messages.hxx:2256-2261) -- but a CTA is FOUR warps:
 //
 //   * warp 0 (compute) runs the node updates of the band out of shared memory only: per step it reads the records of
 //     its anti-diagonal fragment from the tile ring, takes the column neighbour's vector of the band's first row from a
@@ -11,9 +11,11 @@
 //   * warp 1 (in-mover) polls the predecessor band's hand-off slots in L2 -- >= 16 columns per round trip, as deep as the
 //     halo ring is free, so loaded L2 latency is covered by parallelism instead of a fixed prefetch distance -- and moves
 //     them into the halo ring;
-//   * warp 2 (out-mover) claims the band ticket, issues the TMA tile loads as slots become free and the tile stores as
-//     the compute warp completes tiles, and copies the vectors that leave through the band's last row from the tile ring
-//     to the successor's hand-off slots as soon as the step counter says they are final.
+//   * warp 2 (out-mover) claims the band ticket and copies the vectors that leave through the band's last row from the
+//     tile ring to the successor as soon as the step counter says they are final: into the successor's halo ring through
+//     distributed shared memory when it runs in the next CTA of the thread-block cluster, else into its L2 hand-off slots;
+//   * warp 3 (tile warp) issues the TMA tile loads as slots become free and the tile stores as the compute warp completes
+//     tiles (its waits for a store to leave shared memory block, so nothing latency-critical shares the warp).
 //
 // The arithmetic of a node update is the same code in the same order as in wavefront_pass_kernel (bit-identical state).
 #pragma once
@@ -50,7 +52,7 @@ template <int BYTES> __device__ __forceinline__ void st_cluster(uint32_t a, cons
 __device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 
 template <typename Real, int PW, int L, int HOPS, int KSEL>
-__global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_par,
+__global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_par,
                                                             const GridArgs<Real> A) {
   using Cfg = LeanCfg<Real, PW, L, KSEL>;
   constexpr bool ANISO = true;
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
   const uint32_t rec_ring = smem_base + 128;
   const uint32_t par_ring = rec_ring + NSLOT * SLOT_REC_B;
   const uint32_t scratch_all = par_ring + NSLOT * SLOT_PAR_B;
-  const uint32_t ctrl = smem_base + (uint32_t)Cfg::WARP_SMEM;          // +0..+31: super-band queue {index, iteration + 1} x 4, +64: step counter
+  const uint32_t ctrl = smem_base + (uint32_t)Cfg::WARP_SMEM;          // +0..+31: super-band queue {index, iteration + 1} x 4, +64: step counter, +68: hand-out counter
   const uint32_t halo = ctrl + 128;                                    // [HALO][L]
   const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5);
   const bool fwd = A.forward != 0;
@@ -89,11 +91,11 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
   }
   {
     Real* hr = reinterpret_cast<Real*>(smem_raw + Cfg::WARP_SMEM + 128);
-    for (int i = (int)threadIdx.x; i < HALO * L; i += 96) hr[i] = sentinel<Real>();
+    for (int i = (int)threadIdx.x; i < HALO * L; i += 128) hr[i] = sentinel<Real>();
     if (threadIdx.x < 32) reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::WARP_SMEM)[threadIdx.x] = 0u;
     if constexpr (PW == LPMP_PAIRWISE_TRUNCLIN) {
       Real* sc = reinterpret_cast<Real*>(smem_raw + 128 + NSLOT * (SLOT_REC_B + SLOT_PAR_B));
-      for (int i = (int)threadIdx.x; i < Cfg::SCRATCH; i += 96) sc[i] = RealTraits<Real>::inf();
+      for (int i = (int)threadIdx.x; i < Cfg::SCRATCH; i += 128) sc[i] = RealTraits<Real>::inf();
     }
   }
   // CTAs of a thread-block cluster work on CONSECUTIVE bands (rank r of the cluster on band sb * csize + r): the vectors
@@ -114,9 +116,10 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
   uint32_t chunk_base = 0;   // tiles of earlier bands of this CTA: slot / mbarrier-phase sequence continues
   uint32_t step_base = 0;    // steps of earlier bands: the published step counter is monotone over the kernel
   uint32_t halo_n = 0;       // columns that went through the halo ring in earlier bands: slots are used cyclically
+  uint32_t out_base = 0;     // W per earlier band: the out-mover's published hand-out counter is monotone over the kernel
 
   if (wid == 2) {
-    // ======================================= out-mover: ticket, tiles, hand-out =======================================
+    // ========================================== out-mover: ticket, hand-out ==========================================
     const int g = lane / G, gl = lane % G;              // column slot of this lane group inside a batch, label quad
     for (uint32_t iter = 0;; ++iter) {
       unsigned sb = 0;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
       const int trow_hand = fwd ? t_hand : T - 1 - t_hand;
       const uint32_t rec_hand = rec_ring + (uint32_t)(trow_hand * K) * REC_B + o_out_col + (uint32_t)(gl * 4) * S;
       const int n_out = hand_out ? (int)W : 0;
-      int j_load = 0, j_store = 0, q_out = 0;
+      int q_out = 0;
       unsigned spins = 0;
       if (A.trace != nullptr && lane == 0) {
         unsigned long long now;
@@ -196,6 +199,42 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
           }
           if (q_out > avail) q_out = avail;
         }
+        if (moved && lane == 0) sts_volatile_u32(ctrl + 68, out_base + (uint32_t)q_out);   // the tile warp stores a tile after its vectors have left
+        if (c >= nsteps && q_out >= n_out) break;
+        if (moved) spins = 0;
+        else if (timed_out(spins, 1u << 26)) break;
+      }
+      out_base += W;
+      if (lane == 0) sts_volatile_u32(ctrl + 68, out_base);
+      chunk_base += (uint32_t)nchunks;
+      step_base += (uint32_t)nsteps;
+    }
+  } else if (wid == 3) {
+    // ================= tile warp: TMA loads as slots become free, TMA stores as the compute warp completes tiles =================
+    // (its waits for a store to leave shared memory block; nothing on the hand-off path waits behind them)
+    for (uint32_t iter = 0;; ++iter) {
+      unsigned sb = 0;
+      if (lane == 0) {
+        unsigned it1;
+        unsigned spins = 0;
+        do {
+          asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sb), "=r"(it1) : "r"(ctrl + 8 * (iter & 3u)) : "memory");
+        } while (it1 != iter + 1u && !timed_out(spins, 1u << 27));
+        if (it1 != iter + 1u) sb = 0xffffffffu;
+      }
+      sb = __shfl_sync(FULL, sb, 0);
+      if (sb >= num_super) break;
+      const unsigned kb = sb * csize + crank;
+      if (kb >= A.num_bands) continue;
+      const bool last_band = kb + 1 == A.num_bands;
+      const int n_out = (!last_band || (A.out_halo && A.out_boundary != nullptr)) ? (int)W : 0;
+      const int row0_own = fwd ? (int)kb * T : (nb - 1 - (int)kb) * T;
+      int j_load = 0, j_store = 0;
+      unsigned spins = 0;
+      for (;;) {
+        const int c = (int)(lds_volatile_u32(ctrl + 64) - step_base);   // steps of this band the compute warp has completed
+        const int q_out = (int)(lds_volatile_u32(ctrl + 68) - out_base); // columns of this band the out-mover has handed on
+        bool moved = false;
         // ---- 2. tile stores: a tile is final when the band's last group has left it (and its vectors have been handed on) ----
         if (j_store < nchunks) {
           int need = (j_store + 1) * K + T - 1 - qoff;
@@ -233,7 +272,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
           ++j_load;
           moved = true;
         }
-        if (c >= nsteps && q_out >= n_out && j_store >= nchunks) break;
+        if (j_store >= nchunks) break;
         if (moved) spins = 0;
         else if (timed_out(spins, 1u << 26)) break;
       }
@@ -241,6 +280,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
       __syncwarp();
       chunk_base += (uint32_t)nchunks;
       step_base += (uint32_t)nsteps;
+      out_base += W;
     }
     if (lane == 0) tma_wait_all();   // the global writes of the last tiles are complete before the warp exits
   } else if (wid == 1) {
@@ -360,6 +400,7 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
       }
     };
 
+    const bool trace_lane = A.trace_steps != nullptr && lane == 0 && kb - A.trace_band < 2u;   // debug: per-step stamps of two bands
     Real polled[4];   // the halo slot of the NEXT column of group t_in, read one step ahead
 #pragma unroll
     for (int k = 0; k < 4; ++k) polled[k] = Real(0);
@@ -398,18 +439,20 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
       // ---- the column neighbour's vector: shuffle inside the band, halo ring for group t_in ----
       Real col_in[4];
       const bool polling = poller && q >= 0 && q < (int)W;
-      if (__any_sync(FULL, polling && (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3])))) {
-        if (polling) {
-          unsigned spins = 0;
-          while (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3])) {
-            lds_hand<HAND_BYTES>(polled, halo_slot(q));
-            if (timed_out(spins, 1u << 27)) {
+      // (the wait is a warp-UNIFORM loop: lanes parked at a reconvergence point for a long wait wake up slowly -- measured
+      // 1.4 us on the first step of every band, which then stays in the band-to-band lag for the whole pass)
+      bool missing = polling && (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3]));
+      if (__any_sync(FULL, missing)) {
+        unsigned spins = 0;
+        do {
+          lds_hand_if<HAND_BYTES>(missing, polled, halo_slot(q));
+          missing = polling && (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3]));
+          if (timed_out(spins, 1u << 27)) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) polled[k] = Real(0);
-            }
+            for (int k = 0; k < 4; ++k) polled[k] = Real(0);
+            missing = false;
           }
-        }
-        __syncwarp();
+        } while (__any_sync(FULL, missing));
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) col_in[k] = polling ? polled[k] : carry_col[k];
@@ -535,13 +578,20 @@ __global__ void __launch_bounds__(96) wavefront_lean_kernel(const __grid_constan
       asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p fence.proxy.async.shared::cta; }" ::"r"((uint32_t)(((sp - T + 2) & (K - 1)) == 0 || sp + 1 == sp_end)) : "memory");
       __syncwarp();
       asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctrl + 64), "r"(step_base + (uint32_t)(sp - qoff + 1)) : "memory");
+      asm volatile("{ .reg .pred p; .reg .u64 t; setp.ne.u32 p, %0, 0; mov.u64 t, %%globaltimer; @p st.global.u64 [%1], t; }" ::"r"((uint32_t)(trace_lane && sp >= qoff && sp - qoff < 8192)),
+                   "l"(A.trace_steps + (kb - A.trace_band) * 8192u + (uint32_t)(sp - qoff)) : "memory");
     };
 
     const bool fast_band = !A.primal && W >= 3 && H_total_ge2;
     const int sp_fast0 = fast_band ? (last_band ? qoff + T : qoff) : sp_end, sp_fast1 = fast_band ? qoff + (int)W - 2 : sp_end;
     // three loops, so that the fast steps form one compact loop body (a lone warp pays every far jump with a fetch stall)
+    // A band cannot run faster than its predecessor, so whatever its FIRST step loses (the loop body has never been
+    // fetched on this SM: measured 1.4 us) stays in the band-to-band lag for the whole pass.  One dry step at "column -1"
+    // (all groups left of the grid: nothing is stored, carried or published) warms the instruction cache while the
+    // band is waiting for its predecessor anyway -- it runs as iteration -1 of the fast loop itself (same code addresses).
     int sp = qoff;
     for (; sp < sp_fast0 && sp < sp_end; ++sp) do_step(std::false_type{}, sp);
+    if (fast_band && sp == qoff) sp = qoff - 1;
 #pragma unroll 1
     for (; sp <= sp_fast1 && sp < sp_end; ++sp) do_step(std::true_type{}, sp);
     for (; sp < sp_end; ++sp) do_step(std::false_type{}, sp);

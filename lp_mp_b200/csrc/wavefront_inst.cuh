@@ -19,7 +19,7 @@ static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& arg
     if (e != cudaSuccess) return e;
     if constexpr (ANISO && LeanCfg<Real, PW, L, KSEL>::LEAN_FITS) {
       if (tune.lean != 0 && tune.warps_per_cta <= 1) {
-        // lean variant: compute warp + in-mover + out-mover per band (kernels_grid_lean.cuh)
+        // lean variant: compute warp + in-mover + out-mover + tile warp per band (kernels_grid_lean.cuh)
         using LCfg = LeanCfg<Real, PW, L, KSEL>;
         auto lkernel = wavefront_lean_kernel<Real, PW, L, HOPS, KSEL>;
         static bool lconfigured[64] = {};
@@ -29,7 +29,7 @@ static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& arg
           lconfigured[dev & 63] = true;
         }
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lkernel, 96, LCfg::LEAN_SMEM);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lkernel, 128, LCfg::LEAN_SMEM);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         if (tune.ctas_per_sm > 0 && per_sm > tune.ctas_per_sm) per_sm = tune.ctas_per_sm;
@@ -42,7 +42,7 @@ static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& arg
         while (cs > 1 && ((cs & (cs - 1)) != 0 || cs > ctas || (uint32_t)cs > args.num_bands)) --cs;
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute attr[1];
-        cfg.blockDim = dim3(96);
+        cfg.blockDim = dim3(128);
         cfg.dynamicSmemBytes = LCfg::LEAN_SMEM;
         cfg.stream = stream;
         cfg.attrs = attr;
@@ -63,7 +63,7 @@ static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& arg
           (void)cudaGetLastError();
         }
         if (cs <= 1) {
-          lkernel<<<ctas, 96, LCfg::LEAN_SMEM, stream>>>(maps[0], maps[2], args);
+          lkernel<<<ctas, 128, LCfg::LEAN_SMEM, stream>>>(maps[0], maps[2], args);
           return cudaGetLastError();
         }
         cfg.gridDim = dim3((unsigned)ctas);

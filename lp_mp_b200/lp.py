@@ -288,6 +288,12 @@ class LP:
         self._ck(self.api.get_trace(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size))
         return out
 
+    def trace_steps(self, bands):
+        """(wavefront_trace=2) end-of-step globaltimer stamps [2][8192] of bands ``bands // 2`` and ``bands // 2 + 1``"""
+        out = np.zeros(bands * 4 + 2 * 8192, dtype=np.uint64)
+        self._ck(self.api.get_trace(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size))
+        return out[bands * 4:].reshape(2, 8192)
+
     def stream(self) -> int:
         out = C.c_void_p()
         self._ck(self.api.stream(self.h, C.byref(out)))
