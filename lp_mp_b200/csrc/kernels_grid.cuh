@@ -569,22 +569,25 @@ __global__ void __launch_bounds__(RINGS ? 32 * WavefrontCfg<Real, PW, L, KSEL>::
       Real col_in[4];
       const bool polling = poller && q >= 0 && q < (int)W;
       const Real* const hslot = hand_in + (int64_t)q * L;
-      if (__any_sync(FULL, polling && (is_sentinel(polled[0][0]) || is_sentinel(polled[0][1]) || is_sentinel(polled[0][2]) || is_sentinel(polled[0][3])))) {
-        if (polling) {
-          unsigned spins = 0;
-          while (is_sentinel(polled[0][0]) || is_sentinel(polled[0][1]) || is_sentinel(polled[0][2]) || is_sentinel(polled[0][3])) {
-            if (ring_in) lds_hand<HAND_BYTES>(polled[0], in_slot(q));
-            else ld_relaxed<HAND_BYTES>(polled[0], hslot);
-            if ((++spins & 0x3ffu) == 0) {      // bounded wait: a lost producer must not hang the device
-              if (spins > (ring_in ? (1u << 27) : (1u << 22))) atomicExch(A.control + 1, 1u);   // ~1 s either way
-              if (*reinterpret_cast<volatile unsigned int*>(A.control + 1) != 0u) {
+      // the wait is a warp-UNIFORM loop (every lane takes every iteration; the loads are predicated): lanes parked at a
+      // reconvergence point during a long divergent spin wake up slowly (~1.4 us measured), and a band can never make
+      // up time on its predecessor
+      bool missing = polling && (is_sentinel(polled[0][0]) || is_sentinel(polled[0][1]) || is_sentinel(polled[0][2]) || is_sentinel(polled[0][3]));
+      if (__any_sync(FULL, missing)) {
+        unsigned spins = 0;
+        do {
+          if constexpr (RINGS) lds_hand_if<HAND_BYTES>(missing && ring_in, polled[0], in_slot(q));
+          ld_relaxed_if<HAND_BYTES>(missing && !ring_in, polled[0], hslot);
+          missing = polling && (is_sentinel(polled[0][0]) || is_sentinel(polled[0][1]) || is_sentinel(polled[0][2]) || is_sentinel(polled[0][3]));
+          if ((++spins & 0x3ffu) == 0) {      // bounded wait: a lost producer must not hang the device
+            if (spins > (ring_in ? (1u << 27) : (1u << 22))) atomicExch(A.control + 1, 1u);   // ~1 s either way
+            if (*reinterpret_cast<volatile unsigned int*>(A.control + 1) != 0u) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) polled[0][k] = Real(0);
-              }
+              for (int k = 0; k < 4; ++k) polled[0][k] = Real(0);
+              missing = false;
             }
           }
-        }
-        __syncwarp();
+        } while (__any_sync(FULL, missing));
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) col_in[k] = polling ? polled[0][k] : carry_col[k];

@@ -1,0 +1,8 @@
+( timeout 600 python -m pytest tests -m gpu -x -q -k "wavefront or stripe or golden" 2>&1 | grep -v "peak pool\|objects of size" | tail -3 )
+t() { timeout 100 python scripts/time_grid.py "$@" 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print(d['grid'], d['tune'], 'fwd', round(d['fwd_ms'],4), 'bwd', round(d['bwd_ms'],4), 'lb', d['lb'][-1])"; }
+t 1024 1024 16 trunclin f32 wavefront_lean=0
+t 4096 4096 32 potts f32 wavefront_lean=0
+t 1024 1024 16 trunclin f32 wavefront_lean=0,wavefront_warps_per_cta=2
+t 4096 4096 32 potts f32 wavefront_lean=0,wavefront_warps_per_cta=4
