@@ -240,7 +240,7 @@ struct Solver : ISolver {
   DeviceBuffer<double> partial, result;
   DeviceBuffer<unsigned long long> trace;   // debug timeline of the last wavefront pass (set_tuning wavefront_trace=1)
   int want_trace = 0;        // 1: per-band stamps; 2: also per-step stamps of two neighbouring bands (lean variant)
-  DeviceBuffer<unsigned int> control;  // [0] band ticket, [1] sticky abort flag (hand-off poll timed out)
+  DeviceBuffer<unsigned int> control;  // [0] band ticket, [1] sticky abort flag (hand-off poll timed out), [2 + smid] CTA arrivals per SM
   CUtensorMap maps8[3], maps4[3];   // tile width 8 / 4 columns
   std::vector<uint64_t> level_off;     // host
   uint64_t launches = 0, updates = 0;
@@ -697,14 +697,14 @@ struct Solver : ISolver {
         if (striped) { err = "stripes need the wavefront schedule"; return LPMP_ERR_UNSUPPORTED; }
         if (int r = build_grid_levels()) return r;
       } else if (dense) {
-        CUDA_TRY(control.alloc(2));
+        CUDA_TRY(control.alloc(2 + 1024));   // + one arrival counter per SM (role rotation of the lean kernel's warps)
         CUDA_TRY(cudaMemsetAsync(control.p, 0, control.bytes(), stream));
         CUDA_TRY(handoff.alloc((size_t)gridH * gridW * L));
         CUDA_TRY(cudaMemsetAsync(handoff.p, 0xff, handoff.bytes(), stream));
         CUDA_TRY(lb_rows.alloc(gridH));
       } else {
         const uint32_t bands = (gridH + shape.T - 1) / shape.T;
-        CUDA_TRY(control.alloc(2));
+        CUDA_TRY(control.alloc(2 + 1024));   // + one arrival counter per SM (role rotation of the lean kernel's warps)
         CUDA_TRY(cudaMemsetAsync(control.p, 0, control.bytes(), stream));
         if (want_trace) { CUDA_TRY(trace.alloc(4 * (size_t)bands + (want_trace >= 2 ? 2 * 8192 : 0))); CUDA_TRY(cudaMemsetAsync(trace.p, 0, trace.bytes(), stream)); }
         CUDA_TRY(handoff.alloc((size_t)bands * gridW * L));
@@ -793,6 +793,7 @@ struct Solver : ISolver {
       A.in_halo = forward ? has_above : has_below;
       A.out_halo = forward ? has_below : has_above;
       A.tl_reach = tl_reach;
+      A.lean_flags = tune.lean > 0 ? tune.lean : 0;
       A.potts_nonneg = pw == LPMP_PAIRWISE_POTTS && !potts_neg;
       A.control = control.p; A.handoff = handoff.p;
       A.in_boundary = forward ? in_top.p : in_bot.p;

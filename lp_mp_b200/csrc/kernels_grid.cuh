@@ -53,9 +53,11 @@ struct GridArgs {
   uint32_t num_bands;
   int forward, primal, fifo, repam;
   int in_halo, out_halo;    // striped: the band before virtual band 0 / after the last band lives on another device
+  int lean_flags;           // lean variant, experiments: 2 = rotate the warp roles per SM arrival, 4 = idle movers do NOT sleep
   int potts_nonneg;         // Potts: the host has seen no negative lambda (the kernels then skip the two-smallest-entries test)
   int tl_reach;             // truncated linear: max over edges of #{d >= 1 : slope*d < trunc} (host-computed)
-  unsigned int* control;    // [0] band ticket (zeroed before the launch), [1] sticky abort flag (poll timeout)
+  unsigned int* control;    // [0] band ticket (zeroed before the launch), [1] sticky abort flag (poll timeout),
+                            // [2 + smid] CTAs that have arrived on SM smid (lean variant: rotation of the warp roles)
   Real* handoff;            // [num_bands][W][L]: boundary b (1 <= b < num_bands) sits between virtual band b-1 and band b;
                             // all-sentinel between passes
   Real* in_boundary;        // [W][L] boundary 0 when in_halo: the neighbouring stripe's outgoing vectors (same protocol)

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
   const uint32_t scratch_all = par_ring + NSLOT * SLOT_PAR_B;
   const uint32_t ctrl = smem_base + (uint32_t)Cfg::WARP_SMEM;          // +0..+31: super-band queue {index, iteration + 1} x 4, +64: step counter, +68: hand-out counter
   const uint32_t halo = ctrl + 128;                                    // [HALO][L]
-  const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   const bool fwd = A.forward != 0;
   const uint32_t H = A.H, W = pin(A.W);
   const int nchunks = ((int)W + K - 1) >> LOGK;
@@ -98,6 +98,14 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
       for (int i = (int)threadIdx.x; i < Cfg::SCRATCH; i += 128) sc[i] = RealTraits<Real>::inf();
     }
   }
+  // Role of each warp: CTA warp 0 computes, 1 = in-mover, 2 = out-mover, 3 = tile warp.  (Experiment kept behind lean_flags
+  // bit 1: rotating the roles by the CTA's arrival order on its SM, so that the compute warps of co-resident CTAs sit on
+  // different schedulers, made the passes 10-20 % SLOWER on B200 -- profiles/r01c_lean.txt.)
+  if ((A.lean_flags & 2) && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::WARP_SMEM)[24] = atomicAdd(A.control + 2 + (smid & 1023u), 1u);
+  }
   // CTAs of a thread-block cluster work on CONSECUTIVE bands (rank r of the cluster on band sb * csize + r): the vectors
   // that leave band r go straight into the halo ring of rank r + 1 through distributed shared memory; only the boundary
   // between two clusters goes through the L2 hand-off slots
@@ -105,6 +113,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
   const unsigned num_super = (A.num_bands + csize - 1u) / csize;
   if (csize > 1) cluster_sync_all();   // every ring of the cluster is armed before a neighbour may write into it
   else __syncthreads();
+  const int wid = (int)(((threadIdx.x >> 5) + ((A.lean_flags & 2) ? lds_volatile_u32(ctrl + 96) : 0u)) & 3u);   // 0 compute, 1 in-mover, 2 out-mover, 3 tile warp
 
   // bounded waits: a lost partner must not hang the device (sticky abort flag, checked by the host after the pass)
   auto timed_out = [&](unsigned& spins, unsigned limit) {
@@ -219,6 +228,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
         unsigned spins = 0;
         do {
           asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sb), "=r"(it1) : "r"(ctrl + 8 * (iter & 3u)) : "memory");
+          if (it1 != iter + 1u && !(A.lean_flags & 4)) __nanosleep(400);   // idle until the next band: no issue slots taken from the compute warps
         } while (it1 != iter + 1u && !timed_out(spins, 1u << 27));
         if (it1 != iter + 1u) sb = 0xffffffffu;
       }
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
         }
         if (j_store >= nchunks) break;
         if (moved) spins = 0;
-        else if (timed_out(spins, 1u << 26)) break;
+        else { if (!(A.lean_flags & 4)) __nanosleep(200); if (timed_out(spins, 1u << 26)) break; }   // nothing here is latency-critical: leave the issue slots to the compute warps
       }
       if (lane == 0) tma_wait_read<0>();   // every tile of this band has left shared memory before the ring is reused
       __syncwarp();
@@ -294,6 +304,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
         unsigned spins = 0;
         do {
           asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sb), "=r"(it1) : "r"(ctrl + 8 * (iter & 3u)) : "memory");
+          if (it1 != iter + 1u && !(A.lean_flags & 4)) __nanosleep(400);   // idle until the next band: no issue slots taken from the compute warps
         } while (it1 != iter + 1u && !timed_out(spins, 1u << 27));
         if (it1 != iter + 1u) sb = 0xffffffffu;
       }
