@@ -257,7 +257,8 @@ __device__ __forceinline__ void lane_min_plus2(const Real* pa, const Real (&oa)[
   Real gb = rmin(rmin(ob[0], ob[1]), rmin(ob[2], ob[3]));
   if constexpr (PW == LPMP_PAIRWISE_POTTS) {
     const Real la = pa[0], lb = pb[0];
-    if (!potts_nonneg && __any_sync(FULL, la < Real(0) || lb < Real(0))) {   // repulsive Potts somewhere in the warp: the two smallest entries
+    // (Potts instances use HOPS as a flag: 1 = the host has seen no negative lambda, the two-smallest-entries branch is compiled out)
+    if (HOPS == 0 && !potts_nonneg && __any_sync(FULL, la < Real(0) || lb < Real(0))) {   // repulsive Potts somewhere in the warp: the two smallest entries
       const Real INF = RealTraits<Real>::inf();
       TwoMin<Real> ta{INF, INF, 0u}, tb{INF, INF, 0u};
 #pragma unroll

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
       }
     };
 
-    const bool trace_lane = A.trace_steps != nullptr && lane == 0 && kb - A.trace_band < 2u;   // debug: per-step stamps of two bands
+    const bool trace_band = A.trace_steps != nullptr && kb - A.trace_band < 2u;
     Real polled[4];   // the halo slot of the NEXT column of group t_in, read one step ahead
 #pragma unroll
     for (int k = 0; k < 4; ++k) polled[k] = Real(0);
@@ -449,7 +449,8 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
 
       // ---- the column neighbour's vector: shuffle inside the band, halo ring for group t_in ----
       Real col_in[4];
-      const bool polling = poller && q >= 0 && q < (int)W;
+      // (fast steps never reach the last column, so only the left ramp needs the range test there)
+      const bool polling = FAST ? poller && q >= 0 : poller && q >= 0 && q < (int)W;
       // (the wait is a warp-UNIFORM loop: lanes parked at a reconvergence point for a long wait wake up slowly -- measured
       // 1.4 us on the first step of every band, which then stays in the band-to-band lag for the whole pass)
       bool missing = polling && (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3]));
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
 #pragma unroll
         for (int k = 0; k < 4; ++k) sent[k] = sentinel<Real>();
         sts_hand_if<HAND_BYTES>(polling, halo_slot(q), sent);                         // the slot is free again
-        lds_hand_if<HAND_BYTES>(polling && q + 1 < (int)W, polled, halo_slot(q + 1));
+        lds_hand_if<HAND_BYTES>(FAST ? polling : polling && q + 1 < (int)W, polled, halo_slot(q + 1));
       }
 
       Real out_col[4];
@@ -501,12 +502,13 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
           carry_row[k] = started ? own_or[k] : Real(0);
           out_col[k] = own_oc[k];
         }
-        if (row_active && started) {
-          sts4(rec, th);
-          sts4(rec + o_in_row, own_ir);
-          sts4(rec + o_in_col, own_ic);
-          sts4(rec + o_out_row, own_or);
-          sts4(rec + o_out_col, own_oc);
+        {   // predicated stores: no branch in the step
+          const bool on = row_active && started;
+          sts_hand_if<HAND_BYTES>(on, rec, th);
+          sts_hand_if<HAND_BYTES>(on, rec + o_in_row, own_ir);
+          sts_hand_if<HAND_BYTES>(on, rec + o_in_col, own_ic);
+          sts_hand_if<HAND_BYTES>(on, rec + o_out_row, own_or);
+          sts_hand_if<HAND_BYTES>(on, rec + o_out_col, own_oc);
         }
       } else {
         const bool act = row_active && q >= 0 && q < (int)W;
@@ -589,8 +591,13 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
       asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p fence.proxy.async.shared::cta; }" ::"r"((uint32_t)(((sp - T + 2) & (K - 1)) == 0 || sp + 1 == sp_end)) : "memory");
       __syncwarp();
       asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctrl + 64), "r"(step_base + (uint32_t)(sp - qoff + 1)) : "memory");
-      asm volatile("{ .reg .pred p; .reg .u64 t; setp.ne.u32 p, %0, 0; mov.u64 t, %%globaltimer; @p st.global.u64 [%1], t; }" ::"r"((uint32_t)(trace_lane && sp >= qoff && sp - qoff < 8192)),
-                   "l"(A.trace_steps + (kb - A.trace_band) * 8192u + (uint32_t)(sp - qoff)) : "memory");
+      if (trace_band) {   // debug: per-step stamps of two bands (warp-uniform, normally not taken)
+        if (lane == 0 && sp >= qoff && sp - qoff < 8192) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          A.trace_steps[(kb - A.trace_band) * 8192u + (uint32_t)(sp - qoff)] = now;
+        }
+      }
     };
 
     const bool fast_band = !A.primal && W >= 3 && H_total_ge2;

@@ -112,6 +112,9 @@ static cudaError_t launch_hops(const CUtensorMap* maps, const GridArgs<Real>& ar
   if constexpr (PW == LPMP_PAIRWISE_TRUNCLIN) {
     if (hops == 1) return launch_k<Real, PW, L, 1, ANISO>(maps, args, ksel, tune, num_sms, stream);
     if (hops == 2 && L >= 16) return launch_k<Real, PW, L, 2, ANISO>(maps, args, ksel, tune, num_sms, stream);
+  } else if constexpr (ANISO) {
+    // Potts, anisotropic passes: the instance without the repulsive (two smallest entries) branch when no lambda is negative
+    if (args.potts_nonneg) return launch_k<Real, PW, L, 1, ANISO>(maps, args, ksel, tune, num_sms, stream);
   }
   return launch_k<Real, PW, L, 0, ANISO>(maps, args, ksel, tune, num_sms, stream);
 }
