@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -45,17 +47,79 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // ---- small helpers ----------------------------------------------------------------------------------------------
+// Process-wide cache of released device blocks (exact-size reuse per device).  A solver loop that builds one LP per problem
+// instance otherwise pays cudaMalloc / cudaFree for every buffer of every instance -- they synchronise the device and were
+// measured at 1-400 ms per large block on B200, more than the solve itself (bench.py e2e arm).  Blocks stay cached up to a
+// quarter of the device memory; an allocation that fails flushes the cache and retries.
+class BlockCache {
+ public:
+  static BlockCache& get() { static BlockCache* c = new BlockCache; return *c; }   // leaked on purpose: no cudaFree after context teardown
+  void* take(int dev, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = free_.find({dev, bytes});
+    if (it == free_.end()) return nullptr;
+    void* p = it->second;
+    free_.erase(it);
+    cached_[dev & 63] -= bytes;
+    return p;
+  }
+  bool give(int dev, size_t bytes, void* p) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (limit_[dev & 63] == 0) {
+      size_t fr = 0, tot = 0;
+      limit_[dev & 63] = cudaMemGetInfo(&fr, &tot) == cudaSuccess ? tot / 4 : (size_t)1 << 30;
+    }
+    if (cached_[dev & 63] + bytes > limit_[dev & 63]) return false;
+    free_.insert({{dev, bytes}, p});
+    cached_[dev & 63] += bytes;
+    return true;
+  }
+  void flush(int dev) {
+    std::lock_guard<std::mutex> g(mu_);
+    for (auto it = free_.begin(); it != free_.end();) {
+      if (it->first.first == dev) { cudaFree(it->second); cached_[dev & 63] -= it->first.second; it = free_.erase(it); }
+      else ++it;
+    }
+  }
+ private:
+  std::mutex mu_;
+  std::multimap<std::pair<int, size_t>, void*> free_;
+  size_t cached_[64] = {}, limit_[64] = {};
+};
+
 template <typename T>
 struct DeviceBuffer {
   T* p = nullptr;
   size_t n = 0;
+  int dev = 0;
   cudaError_t alloc(size_t count) {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
-    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+    cudaGetDevice(&dev);
+    const size_t bytes = count * sizeof(T);
+    if (void* q = BlockCache::get().take(dev, bytes)) { p = static_cast<T*>(q); return cudaSuccess; }
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), bytes);
+    if (e == cudaErrorMemoryAllocation) {   // make room: give the cached blocks back to the driver and try again
+      (void)cudaGetLastError();
+      BlockCache::get().flush(dev);
+      e = cudaMalloc(reinterpret_cast<void**>(&p), bytes);
+    }
+    if (e != cudaSuccess) { p = nullptr; n = 0; }
+    return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() {
+    if (p) {
+      // the block may still be in use by work queued on the owner's stream: wait for the device as cudaFree would
+      int cur = 0;
+      cudaGetDevice(&cur);
+      if (cur != dev) cudaSetDevice(dev);
+      cudaDeviceSynchronize();
+      if (!BlockCache::get().give(dev, n * sizeof(T), p)) cudaFree(p);
+      if (cur != dev) cudaSetDevice(cur);
+    }
+    p = nullptr; n = 0;
+  }
   size_t bytes() const { return n * sizeof(T); }
   ~DeviceBuffer() { release(); }
 };
@@ -251,9 +315,7 @@ struct Solver : ISolver {
 
   int init() {
     CUDA_TRY(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));   // (cudaGetDeviceProperties costs ~2 ms per handle)
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CUDA_TRY(partial.alloc(kBoundCtas));
     CUDA_TRY(result.alloc(1));
