@@ -563,6 +563,31 @@ def test_full_size_properties(H, W, L, kind, lo, hi):
     assert np.array_equal(other.labeling(), labels) and other.EvaluatePrimal() == primal
 
 
+@pytest.mark.parametrize("H,W,L,kind,lo,hi", [(1024, 1024, 16, "trunclin", 0.25, 1.0), (1024, 4096, 32, "potts", 0.1, 1.0)])
+def test_full_size_kernel_variants_are_bit_identical(H, W, L, kind, lo, hi):
+    """config 2 at full size and config 3 at full width: the one-warp kernel, the lean variant without clusters (every band
+    boundary through the L2 hand-off slots) and with clusters of 4 / 8 (distributed shared memory) leave bit-identical
+    theta / messages / labels after two iterations and a rounding pass: the schedule is exact whatever moves the data."""
+    ref = None
+    for tuning in (dict(wavefront_lean=0), dict(wavefront_cluster=1), dict(wavefront_cluster=4, wavefront_tile_cols=4), dict()):
+        lp = cuda_lp("f32").grid_create(H, W, L, kind)
+        lp.set_tuning(**tuning)
+        lp.grid_fill_synthetic(0x5EED, lo, hi)
+        lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+        for it in range(2):
+            lp.ComputePass(it)
+        lb = lp.LowerBound()
+        lp.ComputeForwardPassAndPrimal(2)
+        state = (lp.unaries(), *lp.messages(), lp.labeling(), lb)
+        del lp
+        if ref is None:
+            ref = state
+        else:
+            for x, y in zip(ref[:4], state[:4]):
+                assert np.array_equal(x, y), tuning
+            assert state[4] == ref[4]
+
+
 def test_mid_size_grid_against_oracle():
     """256x256 crops of configs 2 / 3 against the oracle (seconds on the CPU), f32 bit-exact"""
     for kind, L, lo, hi in (("trunclin", 16, 0.25, 1.0), ("potts", 32, 0.1, 1.0)):
