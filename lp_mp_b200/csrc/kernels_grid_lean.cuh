@@ -423,8 +423,12 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
     wait_chunk(0);
     stamp(1);
 
-    auto do_step = [&](auto fast_tag, const int sp) {
-      constexpr bool FAST = decltype(fast_tag)::value;
+    // kind 0: general step; 1: fast step (interior columns, anisotropic, no rounding); 2: STEADY fast step -- in addition every
+    // group has entered the grid, every row of the band exists and has a row below, and group 0 takes its column neighbour
+    // from the halo ring: no existence selects at all (each instruction of this step is paid (H + W) times per pass)
+    auto do_step = [&](auto kind_tag, const int sp) {
+      constexpr int KIND = decltype(kind_tag)::value;
+      constexpr bool FAST = KIND >= 1, STEADY = KIND == 2;
       if ((sp & (K - 1)) == 0 && sp > 0) {               // group 0 enters a new tile (warp-uniform)
         if (sp == K) stamp(2);
         const int j = sp >> LOGK;
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
       // ---- the column neighbour's vector: shuffle inside the band, halo ring for group t_in ----
       Real col_in[4];
       // (fast steps never reach the last column, so only the left ramp needs the range test there)
-      const bool polling = FAST ? poller && q >= 0 : poller && q >= 0 && q < (int)W;
+      const bool polling = STEADY ? poller : FAST ? poller && q >= 0 : poller && q >= 0 && q < (int)W;
       // (the wait is a warp-UNIFORM loop: lanes parked at a reconvergence point for a long wait wake up slowly -- measured
       // 1.4 us on the first step of every band, which then stays in the band-to-band lag for the whole pass)
       bool missing = polling && (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3]));
@@ -491,19 +495,19 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
         // missing edges: the left column (q = 0) and the first row have all-zero in-side slots and parameters, so their
         // receives are exact no-ops; the last grid row has no out_col edge (select); groups that have not reached
         // column 0 yet (q < 0) and rows beyond the grid compute on garbage and neither store nor carry
-        const bool started = q >= 0;
+        const bool started = STEADY || q >= 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const Real d = w_fast * th[k];   // every send uses the same snapshot value
-          const Real d_oc = out_col_exists ? d : Real(0);
+          const Real d_oc = STEADY || out_col_exists ? d : Real(0);
           own_oc[k] = own_oc[k] + d_oc;
           own_or[k] = own_or[k] + d;
           th[k] = (th[k] - d_oc) - d;
-          carry_row[k] = started ? own_or[k] : Real(0);
+          carry_row[k] = STEADY || started ? own_or[k] : Real(0);
           out_col[k] = own_oc[k];
         }
         {   // predicated stores: no branch in the step
-          const bool on = row_active && started;
+          const bool on = STEADY || (row_active && started);
           sts_hand_if<HAND_BYTES>(on, rec, th);
           sts_hand_if<HAND_BYTES>(on, rec + o_in_row, own_ir);
           sts_hand_if<HAND_BYTES>(on, rec + o_in_col, own_ic);
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const Real up = __shfl_up_sync(FULL, out_col[k], G);
-        carry_col[k] = t <= t_in ? Real(0) : up;
+        carry_col[k] = !STEADY && t <= t_in ? Real(0) : up;   // (steady: group 0 = t_in reads the halo ring, its carry is unused)
       }
       // ---- publish the step: records (and re-armed halo slots) of this step are in shared memory ----
       // (predicated, no branch: this step completes a tile, the out-mover's TMA store reads it through the async proxy)
@@ -601,6 +605,8 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
     };
 
     const bool fast_band = !A.primal && W >= 3 && H_total_ge2;
+    // steady steps: interior bands (a predecessor and a successor band, all T rows present) once the left ramp is over
+    const bool steady_band = fast_band && !PARTIAL_WARP && kb > 0 && !last_band && (int)kb * T - roff >= 0 && (int)kb * T - roff + T <= (int)H;
     const int sp_fast0 = fast_band ? (last_band ? qoff + T : qoff) : sp_end, sp_fast1 = fast_band ? qoff + (int)W - 2 : sp_end;
     // three loops, so that the fast steps form one compact loop body (a lone warp pays every far jump with a fetch stall)
     // A band cannot run faster than its predecessor, so whatever its FIRST step loses (the loop body has never been
@@ -608,11 +614,13 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
     // (all groups left of the grid: nothing is stored, carried or published) warms the instruction cache while the
     // band is waiting for its predecessor anyway -- it runs as iteration -1 of the fast loop itself (same code addresses).
     int sp = qoff;
-    for (; sp < sp_fast0 && sp < sp_end; ++sp) do_step(std::false_type{}, sp);
+    for (; sp < sp_fast0 && sp < sp_end; ++sp) do_step(std::integral_constant<int, 0>{}, sp);
     if (fast_band && sp == qoff) sp = qoff - 1;
 #pragma unroll 1
-    for (; sp <= sp_fast1 && sp < sp_end; ++sp) do_step(std::true_type{}, sp);
-    for (; sp < sp_end; ++sp) do_step(std::false_type{}, sp);
+    for (; sp <= sp_fast1 && sp < sp_end && (!steady_band || sp < qoff + T - 1); ++sp) do_step(std::integral_constant<int, 1>{}, sp);
+#pragma unroll 1
+    for (; steady_band && sp <= sp_fast1 && sp < sp_end; ++sp) do_step(std::integral_constant<int, 2>{}, sp);
+    for (; sp < sp_end; ++sp) do_step(std::integral_constant<int, 0>{}, sp);
     stamp(3);
     chunk_base += (uint32_t)nchunks;
     step_base += (uint32_t)(W + T - 1);
