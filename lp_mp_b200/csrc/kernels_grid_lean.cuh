@@ -51,6 +51,15 @@ template <int BYTES> __device__ __forceinline__ void st_cluster(uint32_t a, cons
 }
 __device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 
+// debug (wavefront_trace = 2): end-of-step stamp of one of the two traced bands; deliberately not inlined
+static __device__ __noinline__ void trace_step_stamp(unsigned long long* trace_steps, uint32_t which, int step) {
+  if ((threadIdx.x & 31) == 0 && step >= 0 && step < 8192) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    trace_steps[which * 8192u + (uint32_t)step] = now;
+  }
+}
+
 template <typename Real, int PW, int L, int HOPS, int KSEL>
 __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_par,
                                                             const GridArgs<Real> A) {
@@ -595,13 +604,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
       asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p fence.proxy.async.shared::cta; }" ::"r"((uint32_t)(((sp - T + 2) & (K - 1)) == 0 || sp + 1 == sp_end)) : "memory");
       __syncwarp();
       asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctrl + 64), "r"(step_base + (uint32_t)(sp - qoff + 1)) : "memory");
-      if (trace_band) {   // debug: per-step stamps of two bands (warp-uniform, normally not taken)
-        if (lane == 0 && sp >= qoff && sp - qoff < 8192) {
-          unsigned long long now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          A.trace_steps[(kb - A.trace_band) * 8192u + (uint32_t)(sp - qoff)] = now;
-        }
-      }
+      if (trace_band) trace_step_stamp(A.trace_steps, kb - A.trace_band, sp - qoff);   // debug; a call, so that nothing of it is if-converted into the step
     };
 
     const bool fast_band = !A.primal && W >= 3 && H_total_ge2;
