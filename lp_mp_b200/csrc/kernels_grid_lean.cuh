@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
       const bool polling = STEADY ? poller : FAST ? poller && q >= 0 : poller && q >= 0 && q < (int)W;
       // (the wait is a warp-UNIFORM loop: lanes parked at a reconvergence point for a long wait wake up slowly -- measured
       // 1.4 us on the first step of every band, which then stays in the band-to-band lag for the whole pass)
-      bool missing = polling && (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3]));
+      // (steady steps: only the polling lanes ever hold a sentinel -- the others keep their initial zeros -- so no lane test)
+      bool missing = (STEADY || polling) && (is_sentinel(polled[0]) || is_sentinel(polled[1]) || is_sentinel(polled[2]) || is_sentinel(polled[3]));
       if (__any_sync(FULL, missing)) {
         unsigned spins = 0;
         do {
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(128) wavefront_lean_kernel(const __grid_consta
       }
       // ---- publish the step: records (and re-armed halo slots) of this step are in shared memory ----
       // (predicated, no branch: this step completes a tile, the out-mover's TMA store reads it through the async proxy)
-      asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p fence.proxy.async.shared::cta; }" ::"r"((uint32_t)(((sp - T + 2) & (K - 1)) == 0 || sp + 1 == sp_end)) : "memory");
+      asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p fence.proxy.async.shared::cta; }" ::"r"((uint32_t)(((sp - T + 2) & (K - 1)) == 0 || (!STEADY && sp + 1 == sp_end))) : "memory");
       __syncwarp();
       asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctrl + 64), "r"(step_base + (uint32_t)(sp - qoff + 1)) : "memory");
       if (trace_band) trace_step_stamp(A.trace_steps, kb - A.trace_band, sp - qoff);   // debug; a call, so that nothing of it is if-converted into the step
