@@ -288,8 +288,12 @@ def graph_main(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     s = 4 if args.dtype == "f32" else 8
 
+    tune = {k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)}
+
     def build():
         lp = lp_mp_b200.LP(dtype=args.dtype, device=local_rank)
+        if tune:
+            lp.set_tuning(**tune)
         lp.add_unaries(theta)
         lp.add_pairwise_dense(ei, ej, tables)
         colour, nc = lp.greedy_colouring(ei, ej)

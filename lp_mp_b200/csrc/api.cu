@@ -409,6 +409,7 @@ struct Solver : ISolver {
     else if (k == "wavefront_warps_per_cta") tune.warps_per_cta = value;
     else if (k == "wavefront_lean") tune.lean = value;
     else if (k == "wavefront_cluster") tune.cluster = value;
+    else if (k == "level_group") tune.level_group = value;
     else if (k == "wavefront_trace") want_trace = value;
     else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
     return LPMP_OK;
@@ -808,7 +809,11 @@ struct Solver : ISolver {
       if (int r = build_grid_levels()) return r;
     }
     if (schedule == LPMP_SCHEDULE_LEVELS || (dense_wf && repam != LPMP_REPAM_ANISOTROPIC)) {
-      const int G = group_size_for(L);
+      // lanes per node: the update of a node is a chain of dependent gathers (incidence -> edge -> vectors / table), so the
+      // level kernel is bound by the number of nodes in flight; fewer lanes per node = more nodes per SM ("level_group")
+      int G = group_size_for(L);
+      if (tune.level_group > 0 && tune.level_group < G && (tune.level_group & (tune.level_group - 1)) == 0) G = tune.level_group;
+      else if (tune.level_group == 0 && L == 8) G = 4;   // measured on C4 (profiles/README.md): 8 lanes 0.133 ms / launch, 4 lanes 0.123, 2 lanes 0.188
       int threads = 256;
       size_t per_group = 4 * (size_t)L * sizeof(Real);
       while (threads > G && (threads / G) * per_group > 48 * 1024) threads >>= 1;

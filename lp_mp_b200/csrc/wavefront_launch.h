@@ -19,6 +19,7 @@ struct WavefrontTuning {
                         // -1 automatic (on where it fits; profiles/r01c_lean.txt)
   int cluster = 0;      // lean variant: CTAs per thread-block cluster (consecutive bands, hand-off through distributed shared
                         // memory); 0 = automatic (8), 1 = no clusters
+  int level_group = 0;  // level kernel: lanes per node (power of two below the default pow2 >= L); 0 = default
   int warps_per_cta = 0;  // consecutive bands per CTA (<= 8 and what the shared memory holds); 0 or 1 = one band per CTA
 };
 
