@@ -26,10 +26,16 @@ namespace lpmp {
 template <typename Real, int PW, int L, int KSEL>
 struct LeanCfg : WavefrontCfg<Real, PW, L, KSEL> {
   using Base = WavefrontCfg<Real, PW, L, KSEL>;
-  static constexpr int HALO = 32;   // columns of the halo ring (power of two)
-  // [per-band region of the base kernel | control words (128 B) | halo ring]
-  static constexpr size_t LEAN_SMEM = Base::WARP_SMEM + 128 + (size_t)HALO * L * sizeof(Real);
+  static constexpr int HALO = Base::T >= 8 ? 32 : 16;   // columns of the halo ring (power of two; short bands follow closely)
+  // tile slots hold exactly the T rows of the band (the one-warp kernel reserves a row more for the uniform modes): with
+  // L = 32 this is what lets FIVE bands instead of four be resident per SM
+  static constexpr int SLOT_REC = Base::T * Base::K * Base::REC;
+  static constexpr size_t SMEM_BYTES = 128 + (size_t)(Base::NSLOT * (SLOT_REC + Base::SLOT_PAR) + Base::SCRATCH) * sizeof(Real);
+  static constexpr size_t WARP_SMEM = (SMEM_BYTES + 127) / 128 * 128;
+  // [per-band region: mbarriers, tile ring, staging | control words (128 B) | halo ring]
+  static constexpr size_t LEAN_SMEM = WARP_SMEM + 128 + (size_t)HALO * L * sizeof(Real);
   static constexpr bool LEAN_FITS = Base::FITS && LEAN_SMEM <= 220 * 1024;
+  static_assert((SLOT_REC * sizeof(Real)) % 128 == 0, "TMA destination alignment");
 };
 
 __device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
