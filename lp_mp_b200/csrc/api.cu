@@ -306,6 +306,8 @@ struct Solver : ISolver {
   int want_trace = 0;        // 1: per-band stamps; 2: also per-step stamps of two neighbouring bands (lean variant)
   DeviceBuffer<unsigned int> control;  // [0] band ticket, [1] sticky abort flag (hand-off poll timed out), [2 + smid] CTA arrivals per SM
   CUtensorMap maps8[3], maps4[3];   // tile width 8 / 4 columns
+  CUtensorMap maps_rows[2];         // one-label-per-lane variant: records / parameter records, rows_band_rows(L) / 4 rows x 8 columns
+  bool rows_ok = false;             // ... its tensor maps exist
   std::vector<uint64_t> level_off;     // host
   uint64_t launches = 0, updates = 0;
   static constexpr int kBoundCtas = 148 * 4;
@@ -350,6 +352,8 @@ struct Solver : ISolver {
       note_trunclin((double)ls, (double)lt);
     }
   }
+  // automatic choice: the rows variant where the pass is bound by the dependency chain rather than by HBM (small label counts)
+  bool use_rows() const { return tune.rows > 0 || (tune.rows < 0 && L <= 16); }
   int tl_hops() const {
     if (pw != LPMP_PAIRWISE_TRUNCLIN || tl_irregular) return 0;
     if (tl_reach <= 4) return 1;
@@ -410,6 +414,7 @@ struct Solver : ISolver {
     else if (k == "wavefront_lean") tune.lean = value;
     else if (k == "wavefront_cluster") tune.cluster = value;
     else if (k == "level_group") tune.level_group = value;
+    else if (k == "wavefront_rows") tune.rows = value;
     else if (k == "wavefront_trace") want_trace = value;
     else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
     return LPMP_OK;
@@ -779,6 +784,12 @@ struct Solver : ISolver {
           if (int r = encode_map(&m[1], rec.p, L, REC_VECS, (uint32_t)shape.T + 1, (uint32_t)ks)) return r;
           if (int r = encode_map(&m[2], par.p, (uint32_t)PREC(), 1, (uint32_t)shape.T, (uint32_t)ks)) return r;
         }
+        if (rows_supported<Real>(pw, L) && rows_band_rows(L) >= shape.T) {   // (the hand-off buffer is sized for bands of shape.T rows)
+          const uint32_t rpw = (uint32_t)rows_band_rows(L) / 4;
+          if (int r = encode_map(&maps_rows[0], rec.p, L, REC_VECS, rpw, 8)) return r;
+          if (int r = encode_map(&maps_rows[1], par.p, (uint32_t)PREC(), 1, rpw, 8)) return r;
+          rows_ok = true;
+        }
       }
     }
     CUDA_TRY(labels.alloc(N));
@@ -870,6 +881,18 @@ struct Solver : ISolver {
       A.trace_steps = (trace.p && want_trace >= 2) ? trace.p + 4 * (size_t)A.num_bands : nullptr;
       A.trace_band = A.num_bands / 2;
       CUDA_TRY(cudaMemsetAsync(control.p, 0, sizeof(unsigned int), stream));
+      // one label per lane (kernels_grid_rows.cuh): the anisotropic passes of grids whose pass time is the dependency chain
+      const int rows_win = pw == LPMP_PAIRWISE_POTTS ? (potts_neg ? 0 : 1) : (tl_irregular || tl_reach > 8 || (tl_reach > 4 && L < 16) ? -1 : std::max(tl_reach, 1));
+      if (rows_ok && repam == LPMP_REPAM_ANISOTROPIC && rows_win >= 0 && use_rows()) {
+        A.num_bands = (gridH + (uint32_t)rows_band_rows(L) - 1) / (uint32_t)rows_band_rows(L);
+        const cudaError_t le = pw == LPMP_PAIRWISE_POTTS ? launch_rows<Real, LPMP_PAIRWISE_POTTS>(maps_rows, A, L, rows_win, tune, num_sms, stream)
+                                                         : launch_rows<Real, LPMP_PAIRWISE_TRUNCLIN>(maps_rows, A, L, rows_win, tune, num_sms, stream);
+        CUDA_TRY(le);
+        ++launches;
+        updates += 2 * E;
+        if (primal) labels_valid = true;
+        return LPMP_OK;
+      }
       // tile width: 8 columns unless the bands outnumber the resident warps and the narrow tile doubles residency
       int ksel = shape.default_k();
       if (repam == LPMP_REPAM_ANISOTROPIC && shape.fits8 && shape.fits4) {

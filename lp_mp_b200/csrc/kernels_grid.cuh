@@ -201,6 +201,8 @@ template <int BYTES> __device__ __forceinline__ void sts_hand_if(bool on, uint32
                  "r"(d[4 * o + 1]), "r"(d[4 * o + 2]), "r"(d[4 * o + 3]), "r"((uint32_t)on)
                  : "memory");
 }
+__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_volatile_u32(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 // pins a kernel parameter in a register (the compiler otherwise re-reads the constant bank inside the step loop)
 __device__ __forceinline__ uint32_t pin(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 

@@ -38,8 +38,6 @@ struct LeanCfg : WavefrontCfg<Real, PW, L, KSEL> {
   static_assert((SLOT_REC * sizeof(Real)) % 128 == 0, "TMA destination alignment");
 };
 
-__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void sts_volatile_u32(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // ---- thread-block cluster / distributed shared memory primitives ----
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }

@@ -21,6 +21,7 @@ struct WavefrontTuning {
                         // memory); 0 = automatic (8), 1 = no clusters
   int level_group = 0;  // level kernel: lanes per node (power of two below the default pow2 >= L); 0 = default
   int warps_per_cta = 0;  // consecutive bands per CTA (<= 8 and what the shared memory holds); 0 or 1 = one band per CTA
+  int rows = -1;        // one-label-per-lane variant for the anisotropic passes (kernels_grid_rows.cuh): 1 on, 0 off, -1 automatic
 };
 
 // tile shapes of the kernel instances for (Real, pw, L): rows per band; per tile width (8 / 4 columns) whether the
@@ -64,6 +65,18 @@ inline bool wavefront_shape(int pw, uint32_t L, WavefrontShape& s) {
 template <typename Real, int PW, bool ANISO>
 cudaError_t launch_family(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int hops, int ksel, const WavefrontTuning& tune, int num_sms,
                           cudaStream_t stream);
+
+// one-label-per-lane variant (kernels_grid_rows.cuh): anisotropic passes, L in {8, 16, 32}.  maps: [0] records, [1] parameter
+// records, boxes of rows_band_rows(L) / 4 rows x 8 columns.  win: truncated linear: label window (host: slope * (win + 1) >=
+// trunc for every edge, win <= 8); Potts: 1 = no negative lambda seen, 0 = general.
+inline int rows_band_rows(uint32_t L) { return L == 8 || L == 16 || L == 32 ? 4 * (32 / (int)L) : 0; }
+template <typename Real>
+inline bool rows_supported(int pw, uint32_t L) {
+  if (pw != LPMP_PAIRWISE_POTTS && pw != LPMP_PAIRWISE_TRUNCLIN) return false;
+  return rows_band_rows(L) != 0;
+}
+template <typename Real, int PW>
+cudaError_t launch_rows(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int win, const WavefrontTuning& tune, int num_sms, cudaStream_t stream);
 
 // dense-table grids (kernels_grid_dense.cuh): anisotropic passes for L in {16, 32, 64}
 template <typename Real>
