@@ -308,6 +308,8 @@ struct Solver : ISolver {
   CUtensorMap maps8[3], maps4[3];   // tile width 8 / 4 columns
   CUtensorMap maps_rows[2];         // one-label-per-lane variant: records / parameter records, rows_band_rows(L) / 4 rows x 8 columns
   bool rows_ok = false;             // ... its tensor maps exist
+  CUtensorMap maps_split[2];        // edge-split variant: records / parameter records, 1 row x 8 columns
+  bool split_ok = false;
   std::vector<uint64_t> level_off;     // host
   uint64_t launches = 0, updates = 0;
   static constexpr int kBoundCtas = 148 * 4;
@@ -353,6 +355,7 @@ struct Solver : ISolver {
     }
   }
   // automatic choice: the rows variant where the pass is bound by the dependency chain rather than by HBM (small label counts)
+  bool use_split() const { return tune.split > 0 || (tune.split < 0 && tune.rows <= 0 && L <= 16); }
   bool use_rows() const { return tune.rows > 0 || (tune.rows < 0 && L <= 16); }
   int tl_hops() const {
     if (pw != LPMP_PAIRWISE_TRUNCLIN || tl_irregular) return 0;
@@ -415,6 +418,7 @@ struct Solver : ISolver {
     else if (k == "wavefront_cluster") tune.cluster = value;
     else if (k == "level_group") tune.level_group = value;
     else if (k == "wavefront_rows") tune.rows = value;
+    else if (k == "wavefront_split") tune.split = value;
     else if (k == "wavefront_trace") want_trace = value;
     else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
     return LPMP_OK;
@@ -790,6 +794,11 @@ struct Solver : ISolver {
           if (int r = encode_map(&maps_rows[1], par.p, (uint32_t)PREC(), 1, rpw, 8)) return r;
           rows_ok = true;
         }
+        if (split_supported<Real>(pw, L) && kSplitBandRows >= shape.T) {
+          if (int r = encode_map(&maps_split[0], rec.p, L, REC_VECS, 1, 8)) return r;
+          if (int r = encode_map(&maps_split[1], par.p, (uint32_t)PREC(), 1, 1, 8)) return r;
+          split_ok = true;
+        }
       }
     }
     CUDA_TRY(labels.alloc(N));
@@ -883,6 +892,16 @@ struct Solver : ISolver {
       CUDA_TRY(cudaMemsetAsync(control.p, 0, sizeof(unsigned int), stream));
       // one label per lane (kernels_grid_rows.cuh): the anisotropic passes of grids whose pass time is the dependency chain
       const int rows_win = pw == LPMP_PAIRWISE_POTTS ? (potts_neg ? 0 : 1) : (tl_irregular || tl_reach > 8 || (tl_reach > 4 && L < 16) ? -1 : std::max(tl_reach, 1));
+      if (split_ok && repam == LPMP_REPAM_ANISOTROPIC && rows_win >= 0 && (pw == LPMP_PAIRWISE_POTTS || L == 16) && use_split()) {
+        A.num_bands = (gridH + (uint32_t)kSplitBandRows - 1) / (uint32_t)kSplitBandRows;
+        const cudaError_t le = pw == LPMP_PAIRWISE_POTTS ? launch_split<Real, LPMP_PAIRWISE_POTTS>(maps_split, A, L, rows_win, tune, num_sms, stream)
+                                                         : launch_split<Real, LPMP_PAIRWISE_TRUNCLIN>(maps_split, A, L, rows_win, tune, num_sms, stream);
+        CUDA_TRY(le);
+        ++launches;
+        updates += 2 * E;
+        if (primal) labels_valid = true;
+        return LPMP_OK;
+      }
       if (rows_ok && repam == LPMP_REPAM_ANISOTROPIC && rows_win >= 0 && use_rows()) {
         A.num_bands = (gridH + (uint32_t)rows_band_rows(L) - 1) / (uint32_t)rows_band_rows(L);
         const cudaError_t le = pw == LPMP_PAIRWISE_POTTS ? launch_rows<Real, LPMP_PAIRWISE_POTTS>(maps_rows, A, L, rows_win, tune, num_sms, stream)

@@ -36,9 +36,10 @@ struct RowsCfg {
   static constexpr int P = ParamCount<PW>::value;
   static constexpr int REC = REC_VECS * L, PREC = PAR_EDGES * P;
   static constexpr int SLOT_REC = RPW * K * REC, SLOT_PAR = RPW * K * PREC;   // reals per tile
-  static constexpr int RING = 16;                          // columns per hand-off ring (power of two)
+  static constexpr int RING = 32;                          // columns per hand-off ring (power of two, >= 4 tiles of columns)
   static constexpr size_t SLOT_BYTES = (size_t)(SLOT_REC + SLOT_PAR) * sizeof(Real);
-  static constexpr size_t RINGS_OFF = 384;                 // [0,256) mbarriers, [256,384) control words
+  static constexpr size_t GSTORE_OFF = 384;                // [0,256) mbarriers, [256,384) control words, [384,640) tile warp's bookkeeping
+  static constexpr size_t RINGS_OFF = 640;
   static constexpr size_t TILES_OFF = (RINGS_OFF + (size_t)NW * RING * L * sizeof(Real) + 127) / 128 * 128;
   static constexpr int NSLOT = TILES_OFF + 8 * NW * SLOT_BYTES <= 200 * 1024 ? 8 : 4;   // tiles per ring (power of two)
   static constexpr size_t WARP_TILE_BYTES = (size_t)NSLOT * SLOT_BYTES;
@@ -135,6 +136,9 @@ __device__ __forceinline__ void rows_min_plus2(const Real* pa, Real oa, Real& ha
 template <typename Real> __device__ __forceinline__ Real lds1v(uint32_t a);
 template <> __device__ __forceinline__ float lds1v<float>(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 template <> __device__ __forceinline__ double lds1v<double>(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+template <typename Real> __device__ __forceinline__ Real lds1_volatile(uint32_t a);
+template <> __device__ __forceinline__ float lds1_volatile<float>(uint32_t a) { float v; asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+template <> __device__ __forceinline__ double lds1_volatile<double>(uint32_t a) { double v; asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts1_if(bool on, uint32_t a, float v) {
   asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.f32 [%0], %1; }" ::"r"(a), "f"(v), "r"((uint32_t)on) : "memory");
 }
@@ -160,7 +164,17 @@ __device__ __forceinline__ void stg1_relaxed_if(bool on, double* p, double v) {
   asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.relaxed.sys.global.f64 [%0], %1; }" ::"l"(p), "d"(v), "r"((uint32_t)on) : "memory");
 }
 
-template <typename Real, int PW, int L, int WIN>
+// bounded waits: a lost partner must not hang the device.  Called every 2^10 .. 2^16 spins of a wait loop: true once the sticky
+// abort flag is set (checked by the host after the pass) or the kernel has been running for kWaitLimitNs
+constexpr unsigned long long kWaitLimitNs = 4000000000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+static __device__ __noinline__ bool wait_expired(unsigned int* control, unsigned long long t_launch) {
+  if (*reinterpret_cast<volatile unsigned int*>(control + 1) != 0u) return true;
+  if (globaltimer_ns() - t_launch > kWaitLimitNs) { atomicExch(control + 1, 1u); return true; }
+  return false;
+}
+
+template <typename Real, int PW, int L, int WIN, bool FWD>
 __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_rows_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_par,
                                                                                          const GridArgs<Real> A) {
   using Cfg = RowsCfg<Real, PW, L>;
@@ -170,6 +184,7 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
   constexpr uint32_t TILE_BYTES = SLOT_REC_B + SLOT_PAR_B;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int HAND_BYTES = 4 * (int)sizeof(Real);
+  constexpr bool fwd = FWD;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t bars = smem_base;                         // [NW][NSLOT] mbarriers
@@ -177,14 +192,14 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
   const uint32_t rings = smem_base + (uint32_t)Cfg::RINGS_OFF;   // [NW][RING][L]: ring w feeds the first row of compute warp w
   const uint32_t tiles = smem_base + (uint32_t)Cfg::TILES_OFF;   // per compute warp: [NSLOT] record tiles, then [NSLOT] parameter tiles
   const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5);
-  const bool fwd = A.forward != 0;
   const uint32_t H = A.H, W = pin(A.W);
   const int nchunks = ((int)W + K - 1) >> LOGK;
   const int nb = (int)A.num_bands;
   const int qoff = fwd ? 0 : nchunks * K - (int)W;         // padding columns / rows in front of virtual column / row 0
   const int roff = fwd ? 0 : nb * T - (int)H;              // (tiles are anchored at row 0 / column 0 in both directions)
   const int nsteps = (int)W + RPW - 1;
-  const int kxor = fwd ? 0 : K - 1;
+  constexpr int kxor = fwd ? 0 : K - 1;
+  // ring slot of a column: its tile-space index q' = q + qoff modulo RING (so that tiles and ring slots wrap together)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NW * NSLOT; ++i) mbar_init(bars + 8 * i, 1);
@@ -198,10 +213,10 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
   __syncthreads();
 
   // bounded waits: a lost partner must not hang the device (sticky abort flag, checked by the host after the pass)
-  auto timed_out = [&](unsigned& spins, unsigned limit) {
+  const unsigned long long t_launch = globaltimer_ns();
+  auto timed_out = [&](unsigned& spins, unsigned) {
     if ((++spins & 0x3ffu) != 0) return false;
-    if (spins > limit) atomicExch(A.control + 1, 1u);
-    return *reinterpret_cast<volatile unsigned int*>(A.control + 1) != 0u;
+    return wait_expired(A.control, t_launch);
   };
   // rows [kb T - roff + w RPW, + RPW) of virtual band kb: does compute warp w own a grid row?
   auto warp_live = [&](unsigned kb, int w) {
@@ -219,7 +234,6 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
     __syncthreads();
     const unsigned kb = lds_volatile_u32(ctrl);
     if (kb >= A.num_bands) break;
-    const bool last_band = kb + 1 == A.num_bands;
     const int t_in = kb == 0 ? roff : 0;                   // first grid row of the band (virtual row inside the band)
     const bool band_in = kb > 0 || A.in_halo;              // row t_in has a column neighbour in the previous band / stripe
 
@@ -227,7 +241,7 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
       // ================= tile warp: TMA loads as slots become free, TMA stores as the compute warps complete tiles =================
       if (lane == 0) {
         int j_load[NW], j_store[NW];
-        uint32_t g_store[NW][NSLOT];       // bulk-group sequence number of the last store that read each slot
+        volatile uint32_t* const g_store = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::GSTORE_OFF);   // [NW][NSLOT] bulk-group sequence number of the last store that read each slot
         uint32_t groups = 0;
         bool live[NW];
         int open = 0;
@@ -236,7 +250,7 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
 #pragma unroll
         for (int w = 0; w < NW; ++w)
 #pragma unroll
-          for (int s = 0; s < NSLOT; ++s) g_store[w][s] = 0;
+          for (int sl = 0; sl < NSLOT; ++sl) g_store[w * NSLOT + sl] = 0;
         unsigned spins = 0;
         while (open > 0) {
           bool moved = false;
@@ -254,26 +268,27 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
               const int col0 = fwd ? j_store[w] * K : (nchunks - 1 - j_store[w]) * K;
               tma_store_4d(&tm_rec, col0, row0, rec_ring + slot * SLOT_REC_B);
               tma_commit();
-              g_store[w][slot] = ++groups;
+              g_store[w * NSLOT + (int)slot] = ++groups;
               if (++j_store[w] >= nchunks) --open;
               moved = true;
             }
             // ---- loads: as soon as the slot's previous tile has left shared memory ----
-            if (j_load[w] < nchunks && j_load[w] < j_store[w] + NSLOT) {
+            // (not into the slot of the store just issued: cp.async.bulk.wait_group.read would block this warp, which serves
+            // every compute warp of the CTA, for the duration of that store)
+            if (j_load[w] < nchunks && j_load[w] < j_store[w] + NSLOT - (NSLOT >= 8 ? 2 : 1)) {
               const uint32_t slot = (chunk_base[w] + (uint32_t)j_load[w]) & (NSLOT - 1);
-              if (j_load[w] >= NSLOT || chunk_base[w] > 0) {
-                const uint32_t younger = groups - g_store[w][slot];   // bulk groups committed after the store that read this slot
-                if (g_store[w][slot] != 0) {
-                  if (younger == 0) tma_wait_read<0>();
-                  else if (younger == 1) tma_wait_read<1>();
-                  else if (younger == 2) tma_wait_read<2>();
-                  else if (younger == 3) tma_wait_read<3>();
-                  else if (younger <= 5) tma_wait_read<4>();
-                  else if (younger <= 7) tma_wait_read<6>();
-                  else if (younger <= 11) tma_wait_read<8>();
-                  else if (younger <= 15) tma_wait_read<12>();
-                  else tma_wait_read<16>();
-                }
+              const uint32_t gs = g_store[w * NSLOT + (int)slot];
+              if (gs != 0) {
+                const uint32_t younger = groups - gs;   // bulk groups committed after the store that read this slot
+                if (younger == 0) tma_wait_read<0>();
+                else if (younger == 1) tma_wait_read<1>();
+                else if (younger == 2) tma_wait_read<2>();
+                else if (younger == 3) tma_wait_read<3>();
+                else if (younger <= 5) tma_wait_read<4>();
+                else if (younger <= 7) tma_wait_read<6>();
+                else if (younger <= 11) tma_wait_read<8>();
+                else if (younger <= 15) tma_wait_read<12>();
+                else tma_wait_read<16>();
               }
               const int col0 = fwd ? j_load[w] * K : (nchunks - 1 - j_load[w]) * K;
               const uint32_t bar = bars + 8 * ((uint32_t)w * NSLOT + slot);
@@ -291,19 +306,34 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
       }
       __syncwarp();
     } else if (wid == NW) {
-      // ============================== in-mover: predecessor's hand-off slots (L2) -> ring of the band's first grid row ==============================
+      // ====== in-mover: predecessor's hand-off slots (L2) -> ring of the band's first grid row (zeros if there is no predecessor) ======
       constexpr int G4 = L / 4, TG = 32 / G4;               // lanes per column (4 labels each), columns per load
       constexpr int NBATCH = TG >= 16 ? 1 : 16 / TG;        // >= 16 columns polled per L2 round trip
       const int g = lane / G4, gl = lane % G4;
       const int w_in = t_in / RPW;                          // the compute warp that owns row t_in
-      if (band_in && warp_live(kb, w_in)) {
-        const Real* const hand_in = (kb == 0 ? A.in_boundary : A.handoff + (uint64_t)kb * W * L) + gl * 4;
-        const uint32_t ring = rings + (uint32_t)w_in * RING * LB;
-        const int hr_in = t_in % RPW;                       // that row processes column q at step q + hr_in
-        int q_in = 0;
-        unsigned spins = 0;
+      const uint32_t ring = rings + (uint32_t)w_in * RING * LB;
+      const int hr_in = t_in % RPW;                         // that row processes column q at step q + hr_in
+      const uint32_t ctr_in = ctrl + 16 + 4 * (uint32_t)w_in;
+      int q_in = 0;
+      unsigned spins = 0;
+      if (!band_in) {
+        Real zero[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) zero[k] = Real(0);
         while (q_in < (int)W) {
-          const int c = (int)(lds_volatile_u32(ctrl + 16 + 4 * w_in) - step_base);
+          const int c = (int)(lds_volatile_u32(ctr_in) - step_base);
+          int limit = (c - hr_in > 0 ? c - hr_in : 0) + RING;
+          if (limit > (int)W) limit = (int)W;
+          if (q_in < limit) {
+            for (int q = q_in + g; q < limit; q += TG) sts4(ring + (((uint32_t)(q + qoff) & (uint32_t)(RING - 1)) * L + (uint32_t)(gl * 4)) * S, zero);
+            q_in = limit;
+            spins = 0;
+          } else { __nanosleep(200); if (timed_out(spins, 1u << 26)) break; }
+        }
+      } else {
+        const Real* const hand_in = (kb == 0 ? A.in_boundary : A.handoff + (uint64_t)kb * W * L) + gl * 4;
+        while (q_in < (int)W) {
+          const int c = (int)(lds_volatile_u32(ctr_in) - step_base);
           int limit = (c - hr_in > 0 ? c - hr_in : 0) + RING;   // the consumer has consumed (and re-armed) c - hr_in columns
           if (limit > (int)W) limit = (int)W;
           Real v[NBATCH][4];
@@ -323,7 +353,7 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
             const unsigned bad = ~__ballot_sync(FULL, ok);
             const int n_ok = !open ? 0 : bad ? (__ffs((int)bad) - 1) / G4 : TG;
             if (g < n_ok) {
-              sts4(ring + (((uint32_t)q & (uint32_t)(RING - 1)) * L + (uint32_t)(gl * 4)) * S, v[b]);
+              sts4(ring + (((uint32_t)(q + qoff) & (uint32_t)(RING - 1)) * L + (uint32_t)(gl * 4)) * S, v[b]);
               Real sent[4];
 #pragma unroll
               for (int k = 0; k < 4; ++k) sent[k] = sentinel<Real>();
@@ -337,7 +367,10 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
           else if (timed_out(spins, 1u << 24)) break;
         }
       }
-    } else if (warp_live(kb, wid)) {
+    } else if (!warp_live(kb, wid)) {
+      // no grid row in this band (padding rows of the first / last band): the step counter still moves on with the band
+      if (lane == 0) sts_volatile_u32(ctrl + 16 + 4 * (uint32_t)wid, step_base + (uint32_t)nsteps);
+    } else {
       // =================================================== compute warps ===================================================
       const int w = wid;
       const int hr = lane / L, x = lane % L;                // row of this lane inside the warp, label
@@ -346,8 +379,8 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
       const bool row_active = u >= 0 && u < (int)H;
       const uint32_t r = fwd ? (uint32_t)u : H - 1 - (uint32_t)u;
       const bool in_col_exists = row_active && (u > 0 || A.in_halo), out_col_exists = row_active && (u + 1 < (int)H || A.out_halo);
-      const bool poller = in_col_exists && (t == t_in || hr == 0);        // takes its column neighbour's vector from ring w
-      const bool from_shfl = in_col_exists && !poller;                     // ... from the row above in the same warp
+      const bool poller = row_active && (t == t_in || hr == 0);           // takes its column neighbour's vector from ring w
+      const bool from_shfl = row_active && !poller;                        // ... from the row above in the same warp
       // where this row's outgoing column vector goes (besides the shuffle to the next row of the warp)
       const bool grid_last_row = row_active && u + 1 == (int)H;
       const bool out_ring = row_active && !grid_last_row && hr == RPW - 1 && w + 1 < NW;
@@ -357,13 +390,13 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
       const uint32_t ring_out = rings + (uint32_t)(w + 1 < NW ? w + 1 : w) * RING * LB + (uint32_t)x * S;
       const bool warp_out_ring = __any_sync(FULL, out_ring);
       const uint32_t rec_ring = tiles + (uint32_t)w * (uint32_t)Cfg::WARP_TILE_BYTES, par_ring = rec_ring + NSLOT * SLOT_REC_B;
+      constexpr uint32_t o_in_row = (fwd ? REC_BL : REC_AR) * LB, o_in_col = (fwd ? REC_BU : REC_AD) * LB;
+      constexpr uint32_t o_out_row = (fwd ? REC_AR : REC_BL) * LB, o_out_col = (fwd ? REC_AD : REC_BU) * LB;
+      constexpr uint32_t p_in_row = (fwd ? PAR_L : PAR_R) * P * S, p_in_col = (fwd ? PAR_U : PAR_D) * P * S;
       const int trow = fwd ? hr : RPW - 1 - hr;             // row of this lane inside the tiles
       const uint32_t rec_lane = rec_ring + (uint32_t)(trow * K) * REC_B + (uint32_t)x * S;
       const uint32_t par_lane = par_ring + (uint32_t)(trow * K) * PREC_B;
-      const uint32_t o_in_row = (fwd ? REC_BL : REC_AR) * LB, o_in_col = (fwd ? REC_BU : REC_AD) * LB;
-      const uint32_t o_out_row = (fwd ? REC_AR : REC_BL) * LB, o_out_col = (fwd ? REC_AD : REC_BU) * LB;
-      const uint32_t p_in_row = (fwd ? PAR_L : PAR_R) * P * S, p_in_col = (fwd ? PAR_U : PAR_D) * P * S;
-      const bool recv_row_first = fwd ? !A.fifo : (A.fifo != 0);
+      const bool recv_row_first = pin((uint32_t)(fwd ? !A.fifo : (A.fifo != 0))) != 0u;
       const Real w_fast = (Real)(1.0 / 2.0);
       const uint32_t cbase = chunk_base[w];
       const int lane_q0 = (int)(cbase << LOGK) - hr + qoff; // tile-ring column of this lane at step 0
@@ -378,14 +411,13 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
         while (!mbar_try_wait(bar, parity)) { if (timed_out(spins, 1u << 24)) break; }
       };
 
-      Real polled = Real(0);                                // ring slot of the NEXT column of the polling row, read one step ahead
-      lds1_volatile_if(poller, polled, ring_in);
       Real carry_row = Real(0), carry_col = Real(0);
       int free_upto = RING;                                 // columns the next warp's ring is known to have room for
       wait_chunk(0);
 
+      // ---- single steps ----
       // kind 0: general step (any column, rounding); 1: edge step (any column of a row that is neither the first nor the last of
-      // the grid: weight 1/2, existence by selects); 2: steady step (every row of the warp is at an interior column)
+      // the grid: weight 1/2, existence by selects); 2: interior column for every row of the warp
       auto do_step = [&](auto kind_tag, const int s) {
         constexpr int KIND = decltype(kind_tag)::value;
         const int sp = s + qoff;
@@ -400,6 +432,7 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
         const uint32_t rec = rec_lane + slot * SLOT_REC_B + kk * REC_B;
         const uint32_t par = par_lane + slot * SLOT_PAR_B + kk * PREC_B;
         const bool valid = KIND == 2 || (q >= 0 && q < (int)W);
+        const uint32_t rslot = ((uint32_t)(sp - hr) & (uint32_t)(RING - 1)) * LB;
 
         Real par_ir[P], par_ic[P];
         lds_par<Real, P>(par_ir, par + p_in_row);
@@ -407,20 +440,20 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
         Real th = lds1v<Real>(rec), own_ir = lds1v<Real>(rec + o_in_row), own_ic = lds1v<Real>(rec + o_in_col);
         Real own_or = lds1v<Real>(rec + o_out_row), own_oc = lds1v<Real>(rec + o_out_col);
 
-        // ---- the column neighbour's vector: ring slot (read one step ahead) or the shuffle of the previous step ----
+        // ---- the column neighbour's vector: ring slot or the shuffle of the previous step ----
         const bool polling = poller && valid;
-        bool missing = polling && is_sentinel(polled);
-        if (__any_sync(FULL, missing)) {                   // warp-uniform wait loop
+        Real polled = Real(0);
+        bool missing = polling;
+        {                                                   // warp-uniform wait loop
           unsigned spins = 0;
           do {
-            lds1_volatile_if(missing, polled, ring_in + ((uint32_t)q & (uint32_t)(RING - 1)) * LB);
+            lds1_volatile_if(missing, polled, ring_in + rslot);
             missing = polling && is_sentinel(polled);
             if (timed_out(spins, 1u << 27)) { polled = Real(0); missing = false; }
           } while (__any_sync(FULL, missing));
         }
         const Real col_in = polling ? polled : carry_col;
-        sts1_volatile_if(polling, ring_in + ((uint32_t)q & (uint32_t)(RING - 1)) * LB, sentinel<Real>());   // the slot is free again
-        lds1_volatile_if(KIND == 2 ? polling : polling && q + 1 < (int)W, polled, ring_in + ((uint32_t)(q + 1) & (uint32_t)(RING - 1)) * LB);
+        sts1_volatile_if(polling, ring_in + rslot, sentinel<Real>());   // the slot is free again
 
         Real out_col;
         if constexpr (KIND >= 1) {
@@ -496,17 +529,92 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
             free_upto = (int)(lds_volatile_u32(ctr_next) - step_base) + RING;
           } while (s - (RPW - 1) >= free_upto && !timed_out(spins, 1u << 27));
         }
-        sts1_volatile_if(out_ring && valid, ring_out + ((uint32_t)q & (uint32_t)(RING - 1)) * LB, out_col);
+        sts1_volatile_if(out_ring && valid, ring_out + rslot, out_col);
         stg1_relaxed_if(out_glob && valid, out_ptr + (int64_t)q * L, out_col);
         if constexpr (RPW > 1) {
           const Real up = __shfl_up_sync(FULL, out_col, L);
           carry_col = from_shfl ? up : Real(0);
         }
         // ---- publish the step: records (and re-armed ring slots) of this step are in shared memory ----
-        // (the fence is predicated, no branch: this step completes a tile, the tile warp's TMA store reads it through the async proxy)
-        asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p fence.proxy.async.shared::cta; }" ::"r"((uint32_t)(((sp - RPW + 2) & (K - 1)) == 0 || s + 1 == nsteps)) : "memory");
+        // (the tile warp's TMA store reads a completed tile through the async proxy)
+        if (((sp - RPW + 2) & (K - 1)) == 0 || s + 1 == nsteps) fence_proxy_async();
         __syncwarp();
         asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctr), "r"(step_base + (uint32_t)(s + 1)) : "memory");
+      };
+
+      // ---- steady steps, one tile (8 columns of row 0 of the warp) at a time: every address is a per-tile base + an immediate ----
+      // (each instruction of a step is paid W + H times per pass: no index arithmetic, no vote, one publication per tile)
+      auto do_tile = [&](const int j) {
+        wait_chunk(j);
+        const int s0 = (j << LOGK) - qoff;                  // step at which row 0 of the warp enters tile j
+        const uint32_t n = cbase + (uint32_t)j;
+        const uint32_t slot = n & (NSLOT - 1), slotp = (n - 1u) & (NSLOT - 1);
+        // row hr works on column jj - hr of the tile at step jj: for jj < hr that is a column of the PREVIOUS tile
+        const uint32_t Tcur = rec_lane + slot * SLOT_REC_B + (uint32_t)(fwd ? -hr : K - 1 + hr) * REC_B;
+        const uint32_t Tprev = rec_lane + slotp * SLOT_REC_B + (uint32_t)(fwd ? K - hr : hr - 1) * REC_B;
+        const uint32_t Pcur = par_lane + slot * SLOT_PAR_B + (uint32_t)(fwd ? -hr : K - 1 + hr) * PREC_B;
+        const uint32_t Pprev = par_lane + slotp * SLOT_PAR_B + (uint32_t)(fwd ? K - hr : hr - 1) * PREC_B;
+        const uint32_t c0 = (uint32_t)(j << LOGK) & (uint32_t)(RING - 1);           // ring slot of row 0's column at jj = 0
+        const uint32_t Rin = ring_in + c0 * LB;                                      // every lane watches the slot of row 0's column
+        const uint32_t Rout = ring_out + (c0 - (uint32_t)(RPW - 1)) * LB;            // the last row of the warp is RPW - 1 columns behind
+        const uint32_t Routp = ring_out + (((uint32_t)(j << LOGK) - (uint32_t)(RPW - 1)) & (uint32_t)(RING - 1)) * LB;
+        Real* const Gout = out_ptr + (int64_t)(s0 - hr) * L;
+        if (warp_out_ring && s0 + K - 1 - (RPW - 1) >= free_upto) {   // room in the next warp's ring for the whole tile (warp-uniform, rare)
+          unsigned spins = 0;
+          do {
+            free_upto = (int)(lds_volatile_u32(ctr_next) - step_base) + RING;
+          } while (s0 + K - 1 - (RPW - 1) >= free_upto && !timed_out(spins, 1u << 27));
+        }
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+          constexpr int SG = fwd ? 1 : -1;
+          const uint32_t rec = (jj < RPW - 1 ? (jj < hr ? Tprev : Tcur) : Tcur) + (uint32_t)(SG * jj * (int)REC_B);
+          const uint32_t par = (jj < RPW - 1 ? (jj < hr ? Pprev : Pcur) : Pcur) + (uint32_t)(SG * jj * (int)PREC_B);
+          const uint32_t rin = Rin + (uint32_t)jj * LB;
+          // the polled slot: every lane of the warp reads the words of row 0's column (identical outcome in every lane, no vote)
+          Real pv = lds1_volatile<Real>(rin);
+          Real par_ir[P], par_ic[P];
+          lds_par<Real, P>(par_ir, par + p_in_row);
+          lds_par<Real, P>(par_ic, par + p_in_col);
+          Real th = lds1v<Real>(rec), own_ir = lds1v<Real>(rec + o_in_row), own_ic = lds1v<Real>(rec + o_in_col);
+          Real own_or = lds1v<Real>(rec + o_out_row), own_oc = lds1v<Real>(rec + o_out_col);
+          if (is_sentinel(pv)) {
+            unsigned spins = 0;
+            do { pv = lds1_volatile<Real>(rin); } while (is_sentinel(pv) && ((++spins & 0xffffu) != 0 || !wait_expired(A.control, t_launch)));
+            if (is_sentinel(pv)) pv = Real(0);
+          }
+          sts1_volatile_if(poller, rin, sentinel<Real>());   // the slot is free again
+          const Real col_in = poller ? pv : carry_col;
+
+          Real h_ir, h_ic;
+          rows_min_plus2<Real, PW, L, WIN>(par_ir, carry_row, h_ir, par_ic, col_in, h_ic);
+          const Real m_ir = h_ir + own_ir, m_ic = h_ic + own_ic;
+          own_ir = own_ir - m_ir;
+          own_ic = own_ic - m_ic;
+          th = recv_row_first ? (th + m_ir) + m_ic : (th + m_ic) + m_ir;
+          const Real d = w_fast * th;
+          const Real d_oc = out_col_exists ? d : Real(0);
+          own_oc = own_oc + d_oc;
+          own_or = own_or + d;
+          th = (th - d_oc) - d;
+          carry_row = own_or;
+          sts1_if(row_active, rec, th);
+          sts1_if(row_active, rec + o_in_row, own_ir);
+          sts1_if(row_active, rec + o_in_col, own_ic);
+          sts1_if(row_active, rec + o_out_row, own_or);
+          sts1_if(row_active, rec + o_out_col, own_oc);
+          sts1_volatile_if(out_ring, (jj < RPW - 1 ? Routp : Rout) + (uint32_t)jj * LB, own_oc);
+          stg1_relaxed_if(out_glob, Gout + jj * L, own_oc);
+          if constexpr (RPW > 1) {
+            const Real up = __shfl_up_sync(FULL, own_oc, L);
+            carry_col = from_shfl ? up : Real(0);
+          }
+          if (jj == RPW - 1) {   // the last row of the warp has left the previous tile: publish (once per tile)
+            fence_proxy_async();
+            __syncwarp();
+            asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctr), "r"(step_base + (uint32_t)(s0 + jj + 1)) : "memory");
+          }
+        }
       };
 
       // general steps for the whole band: rounding, tiny grids; for the ramps of the warps that own the first / last grid row
@@ -514,6 +622,7 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
       const bool all_general = A.primal != 0 || (int)W < 2 * RPW + 2 || (H < 2 && !(A.in_halo || A.out_halo));
       const int u_first = (int)kb * T + w * RPW - roff;
       const bool corner_warp = (u_first <= 0 && !A.in_halo) || (u_first + RPW >= (int)H && !A.out_halo);
+      const bool poll_row0 = __all_sync(FULL, !poller || hr == 0);   // the polling row of the warp is its row 0 (else: single steps only)
       int s = 0;
       if (all_general) {
         for (; s < nsteps; ++s) do_step(std::integral_constant<int, 0>{}, s);
@@ -521,6 +630,14 @@ __global__ void __launch_bounds__(RowsCfg<Real, PW, L>::THREADS, 1) wavefront_ro
         const int s_steady0 = RPW, s_steady1 = (int)W - 2;  // steady: 1 <= s - hr <= W - 2 for every row of the warp
         if (corner_warp) { for (; s < s_steady0; ++s) do_step(std::integral_constant<int, 0>{}, s); }
         else { for (; s < s_steady0; ++s) do_step(std::integral_constant<int, 1>{}, s); }
+        // whole tiles inside the steady range
+        const int j0 = (s_steady0 + qoff + K - 1) >> LOGK, j1 = ((s_steady1 + 1 + qoff) >> LOGK) - 1;   // tiles j0 .. j1
+        if (poll_row0 && j1 >= j0) {
+          for (; s < (j0 << LOGK) - qoff; ++s) do_step(std::integral_constant<int, 2>{}, s);
+#pragma unroll 1
+          for (int j = j0; j <= j1; ++j) do_tile(j);
+          s = ((j1 + 1) << LOGK) - qoff;
+        }
 #pragma unroll 1
         for (; s <= s_steady1; ++s) do_step(std::integral_constant<int, 2>{}, s);
         if (corner_warp) { for (; s < nsteps; ++s) do_step(std::integral_constant<int, 0>{}, s); }

@@ -1,0 +1,607 @@
+// Wavefront pass, "split" variant for the anisotropic (SRMP) passes: ONE ROW PER WARP, the two receive edges of a node split
+// over the two half-warps.
+//
+// Replaces LP::ComputePass over forward/backwardUpdateOrdering_ (/root/reference/include/LP_MP.h:981-1005,1592-1602) and
+// FactorContainer::UpdateFactor (include/factors_messages.hxx:2256-2261); same storage, TMA tiles and self-validating hand-off
+// slots as the other wavefront kernels (kernels_grid.cuh), same sequence of IEEE operations per node (bit-identical state).
+//
+// Why: a pass in the reference order is a dependency chain of H + W - 1 node updates; its duration is W * tau_x + H * tau_y
+// (tau_x / tau_y: latency of one update as seen by the row / column neighbour), and on one in-order warp tau is essentially the
+// LENGTH OF THE INSTRUCTION STREAM of a step (measured ~3.5 cycles per instruction: dependent issue).  So a step must be as few
+// instructions as possible:
+//   * lanes 0-15 min-marginalise the edge to the ROW neighbour, lanes 16-31 the edge to the COLUMN neighbour -- one min-plus
+//     instruction stream serves both (LPL = L/16 labels per lane); the two min-marginals meet through one xor-16 shuffle;
+//   * the group minimum of a half-warp is redux.sync.min.f32 (CREDUX.MIN.F32, sm_100a; 19 cycles against 4 dependent
+//     shuffle+min rounds, scripts/repro/lat.cu), the truncated-linear label window is 2*WIN independent 16-lane shuffles;
+//   * steady steps are unrolled per tile of K = 8 columns: every shared-memory address is a per-tile base + an immediate, one
+//     publication of the step counter per tile, no vote in the hand-off poll (every lane watches the same slot);
+//   * the row neighbour's vector stays in the registers of the lower half-warp; the column neighbour's vector comes from the
+//     warp above through a ring of self-validating slots in shared memory (next CTA: L2 hand-off slots, in-mover warp).
+// CTA = NW = 8 compute warps (band of 8 consecutive rows) + one in-mover warp + one tile warp (all TMA traffic of the CTA).
+#pragma once
+#include "kernels_grid.cuh"
+#include "kernels_grid_rows.cuh"
+
+namespace lpmp {
+
+template <typename Real, int PW, int L>
+struct SplitCfg {
+  static constexpr int LPL = L / 16;                       // labels per lane (16 lanes per edge)
+  static constexpr int NW = 8;                             // compute warps = rows per CTA
+  static constexpr int T = NW;
+  static constexpr int K = 8, LOGK = 3;                    // columns per tile
+  static constexpr int P = ParamCount<PW>::value;
+  static constexpr int REC = REC_VECS * L, PREC = PAR_EDGES * P;
+  static constexpr int SLOT_REC = K * REC, SLOT_PAR = K * PREC;   // reals per tile (one row)
+  static constexpr int RING = 32;                          // columns per hand-off ring (power of two)
+  static constexpr size_t SLOT_BYTES = (size_t)(SLOT_REC + SLOT_PAR) * sizeof(Real);
+  static constexpr size_t CTRL_OFF = 512;                  // [0,512) mbarriers, [512,640) control words, [640,1024) tile warp's bookkeeping
+  static constexpr size_t GSTORE_OFF = 640;
+  static constexpr size_t RINGS_OFF = 1024;
+  static constexpr size_t TILES_OFF = (RINGS_OFF + (size_t)NW * RING * L * sizeof(Real) + 127) / 128 * 128;
+  static constexpr int NSLOT = TILES_OFF + 8 * NW * SLOT_BYTES <= 216 * 1024 ? 8 : 4;   // tiles per ring (power of two)
+  static constexpr size_t WARP_TILE_BYTES = (size_t)NSLOT * SLOT_BYTES;
+  static constexpr size_t SMEM = TILES_OFF + NW * WARP_TILE_BYTES;
+  static constexpr int THREADS = 32 * (NW + 2);
+  static constexpr bool FITS = (L == 16 || L == 32) && SMEM <= 220 * 1024 && NW * NSLOT * 8 <= 512 && (PW == LPMP_PAIRWISE_POTTS || LPL == 1);
+};
+
+// minimum over the 16 lanes of each half-warp
+template <typename Real>
+__device__ __forceinline__ Real half_min(Real v) {
+  if constexpr (std::is_same<Real, float>::value) {
+    const bool lo = (threadIdx.x & 16u) == 0u;
+    const float INF = RealTraits<float>::inf();
+    const float a0 = credux_min(lo ? v : INF), a1 = credux_min(lo ? INF : v);
+    return lo ? a0 : a1;
+  } else {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = rmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+}
+
+// h(x) = min_y [c(x,y) + o(y)] for the LPL labels x = (lane & 15) * LPL + k of this lane, o spread over the 16 lanes of the
+// half-warp.  Truncated linear (LPL = 1; slope, trunc >= 0; host: slope * (WIN + 1) >= trunc): far terms collapse to trunc + min(o),
+// near terms are 2 * WIN shuffles inside the half-warp (a shuffle that leaves it returns the lane's own value: c_d + o(x) >= o(x)
+// is harmless).  Potts: WIN = 1: all lambda >= 0 (one minimum); WIN = 0: the two smallest entries.
+template <typename Real, int PW, int LPL, int WIN>
+__device__ __forceinline__ void split_min_plus(const Real* p, const Real (&o)[LPL], Real (&h)[LPL]) {
+  constexpr unsigned FULL = 0xffffffffu;
+  Real lm = o[0];
+#pragma unroll
+  for (int k = 1; k < LPL; ++k) lm = rmin(lm, o[k]);
+  if constexpr (PW == LPMP_PAIRWISE_POTTS) {
+    const Real lam = p[0];
+    if (WIN == 0 && __any_sync(FULL, lam < Real(0))) {
+      const Real INF = RealTraits<Real>::inf();
+      const unsigned lane = threadIdx.x & 31u;
+      const unsigned segmask = 0xffffu << (lane & 16u);
+      const Real g = half_min<Real>(lm);
+      const unsigned il = (unsigned)__ffs((int)(__ballot_sync(FULL, lm == g) & segmask)) - 1u;   // first lane holding the minimum
+      int kf = 0;                                                                                    // ... and its first label there
+#pragma unroll
+      for (int k = LPL - 1; k >= 0; --k) if (o[k] == g) kf = k;
+      const int k1 = __shfl_sync(FULL, kf, (int)il);
+      Real sm = INF;
+#pragma unroll
+      for (int k = 0; k < LPL; ++k) sm = rmin(sm, lane == il && k == k1 ? INF : o[k]);
+      const Real g2 = half_min<Real>(sm);
+#pragma unroll
+      for (int k = 0; k < LPL; ++k) h[k] = rmin(o[k], Real(lam + (lane == il && k == k1 ? g2 : g)));
+    } else {
+      const Real f = lam + half_min<Real>(lm);
+#pragma unroll
+      for (int k = 0; k < LPL; ++k) h[k] = rmin(o[k], f);
+    }
+  } else {
+    static_assert(PW == LPMP_PAIRWISE_POTTS || LPL == 1, "truncated linear: one label per lane");
+    const Real slope = p[0], trunc = p[1];
+    Real up[WIN], dn[WIN];
+#pragma unroll
+    for (int d = 1; d <= WIN; ++d) {
+      up[d - 1] = __shfl_up_sync(FULL, o[0], d, 16);
+      dn[d - 1] = __shfl_down_sync(FULL, o[0], d, 16);
+    }
+    Real r = rmin(o[0], Real(trunc + half_min<Real>(lm)));
+#pragma unroll
+    for (int d = 1; d <= WIN; ++d) {
+      const Real c = rmin(Real(slope * Real(d)), trunc);
+      r = rmin(r, rmin(Real(c + up[d - 1]), Real(c + dn[d - 1])));
+    }
+    h[0] = r;
+  }
+}
+
+// LPL consecutive reals of this lane (shared memory, 32-bit shared address)
+template <typename Real, int N> __device__ __forceinline__ void lds_n(Real (&v)[N], uint32_t a);
+template <> __device__ __forceinline__ void lds_n<float, 1>(float (&v)[1], uint32_t a) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(a)); }
+template <> __device__ __forceinline__ void lds_n<float, 2>(float (&v)[2], uint32_t a) { asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(a)); }
+template <> __device__ __forceinline__ void lds_n<double, 1>(double (&v)[1], uint32_t a) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[0]) : "r"(a)); }
+template <> __device__ __forceinline__ void lds_n<double, 2>(double (&v)[2], uint32_t a) { asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a)); }
+template <typename Real, int N> __device__ __forceinline__ void lds_n_volatile(Real (&v)[N], uint32_t a);
+template <> __device__ __forceinline__ void lds_n_volatile<float, 1>(float (&v)[1], uint32_t a) { asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(a) : "memory"); }
+template <> __device__ __forceinline__ void lds_n_volatile<float, 2>(float (&v)[2], uint32_t a) { asm volatile("ld.volatile.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(a) : "memory"); }
+template <> __device__ __forceinline__ void lds_n_volatile<double, 1>(double (&v)[1], uint32_t a) { asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v[0]) : "r"(a) : "memory"); }
+template <> __device__ __forceinline__ void lds_n_volatile<double, 2>(double (&v)[2], uint32_t a) { asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a) : "memory"); }
+__device__ __forceinline__ void sts_n_if(bool on, uint32_t a, const float (&v)[1]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.volatile.shared.f32 [%0], %1; }" ::"r"(a), "f"(v[0]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void sts_n_if(bool on, uint32_t a, const float (&v)[2]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.volatile.shared.v2.f32 [%0], {%1,%2}; }" ::"r"(a), "f"(v[0]), "f"(v[1]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void sts_n_if(bool on, uint32_t a, const double (&v)[1]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.volatile.shared.f64 [%0], %1; }" ::"r"(a), "d"(v[0]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void sts_n_if(bool on, uint32_t a, const double (&v)[2]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.volatile.shared.v2.f64 [%0], {%1,%2}; }" ::"r"(a), "d"(v[0]), "d"(v[1]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void stg_n_relaxed_if(bool on, float* p, const float (&v)[1]) { stg1_relaxed_if(on, p, v[0]); }
+__device__ __forceinline__ void stg_n_relaxed_if(bool on, double* p, const double (&v)[1]) { stg1_relaxed_if(on, p, v[0]); }
+__device__ __forceinline__ void stg_n_relaxed_if(bool on, float* p, const float (&v)[2]) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.relaxed.sys.global.v2.f32 [%0], {%1,%2}; }" ::"l"(p), "f"(v[0]), "f"(v[1]), "r"((uint32_t)on) : "memory");
+}
+__device__ __forceinline__ void stg_n_relaxed_if(bool on, double* p, const double (&v)[2]) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.relaxed.sys.global.v2.f64 [%0], {%1,%2}; }" ::"l"(p), "d"(v[0]), "d"(v[1]), "r"((uint32_t)on) : "memory");
+}
+
+template <typename Real, int PW, int L, int WIN, bool FWD>
+__global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_split_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_par,
+                                                                                           const GridArgs<Real> A) {
+  using Cfg = SplitCfg<Real, PW, L>;
+  constexpr int LPL = Cfg::LPL, NW = Cfg::NW, T = Cfg::T, K = Cfg::K, LOGK = Cfg::LOGK, P = Cfg::P, REC = Cfg::REC, PREC = Cfg::PREC, NSLOT = Cfg::NSLOT, RING = Cfg::RING;
+  constexpr uint32_t S = (uint32_t)sizeof(Real);
+  constexpr uint32_t REC_B = REC * S, PREC_B = PREC * S, SLOT_REC_B = Cfg::SLOT_REC * S, SLOT_PAR_B = Cfg::SLOT_PAR * S, LB = L * S;
+  constexpr uint32_t TILE_BYTES = SLOT_REC_B + SLOT_PAR_B;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int HAND_BYTES = 4 * (int)sizeof(Real);
+  constexpr bool fwd = FWD;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t bars = smem_base;                         // [NW][NSLOT] mbarriers
+  const uint32_t ctrl = smem_base + (uint32_t)Cfg::CTRL_OFF;     // +0: band ticket, +16 + 4 w: steps completed by compute warp w (monotone over the kernel)
+  const uint32_t rings = smem_base + (uint32_t)Cfg::RINGS_OFF;   // [NW][RING][L]: ring w feeds compute warp w with the vectors of the row above
+  const uint32_t tiles = smem_base + (uint32_t)Cfg::TILES_OFF;   // per compute warp: [NSLOT] record tiles, then [NSLOT] parameter tiles
+  const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5);
+  const uint32_t H = A.H, W = pin(A.W);
+  const int nchunks = ((int)W + K - 1) >> LOGK;
+  const int nb = (int)A.num_bands;
+  const int qoff = fwd ? 0 : nchunks * K - (int)W;         // padding columns / rows in front of virtual column / row 0
+  const int roff = fwd ? 0 : nb * T - (int)H;              // (tiles are anchored at row 0 / column 0 in both directions)
+  const int nsteps = (int)W;
+  constexpr int kxor = fwd ? 0 : K - 1;
+  // ring slot of a column: its tile-space index q' = q + qoff modulo RING (tiles and ring slots wrap together)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NW * NSLOT; ++i) mbar_init(bars + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    Real* rg = reinterpret_cast<Real*>(smem_raw + Cfg::RINGS_OFF);
+    for (int i = (int)threadIdx.x; i < NW * RING * L; i += Cfg::THREADS) rg[i] = sentinel<Real>();
+    if (threadIdx.x < 32) reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::CTRL_OFF)[threadIdx.x] = 0u;
+  }
+  __syncthreads();
+
+  // bounded waits: a lost partner must not hang the device (sticky abort flag, checked by the host after the pass)
+  const unsigned long long t_launch = globaltimer_ns();
+  auto timed_out = [&](unsigned& spins, unsigned) {
+    if ((++spins & 0x3ffu) != 0) return false;
+    return wait_expired(A.control, t_launch);
+  };
+  auto warp_live = [&](unsigned kb, int w) {               // does compute warp w own a grid row in virtual band kb?
+    const int u = (int)kb * T + w - roff;
+    return u >= 0 && u < (int)H;
+  };
+
+  uint32_t step_base = 0;                 // steps of earlier bands: the published step counters are monotone
+  uint32_t chunk_base[NW];                // per compute warp: tiles of earlier bands (slot / mbarrier-phase sequence continues)
+#pragma unroll
+  for (int w = 0; w < NW; ++w) chunk_base[w] = 0;
+
+  for (;;) {
+    if (threadIdx.x == 0) sts_volatile_u32(ctrl, atomicAdd(A.control, 1u));
+    __syncthreads();
+    const unsigned kb = lds_volatile_u32(ctrl);
+    if (kb >= A.num_bands) break;
+    const int t_in = kb == 0 ? roff : 0;                   // first grid row of the band (virtual row inside the band = compute warp)
+    const bool band_in = kb > 0 || A.in_halo;              // row t_in has a column neighbour in the previous band / stripe
+
+    if (wid == NW + 1) {
+      // ================= tile warp: TMA loads as slots become free, TMA stores as the compute warps complete tiles =================
+      if (lane == 0) {
+        int j_load[NW], j_store[NW];
+        volatile uint32_t* const g_store = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::GSTORE_OFF);   // [NW][NSLOT] bulk-group sequence number of the last store that read each slot
+        uint32_t groups = 0;
+        bool live[NW];
+        int open = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { j_load[w] = j_store[w] = 0; live[w] = warp_live(kb, w); open += live[w] ? 1 : 0; }
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+          for (int sl = 0; sl < NSLOT; ++sl) g_store[w * NSLOT + sl] = 0;
+        unsigned spins = 0;
+        while (open > 0) {
+          bool moved = false;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) {
+            if (!live[w] || j_store[w] >= nchunks) continue;
+            const int row0 = (int)((fwd ? kb : (unsigned)nb - 1u - kb) * T) + (fwd ? w : NW - 1 - w);
+            const uint32_t rec_ring = tiles + (uint32_t)w * (uint32_t)Cfg::WARP_TILE_BYTES, par_ring = rec_ring + NSLOT * SLOT_REC_B;
+            // ---- stores: a tile is final when the row has left it ----
+            const int c = (int)(lds_volatile_u32(ctrl + 16 + 4 * w) - step_base);
+            int need = (j_store[w] + 1) * K - qoff;
+            if (need > nsteps) need = nsteps;
+            if (c >= need) {
+              const uint32_t slot = (chunk_base[w] + (uint32_t)j_store[w]) & (NSLOT - 1);
+              const int col0 = fwd ? j_store[w] * K : (nchunks - 1 - j_store[w]) * K;
+              tma_store_4d(&tm_rec, col0, row0, rec_ring + slot * SLOT_REC_B);
+              tma_commit();
+              g_store[w * NSLOT + (int)slot] = ++groups;
+              if (++j_store[w] >= nchunks) --open;
+              moved = true;
+            }
+            // ---- loads: as soon as the slot's previous tile has left shared memory ----
+            // (not into the slot of the store just issued: cp.async.bulk.wait_group.read would block this warp, which serves
+            // every compute warp of the CTA, for the duration of that store)
+            if (j_load[w] < nchunks && j_load[w] < j_store[w] + NSLOT - (NSLOT >= 8 ? 2 : 1)) {
+              const uint32_t slot = (chunk_base[w] + (uint32_t)j_load[w]) & (NSLOT - 1);
+              const uint32_t gs = g_store[w * NSLOT + (int)slot];
+              if (gs != 0) {
+                const uint32_t younger = groups - gs;   // bulk groups committed after the store that read this slot
+                if (younger == 0) tma_wait_read<0>();
+                else if (younger == 1) tma_wait_read<1>();
+                else if (younger == 2) tma_wait_read<2>();
+                else if (younger == 3) tma_wait_read<3>();
+                else if (younger <= 5) tma_wait_read<4>();
+                else if (younger <= 7) tma_wait_read<6>();
+                else if (younger <= 11) tma_wait_read<8>();
+                else if (younger <= 15) tma_wait_read<12>();
+                else if (younger <= 31) tma_wait_read<16>();
+                else tma_wait_read<32>();
+              }
+              const int col0 = fwd ? j_load[w] * K : (nchunks - 1 - j_load[w]) * K;
+              const uint32_t bar = bars + 8 * ((uint32_t)w * NSLOT + slot);
+              mbar_expect_tx(bar, TILE_BYTES);
+              tma_load_4d(rec_ring + slot * SLOT_REC_B, &tm_rec, col0, row0, bar);
+              tma_load_3d(par_ring + slot * SLOT_PAR_B, &tm_par, col0, row0, bar);
+              ++j_load[w];
+              moved = true;
+            }
+          }
+          if (moved) spins = 0;
+          else { __nanosleep(100); if (timed_out(spins, 1u << 26)) break; }
+        }
+        tma_wait_read<0>();   // every tile of this band has left shared memory before the rings are reused
+      }
+      __syncwarp();
+    } else if (wid == NW) {
+      // ====== in-mover: predecessor's hand-off slots (L2) -> ring of the band's first grid row (zeros if there is no predecessor) ======
+      constexpr int G4 = L / 4, TG = 32 / G4;               // lanes per column (4 labels each), columns per load
+      constexpr int NBATCH = TG >= 16 ? 1 : 16 / TG;        // >= 16 columns polled per L2 round trip
+      const int g = lane / G4, gl = lane % G4;
+      const int w_in = t_in;                                // the compute warp that owns row t_in
+      const uint32_t ring = rings + (uint32_t)w_in * RING * LB;
+      const uint32_t ctr_in = ctrl + 16 + 4 * (uint32_t)w_in;
+      int q_in = 0;
+      unsigned spins = 0;
+      if (!band_in) {
+        Real zero[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) zero[k] = Real(0);
+        while (q_in < (int)W) {
+          const int c = (int)(lds_volatile_u32(ctr_in) - step_base);
+          int limit = c + RING;
+          if (limit > (int)W) limit = (int)W;
+          if (q_in < limit) {
+            for (int q = q_in + g; q < limit; q += TG) sts4(ring + (((uint32_t)(q + qoff) & (uint32_t)(RING - 1)) * L + (uint32_t)(gl * 4)) * S, zero);
+            q_in = limit;
+            spins = 0;
+          } else { __nanosleep(200); if (timed_out(spins, 1u << 26)) break; }
+        }
+      } else {
+        const Real* const hand_in = (kb == 0 ? A.in_boundary : A.handoff + (uint64_t)kb * W * L) + gl * 4;
+        while (q_in < (int)W) {
+          const int c = (int)(lds_volatile_u32(ctr_in) - step_base);
+          int limit = c + RING;                             // the consumer has consumed (and re-armed) c columns
+          if (limit > (int)W) limit = (int)W;
+          Real v[NBATCH][4];
+#pragma unroll
+          for (int b = 0; b < NBATCH; ++b) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[b][k] = sentinel<Real>();
+            const int q = q_in + b * TG + g;
+            ld_relaxed_if<HAND_BYTES>(q < limit, v[b], hand_in + (int64_t)q * L);
+          }
+          int done = 0;
+          bool open = true;   // the ring fills in column order: stop at the first column that has not arrived
+#pragma unroll
+          for (int b = 0; b < NBATCH; ++b) {
+            const int q = q_in + b * TG + g;
+            const bool ok = q < limit && !(is_sentinel(v[b][0]) || is_sentinel(v[b][1]) || is_sentinel(v[b][2]) || is_sentinel(v[b][3]));
+            const unsigned bad = ~__ballot_sync(FULL, ok);
+            const int n_ok = !open ? 0 : bad ? (__ffs((int)bad) - 1) / G4 : TG;
+            if (g < n_ok) {
+              sts4(ring + (((uint32_t)(q + qoff) & (uint32_t)(RING - 1)) * L + (uint32_t)(gl * 4)) * S, v[b]);
+              Real sent[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) sent[k] = sentinel<Real>();
+              st_relaxed<HAND_BYTES>(const_cast<Real*>(hand_in) + (int64_t)q * L, sent);   // the slot is free again for the next pass
+            }
+            done += n_ok;
+            open = open && n_ok == TG;
+          }
+          q_in += done;
+          if (done > 0) spins = 0;
+          else if (timed_out(spins, 1u << 24)) break;
+        }
+      }
+    } else if (!warp_live(kb, wid)) {
+      // no grid row in this band (padding rows of the first / last band): the step counter still moves on with the band
+      if (lane == 0) sts_volatile_u32(ctrl + 16 + 4 * (uint32_t)wid, step_base + (uint32_t)nsteps);
+    } else {
+      // =================================================== compute warps ===================================================
+      const int w = wid;
+      const bool hi = lane >= 16;                           // 0: the edge to the row neighbour, 1: the edge to the column neighbour
+      const int xl = (lane & 15) * LPL;                     // first label of this lane
+      const int u = (int)kb * T + w - roff;                 // virtual grid row of this warp
+      const uint32_t r = fwd ? (uint32_t)u : H - 1 - (uint32_t)u;
+      const bool in_col_exists = u > 0 || A.in_halo, out_col_exists = u + 1 < (int)H || A.out_halo;
+      const bool grid_last_row = u + 1 == (int)H;
+      // where the outgoing column vector (upper half-warp) goes: next warp (ring), next band (L2 hand-off slots), next stripe
+      const bool out_ring = hi && !grid_last_row && w + 1 < NW;
+      const bool out_glob = hi && (grid_last_row ? (A.out_halo && A.out_boundary != nullptr) : w + 1 == NW);
+      Real* const out_ptr = (grid_last_row ? A.out_boundary : A.handoff + (uint64_t)(kb + 1) * W * L) + xl;
+      const uint32_t ring_in = rings + (uint32_t)w * RING * LB + (uint32_t)xl * S;
+      const uint32_t ring_out = rings + (uint32_t)(w + 1 < NW ? w + 1 : w) * RING * LB + (uint32_t)xl * S;
+      const bool warp_out_ring = !grid_last_row && w + 1 < NW;
+      const uint32_t rec_ring = tiles + (uint32_t)w * (uint32_t)Cfg::WARP_TILE_BYTES, par_ring = rec_ring + NSLOT * SLOT_REC_B;
+      constexpr uint32_t o_in_row = (fwd ? REC_BL : REC_AR) * LB, o_in_col = (fwd ? REC_BU : REC_AD) * LB;
+      constexpr uint32_t o_out_row = (fwd ? REC_AR : REC_BL) * LB, o_out_col = (fwd ? REC_AD : REC_BU) * LB;
+      constexpr uint32_t p_in_row = (fwd ? PAR_L : PAR_R) * P * S, p_in_col = (fwd ? PAR_U : PAR_D) * P * S;
+      // per-lane record fields: theta (both halves), own side of this half's receive edge, own side of this half's send edge
+      const uint32_t f_th = rec_ring + (uint32_t)xl * S;
+      const uint32_t f_in = f_th + (hi ? o_in_col : o_in_row), f_out = f_th + (hi ? o_out_col : o_out_row);
+      const uint32_t f_par = par_ring + (hi ? p_in_col : p_in_row);
+      const bool recv_row_first = pin((uint32_t)(fwd ? !A.fifo : (A.fifo != 0))) != 0u;
+      const bool self_first = hi != recv_row_first;         // this half's min-marginal is added to theta first
+      const Real w_fast = (Real)(1.0 / 2.0);
+      const uint32_t cbase = chunk_base[w];
+      const uint32_t ctr = ctrl + 16 + 4 * (uint32_t)w;
+      const uint32_t ctr_next = ctrl + 16 + 4 * (uint32_t)(w + 1 < NW ? w + 1 : w);
+
+      auto wait_chunk = [&](int j) {
+        const uint32_t n = cbase + (uint32_t)j;
+        const uint32_t bar = bars + 8 * ((uint32_t)w * NSLOT + (n & (NSLOT - 1)));
+        const uint32_t parity = (n / NSLOT) & 1u;
+        unsigned spins = 0;
+        while (!mbar_try_wait(bar, parity)) { if (timed_out(spins, 1u << 24)) break; }
+      };
+      auto publish = [&](int steps_done) {
+        fence_proxy_async();   // the tile warp's TMA store reads completed tiles through the async proxy
+        __syncwarp();
+        asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctr), "r"(step_base + (uint32_t)steps_done) : "memory");
+      };
+
+      Real oth[LPL];            // lower half: the row neighbour's vector (carried from step to step); upper half: the column neighbour's
+#pragma unroll
+      for (int k = 0; k < LPL; ++k) oth[k] = Real(0);
+      int free_upto = RING;     // columns the next warp's ring is known to have room for
+      wait_chunk(0);
+
+      // ---- single steps: kind 0: general (any column, rounding, corner weights); 1: weight 1/2, any column (existence of the row
+      // edges by selects); 2: interior column ----
+      auto do_step = [&](auto kind_tag, const int s) {
+        constexpr int KIND = decltype(kind_tag)::value;
+        const int sp = s + qoff;
+        if ((sp & (K - 1)) == 0 && s > 0) wait_chunk(sp >> LOGK);
+        const uint32_t qq = (cbase << LOGK) + (uint32_t)sp;
+        const uint32_t slot = (qq >> LOGK) & (NSLOT - 1), kk = (qq & (K - 1)) ^ (uint32_t)kxor;
+        const uint32_t roffs = slot * SLOT_REC_B + kk * REC_B;
+        const uint32_t rslot = ((uint32_t)sp & (uint32_t)(RING - 1)) * LB;
+        Real par[P];
+        lds_par<Real, P>(par, f_par + slot * SLOT_PAR_B + kk * PREC_B);
+        Real th[LPL], oi[LPL], oo[LPL], pv[LPL];
+        lds_n<Real, LPL>(th, f_th + roffs);
+        lds_n<Real, LPL>(oi, f_in + roffs);
+        lds_n<Real, LPL>(oo, f_out + roffs);
+        {   // the column neighbour's vector: every lane watches the slot (identical outcome in every lane)
+          unsigned spins = 0;
+          bool missing;
+          do {
+            lds_n_volatile<Real, LPL>(pv, ring_in + rslot);
+            missing = is_sentinel(pv[0]) || is_sentinel(pv[LPL - 1]);
+            if (missing && timed_out(spins, 1u << 27)) {
+#pragma unroll
+              for (int k = 0; k < LPL; ++k) pv[k] = Real(0);
+              missing = false;
+            }
+          } while (__any_sync(FULL, missing));
+        }
+        {
+          Real sent[LPL];
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) sent[k] = sentinel<Real>();
+          sts_n_if(hi, ring_in + rslot, sent);             // the slot is free again
+        }
+#pragma unroll
+        for (int k = 0; k < LPL; ++k) oth[k] = hi ? pv[k] : oth[k];
+        const bool has_ir = s > 0, has_or = s + 1 < (int)W;
+
+        if constexpr (KIND >= 1) {
+          Real h[LPL], m[LPL], mo[LPL];
+          split_min_plus<Real, PW, LPL, WIN>(par, oth, h);
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) { m[k] = h[k] + oi[k]; oi[k] = oi[k] - m[k]; }
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) mo[k] = __shfl_xor_sync(FULL, m[k], 16);
+          // missing edges: the left column and the first row have all-zero in-side slots and parameters, so their receives are
+          // exact no-ops; the last row / column has no out_col / out_row edge (select)
+          const bool or_on = KIND == 2 || has_or;
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) {
+            const Real v = (th[k] + (self_first ? m[k] : mo[k])) + (self_first ? mo[k] : m[k]);
+            const Real d = w_fast * v;
+            const Real d_oc = out_col_exists ? d : Real(0), d_or = or_on ? d : Real(0);
+            oo[k] = oo[k] + (hi ? d_oc : d_or);
+            th[k] = (v - d_oc) - d_or;
+          }
+        } else {
+          const bool has_ic = in_col_exists, has_oc = out_col_exists;
+          const bool has_i = hi ? has_ic : has_ir;
+          const int n_in = (int)has_ir + (int)has_ic, n_out = (int)has_or + (int)has_oc;
+          Real pz[P], oz[LPL], h[LPL], m[LPL], mo[LPL];
+#pragma unroll
+          for (int p = 0; p < P; ++p) pz[p] = has_i ? par[p] : Real(0);
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) oz[k] = has_i ? oth[k] : Real(0);
+          split_min_plus<Real, PW, LPL, WIN>(pz, oz, h);
+          // m = h + own, own -= m   (RepamLeft / RepamRight)
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) { m[k] = has_i ? Real(h[k] + oi[k]) : Real(0); oi[k] = has_i ? Real(oi[k] - m[k]) : oi[k]; }
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) mo[k] = __shfl_xor_sync(FULL, m[k], 16);
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) {
+            const Real m_ir = hi ? mo[k] : m[k], m_ic = hi ? m[k] : mo[k];
+            Real v = th[k];
+            if (recv_row_first) { if (has_ir) v = v + m_ir; if (has_ic) v = v + m_ic; }
+            else { if (has_ic) v = v + m_ic; if (has_ir) v = v + m_ir; }
+            th[k] = v;
+          }
+          if (A.primal) {   // first minimiser of theta (include/factors_messages.hxx:2363,2382-2389); both halves hold theta
+            Real lm = th[0];
+#pragma unroll
+            for (int k = 1; k < LPL; ++k) lm = rmin(lm, th[k]);
+            const Real g = half_min<Real>(lm);
+            const unsigned il = (unsigned)__ffs((int)(__ballot_sync(FULL, lm == g) & 0xffffu)) - 1u;
+            int kf = 0;
+#pragma unroll
+            for (int k = LPL - 1; k >= 0; --k) if (th[k] == g) kf = k;
+            const int k1 = __shfl_sync(FULL, kf, (int)il);
+            if (lane == 0) A.labels[(uint64_t)r * W + (fwd ? (uint32_t)s : W - 1 - (uint32_t)s)] = il * LPL + (unsigned)k1;
+          }
+          // SendMessages with the snapshot t = theta (weights: include/LP_MP.h:1397)
+          const double wd = n_out > 0 ? 1.0 / (double)(n_in > n_out ? n_in : n_out) : 0.0;
+          const Real wgt = (Real)wd;
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) {
+            const Real d = wgt * th[k];
+            Real v = th[k];
+            if (has_oc) { if (hi) oo[k] = oo[k] + d; v = v - d; }
+            if (has_or) { if (!hi) oo[k] = oo[k] + d; v = v - d; }
+            th[k] = v;
+          }
+        }
+        sts_n_if(!hi, f_th + roffs, th);
+        sts_n_if(true, f_in + roffs, oi);
+        sts_n_if(true, f_out + roffs, oo);
+        // ---- hand the freshly written column vector on: next warp (ring), next band / stripe (global slots) ----
+        if (warp_out_ring && s >= free_upto) {              // warp-uniform, rare: the next warp's ring is full
+          unsigned spins = 0;
+          do {
+            free_upto = (int)(lds_volatile_u32(ctr_next) - step_base) + RING;
+          } while (s >= free_upto && !timed_out(spins, 1u << 27));
+        }
+        sts_n_if(out_ring, ring_out + rslot, oo);
+        stg_n_relaxed_if(out_glob, out_ptr + (int64_t)s * L, oo);
+#pragma unroll
+        for (int k = 0; k < LPL; ++k) oth[k] = oo[k];       // lower half: the row neighbour's vector of the next step
+        publish(s + 1);
+      };
+
+      // ---- steady steps, one tile of 8 columns at a time: every address is a per-tile base + an immediate ----
+      auto do_tile = [&](const int j) {
+        wait_chunk(j);
+        const int s0 = (j << LOGK) - qoff;                  // step (= virtual column) at which the row enters tile j
+        const uint32_t slot = (cbase + (uint32_t)j) & (NSLOT - 1);
+        const uint32_t toff = slot * SLOT_REC_B + (fwd ? 0u : (uint32_t)(K - 1) * REC_B);
+        const uint32_t Tth = f_th + toff, Tin = f_in + toff, Tout = f_out + toff;
+        const uint32_t Tpar = f_par + slot * SLOT_PAR_B + (fwd ? 0u : (uint32_t)(K - 1) * PREC_B);
+        const uint32_t c0 = ((uint32_t)(j << LOGK) & (uint32_t)(RING - 1)) * LB;
+        const uint32_t Rin = ring_in + c0, Rout = ring_out + c0;
+        Real* const Gout = out_ptr + (int64_t)s0 * L;
+        if (warp_out_ring && s0 + K - 1 >= free_upto) {     // room in the next warp's ring for the whole tile (warp-uniform, rare)
+          unsigned spins = 0;
+          do {
+            free_upto = (int)(lds_volatile_u32(ctr_next) - step_base) + RING;
+          } while (s0 + K - 1 >= free_upto && !timed_out(spins, 1u << 27));
+        }
+#pragma unroll
+        for (int jj = 0; jj < K; ++jj) {
+          constexpr int SG = fwd ? 1 : -1;
+          const uint32_t ro = (uint32_t)(SG * jj * (int)REC_B), po = (uint32_t)(SG * jj * (int)PREC_B);
+          const uint32_t rin = Rin + (uint32_t)jj * LB;
+          Real pv[LPL], par[P], th[LPL], oi[LPL], oo[LPL];
+          lds_n_volatile<Real, LPL>(pv, rin);               // the polled slot: every lane reads the words of its labels (no vote)
+          lds_par<Real, P>(par, Tpar + po);
+          lds_n<Real, LPL>(th, Tth + ro);
+          lds_n<Real, LPL>(oi, Tin + ro);
+          lds_n<Real, LPL>(oo, Tout + ro);
+          if (is_sentinel(pv[0]) || is_sentinel(pv[LPL - 1])) {
+            unsigned spins = 0;
+            do { lds_n_volatile<Real, LPL>(pv, rin); } while ((is_sentinel(pv[0]) || is_sentinel(pv[LPL - 1])) && ((++spins & 0xffffu) != 0 || !wait_expired(A.control, t_launch)));
+            if (is_sentinel(pv[0]) || is_sentinel(pv[LPL - 1])) {
+#pragma unroll
+              for (int k = 0; k < LPL; ++k) pv[k] = Real(0);
+            }
+          }
+          {
+            Real sent[LPL];
+#pragma unroll
+            for (int k = 0; k < LPL; ++k) sent[k] = sentinel<Real>();
+            sts_n_if(hi, rin, sent);                        // the slot is free again
+          }
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) oth[k] = hi ? pv[k] : oth[k];
+          Real h[LPL], m[LPL], mo[LPL];
+          split_min_plus<Real, PW, LPL, WIN>(par, oth, h);
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) { m[k] = h[k] + oi[k]; oi[k] = oi[k] - m[k]; }
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) mo[k] = __shfl_xor_sync(FULL, m[k], 16);
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) {
+            const Real v = (th[k] + (self_first ? m[k] : mo[k])) + (self_first ? mo[k] : m[k]);
+            const Real d = w_fast * v;
+            const Real d_oc = out_col_exists ? d : Real(0);
+            oo[k] = oo[k] + (hi ? d_oc : d);
+            th[k] = (v - d_oc) - d;
+          }
+          sts_n_if(out_ring, Rout + (uint32_t)jj * LB, oo);   // hand-off first: the warp below is waiting for it
+          stg_n_relaxed_if(out_glob, Gout + jj * L, oo);
+          sts_n_if(!hi, Tth + ro, th);
+          sts_n_if(true, Tin + ro, oi);
+          sts_n_if(true, Tout + ro, oo);
+#pragma unroll
+          for (int k = 0; k < LPL; ++k) oth[k] = oo[k];
+        }
+        publish(s0 + K);
+      };
+
+      // general steps for the whole band: rounding, tiny grids; for the first / last column of the first / last grid row (corner
+      // weights); everything else runs the edge / steady steps
+      const bool all_general = A.primal != 0 || (int)W < 4 || (H < 2 && !(A.in_halo || A.out_halo));
+      const bool corner_row = (u == 0 && !A.in_halo) || (u + 1 == (int)H && !A.out_halo);
+      int s = 0;
+      if (all_general) {
+        for (; s < nsteps; ++s) do_step(std::integral_constant<int, 0>{}, s);
+      } else {
+        if (corner_row) do_step(std::integral_constant<int, 0>{}, s); else do_step(std::integral_constant<int, 1>{}, s);
+        ++s;
+        const int s_last = (int)W - 2;                      // interior columns: 1 .. W - 2
+        const int j0 = (1 + qoff + K - 1) >> LOGK, j1 = ((s_last + 1 + qoff) >> LOGK) - 1;   // whole tiles j0 .. j1 of interior columns
+        if (j1 >= j0) {
+          for (; s < (j0 << LOGK) - qoff; ++s) do_step(std::integral_constant<int, 2>{}, s);
+#pragma unroll 1
+          for (int j = j0; j <= j1; ++j) do_tile(j);
+          s = ((j1 + 1) << LOGK) - qoff;
+        }
+#pragma unroll 1
+        for (; s <= s_last; ++s) do_step(std::integral_constant<int, 2>{}, s);
+        if (corner_row) do_step(std::integral_constant<int, 0>{}, s); else do_step(std::integral_constant<int, 1>{}, s);
+      }
+    }
+    // ---- end of the band: every ring is drained and re-armed, every tile has left shared memory ----
+#pragma unroll
+    for (int w = 0; w < NW; ++w) if (warp_live(kb, w)) chunk_base[w] += (uint32_t)nchunks;
+    step_base += (uint32_t)nsteps;
+    __syncthreads();
+  }
+  if (wid == NW + 1 && lane == 0) tma_wait_all();   // the global writes of the last tiles are complete before the CTA exits
+}
+
+}  // namespace lpmp

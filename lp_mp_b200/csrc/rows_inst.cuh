@@ -11,14 +11,14 @@ static cudaError_t launch_rows_one(const CUtensorMap* maps, const GridArgs<Real>
   if constexpr (!Cfg::FITS) {
     return cudaErrorInvalidValue;
   } else {
-    auto kernel = wavefront_rows_kernel<Real, PW, L, WIN>;
+    auto kernel = args.forward ? wavefront_rows_kernel<Real, PW, L, WIN, true> : wavefront_rows_kernel<Real, PW, L, WIN, false>;
     int dev = 0;
     cudaGetDevice(&dev);
-    static bool configured[64] = {};
-    if (!configured[dev & 63]) {
+    static bool configured[64][2] = {};
+    if (!configured[dev & 63][args.forward ? 1 : 0]) {
       cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
       if (e != cudaSuccess) return e;
-      configured[dev & 63] = true;
+      configured[dev & 63][args.forward ? 1 : 0] = true;
     }
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Cfg::THREADS, Cfg::SMEM);

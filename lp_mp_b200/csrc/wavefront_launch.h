@@ -21,6 +21,7 @@ struct WavefrontTuning {
                         // memory); 0 = automatic (8), 1 = no clusters
   int level_group = 0;  // level kernel: lanes per node (power of two below the default pow2 >= L); 0 = default
   int warps_per_cta = 0;  // consecutive bands per CTA (<= 8 and what the shared memory holds); 0 or 1 = one band per CTA
+  int split = -1;       // edge-split variant for the anisotropic passes (kernels_grid_split.cuh: one row per warp): 1 on, 0 off, -1 automatic
   int rows = -1;        // one-label-per-lane variant for the anisotropic passes (kernels_grid_rows.cuh): 1 on, 0 off, -1 automatic
 };
 
@@ -77,6 +78,19 @@ inline bool rows_supported(int pw, uint32_t L) {
 }
 template <typename Real, int PW>
 cudaError_t launch_rows(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int win, const WavefrontTuning& tune, int num_sms, cudaStream_t stream);
+
+// edge-split variant (kernels_grid_split.cuh): anisotropic passes, bands of 8 rows, L in {16, 32} where the shared memory holds it
+// (truncated linear: L = 16).  maps: [0] records, [1] parameter records, boxes of 1 row x 8 columns.  win as for launch_rows.
+constexpr int kSplitBandRows = 8;
+template <typename Real, int PW> bool split_fits(uint32_t L);
+template <typename Real>
+inline bool split_supported(int pw, uint32_t L) {
+  if (pw == LPMP_PAIRWISE_POTTS) return split_fits<Real, LPMP_PAIRWISE_POTTS>(L);
+  if (pw == LPMP_PAIRWISE_TRUNCLIN) return split_fits<Real, LPMP_PAIRWISE_TRUNCLIN>(L);
+  return false;
+}
+template <typename Real, int PW>
+cudaError_t launch_split(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int win, const WavefrontTuning& tune, int num_sms, cudaStream_t stream);
 
 // dense-table grids (kernels_grid_dense.cuh): anisotropic passes for L in {16, 32, 64}
 template <typename Real>

@@ -317,6 +317,34 @@ def test_wavefront_rows_variant(kind, L, dtype, tuning):
         run_lockstep(lps, "anisotropic", iters=2, lb_rtol=rt)
 
 
+@pytest.mark.parametrize("kind,L,dtype,tuning", [("trunclin", 16, "f32", dict(wavefront_split=1)), ("trunclin", 16, "f64", dict(wavefront_split=1)),
+                                                 ("trunclin", 16, "f32", dict(wavefront_split=1, wavefront_max_ctas=2)),
+                                                 ("potts", 16, "f32", dict(wavefront_split=1)), ("potts", 32, "f32", dict(wavefront_split=1)),
+                                                 ("potts", 16, "f64", dict(wavefront_split=1, wavefront_max_ctas=3)),
+                                                 ("potts", 32, "f32", dict(wavefront_split=1, wavefront_max_ctas=1))])
+def test_wavefront_split_variant(kind, L, dtype, tuning):
+    """one row per warp, the two receive edges split over the half-warps (kernels_grid_split.cuh): anisotropic passes and
+    rounding; rings wrapping many times, several bands per CTA in sequence, ragged last band / tile, single rows / columns,
+    negative Potts couplings (two smallest entries)"""
+    rt = 1e-6 if dtype == "f32" else 1e-12
+    lps = grid_pair(dtype, 203, 157, L, kind, seed=23, **tuning)
+    run_lockstep(lps, "anisotropic", iters=3, lb_rtol=rt)
+    for H, W in ((1, 40), (40, 1), (3, 3), (9, 2), (17, 70), (2, 5), (5, 9), (33, 8), (4, 4), (11, 17)):
+        lps = grid_pair(dtype, H, W, L, kind, seed=H * 100 + W, **tuning)
+        run_lockstep(lps, "anisotropic", iters=2, lb_rtol=rt)
+
+
+def test_wavefront_split_variant_fifo_and_synthetic():
+    lps = grid_pair("f64", 21, 23, 16, "trunclin", seed=5, edge_order="fifo", wavefront_split=1)
+    run_lockstep(lps, "anisotropic", iters=3)
+    for kind, lo, hi, L in (("trunclin", 0.25, 1.0, 16), ("potts", 0.1, 1.0, 32), ("potts", 0.1, 1.0, 16)):
+        lps = [oracle_lp("f32").grid_create(67, 81, L, kind), cuda_lp("f32").grid_create(67, 81, L, kind)]
+        lps[1].set_tuning(wavefront_split=1)
+        for lp in lps:
+            lp.grid_fill_synthetic(0x5EED, lo, hi)
+        run_lockstep(lps, "anisotropic", iters=3, lb_rtol=1e-6)
+
+
 def test_wavefront_rows_variant_fifo_and_synthetic():
     lps = grid_pair("f64", 21, 23, 16, "trunclin", seed=5, edge_order="fifo", wavefront_rows=1)
     run_lockstep(lps, "anisotropic", iters=3)
