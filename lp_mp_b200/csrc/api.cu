@@ -886,6 +886,7 @@ struct Solver : ISolver {
       A.in_boundary = forward ? in_top.p : in_bot.p;
       A.out_boundary = forward ? peer_bot : peer_top;
       A.labels = labels.p;
+      A.rec = rec.p; A.par = par.p;
       A.trace = trace.p;
       A.trace_steps = (trace.p && want_trace >= 2) ? trace.p + 4 * (size_t)A.num_bands : nullptr;
       A.trace_band = A.num_bands / 2;

@@ -64,6 +64,8 @@ struct GridArgs {
   Real* out_boundary;       // [W][L] where the last band delivers its outgoing vectors when out_halo (the neighbour's
                             // in_boundary, possibly peer memory), or null: not delivered
   uint32_t* labels;         // [H*W]
+  Real* rec;                // node records [H][W][5][L] (the split variant moves whole-row tile runs with 1-D bulk copies, no tensor map)
+  Real* par;                // parameter records [H][W][4][P]
   unsigned long long* trace;   // debug: per band {claimed, first tile ready, first hand-off consumed, done} in ns (globaltimer), or null
   unsigned long long* trace_steps;   // debug (lean variant): [2][8192] end-of-step stamps of bands trace_band and trace_band + 1, or null
   uint32_t trace_band;
@@ -121,6 +123,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, int c2, int 
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1,%2,%3,%4}], [%5];" ::"l"(tm), "r"(0), "r"(0), "r"(c2), "r"(c3),
                "r"(src)
                : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }

@@ -138,13 +138,11 @@ __device__ __forceinline__ void stg_n_relaxed_if(bool on, double* p, const doubl
 }
 
 template <typename Real, int PW, int L, int WIN, bool FWD>
-__global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_split_kernel(const __grid_constant__ CUtensorMap tm_rec, const __grid_constant__ CUtensorMap tm_par,
-                                                                                           const GridArgs<Real> A) {
+__global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_split_kernel(const GridArgs<Real> A) {
   using Cfg = SplitCfg<Real, PW, L>;
   constexpr int LPL = Cfg::LPL, NW = Cfg::NW, T = Cfg::T, K = Cfg::K, LOGK = Cfg::LOGK, P = Cfg::P, REC = Cfg::REC, PREC = Cfg::PREC, NSLOT = Cfg::NSLOT, RING = Cfg::RING;
   constexpr uint32_t S = (uint32_t)sizeof(Real);
   constexpr uint32_t REC_B = REC * S, PREC_B = PREC * S, SLOT_REC_B = Cfg::SLOT_REC * S, SLOT_PAR_B = Cfg::SLOT_PAR * S, LB = L * S;
-  constexpr uint32_t TILE_BYTES = SLOT_REC_B + SLOT_PAR_B;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int HAND_BYTES = 4 * (int)sizeof(Real);
   constexpr bool fwd = FWD;
@@ -200,73 +198,55 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
     const bool band_in = kb > 0 || A.in_halo;              // row t_in has a column neighbour in the previous band / stripe
 
     if (wid == NW + 1) {
-      // ================= tile warp: TMA loads as slots become free, TMA stores as the compute warps complete tiles =================
-      if (lane == 0) {
-        int j_load[NW], j_store[NW];
-        volatile uint32_t* const g_store = reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::GSTORE_OFF);   // [NW][NSLOT] bulk-group sequence number of the last store that read each slot
-        uint32_t groups = 0;
-        bool live[NW];
-        int open = 0;
+      // ================= tile warp: bulk loads as slots become free, bulk stores as the compute warps complete tiles =================
+      // LANE w serves compute warp w (its own ring of NSLOT tiles, its own bulk groups): the bookkeeping of all rings is one SIMT
+      // instruction stream -- a single thread serving every ring in turn was the bottleneck of the whole CTA (profiles/r02_split_tilewarp.txt)
+      constexpr int DROP = NSLOT >= 8 ? 2 : 1;   // tiles of look-ahead given up so that a load never waits for the store just issued
+      const int w = lane < NW ? lane : NW - 1;
+      bool open = lane < NW && warp_live(kb, w);
+      uint32_t cb = 0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) { j_load[w] = j_store[w] = 0; live[w] = warp_live(kb, w); open += live[w] ? 1 : 0; }
-#pragma unroll
-        for (int w = 0; w < NW; ++w)
-#pragma unroll
-          for (int sl = 0; sl < NSLOT; ++sl) g_store[w * NSLOT + sl] = 0;
-        unsigned spins = 0;
-        while (open > 0) {
-          bool moved = false;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) {
-            if (!live[w] || j_store[w] >= nchunks) continue;
-            const int row0 = (int)((fwd ? kb : (unsigned)nb - 1u - kb) * T) + (fwd ? w : NW - 1 - w);
-            const uint32_t rec_ring = tiles + (uint32_t)w * (uint32_t)Cfg::WARP_TILE_BYTES, par_ring = rec_ring + NSLOT * SLOT_REC_B;
-            // ---- stores: a tile is final when the row has left it ----
-            const int c = (int)(lds_volatile_u32(ctrl + 16 + 4 * w) - step_base);
-            int need = (j_store[w] + 1) * K - qoff;
-            if (need > nsteps) need = nsteps;
-            if (c >= need) {
-              const uint32_t slot = (chunk_base[w] + (uint32_t)j_store[w]) & (NSLOT - 1);
-              const int col0 = fwd ? j_store[w] * K : (nchunks - 1 - j_store[w]) * K;
-              tma_store_4d(&tm_rec, col0, row0, rec_ring + slot * SLOT_REC_B);
-              tma_commit();
-              g_store[w * NSLOT + (int)slot] = ++groups;
-              if (++j_store[w] >= nchunks) --open;
-              moved = true;
-            }
-            // ---- loads: as soon as the slot's previous tile has left shared memory ----
-            // (not into the slot of the store just issued: cp.async.bulk.wait_group.read would block this warp, which serves
-            // every compute warp of the CTA, for the duration of that store)
-            if (j_load[w] < nchunks && j_load[w] < j_store[w] + NSLOT - (NSLOT >= 8 ? 2 : 1)) {
-              const uint32_t slot = (chunk_base[w] + (uint32_t)j_load[w]) & (NSLOT - 1);
-              const uint32_t gs = g_store[w * NSLOT + (int)slot];
-              if (gs != 0) {
-                const uint32_t younger = groups - gs;   // bulk groups committed after the store that read this slot
-                if (younger == 0) tma_wait_read<0>();
-                else if (younger == 1) tma_wait_read<1>();
-                else if (younger == 2) tma_wait_read<2>();
-                else if (younger == 3) tma_wait_read<3>();
-                else if (younger <= 5) tma_wait_read<4>();
-                else if (younger <= 7) tma_wait_read<6>();
-                else if (younger <= 11) tma_wait_read<8>();
-                else if (younger <= 15) tma_wait_read<12>();
-                else if (younger <= 31) tma_wait_read<16>();
-                else tma_wait_read<32>();
-              }
-              const int col0 = fwd ? j_load[w] * K : (nchunks - 1 - j_load[w]) * K;
-              const uint32_t bar = bars + 8 * ((uint32_t)w * NSLOT + slot);
-              mbar_expect_tx(bar, TILE_BYTES);
-              tma_load_4d(rec_ring + slot * SLOT_REC_B, &tm_rec, col0, row0, bar);
-              tma_load_3d(par_ring + slot * SLOT_PAR_B, &tm_par, col0, row0, bar);
-              ++j_load[w];
-              moved = true;
-            }
-          }
-          if (moved) spins = 0;
-          else { __nanosleep(100); if (timed_out(spins, 1u << 26)) break; }
+      for (int k = 0; k < NW; ++k) cb = k == w ? chunk_base[k] : cb;
+      const int row0 = (int)((fwd ? kb : (unsigned)nb - 1u - kb) * T) + (fwd ? w : NW - 1 - w);
+      const uint32_t rec_ring = tiles + (uint32_t)w * (uint32_t)Cfg::WARP_TILE_BYTES, par_ring = rec_ring + NSLOT * SLOT_REC_B;
+      const uint32_t ctr_w = ctrl + 16 + 4 * (uint32_t)w;
+      const bool mine = open;
+      int j_load = 0, j_store = 0;
+      unsigned spins = 0;
+      while (__any_sync(FULL, open)) {
+        bool moved = false;
+        // ---- stores: a tile is final when the last row of the warp has left it ----
+        const int c = (int)(lds_volatile_u32(ctr_w) - step_base);
+        int need = (j_store + 1) * K - qoff;
+        if (need > nsteps) need = nsteps;
+        if (open && c >= need) {
+          const uint32_t slot = (cb + (uint32_t)j_store) & (NSLOT - 1);
+          const int col0 = fwd ? j_store * K : (nchunks - 1 - j_store) * K;
+          const uint32_t ncols = (uint32_t)((int)W - col0 < K ? (int)W - col0 : K);   // a tile is one contiguous run of records
+          bulk_store_1d(A.rec + ((uint64_t)row0 * W + (uint32_t)col0) * REC, rec_ring + slot * SLOT_REC_B, ncols * REC_B);
+          tma_commit();
+          ++j_store;
+          moved = true;
         }
-        tma_wait_read<0>();   // every tile of this band has left shared memory before the rings are reused
+        // ---- loads: into a slot whose previous tile has left shared memory (never the slot of the store just issued) ----
+        if (open && j_load < nchunks && j_load < j_store + NSLOT - DROP) {
+          const uint32_t slot = (cb + (uint32_t)j_load) & (NSLOT - 1);
+          if (j_load >= NSLOT) tma_wait_read<DROP>();   // at least DROP younger stores of this lane were committed after the one that read the slot
+          const int col0 = fwd ? j_load * K : (nchunks - 1 - j_load) * K;
+          const uint32_t bar = bars + 8 * ((uint32_t)w * NSLOT + slot);
+          const uint32_t ncols = (uint32_t)((int)W - col0 < K ? (int)W - col0 : K);
+          const uint64_t node0 = (uint64_t)row0 * W + (uint32_t)col0;
+          mbar_expect_tx(bar, ncols * (REC_B + PREC_B));
+          bulk_load_1d(rec_ring + slot * SLOT_REC_B, A.rec + node0 * REC, ncols * REC_B, bar);
+          bulk_load_1d(par_ring + slot * SLOT_PAR_B, A.par + node0 * PREC, ncols * PREC_B, bar);
+          ++j_load;
+          moved = true;
+        }
+        open = open && j_store < nchunks;
+        if (__any_sync(FULL, moved)) spins = 0;
+        else { __nanosleep(100); if (timed_out(spins, 1u << 26)) break; }
       }
+      if (mine) tma_wait_read<0>();   // every tile of this band has left shared memory before the rings are reused
       __syncwarp();
     } else if (wid == NW) {
       // ====== in-mover: predecessor's hand-off slots (L2) -> ring of the band's first grid row (zeros if there is no predecessor) ======
@@ -601,7 +581,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
     step_base += (uint32_t)nsteps;
     __syncthreads();
   }
-  if (wid == NW + 1 && lane == 0) tma_wait_all();   // the global writes of the last tiles are complete before the CTA exits
+  if (wid == NW + 1) tma_wait_all();   // the global writes of the last tiles are complete before the CTA exits
 }
 
 }  // namespace lpmp

@@ -23,7 +23,7 @@ static cudaError_t launch_split_one(const CUtensorMap* maps, const GridArgs<Real
     int ctas = (int)args.num_bands;
     if (ctas > num_sms) ctas = num_sms;   // one CTA per SM; persistent: the ticket loop covers the remaining bands
     if (tune.max_ctas > 0 && ctas > tune.max_ctas) ctas = tune.max_ctas;
-    kernel<<<ctas, Cfg::THREADS, Cfg::SMEM, stream>>>(maps[0], maps[1], args);
+    kernel<<<ctas, Cfg::THREADS, Cfg::SMEM, stream>>>(args);
     return cudaGetLastError();
   }
 }
