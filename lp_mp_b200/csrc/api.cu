@@ -354,9 +354,10 @@ struct Solver : ISolver {
       note_trunclin((double)ls, (double)lt);
     }
   }
-  // automatic choice: the rows variant where the pass is bound by the dependency chain rather than by HBM (small label counts)
-  bool use_split() const { return tune.split > 0 || (tune.split < 0 && tune.rows <= 0 && L <= 16); }
-  bool use_rows() const { return tune.rows > 0 || (tune.rows < 0 && L <= 16); }
+  // automatic choice for the anisotropic passes: edge-split variant where it exists (L = 16, 32), else one label per lane (L = 8;
+  // L = 32 in double), else the band kernels (profiles/README.md, round 2)
+  bool use_split() const { return tune.split > 0 || (tune.split < 0 && tune.rows <= 0 && tune.lean < 0 && tune.warps_per_cta <= 1); }
+  bool use_rows() const { return tune.rows > 0 || (tune.rows < 0 && tune.split <= 0 && tune.lean < 0 && tune.warps_per_cta <= 1); }
   int tl_hops() const {
     if (pw != LPMP_PAIRWISE_TRUNCLIN || tl_irregular) return 0;
     if (tl_reach <= 4) return 1;

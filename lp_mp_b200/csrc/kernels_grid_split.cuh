@@ -35,8 +35,8 @@ struct SplitCfg {
   static constexpr int SLOT_REC = K * REC, SLOT_PAR = K * PREC;   // reals per tile (one row)
   static constexpr int RING = 32;                          // columns per hand-off ring (power of two)
   static constexpr size_t SLOT_BYTES = (size_t)(SLOT_REC + SLOT_PAR) * sizeof(Real);
-  static constexpr size_t CTRL_OFF = 512;                  // [0,512) mbarriers, [512,640) control words, [640,1024) tile warp's bookkeeping
-  static constexpr size_t GSTORE_OFF = 640;
+  static constexpr size_t CTRL_OFF = 512;                  // [0,512) mbarriers, [512,640) band queue {super-band, iteration + 1} x 16,
+  static constexpr size_t CTR_OFF = 640;                   // [640,1024) step counters: +4 w: compute warp w, +64: warp 0 of the next CTA of the cluster
   static constexpr size_t RINGS_OFF = 1024;
   static constexpr size_t TILES_OFF = (RINGS_OFF + (size_t)NW * RING * L * sizeof(Real) + 127) / 128 * 128;
   static constexpr int NSLOT = TILES_OFF + 8 * NW * SLOT_BYTES <= 216 * 1024 ? 8 : 4;   // tiles per ring (power of two)
@@ -45,6 +45,20 @@ struct SplitCfg {
   static constexpr int THREADS = 32 * (NW + 2);
   static constexpr bool FITS = (L == 16 || L == 32) && SMEM <= 220 * 1024 && NW * NSLOT * 8 <= 512 && (PW == LPMP_PAIRWISE_POTTS || LPL == 1);
 };
+
+// ---- thread-block cluster / distributed shared memory primitives ----
+__device__ __forceinline__ uint32_t sp_cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t sp_cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t sp_mapa(uint32_t a, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank)); return r; }
+__device__ __forceinline__ void sp_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t a, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster_n_if(bool on, uint32_t a, const float (&v)[1]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared::cluster.f32 [%0], %1; }" ::"r"(a), "f"(v[0]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void st_cluster_n_if(bool on, uint32_t a, const float (&v)[2]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.shared::cluster.v2.f32 [%0], {%1,%2}; }" ::"r"(a), "f"(v[0]), "f"(v[1]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void st_cluster_n_if(bool on, uint32_t a, const double (&v)[1]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared::cluster.f64 [%0], %1; }" ::"r"(a), "d"(v[0]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void st_cluster_n_if(bool on, uint32_t a, const double (&v)[2]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.shared::cluster.v2.f64 [%0], {%1,%2}; }" ::"r"(a), "d"(v[0]), "d"(v[1]), "r"((uint32_t)on) : "memory"); }
 
 // minimum over the 16 lanes of each half-warp
 template <typename Real>
@@ -149,7 +163,8 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t bars = smem_base;                         // [NW][NSLOT] mbarriers
-  const uint32_t ctrl = smem_base + (uint32_t)Cfg::CTRL_OFF;     // +0: band ticket, +16 + 4 w: steps completed by compute warp w (monotone over the kernel)
+  const uint32_t queue = smem_base + (uint32_t)Cfg::CTRL_OFF;    // band queue: {super-band, iteration + 1} x 16
+  const uint32_t ctrs = smem_base + (uint32_t)Cfg::CTR_OFF;      // +4 w: steps completed by compute warp w (monotone over the kernel); +64: pushed by the next CTA's warp 0
   const uint32_t rings = smem_base + (uint32_t)Cfg::RINGS_OFF;   // [NW][RING][L]: ring w feeds compute warp w with the vectors of the row above
   const uint32_t tiles = smem_base + (uint32_t)Cfg::TILES_OFF;   // per compute warp: [NSLOT] record tiles, then [NSLOT] parameter tiles
   const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5);
@@ -169,9 +184,15 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
   {
     Real* rg = reinterpret_cast<Real*>(smem_raw + Cfg::RINGS_OFF);
     for (int i = (int)threadIdx.x; i < NW * RING * L; i += Cfg::THREADS) rg[i] = sentinel<Real>();
-    if (threadIdx.x < 32) reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::CTRL_OFF)[threadIdx.x] = 0u;
+    if (threadIdx.x < 128) reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::CTRL_OFF)[threadIdx.x] = 0u;
   }
-  __syncthreads();
+  // CTAs of a thread-block cluster work on CONSECUTIVE bands (rank r on band sb * csize + r): the last row of band r hands its
+  // vectors straight into ring 0 of rank r + 1 through distributed shared memory (~0.2 us instead of ~0.8 us through the L2
+  // slots and the in-mover); only the boundary between two clusters goes through L2
+  const uint32_t crank = sp_cluster_ctarank(), csize = sp_cluster_nctarank();
+  const unsigned num_super = (A.num_bands + csize - 1u) / csize;
+  if (csize > 1) sp_cluster_sync();   // every ring of the cluster is armed before a neighbour may write into it
+  else __syncthreads();
 
   // bounded waits: a lost partner must not hang the device (sticky abort flag, checked by the host after the pass)
   const unsigned long long t_launch = globaltimer_ns();
@@ -181,7 +202,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
   };
   auto warp_live = [&](unsigned kb, int w) {               // does compute warp w own a grid row in virtual band kb?
     const int u = (int)kb * T + w - roff;
-    return u >= 0 && u < (int)H;
+    return kb < A.num_bands && u >= 0 && u < (int)H;
   };
 
   uint32_t step_base = 0;                 // steps of earlier bands: the published step counters are monotone
@@ -189,11 +210,25 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
 #pragma unroll
   for (int w = 0; w < NW; ++w) chunk_base[w] = 0;
 
-  for (;;) {
-    if (threadIdx.x == 0) sts_volatile_u32(ctrl, atomicAdd(A.control, 1u));
+  for (uint32_t iter = 0;; ++iter) {
+    // rank 0 claims the next super-band and publishes it to every CTA of the cluster (a rank is at most csize - 1 iterations behind)
+    const uint32_t qslot = queue + 8 * (iter & 15u);
+    if (threadIdx.x == 0) {
+      if (crank == 0) {
+        const unsigned sb0 = atomicAdd(A.control, 1u);
+        for (uint32_t rk = 0; rk < csize; ++rk)
+          asm volatile("st.shared::cluster.v2.u32 [%0], {%1,%2};" ::"r"(sp_mapa(qslot, rk)), "r"(sb0), "r"(iter + 1u) : "memory");
+      }
+      unsigned sbq, it1, spins = 0;
+      do {
+        asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sbq), "=r"(it1) : "r"(qslot) : "memory");
+      } while (it1 != iter + 1u && !timed_out(spins, 1u << 27));
+      if (it1 != iter + 1u) sts_volatile_u32(qslot, 0xffffffffu);   // timed out: leave
+    }
     __syncthreads();
-    const unsigned kb = lds_volatile_u32(ctrl);
-    if (kb >= A.num_bands) break;
+    const unsigned sb = lds_volatile_u32(qslot);
+    if (sb >= num_super) break;
+    const unsigned kb = sb * csize + crank;                // may be >= num_bands in the last super-band: no live warp then
     const int t_in = kb == 0 ? roff : 0;                   // first grid row of the band (virtual row inside the band = compute warp)
     const bool band_in = kb > 0 || A.in_halo;              // row t_in has a column neighbour in the previous band / stripe
 
@@ -209,7 +244,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
       for (int k = 0; k < NW; ++k) cb = k == w ? chunk_base[k] : cb;
       const int row0 = (int)((fwd ? kb : (unsigned)nb - 1u - kb) * T) + (fwd ? w : NW - 1 - w);
       const uint32_t rec_ring = tiles + (uint32_t)w * (uint32_t)Cfg::WARP_TILE_BYTES, par_ring = rec_ring + NSLOT * SLOT_REC_B;
-      const uint32_t ctr_w = ctrl + 16 + 4 * (uint32_t)w;
+      const uint32_t ctr_w = ctrs + 4 * (uint32_t)w;
       const bool mine = open;
       int j_load = 0, j_store = 0;
       unsigned spins = 0;
@@ -255,10 +290,12 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
       const int g = lane / G4, gl = lane % G4;
       const int w_in = t_in;                                // the compute warp that owns row t_in
       const uint32_t ring = rings + (uint32_t)w_in * RING * LB;
-      const uint32_t ctr_in = ctrl + 16 + 4 * (uint32_t)w_in;
+      const uint32_t ctr_in = ctrs + 4 * (uint32_t)w_in;
       int q_in = 0;
       unsigned spins = 0;
-      if (!band_in) {
+      if (kb >= A.num_bands || (kb > 0 && crank > 0)) {
+        // no band, or the previous band runs in the previous CTA of this cluster and writes into ring 0 itself
+      } else if (!band_in) {
         Real zero[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) zero[k] = Real(0);
@@ -311,7 +348,10 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
       }
     } else if (!warp_live(kb, wid)) {
       // no grid row in this band (padding rows of the first / last band): the step counter still moves on with the band
-      if (lane == 0) sts_volatile_u32(ctrl + 16 + 4 * (uint32_t)wid, step_base + (uint32_t)nsteps);
+      if (lane == 0) {
+        sts_volatile_u32(ctrs + 4 * (uint32_t)wid, step_base + (uint32_t)nsteps);
+        if (wid == 0 && crank > 0) st_cluster_u32(sp_mapa(ctrs + 64, crank - 1), step_base + (uint32_t)nsteps);
+      }
     } else {
       // =================================================== compute warps ===================================================
       const int w = wid;
@@ -322,12 +362,15 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
       const bool in_col_exists = u > 0 || A.in_halo, out_col_exists = u + 1 < (int)H || A.out_halo;
       const bool grid_last_row = u + 1 == (int)H;
       // where the outgoing column vector (upper half-warp) goes: next warp (ring), next band (L2 hand-off slots), next stripe
+      const bool to_next_cta = !grid_last_row && w + 1 == NW && crank + 1 < csize;   // the next band runs in the next CTA of the cluster
       const bool out_ring = hi && !grid_last_row && w + 1 < NW;
-      const bool out_glob = hi && (grid_last_row ? (A.out_halo && A.out_boundary != nullptr) : w + 1 == NW);
+      const bool out_dsm = hi && to_next_cta;
+      const bool out_glob = hi && (grid_last_row ? (A.out_halo && A.out_boundary != nullptr) : (w + 1 == NW && !to_next_cta));
       Real* const out_ptr = (grid_last_row ? A.out_boundary : A.handoff + (uint64_t)(kb + 1) * W * L) + xl;
       const uint32_t ring_in = rings + (uint32_t)w * RING * LB + (uint32_t)xl * S;
       const uint32_t ring_out = rings + (uint32_t)(w + 1 < NW ? w + 1 : w) * RING * LB + (uint32_t)xl * S;
-      const bool warp_out_ring = !grid_last_row && w + 1 < NW;
+      const uint32_t ring_dsm = sp_mapa(rings + (uint32_t)xl * S, to_next_cta ? crank + 1 : crank);   // ring 0 of the next CTA
+      const bool warp_out_ring = !grid_last_row && (w + 1 < NW || to_next_cta);
       const uint32_t rec_ring = tiles + (uint32_t)w * (uint32_t)Cfg::WARP_TILE_BYTES, par_ring = rec_ring + NSLOT * SLOT_REC_B;
       constexpr uint32_t o_in_row = (fwd ? REC_BL : REC_AR) * LB, o_in_col = (fwd ? REC_BU : REC_AD) * LB;
       constexpr uint32_t o_out_row = (fwd ? REC_AR : REC_BL) * LB, o_out_col = (fwd ? REC_AD : REC_BU) * LB;
@@ -340,8 +383,10 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
       const bool self_first = hi != recv_row_first;         // this half's min-marginal is added to theta first
       const Real w_fast = (Real)(1.0 / 2.0);
       const uint32_t cbase = chunk_base[w];
-      const uint32_t ctr = ctrl + 16 + 4 * (uint32_t)w;
-      const uint32_t ctr_next = ctrl + 16 + 4 * (uint32_t)(w + 1 < NW ? w + 1 : w);
+      const uint32_t ctr = ctrs + 4 * (uint32_t)w;
+      const uint32_t ctr_next = w + 1 < NW ? ctrs + 4 * (uint32_t)(w + 1) : ctrs + 64;   // the consumer of this row's vectors
+      const bool push_progress = w == 0 && crank > 0;      // ... and this warp is the consumer of the previous CTA's last row
+      const uint32_t ctr_push = sp_mapa(ctrs + 64, push_progress ? crank - 1 : crank);
 
       auto wait_chunk = [&](int j) {
         const uint32_t n = cbase + (uint32_t)j;
@@ -354,12 +399,13 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
         fence_proxy_async();   // the tile warp's TMA store reads completed tiles through the async proxy
         __syncwarp();
         asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p st.volatile.shared.u32 [%1], %2; }" ::"r"((uint32_t)lane), "r"(ctr), "r"(step_base + (uint32_t)steps_done) : "memory");
+        if (push_progress && lane == 0) st_cluster_u32(ctr_push, step_base + (uint32_t)steps_done);
       };
 
       Real oth[LPL];            // lower half: the row neighbour's vector (carried from step to step); upper half: the column neighbour's
 #pragma unroll
       for (int k = 0; k < LPL; ++k) oth[k] = Real(0);
-      int free_upto = RING;     // columns the next warp's ring is known to have room for
+      int free_upto = to_next_cta ? 0 : RING;   // columns the consumer's ring is known to have room for (another CTA: ask first)
       wait_chunk(0);
 
       // ---- single steps: kind 0: general (any column, rounding, corner weights); 1: weight 1/2, any column (existence of the row
@@ -477,6 +523,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
           } while (s >= free_upto && !timed_out(spins, 1u << 27));
         }
         sts_n_if(out_ring, ring_out + rslot, oo);
+        st_cluster_n_if(out_dsm, ring_dsm + rslot, oo);
         stg_n_relaxed_if(out_glob, out_ptr + (int64_t)s * L, oo);
 #pragma unroll
         for (int k = 0; k < LPL; ++k) oth[k] = oo[k];       // lower half: the row neighbour's vector of the next step
@@ -492,7 +539,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
         const uint32_t Tth = f_th + toff, Tin = f_in + toff, Tout = f_out + toff;
         const uint32_t Tpar = f_par + slot * SLOT_PAR_B + (fwd ? 0u : (uint32_t)(K - 1) * PREC_B);
         const uint32_t c0 = ((uint32_t)(j << LOGK) & (uint32_t)(RING - 1)) * LB;
-        const uint32_t Rin = ring_in + c0, Rout = ring_out + c0;
+        const uint32_t Rin = ring_in + c0, Rout = ring_out + c0, Rdsm = ring_dsm + c0;
         Real* const Gout = out_ptr + (int64_t)s0 * L;
         if (warp_out_ring && s0 + K - 1 >= free_upto) {     // room in the next warp's ring for the whole tile (warp-uniform, rare)
           unsigned spins = 0;
@@ -542,6 +589,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
             th[k] = (v - d_oc) - d;
           }
           sts_n_if(out_ring, Rout + (uint32_t)jj * LB, oo);   // hand-off first: the warp below is waiting for it
+          st_cluster_n_if(out_dsm, Rdsm + (uint32_t)jj * LB, oo);
           stg_n_relaxed_if(out_glob, Gout + jj * L, oo);
           sts_n_if(!hi, Tth + ro, th);
           sts_n_if(true, Tin + ro, oi);
@@ -582,6 +630,8 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
     __syncthreads();
   }
   if (wid == NW + 1) tma_wait_all();   // the global writes of the last tiles are complete before the CTA exits
+  // no CTA of the cluster leaves while a neighbour may still write into its rings or counters
+  if (csize > 1) sp_cluster_sync();
 }
 
 }  // namespace lpmp

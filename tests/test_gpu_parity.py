@@ -321,7 +321,12 @@ def test_wavefront_rows_variant(kind, L, dtype, tuning):
                                                  ("trunclin", 16, "f32", dict(wavefront_split=1, wavefront_max_ctas=2)),
                                                  ("potts", 16, "f32", dict(wavefront_split=1)), ("potts", 32, "f32", dict(wavefront_split=1)),
                                                  ("potts", 16, "f64", dict(wavefront_split=1, wavefront_max_ctas=3)),
-                                                 ("potts", 32, "f32", dict(wavefront_split=1, wavefront_max_ctas=1))])
+                                                 ("potts", 32, "f32", dict(wavefront_split=1, wavefront_max_ctas=1)),
+                                                 ("trunclin", 16, "f32", dict(wavefront_split=1, wavefront_cluster=1)),
+                                                 ("trunclin", 16, "f32", dict(wavefront_split=1, wavefront_cluster=2)),
+                                                 ("potts", 16, "f64", dict(wavefront_split=1, wavefront_cluster=4)),
+                                                 ("potts", 32, "f32", dict(wavefront_split=1, wavefront_cluster=4, wavefront_max_ctas=8)),
+                                                 ("trunclin", 16, "f32", dict(wavefront_split=1, wavefront_cluster=8, wavefront_max_ctas=8))])
 def test_wavefront_split_variant(kind, L, dtype, tuning):
     """one row per warp, the two receive edges split over the half-warps (kernels_grid_split.cuh): anisotropic passes and
     rounding; rings wrapping many times, several bands per CTA in sequence, ragged last band / tile, single rows / columns,
