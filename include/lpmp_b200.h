@@ -138,6 +138,20 @@ int LPMP_FN(grid_get_boundary_vectors)(lpmp_solver* h, int which, void* dst_dev)
  * below, whose b-side vectors (the lower stripe's lpmp_grid_get_boundary_vectors(0)) are passed as a device
  * pointer (NULL for the last stripe).  The LP's bound is the sum over stripes (all-reduce). */
 int LPMP_FN(grid_lower_bound_partial)(lpmp_solver* h, const void* below_b, double* out);
+/* the same, left in DEVICE memory (d_out: one double) and ordered on the handle's stream -- no host synchronisation, so that a
+ * multi-GPU driver can all-reduce it (ncclAllReduce on lpmp_stream) and read the LP's bound with one stream-ordered copy */
+int LPMP_FN(grid_lower_bound_partial_device)(lpmp_solver* h, const void* below_b, double* d_out);
+/* stripe share of LP::EvaluatePrimal (include/LP_MP.h:1520-1536), device result as above: own unaries and edges plus the edges to
+ * the stripe below, given that stripe's b-side vectors ([W][L]) and the labels of its first row ([W], lpmp_grid_get_boundary_labels
+ * on the neighbour); +inf while no rounding pass has run */
+int LPMP_FN(grid_evaluate_primal_partial_device)(lpmp_solver* h, const void* below_b, const uint32_t* below_labels, double* d_out);
+/* labels of the first (which = 0) / last (1) row into a device buffer of W uint32, enqueued on the handle's stream */
+int LPMP_FN(grid_get_boundary_labels)(lpmp_solver* h, int which, uint32_t* dst_dev);
+/* per-pass halo without a host round trip: store this stripe's side of boundary `which` (0: bU of the first row, 1: aD of the
+ * last row) into the neighbour's in-buffer (peer-mapped pointer from lpmp_ipc_open, or a pointer of the same process).  The push
+ * obeys the slot protocol -- a slot is only written once the consumer of the previous pass has re-armed it -- so pushes and passes
+ * of neighbouring stripes order themselves through the data, with no collective and no host synchronisation */
+int LPMP_FN(grid_push_boundary)(lpmp_solver* h, int which, void* peer_in_buf);
 /* cudaIpc wrappers (64-byte handles) so that a host language without CUDA bindings can exchange in_buf pointers */
 int LPMP_FN(ipc_export)(const void* devptr, void* handle64);
 int LPMP_FN(ipc_open)(const void* handle64, void** devptr);

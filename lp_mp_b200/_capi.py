@@ -52,6 +52,10 @@ SIGNATURES = {
     "grid_set_peer_boundary": [_vp, _i, _vp],
     "grid_get_boundary_vectors": [_vp, _i, _vp],
     "grid_lower_bound_partial": [_vp, _vp, _pd],
+    "grid_lower_bound_partial_device": [_vp, _vp, _vp],
+    "grid_evaluate_primal_partial_device": [_vp, _vp, _vp, _vp],
+    "grid_get_boundary_labels": [_vp, _i, _vp],
+    "grid_push_boundary": [_vp, _i, _vp],
     "ipc_export": [_vp, _vp],
     "ipc_open": [_vp, C.POINTER(_vp)],
     "ipc_close": [_vp],

@@ -216,6 +216,14 @@ __global__ void synth_tables_kernel(Real* __restrict__ plane, uint32_t H, uint32
   }
 }
 
+// CheckPrimalConsistency: number of labels that are unset (0xffffffff) or out of range, added to *count (zeroed by the host)
+__global__ void count_bad_labels_kernel(const uint32_t* __restrict__ labels, uint64_t n, uint32_t L, unsigned int* count) {
+  unsigned int bad = 0;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) bad += labels[k] >= L ? 1u : 0u;
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, bad);
+}
+
 static inline int grid_for(uint64_t n, int block, int cap = 148 * 16) {
   uint64_t g = (n + block - 1) / block;
   if (g < 1) g = 1;
@@ -251,6 +259,10 @@ struct ISolver {
   virtual int grid_set_peer_boundary(int which, void* peer_in_buf) = 0;
   virtual int grid_get_boundary_vectors(int which, void* dst_dev) = 0;
   virtual int grid_lower_bound_partial(const void* below_b, double* out) = 0;
+  virtual int grid_lower_bound_partial_device(const void* below_b, double* d_out) = 0;
+  virtual int grid_evaluate_primal_partial_device(const void* below_b, const uint32_t* below_labels, double* d_out) = 0;
+  virtual int grid_push_boundary(int which, void* peer_in_buf) = 0;
+  virtual int grid_get_boundary_labels(int which, uint32_t* dst_dev) = 0;
   virtual int finalize() = 0;
   virtual int begin() = 0;
   virtual int set_reparametrization(int mode) = 0;
@@ -302,6 +314,7 @@ struct Solver : ISolver {
   DeviceBuffer<uint64_t> inc_off;
   DeviceBuffer<uint8_t> inc_flags;
   DeviceBuffer<double> partial, result;
+  DeviceBuffer<unsigned int> bad_count;     // CheckPrimalConsistency: labels that are unset / out of range
   DeviceBuffer<unsigned long long> trace;   // debug timeline of the last wavefront pass (set_tuning wavefront_trace=1)
   int want_trace = 0;        // 1: per-band stamps; 2: also per-step stamps of two neighbouring bands (lean variant)
   DeviceBuffer<unsigned int> control;  // [0] band ticket, [1] sticky abort flag (hand-off poll timed out), [2 + smid] CTA arrivals per SM
@@ -323,6 +336,7 @@ struct Solver : ISolver {
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CUDA_TRY(partial.alloc(kBoundCtas));
     CUDA_TRY(result.alloc(1));
+    CUDA_TRY(bad_count.alloc(1));
     return LPMP_OK;
   }
 
@@ -465,6 +479,7 @@ struct Solver : ISolver {
   }
   int grid_set_unaries(const void* th, int src) override {
     if (!is_grid) return bad_state("not a grid");
+    fused_lb_valid = false;
     if (!th) { err = "null theta"; return LPMP_ERR_INVALID; }
     return src == LPMP_F32 ? set_unaries_from(static_cast<const float*>(th)) : set_unaries_from(static_cast<const double*>(th));
   }
@@ -499,6 +514,8 @@ struct Solver : ISolver {
   }
   int grid_set_pairwise(const void* hz, const void* vt, int src) override {
     if (!is_grid) return bad_state("not a grid");
+    if (finalized) return bad_state("grid_set_pairwise after finalize");
+    fused_lb_valid = false;
     int r;
     if (pw == LPMP_PAIRWISE_DENSE) {
       Real* const vplane = tabV() + (uint64_t)gridW * P();
@@ -522,6 +539,8 @@ struct Solver : ISolver {
   }
   int grid_fill_synthetic(uint64_t seed, double lo, double hi) override {
     if (!is_grid) return bad_state("not a grid");
+    if (finalized) return bad_state("grid_fill_synthetic after finalize");
+    fused_lb_valid = false;
     const uint32_t Pn = P();
     if (pw == LPMP_PAIRWISE_DENSE) {
       synth_unary_kernel<Real><<<grid_for(N * L, 256), 256, 0, stream>>>(rec.p, N, L, REC(), (uint64_t)row0 * gridW, seed);
@@ -956,9 +975,18 @@ struct Solver : ISolver {
     return check_abort();
   }
 
-  int bound_launch(const Real* below_b, double add, double* out) {
+  // the same final sum, left in device memory: no host synchronisation (multi-GPU drivers reduce it with NCCL on this stream)
+  int reduce_to(int ctas, double add, double* out, bool to_device, const double* src = nullptr) {
+    if (!to_device) return reduce_to_host(ctas, add, out, src);
+    final_sum_kernel<<<1, 32, 0, stream>>>(src ? src : partial.p, ctas, add, out);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    return LPMP_OK;
+  }
+
+  int bound_launch(const Real* below_b, double add, double* out, bool to_device = false) {
     CUDA_TRY(cudaSetDevice(device));
-    if (fused_lb_valid && !striped) return reduce_to_host((int)gridH, add, out, lb_rows.p);
+    if (fused_lb_valid && !striped) return reduce_to((int)gridH, add, out, to_device, lb_rows.p);
     const int G = group_size_for(L);
     int threads = 256;
     const size_t per_group = 2 * (size_t)L * sizeof(Real);
@@ -974,7 +1002,7 @@ struct Solver : ISolver {
                                                        : launch_grid_bound<Real, LPMP_PAIRWISE_TRUNCLIN>(B, L, tl_hops(), kBoundCtas, &used, stream);
       CUDA_TRY(le);
       ++launches;
-      return reduce_to_host(used, add, out);
+      return reduce_to(used, add, out, to_device);
     }
     if (is_grid) {
       GridTopo<Real> topo{gridH, gridW, slots, below_b};
@@ -985,7 +1013,7 @@ struct Solver : ISolver {
     }
     ++launches;
     CUDA_TRY(cudaGetLastError());
-    return reduce_to_host(ctas, add, out);
+    return reduce_to(ctas, add, out, to_device);
   }
 
   int lower_bound(double* out) override {
@@ -1002,15 +1030,12 @@ struct Solver : ISolver {
     return bound_launch(row0 + gridH < H_total ? static_cast<const Real*>(below_b) : nullptr, row0 == 0 ? constant : 0.0, out);
   }
 
-  int evaluate_primal(double* out) override {
-    if (int r = need_final()) return r;
-    if (!labels_valid) { *out = std::numeric_limits<double>::infinity(); return LPMP_OK; }
-    if (striped) { err = "evaluate_primal of a stripe is not supported"; return LPMP_ERR_UNSUPPORTED; }
+  int primal_launch(const Real* below_b, const uint32_t* below_labels, double add, double* out, bool to_device) {
     CUDA_TRY(cudaSetDevice(device));
     const uint64_t total = N + slots;
     const int ctas = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)kBoundCtas);
     if (is_grid) {
-      GridTopo<Real> topo{gridH, gridW, slots, nullptr};
+      GridTopo<Real> topo{gridH, gridW, slots, below_b, below_labels};
       primal_cost_kernel<Real, GridTopo<Real>><<<ctas, 256, 0, stream>>>(bound_args(topo), labels.p);
     } else {
       GraphTopo topo{d_ei.p, d_ej.p, slots};
@@ -1018,14 +1043,67 @@ struct Solver : ISolver {
     }
     ++launches;
     CUDA_TRY(cudaGetLastError());
-    return reduce_to_host(ctas, constant, out);
+    return reduce_to(ctas, add, out, to_device);
+  }
+  int evaluate_primal(double* out) override {
+    if (int r = need_final()) return r;
+    if (!labels_valid) { *out = std::numeric_limits<double>::infinity(); return LPMP_OK; }
+    if (striped) { err = "evaluate_primal of a stripe: use lpmp_grid_evaluate_primal_partial_device"; return LPMP_ERR_UNSUPPORTED; }
+    return primal_launch(nullptr, nullptr, constant, out, false);
+  }
+  // stripe share of LP::EvaluatePrimal: own unaries and edges plus the edges to the stripe below (their b-side vectors and the
+  // labels of the first row below are passed as device pointers); +inf (as the whole LP's cost) while nothing is labelled
+  int grid_evaluate_primal_partial_device(const void* below_b, const uint32_t* below_labels, double* d_out) override {
+    if (int r = need_final()) return r;
+    if (!is_grid) return bad_state("not a grid");
+    const bool has_below = row0 + gridH < H_total;
+    if (has_below && (!below_b || !below_labels)) { err = "the b-side vectors and labels of the stripe below are required"; return LPMP_ERR_INVALID; }
+    if (!labels_valid) {
+      const double inf = std::numeric_limits<double>::infinity();
+      CUDA_TRY(cudaMemcpyAsync(d_out, &inf, sizeof(double), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      return LPMP_OK;
+    }
+    return primal_launch(has_below ? static_cast<const Real*>(below_b) : nullptr, has_below ? below_labels : nullptr, row0 == 0 ? constant : 0.0, d_out, true);
+  }
+  int grid_lower_bound_partial_device(const void* below_b, double* d_out) override {
+    if (int r = need_final()) return r;
+    if (!is_grid) return bad_state("not a grid");
+    if (row0 + gridH < H_total && !below_b) { err = "the b-side vectors of the stripe below are required"; return LPMP_ERR_INVALID; }
+    return bound_launch(row0 + gridH < H_total ? static_cast<const Real*>(below_b) : nullptr, row0 == 0 ? constant : 0.0, d_out, true);
+  }
+  // per-pass halo through peer memory: own side of a stripe boundary (0: bU of the first row, 1: aD of the last row) into the
+  // neighbour's in-buffer (slot protocol, see push_boundary_kernel); enqueued on the handle's stream
+  int grid_push_boundary(int which, void* peer_in_buf) override {
+    if (!is_grid || !finalized) return bad_state("grid_push_boundary: need a finalized grid");
+    if (!peer_in_buf) { err = "null destination"; return LPMP_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(device));
+    const Real* src = which == 0 ? rec.p + (uint64_t)REC_BU * L : rec.p + (uint64_t)(gridH - 1) * gridW * REC() + (uint64_t)REC_AD * L;
+    push_boundary_kernel<Real><<<grid_for((uint64_t)gridW * L, 256, 148 * 4), 256, 0, stream>>>(static_cast<Real*>(peer_in_buf), src, gridW, L, REC(), control.p);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    return LPMP_OK;
+  }
+  int grid_get_boundary_labels(int which, uint32_t* dst_dev) override {
+    if (!is_grid || !finalized) return bad_state("grid_get_boundary_labels: need a finalized grid");
+    CUDA_TRY(cudaMemcpyAsync(dst_dev, labels.p + (which == 0 ? 0 : (uint64_t)(gridH - 1) * gridW), (uint64_t)gridW * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+    return LPMP_OK;
   }
 
   int check_primal_consistency(int* out) override {
     if (int r = need_final()) return r;
-    // pairwise factors hold copies of the unary labels written in the same pass (ComputeRightFromLeftPrimal),
-    // so a completed rounding pass is always consistent; before any rounding pass nothing is labelled.
-    *out = 1;
+    // pairwise factors hold copies of the unary labels written in the same pass (ComputeRightFromLeftPrimal), so the labeling is
+    // consistent exactly when every unary is labelled (a rounding pass labels all of them): count the unset / out-of-range labels
+    if (!labels_valid) { *out = 0; return LPMP_OK; }
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMemsetAsync(bad_count.p, 0, sizeof(unsigned int), stream));
+    count_bad_labels_kernel<<<grid_for(N, 256), 256, 0, stream>>>(labels.p, N, L, bad_count.p);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    unsigned int bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, bad_count.p, sizeof(bad), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    *out = bad == 0 ? 1 : 0;
     return LPMP_OK;
   }
   int add_to_constant(double x) override { constant += x; return LPMP_OK; }
@@ -1284,6 +1362,10 @@ int lpmp_grid_boundary_ptrs(lpmp_solver* h, int which, void** in_buf, uint64_t* 
 int lpmp_grid_set_peer_boundary(lpmp_solver* h, int which, void* peer_in_buf) { return S(h)->grid_set_peer_boundary(which, peer_in_buf); }
 int lpmp_grid_get_boundary_vectors(lpmp_solver* h, int which, void* dst_dev) { return S(h)->grid_get_boundary_vectors(which, dst_dev); }
 int lpmp_grid_lower_bound_partial(lpmp_solver* h, const void* below_b, double* out) { return S(h)->grid_lower_bound_partial(below_b, out); }
+int lpmp_grid_lower_bound_partial_device(lpmp_solver* h, const void* below_b, double* d_out) { return S(h)->grid_lower_bound_partial_device(below_b, d_out); }
+int lpmp_grid_evaluate_primal_partial_device(lpmp_solver* h, const void* below_b, const uint32_t* below_labels, double* d_out) { return S(h)->grid_evaluate_primal_partial_device(below_b, below_labels, d_out); }
+int lpmp_grid_push_boundary(lpmp_solver* h, int which, void* peer_in_buf) { return S(h)->grid_push_boundary(which, peer_in_buf); }
+int lpmp_grid_get_boundary_labels(lpmp_solver* h, int which, uint32_t* dst_dev) { return S(h)->grid_get_boundary_labels(which, dst_dev); }
 
 int lpmp_ipc_export(const void* devptr, void* handle64) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are 64 bytes");

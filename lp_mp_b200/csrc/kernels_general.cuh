@@ -16,6 +16,7 @@ struct GraphTopo {
   const uint32_t* ei;
   const uint32_t* ej;
   uint64_t num_slots;
+  __device__ __forceinline__ uint32_t second_label(const uint32_t* labels, uint64_t e) const { return labels[ej[e]]; }
   __device__ __forceinline__ bool valid(uint64_t) const { return true; }
   __device__ __forceinline__ uint32_t first(uint64_t e) const { return ei[e]; }
   __device__ __forceinline__ uint32_t second(uint64_t e) const { return ej[e]; }
@@ -28,6 +29,12 @@ struct GridTopo {
   uint32_t H, W;
   uint64_t num_slots;
   const Real* below_b;
+  const uint32_t* below_labels = nullptr;   // [W] labels of the first row of the stripe below (primal evaluation of a stripe)
+  __device__ __forceinline__ uint32_t second_label(const uint32_t* labels, uint64_t e) const {
+    const uint64_t HW = (uint64_t)H * W;
+    if (e >= HW && (e - HW) / W + 1 >= H) return below_labels[(e - HW) % W];
+    return labels[second(e)];
+  }
   __device__ __forceinline__ bool valid(uint64_t e) const {
     const uint64_t HW = (uint64_t)H * W;
     if (e < HW) return (e % W) + 1 < W;
@@ -208,13 +215,44 @@ __global__ void __launch_bounds__(256) primal_cost_kernel(BoundArgs<Real, Topo> 
     } else {
       const uint64_t e = k - A.num_nodes;
       if (!A.topo.valid(e)) continue;
-      const uint32_t x = labels[A.topo.first(e)], y = labels[A.topo.second(e)];
+      const uint32_t x = labels[A.topo.first(e)], y = A.topo.second_label(labels, e);
       const Real c = pairwise_cost<Real>(A.pw, A.st.par(e), L, x, y);
-      acc += (double)Real(Real(c + A.st.a(e)[x]) + A.st.b(e)[y]);
+      acc += (double)Real(Real(c + A.st.a(e)[x]) + A.topo.b_of(A.st, e)[y]);
     }
   }
   const double s = block_sum(acc);
   if (threadIdx.x == 0) A.partial[blockIdx.x] = s;
+}
+
+// Stripe boundary push (per-pass halo coupling through peer memory): this stripe's side of the boundary edges, src[c * src_stride
+// + x], into the neighbouring stripe's in-buffer dst[c * L + x] -- self-validating slots: a slot is written only once it holds
+// the sentinel again (the consumer of the previous pass has taken its vector), so consecutive pushes can never overtake the
+// consumer.  One thread per real; bounded wait (sticky abort flag in control[1]).
+template <typename Real>
+__global__ void push_boundary_kernel(Real* dst, const Real* __restrict__ src, uint32_t W, uint32_t L, uint64_t src_stride, unsigned int* control) {
+  const uint64_t total = (uint64_t)W * L;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (uint64_t)gridDim.x * blockDim.x) {
+    const Real v = src[(k / L) * src_stride + (k % L)];
+    unsigned spins = 0;
+    for (;;) {
+      Real cur;
+      if constexpr (sizeof(Real) == 4) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(cur) : "l"(dst + k) : "memory");
+      else asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(cur) : "l"(dst + k) : "memory");
+      bool free_slot;
+      if constexpr (sizeof(Real) == 4) free_slot = __float_as_uint(cur) == 0xffffffffu;
+      else free_slot = __double_as_longlong(cur) == -1ll;
+      if (free_slot) break;
+      if ((++spins & 0xffu) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 4000000000ull) { if (control) atomicExch(control + 1, 1u); break; }
+      }
+    }
+    if constexpr (sizeof(Real) == 4) asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst + k), "f"(v) : "memory");
+    else asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + k), "d"(v) : "memory");
+  }
 }
 
 // fixed-order final sum (deterministic bound): one warp, sequential chunks then a fixed tree

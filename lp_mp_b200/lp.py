@@ -189,6 +189,19 @@ class LP:
         self._ck(self.api.grid_lower_bound_partial(self.h, C.c_void_p(below_ptr or 0), C.byref(out)))
         return out.value
 
+    def grid_lower_bound_partial_device(self, below_ptr, out_ptr):
+        """asynchronous: the stripe's share of LP::LowerBound is left in the device double at `out_ptr`"""
+        self._ck(self.api.grid_lower_bound_partial_device(self.h, C.c_void_p(below_ptr or 0), C.c_void_p(out_ptr)))
+
+    def grid_evaluate_primal_partial_device(self, below_ptr, below_labels_ptr, out_ptr):
+        self._ck(self.api.grid_evaluate_primal_partial_device(self.h, C.c_void_p(below_ptr or 0), C.c_void_p(below_labels_ptr or 0), C.c_void_p(out_ptr)))
+
+    def grid_get_boundary_labels(self, which, dst_ptr):
+        self._ck(self.api.grid_get_boundary_labels(self.h, int(which), C.c_void_p(dst_ptr)))
+
+    def grid_push_boundary(self, which, peer_ptr):
+        self._ck(self.api.grid_push_boundary(self.h, int(which), C.c_void_p(peer_ptr)))
+
     def finalize(self):
         self._flush_pending()
         self._ck(self.api.finalize(self.h))

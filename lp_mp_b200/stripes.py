@@ -3,21 +3,31 @@
 The reference has no distribution at all; its closest notion is the partition pass (include/LP_MP.h:1716-1963), which
 still runs the groups sequentially.  Here a grid of ``H_total`` rows is cut into ``world`` contiguous row stripes
 (SURVEY.md 8e); every rank owns one stripe as an ordinary ``LP`` plus, per stripe boundary, one "in" buffer of
-``W*L`` reals that the neighbouring stripe's outgoing message vectors are delivered to.  Two couplings:
+``W*L`` reals that the neighbouring stripe's outgoing message vectors are delivered to.  Three couplings:
 
 ``pipelined`` (exact)
     The pass kernel of stripe g stores the outgoing vectors of its last band straight into stripe g+1's in-buffer
     through NVLink peer memory (cudaIpc mapping of the buffer), column by column, while stripe g+1's first band polls
-    them: the anti-diagonal wavefront simply continues across GPUs.  Results are bit-identical to the unstriped LP.
-    No collective on the data path; NCCL is only used for the lower-bound all-reduce.
+    them: the anti-diagonal wavefront simply continues across GPUs.  Results are bit-identical to the unstriped LP; the
+    pass time is the dependency chain through ALL rows, so it does not scale.
 
-``halo`` (per-pass halo, block-Jacobi across stripes)
-    Before a pass every rank sends the current vectors of its boundary row to the neighbour that will consume them
-    (NCCL send/recv into the in-buffer); all stripes then sweep concurrently, each using the neighbour's state of the
-    previous pass.  Always a valid reparametrisation (monotone lower bound), but a different fixed point than the
-    sequential order (hard part 2): parity is on the final bound, not per iteration.
+``halo`` (per-pass halo, block-Jacobi across stripes; default)
+    Before a pass every rank stores the current vectors of its boundary row into the in-buffer of the neighbour that will
+    consume them -- one small kernel writing through NVLink peer memory (``lpmp_grid_push_boundary``).  The in-buffer
+    slots carry their own validity (sentinel protocol of the pass kernels), so pushes and passes of neighbouring stripes
+    order themselves through the data: no collective, no host synchronisation on the data path.  All stripes sweep
+    concurrently, each using the neighbour's state of the previous pass: always a valid reparametrisation (monotone
+    lower bound), but a different fixed point than the sequential order (hard part 2).
 
-Only the anisotropic (SRMP) reparametrisation is supported on stripes.
+``halo_nccl``
+    The same semantics with the boundary vectors carried by NCCL send/recv (stream-ordered on the library's stream).
+
+The lower bound / primal cost of the LP is the NCCL all-reduce of the stripes' partial values; everything is enqueued on
+the library's stream and read back with ONE stream-ordered copy into pinned memory (LP::LowerBound,
+include/LP_MP.h:1507-1518; LP::EvaluatePrimal, :1520-1536).
+
+Only the anisotropic (SRMP) reparametrisation runs on stripes (rounding included: ``ComputeForwardPassAndPrimal``);
+the uniform modes need the not-yet-processed neighbour's vectors as well and raise ``LpmpError`` here.
 """
 from __future__ import annotations
 
@@ -27,6 +37,7 @@ from dataclasses import dataclass
 import numpy as np
 
 TOP, BOTTOM = 0, 1
+COUPLINGS = ("halo", "halo_nccl", "pipelined")
 
 
 @dataclass(frozen=True)
@@ -69,7 +80,8 @@ class _DevicePtr:
 def neighbour_exchange(dist, rank: int, world: int, send_which: int, send, recv):
     """One shift along the stripe chain: ``send`` (or None) goes to the neighbour across boundary ``send_which``
     (BOTTOM: rank+1, TOP: rank-1); ``recv`` (or None) is filled by the neighbour on the opposite side.  A single
-    batched isend/irecv group, so there is no ordering deadlock for any world size."""
+    batched isend/irecv group, so there is no ordering deadlock for any world size.  With NCCL the waits are
+    stream-level (the current stream waits for the transfer), not host-level."""
     dst = rank + 1 if send_which == BOTTOM else rank - 1
     src = rank - 1 if send_which == BOTTOM else rank + 1
     ops = []
@@ -82,21 +94,34 @@ def neighbour_exchange(dist, rank: int, world: int, send_which: int, send, recv)
             req.wait()
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class StripedLP:
-    """One stripe per rank behind the LP_TYPE surface (Begin / ComputePass / LowerBound ...).
+    """One stripe per rank behind the LP_TYPE surface that ``Solver`` / ``MpRoundingSolver`` drive (Begin, End,
+    set_reparametrization, Compute*Pass[AndPrimal], LowerBound, EvaluatePrimal, CheckPrimalConsistency, labeling).
 
     ``dist`` is ``torch.distributed`` (initialised, NCCL for GPU runs) or None for a single rank; ``lp`` is this
-    rank's ``LP`` with ``grid_create`` + ``grid_set_stripe`` already applied (``make``)."""
+    rank's ``LP`` with ``grid_create`` + ``grid_set_stripe`` already applied (``make``).  ``device`` is "cuda" for the
+    product; "cpu" exists for the host-logic tests (gloo, a stand-in ``lp``)."""
 
-    def __init__(self, lp, plan: StripePlan, rank: int, dist=None, coupling: str = "halo"):
-        if coupling not in ("halo", "pipelined"):
-            raise ValueError("coupling must be 'halo' or 'pipelined'")
+    def __init__(self, lp, plan: StripePlan, rank: int, dist=None, coupling: str = "halo", device: str = "cuda"):
+        if coupling not in COUPLINGS:
+            raise ValueError(f"coupling must be one of {COUPLINGS}")
         self.lp, self.plan, self.rank, self.dist, self.coupling = lp, plan, rank, dist, coupling
         self.world = plan.world
-        self._torch_stream = None
-        self._in = {}
-        self._stage = {}
-        self._peer = {}
+        self._cuda = device == "cuda"
+        self._dev = device
+        self._ts = None            # the library's stream as a torch stream
+        self._in = {}              # which -> (device pointer, tensor view) of my in-buffers
+        self._stage = {}           # which -> compact [W*L] staging tensor (NCCL halo / bound exchange)
+        self._peer = {}            # which -> mapped pointer of the neighbour's in-buffer across boundary `which`
+        self._ipc_opened = []
         self._setup_done = False
 
     # ---- construction -----------------------------------------------------------------------------------------
@@ -118,22 +143,38 @@ class StripedLP:
             self._setup()
         return self
 
+    def _stream_ctx(self):
+        if not self._cuda:
+            return _NullCtx()
+        import torch
+        return torch.cuda.stream(self._ts)
+
     def _setup(self):
         import torch
         lp, plan, rank = self.lp, self.plan, self.rank
         self._itemsize = 4 if lp.dtype == 0 else 8
         self._tdtype = torch.float32 if self._itemsize == 4 else torch.float64
-        self._count = lp.grid_shape[1] * lp.L
-        self._torch_stream = torch.cuda.ExternalStream(lp.stream())
+        self._W = lp.grid_shape[1]
+        self._count = self._W * lp.L
+        if self._cuda:
+            self._ts = torch.cuda.ExternalStream(lp.stream())
+            self._ev = torch.cuda.Event()
         for which, present in ((TOP, plan.has_above(rank)), (BOTTOM, plan.has_below(rank))):
             if not present:
                 continue
             ptr, nbytes = lp.grid_boundary_ptrs(which)
             assert nbytes == self._count * self._itemsize
-            self._in[which] = (ptr, torch.as_tensor(_DevicePtr(ptr, self._count, self._itemsize), device="cuda"))
-            self._stage[which] = torch.empty(self._count, dtype=self._tdtype, device="cuda")
-        if self.coupling == "pipelined":
-            # exchange cudaIpc handles of the in-buffers; map the neighbours' buffers and hand them to the pass kernel
+            view = torch.as_tensor(_DevicePtr(ptr, self._count, self._itemsize), device="cuda") if self._cuda else None
+            self._in[which] = (ptr, view)
+            self._stage[which] = torch.empty(self._count, dtype=self._tdtype, device=self._dev)
+        # neighbour's side of the boundary edges below me (bound / primal evaluation), labels of its first row
+        self._below_b = torch.empty(self._count, dtype=self._tdtype, device=self._dev) if plan.has_below(rank) else None
+        self._below_lab = torch.empty(self._W, dtype=torch.int32, device=self._dev) if plan.has_below(rank) else None
+        self._my_lab = torch.empty(self._W, dtype=torch.int32, device=self._dev) if plan.has_above(rank) else None
+        self._acc = torch.zeros(2, dtype=torch.float64, device=self._dev)
+        self._host = torch.zeros(2, dtype=torch.float64, pin_memory=True) if self._cuda else torch.zeros(2, dtype=torch.float64)
+        if self.coupling in ("halo", "pipelined"):
+            # exchange cudaIpc handles of the in-buffers and map the neighbours' buffers
             mine = {}
             for which, (ptr, _) in self._in.items():
                 handle = (C.c_ubyte * 64)()
@@ -147,17 +188,24 @@ class StripedLP:
                     buf = (C.c_ubyte * 64).from_buffer_copy(everyone[nb][nb_which])
                     lp.api.check(lp.api.ipc_open(buf, C.byref(peer)))
                     self._peer[which] = peer.value
-                    lp.grid_set_peer_boundary(which, peer.value)
+                    self._ipc_opened.append(peer.value)
+                    if self.coupling == "pipelined":   # the pass kernel itself delivers the vectors of its last band
+                        lp.grid_set_peer_boundary(which, peer.value)
             self.dist.barrier()
         self._setup_done = True
 
-    # ---- halo exchange (coupling == "halo") ---------------------------------------------------------------------
-    def _exchange(self, send_which: int):
-        """every rank sends the vectors of boundary ``send_which`` to the neighbour across it, which receives them
-        into its in-buffer of the opposite boundary; enqueued on the library's stream"""
-        import torch
+    # ---- halo delivery before a pass -------------------------------------------------------------------------------
+    def _deliver(self, send_which: int):
+        """my vectors of boundary ``send_which`` into the in-buffer of the neighbour across it (the forward pass consumes the
+        upper neighbour's last-row vectors, the backward pass the lower neighbour's first-row vectors)"""
+        if self.world == 1 or self.coupling == "pipelined":
+            return
+        if self.coupling == "halo":
+            if send_which in self._peer:
+                self.lp.grid_push_boundary(send_which, self._peer[send_which])
+            return
         recv_which = TOP if send_which == BOTTOM else BOTTOM
-        with torch.cuda.stream(self._torch_stream):
+        with self._stream_ctx():
             send = None
             if send_which in self._stage:
                 self.lp.grid_get_boundary_vectors(send_which, self._stage[send_which].data_ptr())
@@ -169,50 +217,129 @@ class StripedLP:
     def Begin(self):
         self.lp.Begin()
 
+    def End(self):
+        self.lp.End()
+
     def set_reparametrization(self, mode):
         if self.world > 1 and mode not in ("anisotropic", 0):
-            raise ValueError("stripes support the anisotropic reparametrization only")
+            from ._capi import LpmpError
+            raise LpmpError("unsupported: row stripes run the anisotropic reparametrization only "
+                            "(use roundingReparametrization='anisotropic' with StandardVisitor)")
         self.lp.set_reparametrization(mode)
 
     def ComputeForwardPass(self):
-        if self.world > 1 and self.coupling == "halo":
-            self._exchange(BOTTOM)      # the forward pass consumes the upper neighbour's last-row vectors
+        self._deliver(BOTTOM)
         self.lp.ComputeForwardPass()
 
     def ComputeBackwardPass(self):
-        if self.world > 1 and self.coupling == "halo":
-            self._exchange(TOP)         # the backward pass consumes the lower neighbour's first-row vectors
+        self._deliver(TOP)
         self.lp.ComputeBackwardPass()
 
     def ComputePass(self, iteration=0):
         self.ComputeForwardPass()
         self.ComputeBackwardPass()
 
+    def ComputeForwardPassAndPrimal(self, iteration=0):
+        self._deliver(BOTTOM)
+        self.lp.ComputeForwardPassAndPrimal(iteration)
+
+    def ComputeBackwardPassAndPrimal(self, iteration=0):
+        self._deliver(TOP)
+        self.lp.ComputeBackwardPassAndPrimal(iteration)
+
+    def _exchange_below(self, with_labels: bool):
+        """the stripe below sends its side of the shared boundary edges (and the labels of its first row) up"""
+        import torch
+        send = send_lab = None
+        if TOP in self._stage:      # my first row's b side completes the upper neighbour's boundary edges
+            self.lp.grid_get_boundary_vectors(TOP, self._stage[TOP].data_ptr())
+            send = self._stage[TOP]
+            if with_labels:
+                self.lp.grid_get_boundary_labels(TOP, self._my_lab.data_ptr())
+                send_lab = self._my_lab
+        neighbour_exchange(self.dist, self.rank, self.world, TOP, send, self._below_b)
+        if with_labels:
+            neighbour_exchange(self.dist, self.rank, self.world, TOP, send_lab, self._below_lab)
+
+    def _reduce_and_read(self, n: int):
+        """all-reduce the first ``n`` doubles of the accumulator on the library's stream; one stream-ordered copy to the host"""
+        self.dist.all_reduce(self._acc[:n])
+        self._host.copy_(self._acc, non_blocking=True)
+        if self._cuda:
+            self._ev.record()
+
     def LowerBound(self) -> float:
         """LP::LowerBound of the whole grid: partial bounds of the stripes, all-reduced (1 double over NCCL)"""
         if self.world == 1:
             return self.lp.LowerBound()
+        with self._stream_ctx():
+            self._exchange_below(False)
+            self.lp.grid_lower_bound_partial_device(self._below_b.data_ptr() if self._below_b is not None else None,
+                                                    self._acc.data_ptr())
+            self._reduce_and_read(1)
+        if self._cuda:
+            self._ev.synchronize()
+        return float(self._host[0])
+
+    def EvaluatePrimal(self) -> float:
+        """LP::EvaluatePrimal of the whole grid (+inf until a rounding pass has labelled every stripe)"""
+        if self.world == 1:
+            return self.lp.EvaluatePrimal()
+        with self._stream_ctx():
+            self._exchange_below(True)
+            self.lp.grid_evaluate_primal_partial_device(
+                self._below_b.data_ptr() if self._below_b is not None else None,
+                self._below_lab.data_ptr() if self._below_lab is not None else None, self._acc.data_ptr())
+            self._reduce_and_read(1)
+        if self._cuda:
+            self._ev.synchronize()
+        return float(self._host[0])
+
+    def CheckPrimalConsistency(self) -> bool:
+        ok = 1 if self.lp.CheckPrimalConsistency() else 0
+        if self.world == 1:
+            return bool(ok)
         import torch
-        dist, rank = self.dist, self.rank
-        below = None
-        with torch.cuda.stream(self._torch_stream):
-            send = None
-            if TOP in self._stage:      # my first row's b side completes the upper neighbour's boundary edges
-                self.lp.grid_get_boundary_vectors(TOP, self._stage[TOP].data_ptr())
-                send = self._stage[TOP]
-            if BOTTOM in self._stage:
-                below = self._stage[BOTTOM]
-            neighbour_exchange(dist, rank, self.world, TOP, send, below)
-            part = self.lp.grid_lower_bound_partial(below.data_ptr() if below is not None else None)
-            t = torch.tensor([part], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t)
-        return float(t.item())
+        with self._stream_ctx():
+            t = torch.tensor([ok], dtype=torch.int32, device=self._dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+            res = int(t.item())      # inside the stream context: the copy is ordered after the reduction
+        return bool(res)
+
+    def labeling(self):
+        """the labeling of the whole grid on every rank (Solver::RegisterPrimal keeps the best one, include/solver.hxx:321-340)"""
+        mine = self.lp.labeling()
+        if self.world == 1:
+            return mine
+        import torch
+        W = self._W
+        rows_max = max(self.plan.rows(r)[1] for r in range(self.world))
+        pad = torch.zeros(rows_max * W, dtype=torch.int32, device=self._dev)
+        pad[:mine.size] = torch.from_numpy(mine.astype(np.int32)).to(self._dev)
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(parts, pad)
+        out = [parts[r][: self.plan.rows(r)[1] * W].cpu().numpy().astype(np.uint32) for r in range(self.world)]
+        return np.concatenate(out)
+
+    def add_to_constant(self, x):
+        if self.rank == 0:       # the constant enters the bound once (stripe 0 adds it to its partial value)
+            self.lp.add_to_constant(x)
+
+    def GetNumberOfFactors(self) -> int:
+        H, W = self.plan.H_total, self.lp.grid_shape[1]
+        return H * W + H * (W - 1) + (H - 1) * W
+
+    def GetNumberOfMessages(self) -> int:
+        H, W = self.plan.H_total, self.lp.grid_shape[1]
+        return 2 * (H * (W - 1) + (H - 1) * W)
 
     def synchronize(self):
         self.lp.synchronize()
 
     def close(self):
-        for which, ptr in self._peer.items():
-            self.lp.grid_set_peer_boundary(which, None)
+        for which in list(self._peer):
+            if self.coupling == "pipelined":
+                self.lp.grid_set_peer_boundary(which, None)
+        for ptr in self._ipc_opened:
             self.lp.api.ipc_close(C.c_void_p(ptr))
-        self._peer = {}
+        self._peer, self._ipc_opened = {}, []

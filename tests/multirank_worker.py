@@ -1,0 +1,198 @@
+"""Worker of tests/test_gpu_multirank.py: one process per GPU (torchrun), NCCL.  Every case asserts on every rank; a failed
+assertion ends the rank with a non-zero exit code, which torchrun propagates.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+      tests/multirank_worker.py <case>
+
+Cases (reference semantics: one LP, one bound -- include/LP_MP.h:1507-1518; rounding include/LP_MP.h:1592-1602,
+include/solver.hxx:321-340,387-397):
+  pipelined  exact coupling: theta / labels of every stripe bit-identical to the unstriped LP solved on the same GPU,
+             StripedLP.LowerBound / EvaluatePrimal equal to the unstriped values, labeling() gathers the full labeling
+  halo       per-pass halo through peer memory: bound == sum of the ranks' partial bounds computed independently (host path),
+             monotone, below the exact bound; halo_nccl gives bit-identical stripes
+  solver     MpRoundingSolver + StandardVisitor on a StripedLP (pipelined) == the same solver on the unstriped LP
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SEED = 0x5EED
+LB_RTOL = {"f64": 1e-12, "f32": 1e-6}
+
+
+def full_lp(dtype, H, W, L, kind, lo, hi, device):
+    import lp_mp_b200
+    lp = lp_mp_b200.LP(dtype=dtype, device=device).grid_create(H, W, L, kind)
+    lp.grid_fill_synthetic(SEED, lo, hi)
+    lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+    return lp
+
+
+def striped(dtype, H, W, L, kind, lo, hi, rank, world, dist, device, coupling):
+    from lp_mp_b200.stripes import StripedLP
+    slp = StripedLP.make(H, W, L, kind, rank, world, dist=dist, dtype=dtype, device=device, coupling=coupling)
+    slp.lp.grid_fill_synthetic(SEED, lo, hi)
+    slp.finalize(); slp.Begin(); slp.set_reparametrization("anisotropic")
+    return slp
+
+
+def numpy_problem(H, W, L, kind, lo, hi):
+    rng = np.random.default_rng(SEED)
+    theta = rng.random((H, W, L))
+    if kind == "potts":
+        hz, vt = rng.uniform(lo, hi, (H, W - 1, 1)), rng.uniform(lo, hi, (H - 1, W, 1))
+    else:
+        hz, vt = np.tile([lo, hi], (H, W - 1, 1)), np.tile([lo, hi], (H - 1, W, 1))
+    return theta, hz, vt
+
+
+def full_from_numpy(dtype, prob, L, kind, device):
+    import lp_mp_b200
+    theta, hz, vt = prob
+    lp = lp_mp_b200.LP(dtype=dtype, device=device).grid_create(theta.shape[0], theta.shape[1], L, kind)
+    lp.grid_set_unaries(theta); lp.grid_set_pairwise(hz, vt)
+    lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+    return lp
+
+
+def striped_from_numpy(dtype, prob, L, kind, rank, world, dist, device, coupling):
+    from lp_mp_b200.stripes import StripedLP
+    theta, hz, vt = prob
+    H, W = theta.shape[:2]
+    slp = StripedLP.make(H, W, L, kind, rank, world, dist=dist, dtype=dtype, device=device, coupling=coupling)
+    r0, n = slp.plan.rows(rank)
+    slp.lp.grid_set_unaries(theta[r0:r0 + n]); slp.lp.grid_set_pairwise(hz[r0:r0 + n], vt[r0:r0 + n - 1])
+    slp.lp.grid_set_boundary_pairwise(vt[r0 - 1] if r0 > 0 else None, vt[r0 + n - 1] if r0 + n < H else None)
+    slp.finalize(); slp.Begin(); slp.set_reparametrization("anisotropic")
+    return slp
+
+
+def my_rows(x, slp, W):
+    row0, rows = slp.plan.rows(slp.rank)
+    return x.reshape(slp.plan.H_total, W, -1)[row0:row0 + rows].reshape(rows * W, -1)
+
+
+def case_pipelined(rank, world, dist, device):
+    for dtype, kind, L, lo, hi, H, W in (("f64", "trunclin", 16, 0.25, 1.0, 24 * world + 5, 45), ("f32", "potts", 32, 0.1, 1.0, 17 * world + 3, 39),
+                                         ("f64", "potts", 8, 0.1, 1.0, 33 * world, 20)):
+        full = full_lp(dtype, H, W, L, kind, lo, hi, device)
+        slp = striped(dtype, H, W, L, kind, lo, hi, rank, world, dist, device, "pipelined")
+        assert np.isclose(slp.LowerBound(), full.LowerBound(), rtol=LB_RTOL[dtype])
+        assert slp.EvaluatePrimal() == float("inf") and not slp.CheckPrimalConsistency()
+        for it in range(4):
+            full.ComputePass(it); slp.ComputePass(it)
+            slp.synchronize()
+            assert np.array_equal(slp.lp.unaries(), my_rows(full.unaries(), slp, W)), f"theta differs after iteration {it}"
+            lb, want = slp.LowerBound(), full.LowerBound()
+            assert np.isclose(lb, want, rtol=LB_RTOL[dtype]), (it, lb, want)
+        for fwd in (True, False):
+            (full.ComputeForwardPassAndPrimal if fwd else full.ComputeBackwardPassAndPrimal)(4)
+            (slp.ComputeForwardPassAndPrimal if fwd else slp.ComputeBackwardPassAndPrimal)(4)
+            lab = slp.labeling()
+            assert np.array_equal(lab, full.labeling()), "gathered labeling differs from the unstriped LP's"
+            assert slp.CheckPrimalConsistency()
+            assert np.isclose(slp.EvaluatePrimal(), full.EvaluatePrimal(), rtol=LB_RTOL[dtype])
+            assert np.array_equal(slp.lp.unaries(), my_rows(full.unaries(), slp, W))
+        slp.close()
+        dist.barrier()
+
+
+def case_halo(rank, world, dist, device):
+    import torch
+    for dtype, kind, L, lo, hi, H, W in (("f64", "trunclin", 16, 0.25, 1.0, 48 * world, 64), ("f32", "potts", 32, 0.1, 1.0, 20 * world + 1, 70)):
+        prob = numpy_problem(H, W, L, kind, lo, hi)
+        full = full_from_numpy(dtype, prob, L, kind, device)
+        slp = striped_from_numpy(dtype, prob, L, kind, rank, world, dist, device, "halo")
+        alt = striped_from_numpy(dtype, prob, L, kind, rank, world, dist, device, "halo_nccl")
+        prev = slp.LowerBound()
+        assert np.isclose(prev, full.LowerBound(), rtol=LB_RTOL[dtype])
+        for it in range(12):
+            full.ComputePass(it); slp.ComputePass(it); alt.ComputePass(it)
+            lb = slp.LowerBound()
+            # the same bound from the ranks' partial values computed independently on the host path
+            part = slp.lp.grid_lower_bound_partial(slp._below_b.data_ptr() if slp._below_b is not None else None)
+            parts = [None] * world
+            dist.all_gather_object(parts, part)
+            assert np.isclose(lb, sum(parts), rtol=1e-12), (lb, parts)
+            assert np.array_equal(slp.lp.unaries(), alt.lp.unaries()), "peer-memory halo and NCCL halo differ"
+            assert np.isclose(alt.LowerBound(), lb, rtol=1e-12)
+            assert lb >= prev - LB_RTOL[dtype] * abs(prev), (it, lb, prev)
+            prev = lb
+        exact = full.LowerBound()
+        assert prev <= exact + LB_RTOL[dtype] * abs(exact)
+        gap = (exact - prev) / abs(exact)
+        assert gap <= 2e-2, gap
+        slp.ComputeForwardPassAndPrimal(12)
+        cost = slp.EvaluatePrimal()
+        assert np.isfinite(cost) and cost >= prev - 1e-6 * abs(prev) and slp.CheckPrimalConsistency()
+        # the primal cost of the gathered labeling, evaluated on the unstriped problem's ORIGINAL potentials
+        lab = slp.labeling()
+        want = primal_of(prob, lab, kind)
+        assert np.isclose(cost, want, rtol=1e-4 if dtype == "f32" else 1e-10), (cost, want)
+        if rank == 0:
+            print(f"halo[{kind},{dtype},world={world}]: bound {prev:.6f} exact {exact:.6f} rel gap {gap:.2e} primal {cost:.6f}", flush=True)
+        slp.close(); alt.close()
+        dist.barrier()
+
+
+def primal_of(prob, lab, kind):
+    """cost of a labeling under the original potentials (numpy, f64)"""
+    theta, hz, vt = prob
+    lab = lab.reshape(theta.shape[:2]).astype(np.int64)
+    cost = np.take_along_axis(theta, lab[..., None], axis=2).sum()
+    dh, dv = np.abs(lab[:, 1:] - lab[:, :-1]), np.abs(lab[1:] - lab[:-1])
+    if kind == "potts":
+        cost += (hz[..., 0] * (dh != 0)).sum() + (vt[..., 0] * (dv != 0)).sum()
+    else:
+        cost += np.minimum(hz[..., 0] * dh, hz[..., 1]).sum() + np.minimum(vt[..., 0] * dv, vt[..., 1]).sum()
+    return float(cost)
+
+
+def case_solver(rank, world, dist, device):
+    from lp_mp_b200 import MpRoundingSolver, StandardVisitor
+    dtype, kind, L, lo, hi, H, W = "f64", "potts", 8, 0.1, 1.0, 16 * world + 2, 24
+    full = full_lp(dtype, H, W, L, kind, lo, hi, device)
+    slp = striped(dtype, H, W, L, kind, lo, hi, rank, world, dist, device, "pipelined")
+    opts = dict(maxIter=12, roundingReparametrization="anisotropic")
+    a = MpRoundingSolver(full, StandardVisitor(**opts)); a.Solve()
+    b = MpRoundingSolver(slp, StandardVisitor(**opts)); b.Solve()
+    assert len(a.history) == len(b.history) == 12
+    for (la, ua, _), (lb, ub, _) in zip(a.history, b.history):
+        assert np.isclose(la, lb, rtol=1e-12) and (ua == ub or np.isclose(ua, ub, rtol=1e-12)), (la, lb, ua, ub)
+    assert np.array_equal(a.solution_, b.solution_)
+    assert np.isclose(a.lower_bound(), b.lower_bound(), rtol=1e-12) and np.isclose(a.primal_cost(), b.primal_cost(), rtol=1e-12)
+    # the default control law asks for damped_uniform on rounding iterations: not available on stripes -> a clear error
+    from lp_mp_b200._capi import LpmpError
+    try:
+        MpRoundingSolver(slp, StandardVisitor(maxIter=3)).Solve()
+    except LpmpError as e:
+        assert "anisotropic" in str(e)
+    else:
+        if not getattr(slp, "UNIFORM_MODES", False):
+            raise AssertionError("damped_uniform on stripes neither ran nor raised")
+    slp.close()
+    dist.barrier()
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        {"pipelined": case_pipelined, "halo": case_halo, "solver": case_solver}[sys.argv[1]](rank, world, dist, local)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            print(f"multirank case {sys.argv[1]} ok on {world} ranks", flush=True)
+    finally:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
