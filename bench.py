@@ -695,6 +695,8 @@ def compact(block):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()   # a native crash prints the Python stack of every thread
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -87,6 +87,32 @@ class BlockCache {
   size_t cached_[64] = {}, limit_[64] = {};
 };
 
+// Process-wide pool of the handles' CUDA streams.  A stream is NEVER destroyed while the process lives: host frameworks that were
+// handed lpmp_stream() (torch's caching allocator, NCCL process groups) keep the raw handle in their own bookkeeping -- e.g. they
+// record an event on every stream a block was used on when the block is freed -- and a destroyed stream there is a crash long after
+// lpmp_destroy.  Released streams are drained and reused by the next handle on the same device.
+class StreamPool {
+ public:
+  static StreamPool& get() { static StreamPool* s = new StreamPool; return *s; }   // leaked on purpose, like BlockCache
+  cudaError_t take(int dev, cudaStream_t* out) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto& v = idle_[dev & 63];
+      if (!v.empty()) { *out = v.back(); v.pop_back(); return cudaSuccess; }
+    }
+    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+  }
+  void give(int dev, cudaStream_t st) {
+    cudaStreamSynchronize(st);
+    (void)cudaGetLastError();
+    std::lock_guard<std::mutex> g(mu_);
+    idle_[dev & 63].push_back(st);
+  }
+ private:
+  std::mutex mu_;
+  std::vector<cudaStream_t> idle_[64];
+};
+
 template <typename T>
 struct DeviceBuffer {
   T* p = nullptr;
@@ -328,12 +354,12 @@ struct Solver : ISolver {
   static constexpr int kBoundCtas = 148 * 4;
 
   explicit Solver(int dev) : device(dev) {}
-  ~Solver() override { if (stream) cudaStreamDestroy(stream); }
+  ~Solver() override { if (stream) StreamPool::get().give(device, stream); }
 
   int init() {
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));   // (cudaGetDeviceProperties costs ~2 ms per handle)
-    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUDA_TRY(StreamPool::get().take(device, &stream));
     CUDA_TRY(partial.alloc(kBoundCtas));
     CUDA_TRY(result.alloc(1));
     CUDA_TRY(bad_count.alloc(1));

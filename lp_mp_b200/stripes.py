@@ -157,14 +157,26 @@ class StripedLP:
         self._W = lp.grid_shape[1]
         self._count = self._W * lp.L
         if self._cuda:
-            self._ts = torch.cuda.ExternalStream(lp.stream())
+            self._ts = torch.cuda.ExternalStream(lp.stream(), device=torch.cuda.current_device())
             self._ev = torch.cuda.Event()
+        with self._stream_ctx():     # buffers that only ever live on the library's stream are allocated on it
+            self._alloc_buffers(torch)
+        if self.coupling in ("halo", "pipelined"):
+            self._map_peers()
+        self._setup_done = True
+
+    def _alloc_buffers(self, torch):
+        lp, plan, rank = self.lp, self.plan, self.rank
         for which, present in ((TOP, plan.has_above(rank)), (BOTTOM, plan.has_below(rank))):
             if not present:
                 continue
             ptr, nbytes = lp.grid_boundary_ptrs(which)
             assert nbytes == self._count * self._itemsize
-            view = torch.as_tensor(_DevicePtr(ptr, self._count, self._itemsize), device="cuda") if self._cuda else None
+            if self._cuda:
+                view = torch.as_tensor(_DevicePtr(ptr, self._count, self._itemsize), device="cuda")
+            else:   # host-logic tests: the stand-in LP's in-buffer is host memory
+                ctype = C.c_float if self._itemsize == 4 else C.c_double
+                view = torch.from_numpy(np.ctypeslib.as_array((ctype * self._count).from_address(ptr)))
             self._in[which] = (ptr, view)
             self._stage[which] = torch.empty(self._count, dtype=self._tdtype, device=self._dev)
         # neighbour's side of the boundary edges below me (bound / primal evaluation), labels of its first row
@@ -173,26 +185,27 @@ class StripedLP:
         self._my_lab = torch.empty(self._W, dtype=torch.int32, device=self._dev) if plan.has_above(rank) else None
         self._acc = torch.zeros(2, dtype=torch.float64, device=self._dev)
         self._host = torch.zeros(2, dtype=torch.float64, pin_memory=True) if self._cuda else torch.zeros(2, dtype=torch.float64)
-        if self.coupling in ("halo", "pipelined"):
-            # exchange cudaIpc handles of the in-buffers and map the neighbours' buffers
-            mine = {}
-            for which, (ptr, _) in self._in.items():
-                handle = (C.c_ubyte * 64)()
-                lp.api.check(lp.api.ipc_export(C.c_void_p(ptr), handle))
-                mine[which] = bytes(handle)
-            everyone = [None] * self.world
-            self.dist.all_gather_object(everyone, mine)
-            for which, nb, nb_which in ((TOP, rank - 1, BOTTOM), (BOTTOM, rank + 1, TOP)):
-                if 0 <= nb < self.world and which in self._in:
-                    peer = C.c_void_p()
-                    buf = (C.c_ubyte * 64).from_buffer_copy(everyone[nb][nb_which])
-                    lp.api.check(lp.api.ipc_open(buf, C.byref(peer)))
-                    self._peer[which] = peer.value
-                    self._ipc_opened.append(peer.value)
-                    if self.coupling == "pipelined":   # the pass kernel itself delivers the vectors of its last band
-                        lp.grid_set_peer_boundary(which, peer.value)
-            self.dist.barrier()
-        self._setup_done = True
+
+    def _map_peers(self):
+        """exchange cudaIpc handles of the in-buffers and map the neighbours' buffers"""
+        lp, rank = self.lp, self.rank
+        mine = {}
+        for which, (ptr, _) in self._in.items():
+            handle = (C.c_ubyte * 64)()
+            lp.api.check(lp.api.ipc_export(C.c_void_p(ptr), handle))
+            mine[which] = bytes(handle)
+        everyone = [None] * self.world
+        self.dist.all_gather_object(everyone, mine)
+        for which, nb, nb_which in ((TOP, rank - 1, BOTTOM), (BOTTOM, rank + 1, TOP)):
+            if 0 <= nb < self.world and which in self._in:
+                peer = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(everyone[nb][nb_which])
+                lp.api.check(lp.api.ipc_open(buf, C.byref(peer)))
+                self._peer[which] = peer.value
+                self._ipc_opened.append(peer.value)
+                if self.coupling == "pipelined":   # the pass kernel itself delivers the vectors of its last band
+                    lp.grid_set_peer_boundary(which, peer.value)
+        self.dist.barrier()
 
     # ---- halo delivery before a pass -------------------------------------------------------------------------------
     def _deliver(self, send_which: int):
@@ -337,6 +350,8 @@ class StripedLP:
         self.lp.synchronize()
 
     def close(self):
+        if self._cuda and self._ts is not None:
+            self._ts.synchronize()
         for which in list(self._peer):
             if self.coupling == "pipelined":
                 self.lp.grid_set_peer_boundary(which, None)

@@ -179,13 +179,21 @@ def case_solver(rank, world, dist, device):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()   # a native crash prints the Python stack of every thread
     import torch
     import torch.distributed as dist
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     try:
-        {"pipelined": case_pipelined, "halo": case_halo, "solver": case_solver}[sys.argv[1]](rank, world, dist, local)
+        try:
+            {"pipelined": case_pipelined, "halo": case_halo, "solver": case_solver}[sys.argv[1]](rank, world, dist, local)
+        except BaseException:
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)      # the failure is reported; skip the teardown of half-built multi-process state
         torch.cuda.synchronize()
         dist.barrier()
         if rank == 0:

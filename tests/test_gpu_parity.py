@@ -184,7 +184,8 @@ def test_degenerate_graphs():
 
 def test_colouring_schedule():
     """graph-colouring schedule (BASELINE config 4 shape, small): exact parity with the oracle run on the same
-    colour ranks; final bound within 1e-4 relative of the natural-order run."""
+    colour ranks; the final bound of the natural-order device run equals the oracle's (<= 1e-12, criterion
+    1e-4), the colour-order run's gap to it is measured and bounded by 2e-3 (see the comment at the assertion)."""
     rng = np.random.default_rng(17)
     n, L = 400, 8
     # random 3-regular-ish graph: union of a ring and a random perfect matching
@@ -213,10 +214,19 @@ def test_colouring_schedule():
     for it in range(200):
         nat.ComputePass(it)
     # SRMP fixed points depend on the orientation of the relation DAG, so the colour-oriented run and the index-oriented
-    # run converge to different (both valid) bounds; on this instance they differ by 8e-4 relative.  The colour-oriented
-    # ORACLE reaches exactly the device's bound (bit parity above), i.e. the gap is a property of the schedule, not of
-    # the kernel.  BASELINE.json's 1e-4 is met on the grid / Potts instances (test_colouring_final_bound_grid).
-    assert abs(cu.LowerBound() - nat.LowerBound()) <= 2e-3 * abs(nat.LowerBound())
+    # run converge to different (both valid) bounds; on this instance they differ by 8e-4 relative, i.e. BASELINE.json's
+    # 1e-4 is NOT met by the colouring schedule here (DESIGN.md 4.3 records the measured gaps; bench.py's C4 block reports
+    # the gap of every run).  The colour-oriented ORACLE reaches exactly the device's bound (bit parity above): the gap is
+    # a property of the schedule, not of the kernel.  What does meet the criterion -- exactly -- is the device run in the
+    # reference's own order (level sets of the index-oriented DAG, a dozen levels on cubic graphs):
+    gap = abs(cu.LowerBound() - nat.LowerBound()) / abs(nat.LowerBound())
+    assert gap <= 2e-3, gap
+    exact = fill(cuda_lp("f64"), "dense", theta, ei, ej, 4, L)
+    exact.finalize(); exact.Begin(); exact.set_reparametrization("anisotropic")
+    for it in range(200):
+        exact.ComputePass(it)
+    assert abs(exact.LowerBound() - nat.LowerBound()) <= 1e-12 * abs(nat.LowerBound())
+    assert np.array_equal(exact.unaries(), nat.unaries())
 
 
 # ---- grids: wavefront kernel ------------------------------------------------------------------------------------------
@@ -656,6 +666,44 @@ def test_mid_size_grid_against_oracle():
         for lp in lps:
             lp.grid_fill_synthetic(7, lo, hi)
         run_lockstep(lps, "anisotropic", iters=2, lb_rtol=1e-6)
+
+
+# ---- the oracle at BASELINE.json's sizes (it does a C2 iteration in ~0.6 s and a 1 M-node C4 iteration in ~1 s on one core) ---------
+@pytest.mark.parametrize("H,W,L,kind,lo,hi", [(1024, 1024, 16, "trunclin", 0.25, 1.0),      # config 2, full size
+                                              (512, 4096, 32, "potts", 0.1, 1.0),            # config 3: full width, 1/8 of the rows (one stripe at 8 GPUs)
+                                              (12, 2048, 64, "dense", 0.0, 1.0)])            # config 5: full width, 12 rows (oracle tables are f64: 1.5 GB)
+def test_baseline_sizes_bit_exact_against_oracle(H, W, L, kind, lo, hi):
+    """f32 (the bench's storage type): one iteration, the bound, then a forward and a backward rounding pass -- theta, a, b and the
+    labeling bit-identical to the oracle after every step, bound / primal cost to summation order"""
+    lps = [oracle_lp("f32").grid_create(H, W, L, kind), cuda_lp("f32").grid_create(H, W, L, kind)]
+    for lp in lps:
+        lp.grid_fill_synthetic(0x5EED, lo, hi)
+    run_lockstep(lps, "anisotropic", iters=1, lb_rtol=1e-6)
+
+
+def test_config4_full_size_bit_exact_against_oracle():
+    """BASELINE config 4 at full size (random 3-regular graph, 1 M nodes, 8 labels, dense tables, f32): two iterations + rounding on
+    the colour ranks AND in the natural (reference) order, bit-exact against the oracle run on the same ranks"""
+    from bench import random_regular_graph
+    n, L = 1_000_000, 8
+    ei, ej = random_regular_graph(n, 3, 0x5EED)
+    rng = np.random.default_rng(0x5EED)
+    theta, tables = rng.random((n, L)), rng.random((len(ei), L, L))
+    for colouring in (True, False):
+        lps = []
+        for make in (oracle_lp, cuda_lp):
+            lp = make("f32")
+            lp.add_unaries(theta); lp.add_pairwise_dense(ei, ej, tables)
+            lps.append(lp)
+        if colouring:
+            colour, nc = lps[1].greedy_colouring(ei, ej)
+            assert nc <= 4
+            for lp in lps:
+                lp.set_node_ranks(colour.astype(np.uint64) * n + np.arange(n, dtype=np.uint64))
+        run_lockstep(lps, "anisotropic", iters=2, lb_rtol=1e-6)
+        levels = lps[1].stats()["num_levels"]
+        assert levels <= (4 if colouring else 16)   # natural order: the index-oriented DAG of a random cubic graph is 12 levels deep
+        del lps
 
 
 def test_error_behaviour_on_device():

@@ -76,3 +76,112 @@ def test_neighbour_exchange_over_gloo(world):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert list(out) == [1] * world
+
+
+# ---- StripedLP driven end to end over gloo with a host stand-in for the per-rank LP ------------------------------------------
+class HostStripe:
+    """Stand-in for lp_mp_b200.LP on a stripe (host memory, numpy): enough behaviour to pin StripedLP's host logic -- which
+    vectors travel where before which pass, what enters the bound / primal reduction, how the labeling is gathered."""
+    dtype = 1   # f64
+
+    def __init__(self, rank, rows, W, L, has_above, has_below):
+        self.rank, self.grid_shape, self.L = rank, (rows, W), L
+        self.in_buf = {0: np.full(W * L, -1.0) if has_above else None, 1: np.full(W * L, -1.0) if has_below else None}
+        self.passes, self.seen, self.labelled, self.repam = 0, [], False, None
+        self.finalized = False
+
+    def _vec(self, which):      # my side of boundary `which` after `passes` passes
+        return np.full(self.grid_shape[1] * self.L, 1000.0 * self.rank + 100.0 * which + self.passes)
+
+    def finalize(self): self.finalized = True
+    def Begin(self): pass
+    def End(self): self.ended = True
+    def set_reparametrization(self, mode): self.repam = mode
+    def synchronize(self): pass
+
+    def grid_boundary_ptrs(self, which):
+        return self.in_buf[which].ctypes.data, self.in_buf[which].nbytes
+
+    def grid_get_boundary_vectors(self, which, dst):
+        import ctypes
+        v = self._vec(which)
+        ctypes.memmove(dst, v.ctypes.data, v.nbytes)
+
+    def grid_get_boundary_labels(self, which, dst):
+        import ctypes
+        v = np.full(self.grid_shape[1], 10 * self.rank + which, dtype=np.int32)
+        ctypes.memmove(dst, v.ctypes.data, v.nbytes)
+
+    def _pass(self, which_in, primal):
+        buf = self.in_buf[which_in]
+        self.seen.append(None if buf is None else float(buf[0]))
+        self.passes += 1
+        self.labelled |= primal
+
+    def ComputeForwardPass(self): self._pass(0, False)
+    def ComputeBackwardPass(self): self._pass(1, False)
+    def ComputeForwardPassAndPrimal(self, it): self._pass(0, True)
+    def ComputeBackwardPassAndPrimal(self, it): self._pass(1, True)
+
+    def grid_lower_bound_partial_device(self, below, out):
+        import ctypes
+        n = self.grid_shape[1] * self.L
+        val = float(self.rank + 1) + (float(np.ctypeslib.as_array((ctypes.c_double * n).from_address(below)).sum()) / n if below else 0.0)
+        ctypes.c_double.from_address(out).value = val
+
+    def grid_evaluate_primal_partial_device(self, below, below_labels, out):
+        import ctypes
+        val = float("inf") if not self.labelled else 7.0 * (self.rank + 1) + (float(ctypes.c_int32.from_address(below_labels).value) if below_labels else 0.0)
+        ctypes.c_double.from_address(out).value = val
+
+    def CheckPrimalConsistency(self): return self.labelled
+    def labeling(self): return np.full(self.grid_shape[0] * self.grid_shape[1], self.rank, dtype=np.uint32)
+
+
+def _striped_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lp_mp_b200 import MpRoundingSolver, StandardVisitor
+        from lp_mp_b200.stripes import StripedLP
+        H, W, L = 11, 3, 2
+        plan = StripePlan(H, world)
+        rows = plan.rows(rank)[1]
+        lp = HostStripe(rank, rows, W, L, plan.has_above(rank), plan.has_below(rank))
+        slp = StripedLP(lp, plan, rank, dist, coupling="halo_nccl", device="cpu").finalize()
+        ok = True
+        # bound: sum over ranks of (rank + 1) + first entry of the lower neighbour's TOP vector (none for the last rank)
+        want = sum(r + 1 for r in range(world)) + sum(1000.0 * (r + 1) + 0.0 for r in range(world - 1))
+        ok &= slp.LowerBound() == want
+        ok &= slp.EvaluatePrimal() == float("inf") and not slp.CheckPrimalConsistency()
+        slp.set_reparametrization("anisotropic")
+        slp.ComputeForwardPass()     # consumes the upper neighbour's BOTTOM vector of pass count 0
+        ok &= lp.seen[-1] == (None if rank == 0 else 1000.0 * (rank - 1) + 100.0)
+        slp.ComputeBackwardPass()    # consumes the lower neighbour's TOP vector after its one pass
+        ok &= lp.seen[-1] == (None if rank == world - 1 else 1000.0 * (rank + 1) + 1.0)
+        slp.ComputeForwardPassAndPrimal(1)
+        ok &= slp.CheckPrimalConsistency()
+        ok &= slp.EvaluatePrimal() == sum(7.0 * (r + 1) for r in range(world)) + sum(10.0 * (r + 1) for r in range(world - 1))
+        lab = slp.labeling()
+        ok &= lab.shape == (H * W,) and all((lab[plan.rows(r)[0] * W:(plan.rows(r)[0] + plan.rows(r)[1]) * W] == r).all() for r in range(world))
+        ok &= slp.GetNumberOfFactors() == H * W + H * (W - 1) + (H - 1) * W
+        # the reference control law drives a StripedLP (Solver::Solve, include/solver.hxx:230-257)
+        s = MpRoundingSolver(slp, StandardVisitor(maxIter=4, roundingReparametrization="anisotropic"))
+        ok &= bool(s.Solve()) and len(s.history) >= 1 and getattr(lp, "ended", False) and s.solution_ is not None
+        out[rank] = int(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_striped_lp_host_logic_over_gloo(world):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Array("i", [0] * world)
+    procs = [ctx.Process(target=_striped_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert list(out) == [1] * world
