@@ -332,6 +332,7 @@ struct Solver : ISolver {
   DeviceBuffer<Real> tab;    // dense grids: table planes tabH [H][W][L*L] then tabV [H+1][W][L*L] (kernels_grid_dense.cuh)
   DeviceBuffer<double> lb_rows;   // dense grids: per-row bound terms produced by the last backward pass
   bool fused_lb_valid = false;    // lb_rows describes the current state (no state change since that pass)
+  bool fused_lb_open_below = false;   // ... except for the edges to the stripe below (O(L) grids: added from below_b when the bound is asked for)
   bool levels_built = false; // CSR + level sets uploaded (general graphs; grids on demand)
   DeviceBuffer<Real> handoff, in_top, in_bot;   // band-to-band / stripe-to-stripe column vectors (sentinel protocol)
   Real* peer_top = nullptr;  // upper neighbour's in_bot (delivery target of the backward pass), or null
@@ -460,6 +461,7 @@ struct Solver : ISolver {
     else if (k == "level_group") tune.level_group = value;
     else if (k == "wavefront_rows") tune.rows = value;
     else if (k == "wavefront_split") tune.split = value;
+    else if (k == "wavefront_fused_bound") tune.fused_bound = value;
     else if (k == "wavefront_trace") want_trace = value;
     else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
     return LPMP_OK;
@@ -844,6 +846,7 @@ struct Solver : ISolver {
           if (int r = encode_map(&maps_split[0], rec.p, L, REC_VECS, 1, 8)) return r;
           if (int r = encode_map(&maps_split[1], par.p, (uint32_t)PREC(), 1, 1, 8)) return r;
           split_ok = true;
+          CUDA_TRY(lb_rows.alloc(gridH));
         }
       }
     }
@@ -932,6 +935,7 @@ struct Solver : ISolver {
       A.in_boundary = forward ? in_top.p : in_bot.p;
       A.out_boundary = forward ? peer_bot : peer_top;
       A.labels = labels.p;
+      A.lb_rows = nullptr;
       A.rec = rec.p; A.par = par.p;
       A.trace = trace.p;
       A.trace_steps = (trace.p && want_trace >= 2) ? trace.p + 4 * (size_t)A.num_bands : nullptr;
@@ -941,12 +945,18 @@ struct Solver : ISolver {
       const int rows_win = pw == LPMP_PAIRWISE_POTTS ? (potts_neg ? 0 : 1) : (tl_irregular || tl_reach > 8 || (tl_reach > 4 && L < 16) ? -1 : std::max(tl_reach, 1));
       if (split_ok && repam == LPMP_REPAM_ANISOTROPIC && rows_win >= 0 && (pw == LPMP_PAIRWISE_POTTS || L == 16) && use_split()) {
         A.num_bands = (gridH + (uint32_t)kSplitBandRows - 1) / (uint32_t)kSplitBandRows;
+        // backward passes accumulate LP::LowerBound on the fly where the pass is bandwidth-bound (more bands than SMs: the three
+        // extra group minima per step hide under the memory traffic); latency-bound grids keep the separate 0.1 ms sweep
+        const bool fuse = !forward && (tune.fused_bound > 0 || (tune.fused_bound < 0 && A.num_bands > (uint32_t)num_sms));
+        if (fuse) A.lb_rows = lb_rows.p;
         const cudaError_t le = pw == LPMP_PAIRWISE_POTTS ? launch_split<Real, LPMP_PAIRWISE_POTTS>(maps_split, A, L, rows_win, tune, num_sms, stream)
                                                          : launch_split<Real, LPMP_PAIRWISE_TRUNCLIN>(maps_split, A, L, rows_win, tune, num_sms, stream);
         CUDA_TRY(le);
         ++launches;
         updates += 2 * E;
         if (primal) labels_valid = true;
+        fused_lb_valid = fuse;
+        fused_lb_open_below = fuse && has_below;
         return LPMP_OK;
       }
       if (rows_ok && repam == LPMP_REPAM_ANISOTROPIC && rows_win >= 0 && use_rows()) {
@@ -992,8 +1002,8 @@ struct Solver : ISolver {
     return LPMP_OK;
   }
 
-  int reduce_to_host(int ctas, double add, double* out, const double* src = nullptr) {
-    final_sum_kernel<<<1, 32, 0, stream>>>(src ? src : partial.p, ctas, add, result.p);
+  int reduce_to_host(int ctas, double add, double* out, const double* src = nullptr, const double* extra = nullptr, int m = 0) {
+    final_sum_kernel<<<1, 32, 0, stream>>>(src ? src : partial.p, ctas, add, result.p, extra, m);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, result.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -1002,9 +1012,9 @@ struct Solver : ISolver {
   }
 
   // the same final sum, left in device memory: no host synchronisation (multi-GPU drivers reduce it with NCCL on this stream)
-  int reduce_to(int ctas, double add, double* out, bool to_device, const double* src = nullptr) {
-    if (!to_device) return reduce_to_host(ctas, add, out, src);
-    final_sum_kernel<<<1, 32, 0, stream>>>(src ? src : partial.p, ctas, add, out);
+  int reduce_to(int ctas, double add, double* out, bool to_device, const double* src = nullptr, const double* extra = nullptr, int m = 0) {
+    if (!to_device) return reduce_to_host(ctas, add, out, src, extra, m);
+    final_sum_kernel<<<1, 32, 0, stream>>>(src ? src : partial.p, ctas, add, out, extra, m);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     return LPMP_OK;
@@ -1012,12 +1022,20 @@ struct Solver : ISolver {
 
   int bound_launch(const Real* below_b, double add, double* out, bool to_device = false) {
     CUDA_TRY(cudaSetDevice(device));
-    if (fused_lb_valid && !striped) return reduce_to((int)gridH, add, out, to_device, lb_rows.p);
     const int G = group_size_for(L);
     int threads = 256;
     const size_t per_group = 2 * (size_t)L * sizeof(Real);
     while (threads > G && (threads / G) * per_group > 48 * 1024) threads >>= 1;
     const int groups = threads / G;
+    if (fused_lb_valid && (!striped || pw != LPMP_PAIRWISE_DENSE)) {
+      // the last backward pass left the terms of every grid row in lb_rows; a stripe adds the edges to the stripe below
+      if (!(fused_lb_open_below && below_b)) return reduce_to((int)gridH, add, out, to_device, lb_rows.p);
+      const int bctas = (int)std::min<uint64_t>(((uint64_t)gridW + groups - 1) / groups, (uint64_t)kBoundCtas);
+      boundary_bound_kernel<Real><<<bctas, threads, (size_t)groups * per_group, stream>>>(store(), N + (uint64_t)(gridH - 1) * gridW, gridW, L, pw, below_b, partial.p, G);
+      ++launches;
+      CUDA_TRY(cudaGetLastError());
+      return reduce_to((int)gridH, add, out, to_device, lb_rows.p, partial.p, bctas);
+    }
     const uint64_t total = N + slots;
     const int ctas = (int)std::min<uint64_t>((total + groups - 1) / groups, (uint64_t)kBoundCtas);
     if (is_grid && schedule == LPMP_SCHEDULE_WAVEFRONT && pw != LPMP_PAIRWISE_DENSE) {

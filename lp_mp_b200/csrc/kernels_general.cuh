@@ -255,12 +255,44 @@ __global__ void push_boundary_kernel(Real* dst, const Real* __restrict__ src, ui
   }
 }
 
-// fixed-order final sum (deterministic bound): one warp, sequential chunks then a fixed tree
-__global__ void final_sum_kernel(const double* __restrict__ partial, int n, double constant, double* out) {
+// fixed-order final sum (deterministic bound): one warp, sequential chunks then a fixed tree; `extra` (m values, or null) is a
+// second array of partial sums (the stripe-boundary edges next to the per-row terms of a fused bound)
+__global__ void final_sum_kernel(const double* __restrict__ partial, int n, double constant, double* out, const double* __restrict__ extra = nullptr, int m = 0) {
   double v = 0.0;
   for (int k = threadIdx.x; k < n; k += 32) v += partial[k];
+  for (int k = threadIdx.x; k < m; k += 32) v += extra[k];
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if (threadIdx.x == 0) *out = constant + v;
+}
+
+// LP::LowerBound terms of the `count` edges slot0 .. slot0 + count - 1 whose b side lives elsewhere (`ext_b`: [count][L]): the edges
+// from a stripe's last row to the stripe below.  Same arithmetic as the edge branch of lower_bound_kernel.
+template <typename Real>
+__global__ void __launch_bounds__(256) boundary_bound_kernel(Store<Real> st, uint64_t slot0, uint32_t count, uint32_t L, int pw, const Real* __restrict__ ext_b,
+                                                             double* __restrict__ partial, int G) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Real* smem = reinterpret_cast<Real*>(smem_raw);
+  const int groups_per_cta = blockDim.x / G;
+  const int g = threadIdx.x / G, gl = threadIdx.x % G;
+  const unsigned mask = group_mask(G);
+  Real* oth = smem + (size_t)g * 2 * L;
+  Real* hs = oth + L;
+  double acc = 0.0;
+  for (uint32_t k = blockIdx.x * groups_per_cta + g; k < count; k += gridDim.x * groups_per_cta) {
+    const uint64_t e = slot0 + k;
+    __syncwarp(mask);
+    const Real* eb = ext_b + (uint64_t)k * L;
+    const Real* ea = st.a(e);
+    for (uint32_t x = gl; x < L; x += G) oth[x] = eb[x];
+    __syncwarp(mask);
+    group_min_plus<Real>(pw, st.par(e), L, 0u, oth, hs, G, gl, mask);
+    Real m = RealTraits<Real>::inf();
+    for (uint32_t x = gl; x < L; x += G) m = rmin(m, Real(hs[x] + ea[x]));
+    m = group_min(m, G, mask);
+    if (gl == 0) acc += (double)m;
+  }
+  const double s = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
 // ---- single-factor entry points --------------------------------------------------------------------------------

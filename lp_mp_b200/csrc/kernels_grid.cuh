@@ -64,6 +64,7 @@ struct GridArgs {
   Real* out_boundary;       // [W][L] where the last band delivers its outgoing vectors when out_halo (the neighbour's
                             // in_boundary, possibly peer memory), or null: not delivered
   uint32_t* labels;         // [H*W]
+  double* lb_rows;          // [H] or null; split variant, backward pass: LP::LowerBound terms of every grid row, accumulated on the fly
   Real* rec;                // node records [H][W][5][L] (the split variant moves whole-row tile runs with 1-D bulk copies, no tensor map)
   Real* par;                // parameter records [H][W][4][P]
   unsigned long long* trace;   // debug: per band {claimed, first tile ready, first hand-off consumed, done} in ns (globaltimer), or null

@@ -151,8 +151,21 @@ __device__ __forceinline__ void stg_n_relaxed_if(bool on, double* p, const doubl
   asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.relaxed.sys.global.v2.f64 [%0], {%1,%2}; }" ::"l"(p), "d"(v[0]), "d"(v[1]), "r"((uint32_t)on) : "memory");
 }
 
-template <typename Real, int PW, int L, int WIN, bool FWD>
+// minimum over the whole warp of a value that both half-warps hold (theta)
+template <typename Real>
+__device__ __forceinline__ Real both_halves_min(Real v) {
+  if constexpr (std::is_same<Real, float>::value) return credux_min(v);
+  else return half_min<Real>(v);
+}
+
+// LBF (backward passes only): LP::LowerBound (/root/reference/include/LP_MP.h:1507-1518) accumulated on the fly.  In a backward pass
+// node i is the LAST writer of theta_i and of both vectors of its edges to the right / lower neighbour (that neighbour was updated
+// earlier in the pass, its side b is the vector this step min-marginalises), and h(x) = min_y [c(x,y) + b(y)] is in registers: the
+// node's term min theta_i and the two edge terms min_x [a(x) + h(x)] cost three group minima per step, off the dependency chain, and
+// a pass leaves one double per grid row in A.lb_rows -- the separate sweep over all records (kernels_grid_bound.cuh) disappears.
+template <typename Real, int PW, int L, int WIN, bool FWD, bool LBF = false>
 __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_split_kernel(const GridArgs<Real> A) {
+  static_assert(!(LBF && FWD), "the fused bound belongs to the backward pass");
   using Cfg = SplitCfg<Real, PW, L>;
   constexpr int LPL = Cfg::LPL, NW = Cfg::NW, T = Cfg::T, K = Cfg::K, LOGK = Cfg::LOGK, P = Cfg::P, REC = Cfg::REC, PREC = Cfg::PREC, NSLOT = Cfg::NSLOT, RING = Cfg::RING;
   constexpr uint32_t S = (uint32_t)sizeof(Real);
@@ -406,6 +419,20 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
 #pragma unroll
       for (int k = 0; k < LPL; ++k) oth[k] = Real(0);
       int free_upto = to_next_cta ? 0 : RING;   // columns the consumer's ring is known to have room for (another CTA: ask first)
+      double lb_acc = 0.0;      // LBF: bound terms of this row (lane 0's order of additions is the one that counts)
+      // the edge to the stripe below is final only when BOTH stripes have finished their pass: left to the host (api.cu)
+      const bool lb_skip_col = u == 0 && A.in_halo;
+      auto lb_terms = [&](const Real (&th_new)[LPL], const Real (&own_new)[LPL], const Real (&h)[LPL], const bool has_edge) {
+        Real tm = th_new[0], em = own_new[0] + h[0];
+#pragma unroll
+        for (int k = 1; k < LPL; ++k) { tm = rmin(tm, th_new[k]); em = rmin(em, Real(own_new[k] + h[k])); }
+        em = has_edge ? em : RealTraits<Real>::inf();
+        const Real gt = both_halves_min<Real>(tm);
+        Real ge = half_min<Real>(em);
+        ge = (has_edge && !(hi && lb_skip_col)) ? ge : Real(0);
+        const Real go = __shfl_xor_sync(FULL, ge, 16);
+        lb_acc += ((double)gt + (double)ge) + (double)go;
+      };
       wait_chunk(0);
 
       // ---- single steps: kind 0: general (any column, rounding, corner weights); 1: weight 1/2, any column (existence of the row
@@ -465,6 +492,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
             oo[k] = oo[k] + (hi ? d_oc : d_or);
             th[k] = (v - d_oc) - d_or;
           }
+          if constexpr (LBF) lb_terms(th, oi, h, true);
         } else {
           const bool has_ic = in_col_exists, has_oc = out_col_exists;
           const bool has_i = hi ? has_ic : has_ir;
@@ -511,6 +539,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
             if (has_or) { if (!hi) oo[k] = oo[k] + d; v = v - d; }
             th[k] = v;
           }
+          if constexpr (LBF) lb_terms(th, oi, h, has_i);
         }
         sts_n_if(!hi, f_th + roffs, th);
         sts_n_if(true, f_in + roffs, oi);
@@ -596,6 +625,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
           sts_n_if(true, Tout + ro, oo);
 #pragma unroll
           for (int k = 0; k < LPL; ++k) oth[k] = oo[k];
+          if constexpr (LBF) lb_terms(th, oi, h, true);       // after the stores: nothing of the chain waits for these minima
         }
         publish(s0 + K);
       };
@@ -622,6 +652,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
         for (; s <= s_last; ++s) do_step(std::integral_constant<int, 2>{}, s);
         if (corner_row) do_step(std::integral_constant<int, 0>{}, s); else do_step(std::integral_constant<int, 1>{}, s);
       }
+      if constexpr (LBF) { if (lane == 0) A.lb_rows[r] = lb_acc; }
     }
     // ---- end of the band: every ring is drained and re-armed, every tile has left shared memory ----
 #pragma unroll

@@ -11,14 +11,17 @@ static cudaError_t launch_split_one(const CUtensorMap* maps, const GridArgs<Real
   if constexpr (!Cfg::FITS) {
     return cudaErrorInvalidValue;
   } else {
-    auto kernel = args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true> : wavefront_split_kernel<Real, PW, L, WIN, false>;
+    if (args.forward && args.lb_rows) return cudaErrorInvalidValue;   // the fused bound belongs to the backward pass
+    const int variant = args.forward ? 1 : (args.lb_rows ? 2 : 0);
+    auto kernel = args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true, false>
+                               : (args.lb_rows ? wavefront_split_kernel<Real, PW, L, WIN, false, true> : wavefront_split_kernel<Real, PW, L, WIN, false, false>);
     int dev = 0;
     cudaGetDevice(&dev);
-    static bool configured[64][2] = {};
-    if (!configured[dev & 63][args.forward ? 1 : 0]) {
+    static bool configured[64][3] = {};
+    if (!configured[dev & 63][variant]) {
       cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
       if (e != cudaSuccess) return e;
-      configured[dev & 63][args.forward ? 1 : 0] = true;
+      configured[dev & 63][variant] = true;
     }
     int ctas = (int)args.num_bands;
     if (ctas > num_sms) ctas = num_sms;   // one CTA per SM; persistent: the ticket loop covers the remaining bands

@@ -22,6 +22,7 @@ struct WavefrontTuning {
   int level_group = 0;  // level kernel: lanes per node (power of two below the default pow2 >= L); 0 = default
   int warps_per_cta = 0;  // consecutive bands per CTA (<= 8 and what the shared memory holds); 0 or 1 = one band per CTA
   int split = -1;       // edge-split variant for the anisotropic passes (kernels_grid_split.cuh: one row per warp): 1 on, 0 off, -1 automatic
+  int fused_bound = -1; // split variant, backward passes: accumulate LP::LowerBound on the fly: 1 on, 0 off, -1 automatic (bandwidth-bound grids)
   int rows = -1;        // one-label-per-lane variant for the anisotropic passes (kernels_grid_rows.cuh): 1 on, 0 off, -1 automatic
 };
 
