@@ -38,7 +38,7 @@ enum { LPMP_OK = 0, LPMP_ERR_INVALID = 1, LPMP_ERR_STATE = 2, LPMP_ERR_CUDA = 3,
  * include/config.hxx:28); F32 = throughput mode (REAL = float is the commented alternative, :23-26). */
 enum { LPMP_F32 = 0, LPMP_F64 = 1 };
 
-/* LPReparametrizationMode, include/config.hxx:72 (Anisotropic2 / Mixed: out of scope) */
+/* LPReparametrizationMode, include/config.hxx:72 (Mixed: out of scope) */
 enum { LPMP_REPAM_ANISOTROPIC = 0, LPMP_REPAM_UNIFORM = 1, LPMP_REPAM_DAMPED_UNIFORM = 2 };
 
 /* pairwise factor family: PairwiseSimplexFactor / pairwise_potts_factor (test/potts_factor.cpp:21-71) /
@@ -76,6 +76,11 @@ const char* LPMP_FN(last_error)(const lpmp_solver* h);
  * (test/graphical_model.cpp:98-108).  One label count L and one pairwise family per LP.  Inputs are host
  * buffers of doubles and are copied. */
 int LPMP_FN(add_unaries)(lpmp_solver* h, uint64_t n, uint32_t L, const double* theta /* [n][L] */);
+/* the same with one label count per variable (test/graphical_model.cpp:74-96 builds 2-, 3- and 4-label variables in one model;
+ * UnaryPairwiseMessage(4,3) in test/simplex_marginalization.cpp:22-23): theta is packed, L[0] + ... + L[n-1] doubles.  In an LP with
+ * mixed label counts every per-variable / per-edge array of this header is packed the same way (theta_i: L_i entries; a_e: L_i(e),
+ * b_e: L_j(e); dense table of edge e: L_i(e) x L_j(e), x_i major).  General graphs only (level / colouring schedule). */
+int LPMP_FN(add_unaries_var)(lpmp_solver* h, uint64_t n, const uint32_t* L /* [n] */, const double* theta /* packed */);
 int LPMP_FN(add_pairwise_dense)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* tables /* [m][L][L], x_i major */);
 int LPMP_FN(add_pairwise_potts)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* lambda /* [m] */);
 int LPMP_FN(add_pairwise_trunclin)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* slope, const double* trunc /* [m] each */);
@@ -183,6 +188,16 @@ int LPMP_FN(get_unaries)(lpmp_solver* h, double* theta /* [N][L] */);
 int LPMP_FN(get_messages)(lpmp_solver* h, double* a /* [E][L] */, double* b /* [E][L] */); /* edge insertion order */
 int LPMP_FN(set_messages)(lpmp_solver* h, const double* a, const double* b);
 int LPMP_FN(set_unaries)(lpmp_solver* h, const double* theta);
+/* The dual variables in the byte layout of the reference's archive over ALL factors in insertion order
+ * (factor_archive<serialization_functor::dual>, include/factor_archive.hxx:34-48; save_archive / load_archive,
+ * include/serialization.hxx:226-425; FactorContainer::serialize_dual, include/factors_messages.hxx:3196-3209): per factor its
+ * serialize_dual() members as REAL = double -- unary simplex factor: theta (L_i doubles); pairwise simplex factor: msg1 (L_i
+ * doubles) then msg2 (L_j doubles).  Factors appear in the order of the add_* calls (grids: all unaries, then per node the
+ * horizontal edge before the vertical one).  save -> lpmp_create -> same construction calls -> finalize -> load resumes the solve
+ * with a bit-identical trajectory in LPMP_F64 (checkpoint / warm start; tests/test_dual_archive.py). */
+int LPMP_FN(dual_size)(lpmp_solver* h, uint64_t* bytes);
+int LPMP_FN(save_dual)(lpmp_solver* h, void* archive, uint64_t bytes);
+int LPMP_FN(load_dual)(lpmp_solver* h, const void* archive, uint64_t bytes);
 int LPMP_FN(get_stats)(lpmp_solver* h, lpmp_stats* out);
 int LPMP_FN(synchronize)(lpmp_solver* h);
 /* debug timeline of the last wavefront pass (after set_tuning "wavefront_trace" = 1): per band 4 globaltimer stamps in ns

@@ -34,6 +34,7 @@ SIGNATURES = {
     "destroy": [_vp],
     "last_error": [_vp],
     "add_unaries": [_vp, _u64, _u32, _pd],
+    "add_unaries_var": [_vp, _u64, _pu32, _pd],
     "add_pairwise_dense": [_vp, _u64, _pu64, _pu64, _pd],
     "add_pairwise_potts": [_vp, _u64, _pu64, _pu64, _pd],
     "add_pairwise_trunclin": [_vp, _u64, _pu64, _pu64, _pd, _pd],
@@ -79,6 +80,9 @@ SIGNATURES = {
     "get_messages": [_vp, _pd, _pd],
     "set_messages": [_vp, _pd, _pd],
     "set_unaries": [_vp, _pd],
+    "dual_size": [_vp, _pu64],
+    "save_dual": [_vp, _vp, _u64],
+    "load_dual": [_vp, _vp, _u64],
     "get_stats": [_vp, C.POINTER(Stats)],
     "synchronize": [_vp],
     "get_trace": [_vp, _pu64, _u64],

@@ -2,6 +2,7 @@
 // schedule construction (host), kernel launches.  Host logic mirrors LP<FMC> (/root/reference/include/LP_MP.h:200-585)
 // for the SRMP simplex configuration; all arithmetic on potentials happens in the kernels.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -14,6 +15,7 @@
 
 #include "../../include/lpmp_b200.h"
 #include "../../include/lpmp_synthetic.h"
+#include "graph_engine.cuh"
 #include "kernels_general.cuh"
 #include "wavefront_launch.h"
 
@@ -270,6 +272,9 @@ struct ISolver {
   std::string err;
   virtual ~ISolver() {}
   virtual int add_unaries(uint64_t n, uint32_t L, const double* theta) = 0;
+  virtual int add_unaries_var(uint64_t n, const uint32_t* L, const double* theta) = 0;
+  virtual int dual_size(uint64_t* bytes) = 0;
+  virtual int dual_archive(void* archive, uint64_t bytes, bool save) = 0;
   virtual int add_pairwise(int type, uint64_t m, const uint64_t* i, const uint64_t* j, const double* p0, const double* p1) = 0;
   virtual int set_node_ranks(const uint64_t* rank) = 0;
   virtual int set_edge_order(int eo) = 0;
@@ -327,6 +332,17 @@ struct Solver : ISolver {
   // host staging (general graphs)
   std::vector<double> h_theta, h_params;
   std::vector<uint64_t> h_ei, h_ej, h_rank;
+  std::vector<uint32_t> h_counts;   // label count per variable of an LP with mixed counts (add_unaries_var), else empty
+  // factors in insertion order as runs {kind (0 unary, 1 pairwise), first, count}: the order of the reference's f_ (include/LP_MP.h:214)
+  std::vector<std::array<uint64_t, 3>> runs;
+  void note_run(uint64_t kind, uint64_t first, uint64_t count) {
+    if (count == 0) return;
+    if (!runs.empty() && runs.back()[0] == kind && runs.back()[1] + runs.back()[2] == first) runs.back()[2] += count;
+    else runs.push_back({kind, first, count});
+  }
+  bool mixed() const { return !h_counts.empty(); }
+  uint32_t Ln(uint64_t i) const { return mixed() ? h_counts[i] : L; }
+  GraphEngine<Real, DeviceBuffer> graph;   // general graphs: node-record layout + per-level kernels (graph_engine.cuh)
   // device state.  General graphs: theta[N][L], a[E][L], b[E][L], params[E][P].  Grids: rec[N][5][L], par[N][4][P].
   DeviceBuffer<Real> theta, a, b, params, rec, par;
   DeviceBuffer<Real> tab;    // dense grids: table planes tabH [H][W][L*L] then tabV [H+1][W][L*L] (kernels_grid_dense.cuh)
@@ -410,10 +426,26 @@ struct Solver : ISolver {
   int add_unaries(uint64_t n, uint32_t L_, const double* th) override {
     if (finalized) return bad_state("add_unaries after finalize");
     if (is_grid) return bad_state("add_unaries on a grid LP");
-    if (L_ == 0 || (L != 0 && L != L_)) { err = "one label count per LP"; return LPMP_ERR_UNSUPPORTED; }
+    if (mixed()) { std::vector<uint32_t> Ls(n, L_); return add_unaries_var(n, Ls.data(), th); }
+    if (L_ == 0 || (L != 0 && L != L_)) { err = "one label count per LP (lpmp_add_unaries_var takes mixed counts)"; return LPMP_ERR_UNSUPPORTED; }
     if (!th) { err = "null theta"; return LPMP_ERR_INVALID; }
     L = L_;
     h_theta.insert(h_theta.end(), th, th + n * L);
+    note_run(0, N, n);
+    N += n;
+    return LPMP_OK;
+  }
+  int add_unaries_var(uint64_t n, const uint32_t* Ls, const double* th) override {
+    if (finalized) return bad_state("add_unaries after finalize");
+    if (is_grid) return bad_state("add_unaries on a grid LP");
+    if (E != 0 && !mixed()) return bad_state("add_unaries_var after pairwise factors of an LP with one label count");
+    if (!th || !Ls) { err = "null argument"; return LPMP_ERR_INVALID; }
+    for (uint64_t q = 0; q < n; ++q) if (Ls[q] == 0) { err = "variable without labels"; return LPMP_ERR_INVALID; }
+    if (!mixed()) h_counts.assign(N, L);   // what has been added so far had one label count
+    uint64_t total = 0;
+    for (uint64_t q = 0; q < n; ++q) { h_counts.push_back(Ls[q]); L = std::max(L, Ls[q]); total += Ls[q]; }
+    h_theta.insert(h_theta.end(), th, th + total);
+    note_run(0, N, n);
     N += n;
     return LPMP_OK;
   }
@@ -424,12 +456,15 @@ struct Solver : ISolver {
     for (uint64_t k = 0; k < m; ++k)
       if (i[k] >= N || j[k] >= N || i[k] == j[k]) { err = "edge endpoint out of range"; return LPMP_ERR_INVALID; }
     pw = type;
-    const uint32_t Pn = P();
     h_ei.insert(h_ei.end(), i, i + m);
     h_ej.insert(h_ej.end(), j, j + m);
-    if (type == LPMP_PAIRWISE_DENSE) h_params.insert(h_params.end(), p0, p0 + m * Pn);
-    else if (type == LPMP_PAIRWISE_POTTS) h_params.insert(h_params.end(), p0, p0 + m);
+    if (type == LPMP_PAIRWISE_DENSE) {
+      uint64_t total = 0;   // tables of an LP with mixed label counts are packed: L_i x L_j each
+      for (uint64_t k = 0; k < m; ++k) total += (uint64_t)Ln(i[k]) * Ln(j[k]);
+      h_params.insert(h_params.end(), p0, p0 + total);
+    } else if (type == LPMP_PAIRWISE_POTTS) h_params.insert(h_params.end(), p0, p0 + m);
     else for (uint64_t k = 0; k < m; ++k) { h_params.push_back(p0[k]); h_params.push_back(p1[k]); }
+    note_run(1, E, m);
     E += m;
     return LPMP_OK;
   }
@@ -459,6 +494,7 @@ struct Solver : ISolver {
     else if (k == "wavefront_lean") tune.lean = value;
     else if (k == "wavefront_cluster") tune.cluster = value;
     else if (k == "level_group") tune.level_group = value;
+    else if (k == "graph_ctas_per_sm") graph.ctas_per_sm = value;
     else if (k == "wavefront_rows") tune.rows = value;
     else if (k == "wavefront_split") tune.split = value;
     else if (k == "wavefront_fused_bound") tune.fused_bound = value;
@@ -477,6 +513,8 @@ struct Solver : ISolver {
     N = (uint64_t)H * W;
     E = (uint64_t)H * (W - 1) + (uint64_t)(H - 1) * W;
     slots = 2 * N;
+    note_run(0, 0, N);
+    note_run(1, 0, E);
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(rec.alloc(N * REC()));
     CUDA_TRY(cudaMemsetAsync(rec.p, 0, rec.bytes(), stream));
@@ -780,33 +818,11 @@ struct Solver : ISolver {
     if (pw == -1) pw = LPMP_PAIRWISE_POTTS;
     if (!is_grid) {
       slots = E;
-      std::vector<Real> tmp(h_theta.size());
-      for (size_t k = 0; k < tmp.size(); ++k) tmp[k] = (Real)h_theta[k];
-      CUDA_TRY(theta.alloc(N * L));
-      CUDA_TRY(cudaMemcpyAsync(theta.p, tmp.data(), theta.bytes(), cudaMemcpyHostToDevice, stream));
-      CUDA_TRY(cudaStreamSynchronize(stream));
-      CUDA_TRY(a.alloc(std::max<uint64_t>(1, slots * L)));
-      CUDA_TRY(b.alloc(std::max<uint64_t>(1, slots * L)));
-      CUDA_TRY(cudaMemsetAsync(a.p, 0, a.bytes(), stream));
-      CUDA_TRY(cudaMemsetAsync(b.p, 0, b.bytes(), stream));
-      std::vector<Real> ptmp(h_params.size());
-      for (size_t k = 0; k < ptmp.size(); ++k) ptmp[k] = (Real)h_params[k];
-      CUDA_TRY(params.alloc(std::max<uint64_t>(1, ptmp.size())));
-      if (!ptmp.empty()) CUDA_TRY(cudaMemcpyAsync(params.p, ptmp.data(), ptmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
-      std::vector<uint32_t> e32(E);
-      CUDA_TRY(d_ei.alloc(std::max<uint64_t>(1, E)));
-      CUDA_TRY(d_ej.alloc(std::max<uint64_t>(1, E)));
-      for (uint64_t e = 0; e < E; ++e) e32[e] = (uint32_t)h_ei[e];
-      if (E) CUDA_TRY(cudaMemcpyAsync(d_ei.p, e32.data(), E * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-      CUDA_TRY(cudaStreamSynchronize(stream));
-      for (uint64_t e = 0; e < E; ++e) e32[e] = (uint32_t)h_ej[e];
-      if (E) CUDA_TRY(cudaMemcpyAsync(d_ej.p, e32.data(), E * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-      CUDA_TRY(cudaStreamSynchronize(stream));
       if (schedule == LPMP_SCHEDULE_WAVEFRONT) { err = "wavefront schedule needs a grid"; return LPMP_ERR_UNSUPPORTED; }
       schedule = LPMP_SCHEDULE_LEVELS;
-      std::vector<uint64_t> slot(E);
-      std::iota(slot.begin(), slot.end(), uint64_t(0));
-      if (int r = build_levels(h_ei, h_ej, slot)) return r;
+      if (int r = graph.build(N, L, h_counts, h_theta, h_ei, h_ej, h_params, pw, h_rank, edge_order == LPMP_EDGE_ORDER_LIFO, stream, err)) return r;
+      if (partial.n < graph.partial_slots()) CUDA_TRY(partial.alloc(graph.partial_slots()));
+      levels_built = true;
       h_theta.clear(); h_theta.shrink_to_fit(); h_params.clear(); h_params.shrink_to_fit();
     } else {
       const bool dense = pw == LPMP_PAIRWISE_DENSE;
@@ -872,6 +888,15 @@ struct Solver : ISolver {
     fused_lb_valid = false;
     // dense-table grids: the row-dataflow kernel covers the anisotropic mode; the uniform modes of the rounding
     // iterations (include/visitors/standard_visitor.hxx:44) run on the level schedule, built on first use
+    if (!is_grid) {
+      const int n = graph.pass(forward, primal, repam, labels.p, tune.level_group, num_sms, stream, err);
+      if (n < 0) return LPMP_ERR_UNSUPPORTED;
+      launches += (uint64_t)n;
+      CUDA_TRY(cudaGetLastError());
+      updates += (repam == LPMP_REPAM_ANISOTROPIC ? 2 : 4) * E;
+      if (primal) labels_valid = true;
+      return LPMP_OK;
+    }
     const bool dense_wf = schedule == LPMP_SCHEDULE_WAVEFRONT && pw == LPMP_PAIRWISE_DENSE;
     if (dense_wf && repam != LPMP_REPAM_ANISOTROPIC && !levels_built) {
       if (striped) { err = "stripes support the anisotropic reparametrization only"; return LPMP_ERR_UNSUPPORTED; }
@@ -1022,6 +1047,14 @@ struct Solver : ISolver {
 
   int bound_launch(const Real* below_b, double add, double* out, bool to_device = false) {
     CUDA_TRY(cudaSetDevice(device));
+    if (!is_grid) {
+      int used = 0;
+      const int n = graph.bound(partial.p, &used, tune.level_group, num_sms, stream, err);
+      if (n < 0) return LPMP_ERR_UNSUPPORTED;
+      launches += (uint64_t)n;
+      CUDA_TRY(cudaGetLastError());
+      return reduce_to(used, add, out, to_device);
+    }
     const int G = group_size_for(L);
     int threads = 256;
     const size_t per_group = 2 * (size_t)L * sizeof(Real);
@@ -1048,13 +1081,8 @@ struct Solver : ISolver {
       ++launches;
       return reduce_to(used, add, out, to_device);
     }
-    if (is_grid) {
-      GridTopo<Real> topo{gridH, gridW, slots, below_b};
-      lower_bound_kernel<Real, GridTopo<Real>><<<ctas, threads, (size_t)groups * per_group, stream>>>(bound_args(topo), G);
-    } else {
-      GraphTopo topo{d_ei.p, d_ej.p, slots};
-      lower_bound_kernel<Real, GraphTopo><<<ctas, threads, (size_t)groups * per_group, stream>>>(bound_args(topo), G);
-    }
+    GridTopo<Real> topo{gridH, gridW, slots, below_b};
+    lower_bound_kernel<Real, GridTopo<Real>><<<ctas, threads, (size_t)groups * per_group, stream>>>(bound_args(topo), G);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     return reduce_to(ctas, add, out, to_device);
@@ -1076,15 +1104,16 @@ struct Solver : ISolver {
 
   int primal_launch(const Real* below_b, const uint32_t* below_labels, double add, double* out, bool to_device) {
     CUDA_TRY(cudaSetDevice(device));
+    if (!is_grid) {
+      int used = 0;
+      launches += (uint64_t)graph.primal(labels.p, partial.p, &used, stream);
+      CUDA_TRY(cudaGetLastError());
+      return reduce_to(used, add, out, to_device);
+    }
     const uint64_t total = N + slots;
     const int ctas = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)kBoundCtas);
-    if (is_grid) {
-      GridTopo<Real> topo{gridH, gridW, slots, below_b, below_labels};
-      primal_cost_kernel<Real, GridTopo<Real>><<<ctas, 256, 0, stream>>>(bound_args(topo), labels.p);
-    } else {
-      GraphTopo topo{d_ei.p, d_ej.p, slots};
-      primal_cost_kernel<Real, GraphTopo><<<ctas, 256, 0, stream>>>(bound_args(topo), labels.p);
-    }
+    GridTopo<Real> topo{gridH, gridW, slots, below_b, below_labels};
+    primal_cost_kernel<Real, GridTopo<Real>><<<ctas, 256, 0, stream>>>(bound_args(topo), labels.p);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     return reduce_to(ctas, add, out, to_device);
@@ -1141,7 +1170,8 @@ struct Solver : ISolver {
     if (!labels_valid) { *out = 0; return LPMP_OK; }
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaMemsetAsync(bad_count.p, 0, sizeof(unsigned int), stream));
-    count_bad_labels_kernel<<<grid_for(N, 256), 256, 0, stream>>>(labels.p, N, L, bad_count.p);
+    if (mixed()) count_bad_labels_var_kernel<<<grid_for(N, 256), 256, 0, stream>>>(labels.p, graph.lab_i.p, N, bad_count.p);
+    else count_bad_labels_kernel<<<grid_for(N, 256), 256, 0, stream>>>(labels.p, N, L, bad_count.p);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     unsigned int bad = 0;
@@ -1178,8 +1208,9 @@ struct Solver : ISolver {
         for (uint32_t x = 0; x < L; ++x) th[i * L + x] = (double)tmp[i * REC() + x];
       return LPMP_OK;
     }
-    if (int r = download(tmp, theta.p, N * L)) return r;
-    for (uint64_t k = 0; k < N * L; ++k) th[k] = (double)tmp[k];
+    if (int r = download(tmp, graph.vec.p, graph.vec.n)) return r;
+    for (uint64_t i = 0, k = 0; i < N; ++i)
+      for (uint32_t x = 0; x < Ln(i); ++x) th[k++] = (double)tmp[graph.theta_off[i] + x];
     return LPMP_OK;
   }
   // position of edge e's two vectors inside the host copy of the state (insertion order of the edges)
@@ -1206,11 +1237,10 @@ struct Solver : ISolver {
         }
       return LPMP_OK;
     }
-    for (int which = 0; which < 2; ++which) {
-      double* dst = which == 0 ? pa : pb;
-      if (!dst) continue;
-      if (int r = download(tmp, which == 0 ? a.p : b.p, slots * L)) return r;
-      for (uint64_t k = 0; k < E * L; ++k) dst[k] = (double)tmp[k];
+    if (int r = download(tmp, graph.vec.p, graph.vec.n)) return r;
+    for (uint64_t e = 0, ka = 0, kb = 0; e < E; ++e) {
+      for (uint32_t x = 0; x < Ln(h_ei[e]); ++x, ++ka) if (pa) pa[ka] = (double)tmp[graph.a_off[e] + x];
+      for (uint32_t x = 0; x < Ln(h_ej[e]); ++x, ++kb) if (pb) pb[kb] = (double)tmp[graph.b_off[e] + x];
     }
     return LPMP_OK;
   }
@@ -1231,34 +1261,80 @@ struct Solver : ISolver {
       CUDA_TRY(cudaStreamSynchronize(stream));
       return LPMP_OK;
     }
-    for (int which = 0; which < 2; ++which) {
-      const double* src = which == 0 ? pa : pb;
-      if (!src) continue;
-      std::vector<Real> tmp(slots * L, Real(0));
-      for (uint64_t k = 0; k < E * L; ++k) tmp[k] = (Real)src[k];
-      CUDA_TRY(cudaMemcpyAsync(which == 0 ? a.p : b.p, tmp.data(), tmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
-      CUDA_TRY(cudaStreamSynchronize(stream));
+    std::vector<Real> tmp;
+    if (int r = download(tmp, graph.vec.p, graph.vec.n)) return r;
+    for (uint64_t e = 0, ka = 0, kb = 0; e < E; ++e) {
+      for (uint32_t x = 0; x < Ln(h_ei[e]); ++x, ++ka) if (pa) tmp[graph.a_off[e] + x] = (Real)pa[ka];
+      for (uint32_t x = 0; x < Ln(h_ej[e]); ++x, ++kb) if (pb) tmp[graph.b_off[e] + x] = (Real)pb[kb];
     }
+    CUDA_TRY(cudaMemcpyAsync(graph.vec.p, tmp.data(), tmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
     return LPMP_OK;
   }
   int set_unaries(const double* th) override {
     if (int r = need_final()) return r;
     fused_lb_valid = false;
     if (is_grid) return set_unaries_from(th);
-    std::vector<Real> tmp(N * L);
-    for (uint64_t k = 0; k < N * L; ++k) tmp[k] = (Real)th[k];
-    CUDA_TRY(cudaMemcpyAsync(theta.p, tmp.data(), tmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
+    std::vector<Real> tmp;
+    if (int r = download(tmp, graph.vec.p, graph.vec.n)) return r;
+    for (uint64_t i = 0, k = 0; i < N; ++i)
+      for (uint32_t x = 0; x < Ln(i); ++x) tmp[graph.theta_off[i] + x] = (Real)th[k++];
+    CUDA_TRY(cudaMemcpyAsync(graph.vec.p, tmp.data(), tmp.size() * sizeof(Real), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
+  // dual variables in the reference's archive layout (include/factor_archive.hxx:34-48, include/serialization.hxx:226-425): per factor
+  // in insertion order its serialize_dual() members as doubles -- unary: theta; pairwise: msg1 (a), msg2 (b)
+  uint64_t packed_len(int which) const {   // 0 theta, 1 a, 2 b
+    if (!mixed()) return (which == 0 ? N : E) * (uint64_t)L;
+    uint64_t n = 0;
+    if (which == 0) for (uint64_t i = 0; i < N; ++i) n += h_counts[i];
+    else for (uint64_t e = 0; e < E; ++e) n += h_counts[which == 1 ? h_ei[e] : h_ej[e]];
+    return n;
+  }
+  int dual_size(uint64_t* bytes) override {
+    if (int r = need_final()) return r;
+    *bytes = sizeof(double) * (packed_len(0) + packed_len(1) + packed_len(2));
+    return LPMP_OK;
+  }
+  int dual_archive(void* archive, uint64_t bytes, bool save) override {
+    uint64_t want = 0;
+    if (int r = dual_size(&want)) return r;
+    if (!archive || bytes != want) { err = "archive size does not match this LP"; return LPMP_ERR_INVALID; }
+    std::vector<double> th(packed_len(0)), va(packed_len(1)), vb(packed_len(2));
+    if (save) {
+      if (int r = get_unaries(th.data())) return r;
+      if (int r = get_messages(va.data(), vb.data())) return r;
+    }
+    // packed positions of the factors (grids: edges in insertion order, the order get_messages uses)
+    std::vector<uint64_t> to(N + 1, 0), ao(E + 1, 0), bo(E + 1, 0);
+    for (uint64_t i = 0; i < N; ++i) to[i + 1] = to[i] + Ln(i);
+    for (uint64_t e = 0; e < E; ++e) {
+      ao[e + 1] = ao[e] + (mixed() ? Ln(h_ei[e]) : L);
+      bo[e + 1] = bo[e] + (mixed() ? Ln(h_ej[e]) : L);
+    }
+    double* ar = static_cast<double*>(archive);
+    auto move = [&](double* state, uint64_t n) { if (save) std::copy(state, state + n, ar); else std::copy(ar, ar + n, state); ar += n; };
+    for (const auto& r : runs)
+      for (uint64_t k = r[1]; k < r[1] + r[2]; ++k) {
+        if (r[0] == 0) move(th.data() + to[k], to[k + 1] - to[k]);
+        else { move(va.data() + ao[k], ao[k + 1] - ao[k]); move(vb.data() + bo[k], bo[k + 1] - bo[k]); }
+      }
+    if (!save) {
+      if (int r = set_unaries(th.data())) return r;
+      if (int r = set_messages(va.data(), vb.data())) return r;
+    }
     return LPMP_OK;
   }
   int stats(lpmp_stats* out) override {
     std::memset(out, 0, sizeof(*out));
     out->num_nodes = N; out->num_edges = E; out->num_labels = L;
     if (schedule == LPMP_SCHEDULE_WAVEFRONT) out->num_levels = (uint64_t)gridW + gridH - 1;
+    else if (!is_grid) out->num_levels = graph.level_off.empty() ? 0 : graph.level_off.size() - 1;
     else out->num_levels = level_off.empty() ? 0 : level_off.size() - 1;
     out->kernel_launches = launches;
     out->message_updates = updates;
-    out->device_bytes = theta.bytes() + a.bytes() + b.bytes() + params.bytes() + rec.bytes() + par.bytes() + tab.bytes() + labels.bytes() + inc_off.bytes() +
+    out->device_bytes = graph.device_bytes() + theta.bytes() + a.bytes() + b.bytes() + params.bytes() + rec.bytes() + par.bytes() + tab.bytes() + labels.bytes() + inc_off.bytes() +
                         inc_edge.bytes() + inc_flags.bytes() + level_nodes.bytes() + d_ei.bytes() + d_ej.bytes() + control.bytes() + handoff.bytes() +
                         in_top.bytes() + in_bot.bytes();
     out->algorithmic_bytes_per_pass = (double)sizeof(Real) * (2.0 * (double)N * L + (double)E * ((double)P() + 5.0 * L));
@@ -1364,6 +1440,10 @@ int lpmp_destroy(lpmp_solver* h) { delete reinterpret_cast<Handle*>(h); return L
 const char* lpmp_last_error(const lpmp_solver* h) { return h ? S(h)->err.c_str() : "null handle"; }
 
 int lpmp_add_unaries(lpmp_solver* h, uint64_t n, uint32_t L, const double* theta) { return S(h)->add_unaries(n, L, theta); }
+int lpmp_add_unaries_var(lpmp_solver* h, uint64_t n, const uint32_t* L, const double* theta) { return S(h)->add_unaries_var(n, L, theta); }
+int lpmp_dual_size(lpmp_solver* h, uint64_t* bytes) { return S(h)->dual_size(bytes); }
+int lpmp_save_dual(lpmp_solver* h, void* archive, uint64_t bytes) { return S(h)->dual_archive(archive, bytes, true); }
+int lpmp_load_dual(lpmp_solver* h, const void* archive, uint64_t bytes) { return S(h)->dual_archive(const_cast<void*>(archive), bytes, false); }
 int lpmp_add_pairwise_dense(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* t) { return S(h)->add_pairwise(LPMP_PAIRWISE_DENSE, m, i, j, t, nullptr); }
 int lpmp_add_pairwise_potts(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* l) { return S(h)->add_pairwise(LPMP_PAIRWISE_POTTS, m, i, j, l, nullptr); }
 int lpmp_add_pairwise_trunclin(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* s, const double* t) { return S(h)->add_pairwise(LPMP_PAIRWISE_TRUNCLIN, m, i, j, s, t); }

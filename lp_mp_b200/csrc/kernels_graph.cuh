@@ -1,0 +1,334 @@
+// General graphs (level / graph-colouring schedule): node-record storage and its kernels.
+//
+// Replaces, for the SRMP simplex configuration on arbitrary graphs:
+//   LP::ComputePass(it...) + FactorContainer::UpdateFactor / UpdateFactorPrimal
+//        (/root/reference/include/LP_MP.h:981-1005,1592-1602; include/factors_messages.hxx:2256-2261,2332-2373)
+//   LP::LowerBound, LP::EvaluatePrimal (include/LP_MP.h:1507-1536)
+//
+// Layout (graph_engine.cuh builds it).  Nodes are renumbered in SCHEDULE order k (level by level; inside a level the order is
+// free), so a level / colour class is one contiguous range of records:
+//   vec : per node k one record  [theta_k | own_0 | own_1 | ...]   -- its unary and ITS side of every incident edge (a_e if it
+//         is the edge's first variable, b_e otherwise), slots in the reference's per-node message order (LIFO / FIFO);
+//   tab : per incidence q the pairwise parameters in RECEIVER orientation (dense: tab[x_own][y_other], i.e. each table is stored
+//         once per endpoint; Potts / truncated linear: the 1 / 2 parameters), in the same order as the slots;
+//   per incidence: oth_off[q] = where the neighbour's side of that edge lives in vec, flags[q] (bit 0 side, bit 1 "other endpoint
+//         has the higher rank"), oth_node[q] (the neighbour, for the primal cost).
+// A node update therefore streams one record (read + write) and the tables of the edges it receives on, and gathers one vector per
+// received edge -- the only access of a pass that is not a contiguous stream.
+#pragma once
+#include "device_common.cuh"
+
+namespace lpmp {
+
+template <typename Real>
+struct GraphArgs {
+  Real* vec;
+  const Real* tab;
+  const uint32_t* inc_off;    // [n + 1] first incidence of node k
+  const uint32_t* oth_off;    // [Q]
+  const uint8_t* flags;       // [Q]
+  const uint32_t* oth_node;   // [Q] original index of the neighbour
+  const uint32_t* node_of;    // [n] original index of node k
+  const uint4* desc;          // [n][2] fast kernel: {first incidence, original index, degree, -} {oth_off | flags of slots 0..3}: everything the
+                              // loads of a node depend on in ONE 32-byte read indexed by k (two dependent round trips per node instead of three)
+  // mixed label counts (null for one label count per LP)
+  const uint32_t* voff;       // [n + 1] record offsets
+  const uint64_t* toff;       // [Q + 1] parameter offsets
+  const uint32_t* lab_k;      // [n] label count of node k
+  const uint32_t* lab_oth;    // [Q] label count of the neighbour
+  uint32_t* labels;           // [N] by original index
+  double* partial;            // bound / primal: one double per CTA
+  uint32_t first, count;      // nodes [first, first + count) (schedule order)
+  uint32_t L, P;              // label count (the largest one when mixed), parameters per incidence (uniform L)
+  int pw, repam, forward, primal;
+};
+
+// ---- fast path: one label count L = LT (power of two <= 32), dense tables, at most DMAX incident edges ---------------------------
+// LT lanes per node, lane x owns label x of every vector of the record and row x of every table: the min-plus of a receive is LT
+// shuffles, adds and mins, no shared memory.  All loads of a node are issued before the first use.
+// MODE 0: node update; MODE 1: lower-bound terms (read only).
+template <typename Real, int LT, int DMAX, int MODE>
+__global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_node_kernel(const GraphArgs<Real> A) {
+  constexpr int NPC = 256 / LT;   // nodes per CTA
+  const int x = threadIdx.x % LT;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned gmask = (LT == 32 ? 0xffffffffu : ((1u << LT) - 1u)) << (lane & ~(unsigned)(LT - 1));
+  const bool aniso = A.repam == LPMP_REPAM_ANISOTROPIC;
+  const Real INF = RealTraits<Real>::inf();
+  double acc = 0.0;
+  static_assert(DMAX == 4, "the node descriptor holds four slots");
+  // a group serves several nodes in turn; the descriptor of the next one is fetched while this one is processed, so the dependent
+  // chain per node is one round trip (descriptor -> record / tables / neighbour vectors)
+  uint32_t kk = blockIdx.x * NPC + threadIdx.x / LT;
+  uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+  if (kk < A.count) { n0 = __ldg(A.desc + 2 * (uint64_t)(A.first + kk)); n1 = __ldg(A.desc + 2 * (uint64_t)(A.first + kk) + 1); }
+  for (; kk < A.count; kk += gridDim.x * NPC) {
+    const uint32_t k = A.first + kk;
+    const uint4 d0 = n0, d1 = n1;
+    if (kk + gridDim.x * NPC < A.count) {
+      n0 = __ldg(A.desc + 2 * (uint64_t)(k + gridDim.x * NPC));
+      n1 = __ldg(A.desc + 2 * (uint64_t)(k + gridDim.x * NPC) + 1);
+    }
+    const uint32_t q0 = d0.x, deg = d0.z;
+    const uint32_t meta[DMAX] = {d1.x, d1.y, d1.z, d1.w};
+    Real* rec = A.vec + ((uint64_t)k + q0) * LT;
+    Real th = rec[x];
+    Real own[DMAX], oth[DMAX], row[DMAX][LT];   // oth: label x of the neighbour's vector (the group shuffles it around)
+    uint32_t fl[DMAX];
+    bool recv[DMAX];
+    uint32_t n_in = 0, n_out = 0;
+#pragma unroll
+    for (int s = 0; s < DMAX; ++s) {
+      fl[s] = meta[s] & 3u;
+      const bool later = (fl[s] >> 1) & 1u;
+      if (s < (int)deg) { if (later) ++n_out; else ++n_in; }
+      const bool earlier = A.forward ? !later : later;
+      // MODE 1: every edge once, at its first variable
+      recv[s] = s < (int)deg && (MODE == 1 ? (fl[s] & 1u) == 0u : (!aniso || earlier));
+    }
+#pragma unroll
+    for (int s = 0; s < DMAX; ++s) {
+      own[s] = s < (int)deg ? rec[(1 + s) * LT + x] : Real(0);
+      oth[s] = Real(0);
+      if (recv[s]) {
+        oth[s] = A.vec[(meta[s] & ~3u) + x];
+        const Real* t = A.tab + ((uint64_t)(q0 + s) * LT + x) * LT;
+        if constexpr (sizeof(Real) == 4 && LT % 4 == 0) {
+#pragma unroll
+          for (int y = 0; y < LT; y += 4) {
+            const float4 tv = __ldg(reinterpret_cast<const float4*>(t + y));
+            row[s][y] = tv.x; row[s][y + 1] = tv.y; row[s][y + 2] = tv.z; row[s][y + 3] = tv.w;
+          }
+        } else {
+#pragma unroll
+          for (int y = 0; y < LT; y += 2) {
+            const double2 tv = __ldg(reinterpret_cast<const double2*>(t + y));
+            row[s][y] = tv.x; row[s][y + 1] = tv.y;
+          }
+        }
+      }
+    }
+    if constexpr (MODE == 1) {
+      // LP::LowerBound (include/LP_MP.h:1507-1518): min theta_i + sum over the edges whose first variable this node is of
+      // min_x [a(x) + min_y (c(x,y) + b(y))]
+      Real m = th;
+      for (int o = LT >> 1; o > 0; o >>= 1) m = rmin(m, __shfl_xor_sync(gmask, m, o));
+      double term = (double)m;
+#pragma unroll
+      for (int s = 0; s < DMAX; ++s) {
+        Real h = INF;
+        if (recv[s]) {
+#pragma unroll
+          for (int y = 0; y < LT; ++y) h = rmin(h, Real(row[s][y] + __shfl_sync(gmask, oth[s], y, LT)));
+          h = Real(h + own[s]);
+        }
+        for (int o = LT >> 1; o > 0; o >>= 1) h = rmin(h, __shfl_xor_sync(gmask, h, o));
+        if (recv[s]) term += (double)h;
+      }
+      if (x == 0) acc += term;
+    } else {
+      // ReceiveMessages (include/factors_messages.hxx:2440-2471), slots in the reference's message order
+#pragma unroll
+      for (int s = 0; s < DMAX; ++s) {
+        if (recv[s]) {
+          Real h = INF;
+#pragma unroll
+          for (int y = 0; y < LT; ++y) h = rmin(h, Real(row[s][y] + __shfl_sync(gmask, oth[s], y, LT)));
+          const Real m = h + own[s];
+          th = th + m;          // RepamLeft(+)   :498-500
+          own[s] = own[s] - m;  // RepamRight(-)
+        }
+      }
+      if (A.primal) {   // MaximizePotentialAndComputePrimal: first minimum
+        Real v = th;
+        uint32_t idx = (uint32_t)x;
+        for (int o = LT >> 1; o > 0; o >>= 1) {
+          const Real ov = __shfl_xor_sync(gmask, v, o);
+          const uint32_t oi = __shfl_xor_sync(gmask, idx, o);
+          if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        if (x == 0) A.labels[d0.y] = idx;
+      }
+      if (deg > 0) {
+        double wd;
+        if (aniso) wd = 1.0 / (double)(n_in > n_out ? n_in : n_out);                     // include/LP_MP.h:1397
+        else if (A.repam == LPMP_REPAM_UNIFORM) wd = 1.0 / (double)(n_in + n_out);       // :1437, leave_weight 0
+        else wd = 1.0 / (double)(n_in + n_out + 1);                                      // :1437, leave_weight 1
+        const Real w = (Real)wd;
+        const Real d = w * th;   // tmp_factor snapshot (:2801-2805): every send uses the theta left by the receives
+        // CallSendMessages (:2698-2744)
+#pragma unroll
+        for (int s = 0; s < DMAX; ++s) {
+          const bool later = (fl[s] >> 1) & 1u;
+          const bool is_later = A.forward ? later : !later;
+          if (s < (int)deg && (!aniso || is_later)) {
+            own[s] = own[s] + d;  // RepamRight(+) first, :501-503
+            th = th - d;          // RepamLeft(-)
+          }
+        }
+      }
+      rec[x] = th;
+#pragma unroll
+      for (int s = 0; s < DMAX; ++s) if (s < (int)deg) rec[(1 + s) * LT + x] = own[s];
+    }
+  }
+  if constexpr (MODE == 1) {
+    const double sum = block_sum(acc);
+    if (threadIdx.x == 0) A.partial[blockIdx.x] = sum;
+  }
+}
+
+// h(x) = min_y [ c(x,y) + other(y) ] with the parameters in receiver orientation; Lk labels on this side, Lo on the other.
+// One label count: the O(L) forms of group_min_plus (Potts two-min, truncated-linear window); mixed counts: all pairs.
+template <typename Real>
+__device__ __forceinline__ void graph_min_plus(int pw, const Real* __restrict__ p, uint32_t Lk, uint32_t Lo, bool mixed, const Real* oth, Real* hs,
+                                               int G, int gl, unsigned mask) {
+  if (!mixed) { group_min_plus<Real>(pw, p, Lk, 0u, oth, hs, G, gl, mask); return; }
+  const Real INF = RealTraits<Real>::inf();
+  for (uint32_t x = gl; x < Lk; x += G) {
+    Real m = INF;
+    for (uint32_t y = 0; y < Lo; ++y) {
+      Real c;
+      if (pw == LPMP_PAIRWISE_DENSE) c = p[(uint64_t)x * Lo + y];
+      else if (pw == LPMP_PAIRWISE_POTTS) c = x == y ? Real(0) : p[0];
+      else { const uint32_t d = x > y ? x - y : y - x; c = rmin(Real(p[0] * Real(d)), p[1]); }
+      m = rmin(m, Real(c + oth[y]));
+    }
+    hs[x] = m;
+  }
+}
+
+// ---- generic path: any label count (also mixed), any pairwise family, any degree -----------------------------------------------
+// One sub-warp group of G lanes per node, vectors staged in shared memory (per group: th[L], oth[L], hs[L]).
+// MODE 0: node update; MODE 1: lower-bound terms.
+template <typename Real, int MODE>
+__global__ void __launch_bounds__(256) graph_node_generic_kernel(const GraphArgs<Real> A, int G) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Real* smem = reinterpret_cast<Real*>(smem_raw);
+  const int groups_per_cta = blockDim.x / G;
+  const int g = threadIdx.x / G, gl = threadIdx.x % G;
+  const unsigned mask = group_mask(G);
+  Real* th = smem + (size_t)g * 3 * A.L;
+  Real* oth = th + A.L;
+  Real* hs = oth + A.L;
+  const bool aniso = A.repam == LPMP_REPAM_ANISOTROPIC;
+  const bool mixed = A.voff != nullptr;
+  const Real INF = RealTraits<Real>::inf();
+  double acc = 0.0;
+  for (uint32_t kk = blockIdx.x * groups_per_cta + g; kk < A.count; kk += gridDim.x * groups_per_cta) {
+    const uint32_t k = A.first + kk;
+    const uint32_t q0 = A.inc_off[k], q1 = A.inc_off[k + 1];
+    const uint32_t Lk = mixed ? A.lab_k[k] : A.L;
+    Real* rec = A.vec + (mixed ? (uint64_t)A.voff[k] : ((uint64_t)k + q0) * A.L);
+    __syncwarp(mask);
+    for (uint32_t x = gl; x < Lk; x += G) th[x] = rec[x];
+    uint32_t n_in = 0, n_out = 0;
+    double term = 0.0;
+    for (uint32_t q = q0; q < q1; ++q) {
+      const uint32_t fl = A.flags[q];
+      const bool later = (fl >> 1) & 1u;
+      if (later) ++n_out; else ++n_in;
+      const bool earlier = A.forward ? !later : later;
+      if (MODE == 1 ? (fl & 1u) != 0u : (aniso && !earlier)) continue;
+      Real* own = rec + (uint64_t)(1 + q - q0) * Lk;
+      const Real* other = A.vec + A.oth_off[q];
+      const uint32_t Lo = mixed ? A.lab_oth[q] : A.L;
+      const Real* par = A.tab + (mixed ? A.toff[q] : (uint64_t)q * A.P);
+      __syncwarp(mask);
+      for (uint32_t y = gl; y < Lo; y += G) oth[y] = other[y];
+      __syncwarp(mask);
+      graph_min_plus<Real>(A.pw, par, Lk, Lo, mixed, oth, hs, G, gl, mask);
+      if (MODE == 1) {
+        Real m = INF;
+        for (uint32_t x = gl; x < Lk; x += G) m = rmin(m, Real(hs[x] + own[x]));
+        m = group_min(m, G, mask);
+        term += (double)m;
+      } else {
+        for (uint32_t x = gl; x < Lk; x += G) {
+          const Real ow = own[x];
+          const Real m = hs[x] + ow;
+          th[x] = th[x] + m;   // RepamLeft(+)   include/factors_messages.hxx:498-500
+          own[x] = ow - m;     // RepamRight(-)
+        }
+      }
+    }
+    if (MODE == 1) {
+      Real m = INF;
+      for (uint32_t x = gl; x < Lk; x += G) m = rmin(m, th[x]);
+      m = group_min(m, G, mask);
+      if (gl == 0) acc += (double)m + term;
+      continue;
+    }
+    if (A.primal) {  // MaximizePotentialAndComputePrimal: first minimum
+      Real v = INF;
+      uint32_t idx = 0xffffffffu;
+      for (uint32_t x = gl; x < Lk; x += G) if (th[x] < v) { v = th[x]; idx = x; }
+      group_argmin(v, idx, G, mask);
+      if (gl == 0) A.labels[A.node_of[k]] = idx;
+    }
+    if (q1 > q0) {
+      const uint32_t deg = n_in + n_out;
+      double wd;
+      if (aniso) wd = 1.0 / (double)(n_in > n_out ? n_in : n_out);          // include/LP_MP.h:1397
+      else if (A.repam == LPMP_REPAM_UNIFORM) wd = 1.0 / (double)deg;         // :1437, leave_weight 0
+      else wd = 1.0 / (double)(deg + 1);                                      // :1437, leave_weight 1
+      const Real w = (Real)wd;
+      for (uint32_t x = gl; x < Lk; x += G) hs[x] = th[x];  // tmp_factor snapshot, :2801-2805 (each lane reads back its own labels)
+      // CallSendMessages (:2698-2744)
+      for (uint32_t q = q0; q < q1; ++q) {
+        const bool later = (A.flags[q] >> 1) & 1u;
+        const bool is_later = A.forward ? later : !later;
+        if (aniso && !is_later) continue;
+        Real* own = rec + (uint64_t)(1 + q - q0) * Lk;
+        for (uint32_t x = gl; x < Lk; x += G) {
+          const Real d = w * hs[x];
+          own[x] = own[x] + d;  // RepamRight(+) first, :501-503
+          th[x] = th[x] - d;    // RepamLeft(-)
+        }
+      }
+    }
+    for (uint32_t x = gl; x < Lk; x += G) rec[x] = th[x];
+  }
+  if (MODE == 1) {
+    const double sum = block_sum(acc);
+    if (threadIdx.x == 0) A.partial[blockIdx.x] = sum;
+  }
+}
+
+// LP::EvaluatePrimal (include/LP_MP.h:1520-1536): sum_i theta_i(x_i) + sum_e [(c_e(x_i,x_j) + a_e(x_i)) + b_e(x_j)]; one thread
+// per node, every edge at its first variable
+template <typename Real>
+__global__ void __launch_bounds__(256) graph_primal_kernel(const GraphArgs<Real> A) {
+  const bool mixed = A.voff != nullptr;
+  double acc = 0.0;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < A.count; k += gridDim.x * blockDim.x) {
+    const uint32_t q0 = A.inc_off[k], q1 = A.inc_off[k + 1];
+    const uint32_t Lk = mixed ? A.lab_k[k] : A.L;
+    const Real* rec = A.vec + (mixed ? (uint64_t)A.voff[k] : ((uint64_t)k + q0) * A.L);
+    const uint32_t x = A.labels[A.node_of[k]];
+    acc += (double)rec[x];
+    for (uint32_t q = q0; q < q1; ++q) {
+      if (A.flags[q] & 1u) continue;
+      const uint32_t y = A.labels[A.oth_node[q]];
+      const uint32_t Lo = mixed ? A.lab_oth[q] : A.L;
+      const Real* p = A.tab + (mixed ? A.toff[q] : (uint64_t)q * A.P);
+      Real c;
+      if (A.pw == LPMP_PAIRWISE_DENSE) c = p[(uint64_t)x * Lo + y];
+      else if (A.pw == LPMP_PAIRWISE_POTTS) c = x == y ? Real(0) : p[0];
+      else { const uint32_t d = x > y ? x - y : y - x; c = rmin(Real(p[0] * Real(d)), p[1]); }
+      acc += (double)Real(Real(c + rec[(uint64_t)(1 + q - q0) * Lk + x]) + A.vec[A.oth_off[q] + y]);
+    }
+  }
+  const double s = block_sum(acc);
+  if (threadIdx.x == 0) A.partial[blockIdx.x] = s;
+}
+
+// CheckPrimalConsistency with one label count per variable: labels that are unset or out of range
+__global__ void count_bad_labels_var_kernel(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ counts, uint64_t n, unsigned int* count) {
+  unsigned int bad = 0;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) bad += labels[k] >= counts[k] ? 1u : 0u;
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, bad);
+}
+
+}  // namespace lpmp

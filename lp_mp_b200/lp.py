@@ -40,6 +40,8 @@ class LP:
         capi.check(capi.create(self.dtype, int(device), C.byref(h)))
         self.h = h
         self.N = self.E = self.L = 0
+        self.label_counts = None        # per-variable label counts of an LP with mixed counts (add_unaries_var), else None
+        self._edge_list = []            # (i, j) per edge, kept for the packed layouts of mixed-count LPs
         self._pending_unaries, self._pending_pairwise = [], []
         self.grid_shape = None
         self.finalized = False
@@ -60,26 +62,47 @@ class LP:
         self.N += n
         self.L = L
 
-    def _edges(self, i, j):
+    def add_unaries_var(self, costs):
+        """variables with their own label counts (test/graphical_model.cpp:74-96): `costs` is a list of 1-D arrays"""
+        costs = [np.asarray(c, dtype=np.float64).ravel() for c in costs]
+        counts = np.array([len(c) for c in costs], dtype=np.uint32)
+        packed = _f64(np.concatenate(costs)) if costs else np.zeros(0)
+        self._ck(self.api.add_unaries_var(self.h, len(costs), counts.ctypes.data_as(C.POINTER(C.c_uint32)), _pd(packed)))
+        if self.label_counts is None:
+            self.label_counts = [self.L] * self.N
+        self.label_counts += [int(c) for c in counts]
+        self.N += len(costs)
+        self.L = max(self.label_counts)
+
+    def _edges(self, i, j, record=False):
         i = np.ascontiguousarray(i, dtype=np.uint64)
         j = np.ascontiguousarray(j, dtype=np.uint64)
         assert i.shape == j.shape and i.ndim == 1
+        if record and self.label_counts is not None:
+            self._edge_list += list(zip(i.tolist(), j.tolist()))
         return i, j
 
     def add_pairwise_dense(self, i, j, tables):
-        i, j = self._edges(i, j)
-        tables = _f64(tables, (len(i), self.L, self.L))
+        """tables: [m][L][L]; with mixed label counts a list of L_i x L_j arrays (passed packed)"""
+        i, j = self._edges(i, j, record=True)
+        if self.label_counts is not None:
+            tabs = [np.asarray(t, dtype=np.float64) for t in tables]
+            for t, a, b in zip(tabs, i, j):
+                assert t.shape == (self.label_counts[int(a)], self.label_counts[int(b)])
+            tables = _f64(np.concatenate([t.ravel() for t in tabs]))
+        else:
+            tables = _f64(tables, (len(i), self.L, self.L))
         self._ck(self.api.add_pairwise_dense(self.h, len(i), _pu64(i), _pu64(j), _pd(tables)))
         self.E += len(i)
 
     def add_pairwise_potts(self, i, j, lam):
-        i, j = self._edges(i, j)
+        i, j = self._edges(i, j, record=True)
         lam = _f64(lam, (len(i),))
         self._ck(self.api.add_pairwise_potts(self.h, len(i), _pu64(i), _pu64(j), _pd(lam)))
         self.E += len(i)
 
     def add_pairwise_trunclin(self, i, j, slope, trunc):
-        i, j = self._edges(i, j)
+        i, j = self._edges(i, j, record=True)
         slope = _f64(np.broadcast_to(slope, (len(i),)))
         trunc = _f64(np.broadcast_to(trunc, (len(i),)))
         self._ck(self.api.add_pairwise_trunclin(self.h, len(i), _pu64(i), _pu64(j), _pd(slope), _pd(trunc)))
@@ -97,11 +120,14 @@ class LP:
 
     def _flush_pending(self):
         if self._pending_unaries:
-            self.add_unaries(np.stack(self._pending_unaries))
+            if len({len(c) for c in self._pending_unaries}) == 1 and self.label_counts is None:
+                self.add_unaries(np.stack(self._pending_unaries))
+            else:
+                self.add_unaries_var(self._pending_unaries)
             self._pending_unaries = []
         if self._pending_pairwise:
             i, j, t = zip(*self._pending_pairwise)
-            self.add_pairwise_dense(np.array(i), np.array(j), np.stack(t))
+            self.add_pairwise_dense(np.array(i), np.array(j), list(t) if self.label_counts is not None else np.stack(t))
             self._pending_pairwise = []
 
     def set_node_ranks(self, rank):
@@ -269,16 +295,50 @@ class LP:
         self._ck(self.api.get_labeling(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
         return out
 
+    def _unpack(self, packed, counts):
+        """packed per-variable / per-edge vectors of a mixed-count LP -> [n][L] padded with zeros (as checkers.RefLP reports them)"""
+        out = np.zeros((len(counts), self.L), dtype=np.float64)
+        k = 0
+        for r, c in enumerate(counts):
+            out[r, :c] = packed[k:k + c]
+            k += c
+        return out
+
     def unaries(self):
+        if self.label_counts is not None:
+            packed = np.zeros(sum(self.label_counts), dtype=np.float64)
+            self._ck(self.api.get_unaries(self.h, _pd(packed)))
+            return self._unpack(packed, self.label_counts)
         out = np.zeros((self.N, self.L), dtype=np.float64)
         self._ck(self.api.get_unaries(self.h, _pd(out)))
         return out
 
     def messages(self):
+        if self.label_counts is not None:
+            ca = [self.label_counts[i] for i, _ in self._edge_list]
+            cb = [self.label_counts[j] for _, j in self._edge_list]
+            pa, pb = np.zeros(sum(ca), dtype=np.float64), np.zeros(sum(cb), dtype=np.float64)
+            self._ck(self.api.get_messages(self.h, _pd(pa), _pd(pb)))
+            return self._unpack(pa, ca), self._unpack(pb, cb)
         a = np.zeros((self.E, self.L), dtype=np.float64)
         b = np.zeros((self.E, self.L), dtype=np.float64)
         self._ck(self.api.get_messages(self.h, _pd(a), _pd(b)))
         return a, b
+
+    # dual variables in the reference's archive layout (include/factor_archive.hxx:34-48): checkpoint / warm start
+    def dual_size(self) -> int:
+        out = C.c_uint64()
+        self._ck(self.api.dual_size(self.h, C.byref(out)))
+        return out.value
+
+    def save_dual(self) -> bytes:
+        buf = np.zeros(self.dual_size() // 8, dtype=np.float64)
+        self._ck(self.api.save_dual(self.h, buf.ctypes.data, buf.nbytes))
+        return buf.tobytes()
+
+    def load_dual(self, archive: bytes):
+        buf = np.frombuffer(archive, dtype=np.float64).copy()
+        self._ck(self.api.load_dual(self.h, buf.ctypes.data, buf.nbytes))
 
     def set_messages(self, a, b):
         a, b = _f64(a, (self.E, self.L)), _f64(b, (self.E, self.L))

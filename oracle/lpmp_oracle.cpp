@@ -22,6 +22,7 @@
 //   lower bound, primal cost                        include/LP_MP.h:1507-1536
 //   min-marginal arithmetic                         include/vector.hxx:289-443,850-859,889-944
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -65,13 +66,30 @@ struct Oracle : OracleBase {
   std::vector<uint32_t> n_in, n_out, labels;
   std::vector<Real> h_, t_;  // scratch
   uint64_t message_updates = 0;
+  // mixed label counts (add_unaries_var): every per-variable / per-edge array is packed; L = the largest count
+  bool ragged = false;
+  std::vector<uint32_t> Lv;
+  std::vector<uint64_t> toff, aoff, boff, poff;
+  // factors in insertion order as runs {kind (0 unary, 1 pairwise), first, count}: the order of the reference's f_ (include/LP_MP.h:214)
+  std::vector<std::array<uint64_t, 3>> runs;
+  void note_run(uint64_t kind, uint64_t first, uint64_t count) {
+    if (count == 0) return;
+    if (!runs.empty() && runs.back()[0] == kind && runs.back()[1] + runs.back()[2] == first) runs.back()[2] += count;
+    else runs.push_back({kind, first, count});
+  }
 
   uint32_t P() const { return pw == LPMP_PAIRWISE_DENSE ? L * L : (pw == LPMP_PAIRWISE_POTTS ? 1u : 2u); }
+  uint32_t Ln(uint64_t i) const { return ragged ? Lv[i] : L; }
+  uint64_t to(uint64_t i) const { return ragged ? toff[i] : i * L; }
+  uint64_t ao(uint64_t e) const { return ragged ? aoff[e] : e * L; }
+  uint64_t bo(uint64_t e) const { return ragged ? boff[e] : e * L; }
+  uint64_t po(uint64_t e) const { return ragged ? poff[e] : e * P(); }
+  uint64_t theta_len() const { return ragged ? toff[N] : N * L; }
 
   // c_e(x,y) of the materialised table (defines Potts / truncated linear: test/potts_factor.cpp:8-19)
   Real cost(uint64_t e, uint32_t x, uint32_t y) const {
-    const Real* p = &params[e * P()];
-    if (pw == LPMP_PAIRWISE_DENSE) return p[x * L + y];
+    const Real* p = &params[po(e)];
+    if (pw == LPMP_PAIRWISE_DENSE) return p[x * Ln(ej[e]) + y];
     if (pw == LPMP_PAIRWISE_POTTS) return x == y ? Real(0) : p[0];
     const uint32_t d = x > y ? x - y : y - x;
     return std::min(Real(p[0] * Real(d)), p[1]);
@@ -79,13 +97,14 @@ struct Oracle : OracleBase {
 
   // h(x) = min_y [ c_e(.,.) + other_side(y) ], x on `side`.  matrix::min1(v)/min2(v): include/vector.hxx:850-859,889-913
   void min_plus(uint64_t e, uint32_t side, Real* h) const {
-    const Real* other = side == 0 ? &b[e * L] : &a[e * L];
+    const Real* other = side == 0 ? &b[bo(e)] : &a[ao(e)];
     const Real INF = std::numeric_limits<Real>::infinity();
     const bool tl_fast_ok = pw != LPMP_PAIRWISE_TRUNCLIN || (params[2 * e] >= Real(0) && params[2 * e + 1] >= Real(0));
-    if (pw == LPMP_PAIRWISE_DENSE || force_dense || !tl_fast_ok) {
-      for (uint32_t x = 0; x < L; ++x) {
+    if (pw == LPMP_PAIRWISE_DENSE || force_dense || ragged || !tl_fast_ok) {
+      const uint32_t Lown = Ln(side == 0 ? ei[e] : ej[e]), Loth = Ln(side == 0 ? ej[e] : ei[e]);
+      for (uint32_t x = 0; x < Lown; ++x) {
         Real m = INF;
-        for (uint32_t y = 0; y < L; ++y) {
+        for (uint32_t y = 0; y < Loth; ++y) {
           const Real c = side == 0 ? cost(e, x, y) : cost(e, y, x);
           m = std::min(m, Real(c + other[y]));
         }
@@ -133,15 +152,16 @@ struct Oracle : OracleBase {
   void update_node(uint64_t i, bool forward, bool primal) {
     const uint64_t k0 = inc_off[i], k1 = inc_off[i + 1];
     if (k0 == k1 && !primal) return;
-    Real* th = &theta[i * L];
+    Real* th = &theta[to(i)];
     Real* h = h_.data();
+    const uint32_t L = Ln(i);   // (shadows the LP-wide count: everything below is per variable)
     const bool aniso = repam == LPMP_REPAM_ANISOTROPIC;
     for (uint64_t k = k0; k < k1; ++k) {  // ReceiveMessages, :2440-2471
       const Incidence& c = inc[k];
       const bool earlier = forward ? !c.later : c.later;
       if (aniso && !earlier) continue;
       min_plus(c.edge, c.side, h);
-      Real* own = c.side == 0 ? &a[c.edge * L] : &b[c.edge * L];
+      Real* own = c.side == 0 ? &a[ao(c.edge)] : &b[bo(c.edge)];
       for (uint32_t x = 0; x < L; ++x) {
         const Real m = h[x] + own[x];
         th[x] += m;   // RepamLeft(+)  :498-500
@@ -162,7 +182,7 @@ struct Oracle : OracleBase {
       const Incidence& c = inc[k];
       const bool later = forward ? c.later : !c.later;
       if (aniso && !later) continue;
-      Real* own = c.side == 0 ? &a[c.edge * L] : &b[c.edge * L];
+      Real* own = c.side == 0 ? &a[ao(c.edge)] : &b[bo(c.edge)];
       for (uint32_t x = 0; x < L; ++x) {
         const Real d = w * t[x];
         own[x] += d;  // RepamRight(+) first, :501-503
@@ -181,15 +201,15 @@ struct Oracle : OracleBase {
   double lower_bound() {  // LP::LowerBound, include/LP_MP.h:1507-1518: unaries first, then pairwise, in double
     double lb = constant;
     for (uint64_t i = 0; i < N; ++i) {
-      Real m = theta[i * L];
-      for (uint32_t x = 1; x < L; ++x) m = std::min(m, theta[i * L + x]);
+      Real m = theta[to(i)];
+      for (uint32_t x = 1; x < Ln(i); ++x) m = std::min(m, theta[to(i) + x]);
       lb += double(m);
     }
     Real* h = h_.data();
     for (uint64_t e = 0; e < E; ++e) {
       min_plus(e, 0, h);
       Real m = std::numeric_limits<Real>::infinity();
-      for (uint32_t x = 0; x < L; ++x) m = std::min(m, Real(h[x] + a[e * L + x]));
+      for (uint32_t x = 0; x < Ln(ei[e]); ++x) m = std::min(m, Real(h[x] + a[ao(e) + x]));
       lb += double(m);
     }
     return lb;
@@ -198,20 +218,44 @@ struct Oracle : OracleBase {
   double evaluate_primal() const {  // LP::EvaluatePrimal, include/LP_MP.h:1520-1536
     if (!labels_valid) return std::numeric_limits<double>::infinity();
     double cost_sum = constant;
-    for (uint64_t i = 0; i < N; ++i) cost_sum += double(theta[i * L + labels[i]]);
+    for (uint64_t i = 0; i < N; ++i) cost_sum += double(theta[to(i) + labels[i]]);
     for (uint64_t e = 0; e < E; ++e) {
       const uint32_t x = labels[ei[e]], y = labels[ej[e]];
-      cost_sum += double(Real(Real(cost(e, x, y) + a[e * L + x]) + b[e * L + y]));
+      cost_sum += double(Real(Real(cost(e, x, y) + a[ao(e) + x]) + b[bo(e) + y]));
     }
     return cost_sum;
   }
 
   int add_unaries(uint64_t n, uint32_t L_, const double* th) {
     if (finalized) { err = "add_unaries after finalize"; return LPMP_ERR_STATE; }
-    if (L_ == 0 || (L != 0 && L != L_)) { err = "one label count per LP"; return LPMP_ERR_UNSUPPORTED; }
+    if (ragged) { std::vector<uint32_t> Ls(n, L_); return add_unaries_var(n, Ls.data(), th); }
+    if (L_ == 0 || (L != 0 && L != L_)) { err = "one label count per LP (add_unaries_var takes mixed counts)"; return LPMP_ERR_UNSUPPORTED; }
     L = L_;
     theta.reserve((N + n) * L);
     for (uint64_t k = 0; k < n * L; ++k) theta.push_back(Real(th[k]));
+    note_run(0, N, n);
+    N += n;
+    return LPMP_OK;
+  }
+  int add_unaries_var(uint64_t n, const uint32_t* Ls, const double* th) {
+    if (finalized) { err = "add_unaries after finalize"; return LPMP_ERR_STATE; }
+    if (gridH) { err = "add_unaries on a grid LP"; return LPMP_ERR_STATE; }
+    if (E != 0 && !ragged) { err = "add_unaries_var after pairwise factors of a uniform LP"; return LPMP_ERR_STATE; }
+    if (!ragged) {   // what has been added so far had one label count
+      ragged = true;
+      Lv.assign(N, L);
+      toff.resize(N + 1);
+      for (uint64_t i = 0; i <= N; ++i) toff[i] = i * L;
+    }
+    uint64_t k = 0;
+    for (uint64_t q = 0; q < n; ++q) {
+      if (Ls[q] == 0) { err = "variable without labels"; return LPMP_ERR_INVALID; }
+      Lv.push_back(Ls[q]);
+      L = std::max(L, Ls[q]);
+      for (uint32_t x = 0; x < Ls[q]; ++x) theta.push_back(Real(th[k++]));
+      toff.push_back(theta.size());
+    }
+    note_run(0, N, n);
     N += n;
     return LPMP_OK;
   }
@@ -221,16 +265,41 @@ struct Oracle : OracleBase {
     if (pw != -1 && pw != type) { err = "one pairwise family per LP"; return LPMP_ERR_UNSUPPORTED; }
     pw = type;
     const uint32_t Pn = P();
+    uint64_t src = 0;   // read position in p0 (dense tables of a ragged LP are packed)
     for (uint64_t k = 0; k < m; ++k) {
       if (i[k] >= N || j[k] >= N || i[k] == j[k]) { err = "edge endpoint out of range"; return LPMP_ERR_INVALID; }
       ei.push_back(i[k]);
       ej.push_back(j[k]);
-      if (type == LPMP_PAIRWISE_DENSE) for (uint32_t q = 0; q < Pn; ++q) params.push_back(Real(p0[k * Pn + q]));
+      if (ragged) {
+        if (poff.empty()) { poff.push_back(0); aoff.push_back(0); boff.push_back(0); }
+        aoff.push_back(aoff.back() + Lv[i[k]]);
+        boff.push_back(boff.back() + Lv[j[k]]);
+        poff.push_back(poff.back() + (type == LPMP_PAIRWISE_DENSE ? uint64_t(Lv[i[k]]) * Lv[j[k]] : (type == LPMP_PAIRWISE_POTTS ? 1 : 2)));
+      }
+      const uint64_t Pe = ragged && type == LPMP_PAIRWISE_DENSE ? uint64_t(Lv[i[k]]) * Lv[j[k]] : Pn;
+      if (type == LPMP_PAIRWISE_DENSE) for (uint64_t q = 0; q < Pe; ++q) params.push_back(Real(p0[src++]));
       else if (type == LPMP_PAIRWISE_POTTS) params.push_back(Real(p0[k]));
       else { params.push_back(Real(p0[k])); params.push_back(Real(p1[k])); }
     }
+    note_run(1, E, m);
     E += m;
     return LPMP_OK;
+  }
+
+  // dual variables in the reference's archive layout (include/factor_archive.hxx:34-48, include/serialization.hxx:226-425): per factor
+  // in insertion order its serialize_dual() members as doubles -- unary: theta; pairwise: msg1 (a), msg2 (b)
+  uint64_t dual_bytes() const { return sizeof(double) * (theta.size() + a.size() + b.size()); }
+  template <bool SAVE>
+  void dual_archive(double* ar) {
+    for (const auto& r : runs)
+      for (uint64_t k = r[1]; k < r[1] + r[2]; ++k) {
+        if (r[0] == 0) {
+          for (uint32_t x = 0; x < Ln(k); ++x, ++ar) { if (SAVE) *ar = double(theta[to(k) + x]); else theta[to(k) + x] = Real(*ar); }
+        } else {
+          for (uint32_t x = 0; x < Ln(ei[k]); ++x, ++ar) { if (SAVE) *ar = double(a[ao(k) + x]); else a[ao(k) + x] = Real(*ar); }
+          for (uint32_t x = 0; x < Ln(ej[k]); ++x, ++ar) { if (SAVE) *ar = double(b[bo(k) + x]); else b[bo(k) + x] = Real(*ar); }
+        }
+      }
   }
 
   int finalize() {
@@ -238,8 +307,9 @@ struct Oracle : OracleBase {
     if (N == 0) { err = "no factors"; return LPMP_ERR_STATE; }
     if (pw == -1) pw = LPMP_PAIRWISE_POTTS;
     if (rank.empty()) { rank.resize(N); std::iota(rank.begin(), rank.end(), uint64_t(0)); }
-    a.assign(E * L, Real(0));
-    b.assign(E * L, Real(0));
+    if (ragged && poff.empty()) { poff.push_back(0); aoff.push_back(0); boff.push_back(0); }
+    a.assign(ragged ? aoff[E] : E * L, Real(0));
+    b.assign(ragged ? boff[E] : E * L, Real(0));
     labels.assign(N, NO_LABEL);
     h_.resize(L);
     t_.resize(L);
@@ -315,6 +385,8 @@ int grid_create(O& o, uint32_t Hh, uint32_t W, uint32_t L, int type) {
     }
   o.E = o.ei.size();
   o.params.assign(o.E * o.P(), 0);
+  o.note_run(0, 0, o.N);
+  o.note_run(1, 0, o.E);
   return LPMP_OK;
 }
 
@@ -388,6 +460,7 @@ int LPMP_FN(destroy)(lpmp_solver* h) { delete H(h); return LPMP_OK; }
 const char* LPMP_FN(last_error)(const lpmp_solver* h) { return h ? GET_ERR(H(h)).c_str() : "null handle"; }
 
 int LPMP_FN(add_unaries)(lpmp_solver* h, uint64_t n, uint32_t L, const double* theta) { return DISPATCH(H(h), o.add_unaries(n, L, theta)); }
+int LPMP_FN(add_unaries_var)(lpmp_solver* h, uint64_t n, const uint32_t* L, const double* theta) { return DISPATCH(H(h), o.add_unaries_var(n, L, theta)); }
 int LPMP_FN(add_pairwise_dense)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* t) { return DISPATCH(H(h), o.add_pairwise(LPMP_PAIRWISE_DENSE, m, i, j, t, nullptr)); }
 int LPMP_FN(add_pairwise_potts)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* l) { return DISPATCH(H(h), o.add_pairwise(LPMP_PAIRWISE_POTTS, m, i, j, l, nullptr)); }
 int LPMP_FN(add_pairwise_trunclin)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j, const double* s, const double* t) { return DISPATCH(H(h), o.add_pairwise(LPMP_PAIRWISE_TRUNCLIN, m, i, j, s, t)); }
@@ -490,11 +563,12 @@ int LPMP_FN(num_factors)(const lpmp_solver* h, uint64_t* out) { return DISPATCH(
 int LPMP_FN(num_messages)(const lpmp_solver* h, uint64_t* out) { return DISPATCH(H(h), ([&] { *out = 2 * o.E; return int(LPMP_OK); })()); }
 
 int LPMP_FN(get_labeling)(lpmp_solver* h, uint32_t* out) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; std::copy(o.labels.begin(), o.labels.end(), out); return int(LPMP_OK); })()); }
-int LPMP_FN(get_unaries)(lpmp_solver* h, double* th) { return DISPATCH(H(h), ([&] { for (uint64_t k = 0; k < o.N * o.L; ++k) th[k] = double(o.theta[k]); return int(LPMP_OK); })()); }
+int LPMP_FN(get_unaries)(lpmp_solver* h, double* th) { return DISPATCH(H(h), ([&] { for (uint64_t k = 0; k < o.theta.size(); ++k) th[k] = double(o.theta[k]); return int(LPMP_OK); })()); }
 int LPMP_FN(get_messages)(lpmp_solver* h, double* a, double* b) {
   return DISPATCH(H(h), ([&] {
     if (int r = need_final(o)) return r;
-    for (uint64_t k = 0; k < o.E * o.L; ++k) { if (a) a[k] = double(o.a[k]); if (b) b[k] = double(o.b[k]); }
+    for (uint64_t k = 0; k < o.a.size(); ++k) if (a) a[k] = double(o.a[k]);
+    for (uint64_t k = 0; k < o.b.size(); ++k) if (b) b[k] = double(o.b[k]);
     return int(LPMP_OK);
   })());
 }
@@ -502,14 +576,32 @@ int LPMP_FN(set_messages)(lpmp_solver* h, const double* a, const double* b) {
   return DISPATCH(H(h), ([&] {
     if (int r = need_final(o)) return r;
     using Real = typename std::remove_reference<decltype(o.a[0])>::type;
-    for (uint64_t k = 0; k < o.E * o.L; ++k) { if (a) o.a[k] = Real(a[k]); if (b) o.b[k] = Real(b[k]); }
+    for (uint64_t k = 0; k < o.a.size(); ++k) if (a) o.a[k] = Real(a[k]);
+    for (uint64_t k = 0; k < o.b.size(); ++k) if (b) o.b[k] = Real(b[k]);
     return int(LPMP_OK);
   })());
 }
 int LPMP_FN(set_unaries)(lpmp_solver* h, const double* th) {
   return DISPATCH(H(h), ([&] {
     using Real = typename std::remove_reference<decltype(o.theta[0])>::type;
-    for (uint64_t k = 0; k < o.N * o.L; ++k) o.theta[k] = Real(th[k]);
+    for (uint64_t k = 0; k < o.theta.size(); ++k) o.theta[k] = Real(th[k]);
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(dual_size)(lpmp_solver* h, uint64_t* bytes) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; *bytes = o.dual_bytes(); return int(LPMP_OK); })()); }
+int LPMP_FN(save_dual)(lpmp_solver* h, void* archive, uint64_t bytes) {
+  return DISPATCH(H(h), ([&] {
+    if (int r = need_final(o)) return r;
+    if (!archive || bytes != o.dual_bytes()) { o.err = "archive size does not match this LP"; return int(LPMP_ERR_INVALID); }
+    o.template dual_archive<true>(static_cast<double*>(archive));
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(load_dual)(lpmp_solver* h, const void* archive, uint64_t bytes) {
+  return DISPATCH(H(h), ([&] {
+    if (int r = need_final(o)) return r;
+    if (!archive || bytes != o.dual_bytes()) { o.err = "archive size does not match this LP"; return int(LPMP_ERR_INVALID); }
+    o.template dual_archive<false>(const_cast<double*>(static_cast<const double*>(archive)));
     return int(LPMP_OK);
   })());
 }

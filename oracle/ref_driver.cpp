@@ -175,7 +175,17 @@ public:
   std::vector<int> flags;
 };
 
-using RefSolver = MpRoundingSolver<Solver<LP<FMC_SRMP_RESTATED>, RecordingVisitor>>;
+#ifdef LPMP_DRIVE_LP_CUDA
+}  // namespace LP_MP
+// the SAME driver around the product's reference-side binding (include/LP_cuda.hxx): the reference's unmodified Solver::Solve()
+// loop, MpRoundingSolver::Iterate and StandardVisitor control law drive the CUDA library instead of LP<FMC>
+#include "LP_cuda.hxx"
+namespace LP_MP {
+using DrivenLP = LP_cuda;
+#else
+using DrivenLP = LP<FMC_SRMP_RESTATED>;
+#endif
+using RefSolver = MpRoundingSolver<Solver<DrivenLP, RecordingVisitor>>;
 
 struct RefSolverAccess : public RefSolver {
   using RefSolver::RefSolver;
@@ -184,9 +194,19 @@ struct RefSolverAccess : public RefSolver {
 
 struct RefHandle {
   std::unique_ptr<RefSolverAccess> solver;
+#ifdef LPMP_DRIVE_LP_CUDA
+  std::vector<LP_cuda::factor*> unaries, pairwise;
+#else
   std::vector<FMC_SRMP_RESTATED::UnaryFactor*> unaries;
   std::vector<FMC_SRMP_RESTATED::PairwiseFactor*> pairwise;
+#endif
   std::vector<std::array<INDEX, 2>> edges;
+};
+
+// row-major table view with the call operator AddPairwiseFactor expects (matrix<REAL>, include/vector.hxx:833)
+struct TableView {
+  const double* p; INDEX d2;
+  double operator()(const INDEX x, const INDEX y) const { return p[x * d2 + y]; }
 };
 
 }  // namespace LP_MP
@@ -210,7 +230,11 @@ void lpmp_ref_destroy(void* hv) { delete static_cast<RefHandle*>(hv); }
 int64_t lpmp_ref_add_unary(void* hv, uint64_t L, const double* theta) {
   auto* h = static_cast<RefHandle*>(hv);
   auto& lp = h->solver->GetLP();
+#ifdef LPMP_DRIVE_LP_CUDA
+  auto* f = lp.AddUnaryFactor(std::vector<REAL>(theta, theta + L));
+#else
   auto* f = lp.template add_factor<FMC_SRMP_RESTATED::UnaryFactor>(theta, INDEX(L));
+#endif
   h->unaries.push_back(f);
   return int64_t(h->unaries.size()) - 1;
 }
@@ -221,6 +245,11 @@ int64_t lpmp_ref_add_pairwise(void* hv, uint64_t i, uint64_t j, const double* ta
   auto* h = static_cast<RefHandle*>(hv);
   if (i >= h->unaries.size() || j >= h->unaries.size() || i == j) return -1;
   auto& lp = h->solver->GetLP();
+#ifdef LPMP_DRIVE_LP_CUDA
+  h->pairwise.push_back(lp.AddPairwiseFactor(i, j, TableView{table, lp.GetNumberOfLabels(j)}));
+  h->edges.push_back({INDEX(i), INDEX(j)});
+  return int64_t(h->pairwise.size()) - 1;
+#else
   auto* ui = h->unaries[i];
   auto* uj = h->unaries[j];
   const INDEX d1 = ui->GetFactor()->size(), d2 = uj->GetFactor()->size();
@@ -232,6 +261,7 @@ int64_t lpmp_ref_add_pairwise(void* hv, uint64_t i, uint64_t j, const double* ta
   h->pairwise.push_back(p);
   h->edges.push_back({INDEX(i), INDEX(j)});
   return int64_t(h->pairwise.size()) - 1;
+#endif
 }
 
 void lpmp_ref_add_to_constant(void* hv, double x) { static_cast<RefHandle*>(hv)->solver->GetLP().add_to_constant(x); }
@@ -260,6 +290,47 @@ double lpmp_ref_evaluate_primal(void* hv) { return static_cast<RefHandle*>(hv)->
 
 uint64_t lpmp_ref_num_factors(void* hv) { return static_cast<RefHandle*>(hv)->solver->GetLP().GetNumberOfFactors(); }
 uint64_t lpmp_ref_num_messages(void* hv) { return static_cast<RefHandle*>(hv)->solver->GetLP().GetNumberOfMessages(); }
+#ifdef LPMP_DRIVE_LP_CUDA
+// state of the CUDA LP through the C ABI (packed layouts, include/lpmp_b200.h)
+static std::vector<double> cuda_unaries(RefHandle* h) {
+  auto& lp = h->solver->GetLP();
+  INDEX n = 0;
+  for (INDEX i = 0; i < h->unaries.size(); ++i) n += lp.GetNumberOfLabels(i);
+  std::vector<double> th(n);
+  if (lpmp_get_unaries(lp.handle(), th.data()) != LPMP_OK) throw std::runtime_error(lpmp_last_error(lp.handle()));
+  return th;
+}
+uint64_t lpmp_ref_no_send_messages(void*, uint64_t) { return 0; }
+void lpmp_ref_get_unary(void* hv, uint64_t i, double* out) {
+  auto* h = static_cast<RefHandle*>(hv);
+  auto& lp = h->solver->GetLP();
+  const std::vector<double> th = cuda_unaries(h);
+  INDEX off = 0;
+  for (INDEX k = 0; k < i; ++k) off += lp.GetNumberOfLabels(k);
+  for (INDEX x = 0; x < lp.GetNumberOfLabels(i); ++x) out[x] = th[off + x];
+}
+void lpmp_ref_get_pairwise_msgs(void* hv, uint64_t e, double* msg1, double* msg2) {
+  auto* h = static_cast<RefHandle*>(hv);
+  auto& lp = h->solver->GetLP();
+  INDEX na = 0, nb = 0, oa = 0, ob = 0;
+  for (INDEX k = 0; k < h->edges.size(); ++k) {
+    if (k == e) { oa = na; ob = nb; }
+    na += lp.GetNumberOfLabels(h->edges[k][0]); nb += lp.GetNumberOfLabels(h->edges[k][1]);
+  }
+  std::vector<double> a(na), b(nb);
+  if (lpmp_get_messages(lp.handle(), a.data(), b.data()) != LPMP_OK) throw std::runtime_error(lpmp_last_error(lp.handle()));
+  for (INDEX x = 0; x < lp.GetNumberOfLabels(h->edges[e][0]); ++x) msg1[x] = a[oa + x];
+  for (INDEX x = 0; x < lp.GetNumberOfLabels(h->edges[e][1]); ++x) msg2[x] = b[ob + x];
+}
+void lpmp_ref_get_labels(void* hv, uint64_t* out) {
+  auto* h = static_cast<RefHandle*>(hv);
+  const std::vector<uint32_t> l = h->solver->GetLP().labeling();
+  for (std::size_t i = 0; i < l.size(); ++i) out[i] = l[i] == 0xffffffffu ? no_label : l[i];
+}
+uint64_t lpmp_ref_dual_size(void* hv) { return static_cast<RefHandle*>(hv)->solver->GetLP().dual_size_in_bytes(); }
+void lpmp_ref_save_dual(void* hv, void* out) { static_cast<RefHandle*>(hv)->solver->GetLP().save_dual(out); }
+void lpmp_ref_load_dual(void* hv, const void* in) { static_cast<RefHandle*>(hv)->solver->GetLP().load_dual(in); }
+#else
 uint64_t lpmp_ref_no_send_messages(void* hv, uint64_t i) { return static_cast<RefHandle*>(hv)->unaries[i]->no_send_messages(); }
 
 void lpmp_ref_get_unary(void* hv, uint64_t i, double* out) {
@@ -275,6 +346,35 @@ void lpmp_ref_get_labels(void* hv, uint64_t* out) {
   auto* h = static_cast<RefHandle*>(hv);
   for (std::size_t i = 0; i < h->unaries.size(); ++i) out[i] = h->unaries[i]->GetFactor()->primal;
 }
+
+// The dual variables of ALL factors in the reference's own archive: exactly what factor_archive<serialization_functor::dual>
+// (include/factor_archive.hxx:34-48) does -- an allocate_archive pass for the size, then save_archive / load_archive over the
+// factors in f_ order (include/serialization.hxx:226-425; FactorContainer::serialize_dual, include/factors_messages.hxx:3196-3209)
+uint64_t lpmp_ref_dual_size(void* hv) {
+  auto& lp = static_cast<RefHandle*>(hv)->solver->GetLP();
+  allocate_archive aa;
+  for (INDEX i = 0; i < lp.GetNumberOfFactors(); ++i) lp.GetFactor(i)->serialize_dual(aa);
+  return aa.size();
+}
+void lpmp_ref_save_dual(void* hv, void* out) {
+  auto& lp = static_cast<RefHandle*>(hv)->solver->GetLP();
+  allocate_archive aa;
+  for (INDEX i = 0; i < lp.GetNumberOfFactors(); ++i) lp.GetFactor(i)->serialize_dual(aa);
+  serialization_archive ar(aa);
+  save_archive sa(ar);
+  for (INDEX i = 0; i < lp.GetNumberOfFactors(); ++i) lp.GetFactor(i)->serialize_dual(sa);
+  std::memcpy(out, ar.begin(), ar.size());
+}
+void lpmp_ref_load_dual(void* hv, const void* in) {
+  auto& lp = static_cast<RefHandle*>(hv)->solver->GetLP();
+  allocate_archive aa;
+  for (INDEX i = 0; i < lp.GetNumberOfFactors(); ++i) lp.GetFactor(i)->serialize_dual(aa);
+  serialization_archive ar(aa);
+  std::memcpy(ar.begin(), in, ar.size());
+  load_archive la(ar);
+  for (INDEX i = 0; i < lp.GetNumberOfFactors(); ++i) lp.GetFactor(i)->serialize_dual(la);
+}
+#endif
 
 // single-factor entry points (goldens of test/simplex.cpp, test/simplex_marginalization.cpp)
 double lpmp_ref_unary_lower_bound(uint64_t L, const double* theta) {

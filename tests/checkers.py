@@ -33,8 +33,11 @@ def oracle_lp(dtype="f64", **kw):
     return LP(dtype=dtype, capi=oracle_capi(), **kw)
 
 
-def ref_library(fifo=False):
-    path = os.path.join(ORACLE_DIR, "_ref", "liblpmp_ref_fifo.so" if fifo else "liblpmp_ref.so")
+def ref_library(fifo=False, cuda_adapter=False):
+    """the reference core (oracle/ref_driver.cpp); cuda_adapter: the same driver -- the reference's unmodified Solver /
+    MpRoundingSolver / StandardVisitor -- around the product's binding include/LP_cuda.hxx (needs a GPU at run time)"""
+    name = "liblpmp_ref_cuda.so" if cuda_adapter else ("liblpmp_ref_fifo.so" if fifo else "liblpmp_ref.so")
+    path = os.path.join(ORACLE_DIR, "_ref", name)
     if not os.path.exists(path):
         if os.path.isdir("/root/reference/include"):
             build_oracle()
@@ -66,6 +69,9 @@ def ref_library(fifo=False):
         "lpmp_ref_unary_lower_bound": ([u64, pd], d),
         "lpmp_ref_pairwise_min_marginal": ([u64, u64, pd, pd, pd, C.c_int, pd, pd], None),
         "lpmp_ref_solve": ([vp, pd, pd, C.POINTER(C.c_int32), u64, pd, pd, pd], u64),
+        "lpmp_ref_dual_size": ([vp], u64),
+        "lpmp_ref_save_dual": ([vp, vp], None),
+        "lpmp_ref_load_dual": ([vp, vp], None),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)
@@ -145,6 +151,16 @@ class RefLP:
         out = np.zeros(self.N, dtype=np.uint64)
         self.lib.lpmp_ref_get_labels(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64)))
         return out
+
+    def save_dual(self) -> bytes:
+        buf = np.zeros(self.lib.lpmp_ref_dual_size(self.h) // 8, dtype=np.float64)
+        self.lib.lpmp_ref_save_dual(self.h, buf.ctypes.data)
+        return buf.tobytes()
+
+    def load_dual(self, archive: bytes):
+        buf = np.frombuffer(archive, dtype=np.float64).copy()
+        assert buf.nbytes == self.lib.lpmp_ref_dual_size(self.h)
+        self.lib.lpmp_ref_load_dual(self.h, buf.ctypes.data)
 
     def solve(self, cap=100000):
         lb, ub = np.zeros(cap), np.zeros(cap)

@@ -1,0 +1,175 @@
+"""GPU parity of the general-graph path (node-record layout, kernels_graph.cuh) beyond what tests/test_gpu_parity.py covers:
+mixed label counts, the dual archive (8f-3), and the reference's UNMODIFIED Solver / MpRoundingSolver /
+StandardVisitor driving the product's C++ binding include/LP_cuda.hxx (8b).  All calls go through the C ABI."""
+import numpy as np
+import pytest
+
+import lp_mp_b200
+from checkers import RefLP, grid_edges, oracle_lp, ref_library
+from test_dual_archive import build, mixed_instance, same_state
+
+pytestmark = pytest.mark.gpu
+MODES = ["anisotropic", "uniform", "damped_uniform"]
+
+
+def cuda_lp(dtype="f64"):
+    return lp_mp_b200.LP(dtype=dtype, device=0)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("edge_order", ["lifo", "fifo"])
+def test_mixed_label_counts_bit_parity(dtype, mode, edge_order):
+    """variables with 2..5 labels in one LP (test/graphical_model.cpp:74-96): theta / messages / labels bit-identical to the oracle"""
+    theta, edges, tables = mixed_instance(23, n=60, m=130)
+    lps = [oracle_lp(dtype), cuda_lp(dtype)]
+    for lp in lps:
+        build(lp, theta, edges, tables)
+        lp.set_edge_order(edge_order)
+        lp.finalize(); lp.Begin(); lp.set_reparametrization(mode)
+    o, c = lps
+    assert np.isclose(c.LowerBound(), o.LowerBound(), rtol=1e-12 if dtype == "f64" else 1e-6)
+    for it in range(4):
+        o.ComputePass(it); c.ComputePass(it)
+        assert same_state(o, c), it
+        assert np.isclose(c.LowerBound(), o.LowerBound(), rtol=1e-12 if dtype == "f64" else 1e-6)
+    for it in (4, 5):
+        o.ComputeForwardPassAndPrimal(it); c.ComputeForwardPassAndPrimal(it)
+        assert np.array_equal(o.labeling(), c.labeling())
+        o.ComputeBackwardPassAndPrimal(it); c.ComputeBackwardPassAndPrimal(it)
+        assert np.array_equal(o.labeling(), c.labeling())
+        assert np.isclose(c.EvaluatePrimal(), o.EvaluatePrimal(), rtol=1e-12 if dtype == "f64" else 1e-6)
+        assert c.CheckPrimalConsistency()
+        assert same_state(o, c)
+
+
+def test_mixed_label_counts_against_the_reference_core(ref_lib):
+    theta, edges, tables = mixed_instance(31, n=30, m=64)
+    ref, c = RefLP(ref_lib, ["-v", "0"]), cuda_lp("f64")
+    build(ref, theta, edges, tables); build(c, theta, edges, tables)
+    ref.Begin(); c.Begin()
+    ref.set_reparametrization("anisotropic"); c.set_reparametrization("anisotropic")
+    for it in range(5):
+        ref.ComputePass(it); c.ComputePass(it)
+        assert same_state(ref, c)
+        assert np.isclose(c.LowerBound(), ref.LowerBound(), rtol=1e-12)
+    ref.ComputeForwardPassAndPrimal(5); c.ComputeForwardPassAndPrimal(5)
+    assert np.array_equal(ref.labeling(), c.labeling())
+
+
+@pytest.mark.parametrize("L,deg_heavy", [(4, False), (8, False), (8, True), (16, False), (5, False), (32, False)])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_fast_and_generic_node_kernels(dtype, L, deg_heavy):
+    """L in {4, 8, 16} with at most 4 incident edges runs the register kernel, everything else (other label counts, hubs of
+    higher degree inside the same level) the generic one: both bit-identical to the oracle, all three reparametrisations,
+    natural order and colouring order"""
+    rng = np.random.default_rng(L * 7 + deg_heavy)
+    n = 300
+    perm = rng.permutation(n)
+    edges = {(min(i, (i + 1) % n), max(i, (i + 1) % n)) for i in range(n)}
+    for k in range(0, n, 2):
+        i, j = int(perm[k]), int(perm[k + 1])
+        edges.add((min(i, j), max(i, j)))
+    if deg_heavy:   # a few hubs with more than 4 incident edges
+        for hub in (3, 100, 250):
+            for t in rng.choice(n, size=7, replace=False):
+                if int(t) != hub:
+                    edges.add((min(hub, int(t)), max(hub, int(t))))
+    edges = sorted(edges)
+    ei = np.array([e[0] for e in edges], dtype=np.uint64)
+    ej = np.array([e[1] for e in edges], dtype=np.uint64)
+    theta, tables = rng.random((n, L)), rng.random((len(edges), L, L)) - 0.2
+    for use_colouring in (False, True):
+        for mode in MODES:
+            lps = [oracle_lp(dtype), cuda_lp(dtype)]
+            for lp in lps:
+                lp.add_unaries(theta); lp.add_pairwise_dense(ei, ej, tables)
+            if use_colouring:
+                colour, nc = lps[1].greedy_colouring(ei, ej)
+                rank = colour.astype(np.uint64) * n + np.arange(n, dtype=np.uint64)
+                for lp in lps:
+                    lp.set_node_ranks(rank)
+            for lp in lps:
+                lp.finalize(); lp.Begin(); lp.set_reparametrization(mode)
+            o, c = lps
+            for it in range(3):
+                o.ComputePass(it); c.ComputePass(it)
+                assert same_state(o, c), (use_colouring, mode, it)
+                assert np.isclose(c.LowerBound(), o.LowerBound(), rtol=1e-12 if dtype == "f64" else 1e-6)
+            o.ComputeBackwardPassAndPrimal(3); c.ComputeBackwardPassAndPrimal(3)
+            assert np.array_equal(o.labeling(), c.labeling())
+            assert np.isclose(c.EvaluatePrimal(), o.EvaluatePrimal(), rtol=1e-12 if dtype == "f64" else 1e-6)
+
+
+@pytest.mark.parametrize("shape", ["graph", "mixed", "grid_wavefront", "grid_dense"])
+def test_dual_archive_on_device(shape):
+    """lpmp_save_dual writes the reference's archive layout (== the oracle's bytes, which tests/test_dual_archive.py pins against
+    the reference's own save_archive); save -> new handle -> load resumes with a bit-identical trajectory"""
+    def make(lp):
+        if shape == "mixed":
+            build(lp, *mixed_instance(5, n=40, m=90))
+        elif shape == "graph":
+            rng = np.random.default_rng(4)
+            ei, ej = grid_edges(6, 7)
+            lp.add_unaries(rng.random((42, 8))); lp.add_pairwise_dense(ei, ej, rng.random((len(ei), 8, 8)))
+        elif shape == "grid_wavefront":
+            lp.grid_create(19, 23, 16, "potts"); lp.grid_fill_synthetic(7, -0.2, 1.0)
+        else:
+            lp.grid_create(9, 11, 16, "dense"); lp.grid_fill_synthetic(7, 0.0, 1.0)
+        lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+        return lp
+    o, c = make(oracle_lp("f64")), make(cuda_lp("f64"))
+    for it in range(2):
+        o.ComputePass(it); c.ComputePass(it)
+    blob = c.save_dual()
+    assert blob == o.save_dual()
+    resumed = make(cuda_lp("f64"))
+    resumed.load_dual(blob)
+    assert np.isclose(resumed.LowerBound(), c.LowerBound(), rtol=1e-14)   # (a fused bound sums in another order than the sweep)
+    for it in range(2, 5):
+        c.ComputePass(it); resumed.ComputePass(it); o.ComputePass(it)
+        assert same_state(c, resumed) and same_state(o, c)
+        assert resumed.LowerBound() == c.LowerBound()   # from here on both took the same route to the bound
+    with pytest.raises(lp_mp_b200.LpmpError):
+        resumed.load_dual(blob[8:])
+
+
+# ---- include/LP_cuda.hxx under the reference's own solver -----------------------------------------------------------------------
+def adapter_pair(theta, edges, tables, options):
+    lib_ref, lib_cuda = ref_library(), ref_library(cuda_adapter=True)
+    if lib_ref is None or lib_cuda is None:
+        pytest.skip("oracle/_ref not built (reference tree absent at build time)")
+    ref, cu = RefLP(lib_ref, options), RefLP(lib_cuda, options)
+    build(ref, theta, edges, tables); build(cu, theta, edges, tables)
+    return ref, cu
+
+
+@pytest.mark.parametrize("options", [
+    ["--maxIter", "23", "-v", "0"],                                                    # StandardVisitor defaults: damped-uniform rounding every 5th iteration
+    ["--maxIter", "20", "--roundingReparametrization", "anisotropic", "--primalComputationInterval", "3", "-v", "0"],
+    ["--maxIter", "60", "--minDualImprovement", "1e-3", "--minDualImprovementInterval", "4", "--lowerBoundComputationInterval", "2", "-v", "0"],
+])
+@pytest.mark.parametrize("shape", ["uniform", "mixed"])
+def test_reference_solver_drives_lp_cuda(options, shape):
+    """MpRoundingSolver<Solver<LP_cuda, StandardVisitor>>::Solve() (the reference's unmodified include/solver.hxx:230-257,381-400 and
+    include/visitors/standard_visitor.hxx:48-199 compiled against include/LP_cuda.hxx) == the same Solve() over the reference's own
+    LP<FMC>: every visit reports the same lower bound, primal bound and control flags; same final labeling and state"""
+    if shape == "mixed":
+        theta, edges, tables = mixed_instance(77, n=36, m=80)
+    else:
+        rng = np.random.default_rng(12)
+        ei, ej = grid_edges(7, 8)
+        edges = list(zip(ei.tolist(), ej.tolist()))
+        theta, tables = list(rng.random((56, 6))), list(rng.random((len(edges), 6, 6)) - 0.25)
+    ref, cu = adapter_pair(theta, edges, tables, options)
+    r, c = ref.solve(), cu.solve()
+    assert len(r["lb"]) == len(c["lb"]) and np.array_equal(r["flags"], c["flags"])
+    assert np.allclose(c["lb"], r["lb"], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(np.isinf(r["ub"]), np.isinf(c["ub"]))
+    fin = ~np.isinf(r["ub"])
+    assert np.allclose(c["ub"][fin], r["ub"][fin], rtol=1e-12)
+    assert np.isclose(c["final_lb"], r["final_lb"], rtol=1e-12) and np.isclose(c["final_ub"], r["final_ub"], rtol=1e-12)
+    assert np.array_equal(ref.labeling(), cu.labeling())
+    assert same_state(ref, cu)
+    # the archive of the binding is the reference's archive
+    assert cu.save_dual() == ref.save_dual()
