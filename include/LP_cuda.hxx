@@ -114,15 +114,17 @@ public:
   // ---- the LP_TYPE surface ---------------------------------------------------------------------------------------------------
   void Begin() {   // include/LP_MP.h:704-728
     const std::string& t = reparametrization_type_arg_.getValue();
-    if (t != "shared") throw std::runtime_error("LP_cuda: reparametrizationType " + t + " is not available on the device (shared only)");
+    if (t != "shared" && t != "residual") throw std::runtime_error("LP_cuda: reparametrizationType " + t + " is not available on the device (shared | residual)");
     if (!h_) upload();
     ck(lpmp_begin(h_));
+    ck(lpmp_set_send_mode(h_, t == "residual" ? LPMP_SEND_RESIDUAL : LPMP_SEND_SHARED));
   }
   void End() { ck(lpmp_end(h_)); }
   void set_reparametrization(const LPReparametrizationMode m) {   // include/config.hxx:72
     int mode;
     switch (m) {
       case LPReparametrizationMode::Anisotropic: mode = LPMP_REPAM_ANISOTROPIC; break;
+      case LPReparametrizationMode::Anisotropic2: mode = LPMP_REPAM_ANISOTROPIC2; break;
       case LPReparametrizationMode::Uniform: mode = LPMP_REPAM_UNIFORM; break;
       case LPReparametrizationMode::DampedUniform: mode = LPMP_REPAM_DAMPED_UNIFORM; break;
       default: throw std::runtime_error("no reparametrization mode set");   // as include/LP_MP.h:458

@@ -38,8 +38,17 @@ enum { LPMP_OK = 0, LPMP_ERR_INVALID = 1, LPMP_ERR_STATE = 2, LPMP_ERR_CUDA = 3,
  * include/config.hxx:28); F32 = throughput mode (REAL = float is the commented alternative, :23-26). */
 enum { LPMP_F32 = 0, LPMP_F64 = 1 };
 
-/* LPReparametrizationMode, include/config.hxx:72 (Mixed: out of scope) */
-enum { LPMP_REPAM_ANISOTROPIC = 0, LPMP_REPAM_UNIFORM = 1, LPMP_REPAM_DAMPED_UNIFORM = 2 };
+/* LPReparametrizationMode, include/config.hxx:72 (Mixed: out of scope).  ANISOTROPIC2 = ComputeAnisotropicWeights2
+ * (include/LP_MP.h:1084-1154): the receive mask of ANISOTROPIC, send weight 1 / #{messages sent to factors later in the pass}. */
+enum { LPMP_REPAM_ANISOTROPIC = 0, LPMP_REPAM_UNIFORM = 1, LPMP_REPAM_DAMPED_UNIFORM = 2, LPMP_REPAM_ANISOTROPIC2 = 3 };
+
+/* how a factor sends, --reparametrizationType of the reference LP (include/LP_MP.h:589,704-722,988-1004):
+ * SHARED = FactorContainer::UpdateFactor (every message gets omega * the snapshot), RESIDUAL = update_factor_residual
+ * (include/factors_messages.hxx:2270-2279,2957-3007: after the shared send, message k in turn also receives
+ * (omega_1 + ... + omega_k) * what is left in the factor).  "adaptive" (:2859-2930) needs send_message_to_right_improvement of the
+ * marginalisation message, which lives in the un-mounted sibling repository: lpmp_set_send_mode answers LPMP_ERR_UNSUPPORTED.
+ * "partition" / "overlapping_partition": lpmp_compute_partition_pass below. */
+enum { LPMP_SEND_SHARED = 0, LPMP_SEND_RESIDUAL = 1, LPMP_SEND_ADAPTIVE = 2 };
 
 /* pairwise factor family: PairwiseSimplexFactor / pairwise_potts_factor (test/potts_factor.cpp:21-71) /
  * truncated linear min(slope*|x-y|, trunc) (new, BASELINE.json config 2) */
@@ -170,6 +179,7 @@ int LPMP_FN(finalize)(lpmp_solver* h);
 int LPMP_FN(begin)(lpmp_solver* h);                                  /* LP::Begin, include/LP_MP.h:704-728 */
 int LPMP_FN(end)(lpmp_solver* h);                                    /* LP::End */
 int LPMP_FN(set_reparametrization)(lpmp_solver* h, int mode);        /* LP::set_reparametrization */
+int LPMP_FN(set_send_mode)(lpmp_solver* h, int mode);                /* reparametrization_type_, include/LP_MP.h:704-722 (any time after finalize) */
 int LPMP_FN(compute_pass)(lpmp_solver* h, uint64_t iteration);       /* LP::ComputePass, include/LP_MP.h:869-887 */
 int LPMP_FN(compute_forward_pass)(lpmp_solver* h);                   /* :889-900 */
 int LPMP_FN(compute_backward_pass)(lpmp_solver* h);                  /* :902-911 */

@@ -10,7 +10,8 @@ from __future__ import annotations
 import ctypes as C
 
 F32, F64 = 0, 1
-REPAM = {"anisotropic": 0, "uniform": 1, "damped_uniform": 2}
+REPAM = {"anisotropic": 0, "uniform": 1, "damped_uniform": 2, "anisotropic2": 3}
+SEND_MODE = {"shared": 0, "residual": 1, "adaptive": 2}
 PAIRWISE = {"dense": 0, "potts": 1, "trunclin": 2}
 SCHEDULE = {"levels": 0, "wavefront": 1}
 EDGE_ORDER = {"lifo": 0, "fifo": 1}
@@ -64,6 +65,7 @@ SIGNATURES = {
     "begin": [_vp],
     "end": [_vp],
     "set_reparametrization": [_vp, _i],
+    "set_send_mode": [_vp, _i],
     "compute_pass": [_vp, _u64],
     "compute_forward_pass": [_vp],
     "compute_backward_pass": [_vp],

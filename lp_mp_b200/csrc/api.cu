@@ -297,6 +297,7 @@ struct ISolver {
   virtual int finalize() = 0;
   virtual int begin() = 0;
   virtual int set_reparametrization(int mode) = 0;
+  virtual int set_send_mode(int mode) = 0;
   virtual int pass(bool forward, bool primal) = 0;
   virtual int lower_bound(double* out) = 0;
   virtual int evaluate_primal(double* out) = 0;
@@ -321,7 +322,7 @@ struct Solver : ISolver {
   // problem
   uint64_t N = 0, E = 0, slots = 0;
   uint32_t L = 0, gridH = 0, gridW = 0, row0 = 0, H_total = 0;
-  int pw = -1, repam = -1, edge_order = LPMP_EDGE_ORDER_LIFO, schedule = -1;
+  int pw = -1, repam = -1, edge_order = LPMP_EDGE_ORDER_LIFO, schedule = -1, send_mode = LPMP_SEND_SHARED;
   bool finalized = false, labels_valid = false, is_grid = false, striped = false;
   double constant = 0.0;
   WavefrontTuning tune;
@@ -875,8 +876,17 @@ struct Solver : ISolver {
 
   int begin() override { if (int r = need_final()) return r; repam = -1; return LPMP_OK; }
   int set_reparametrization(int mode) override {
-    if (mode < 0 || mode > 2) { err = "reparametrization mode unknown"; return LPMP_ERR_INVALID; }
+    if (mode < 0 || mode > 3) { err = "reparametrization mode unknown"; return LPMP_ERR_INVALID; }
     repam = mode;
+    return LPMP_OK;
+  }
+  int set_send_mode(int mode) override {
+    if (mode == LPMP_SEND_ADAPTIVE) {
+      err = "adaptive sending needs send_message_to_right_improvement of the marginalisation message (absent from the reference snapshot)";
+      return LPMP_ERR_UNSUPPORTED;
+    }
+    if (mode != LPMP_SEND_SHARED && mode != LPMP_SEND_RESIDUAL) { err = "send mode unknown"; return LPMP_ERR_INVALID; }
+    send_mode = mode;
     return LPMP_OK;
   }
 
@@ -889,20 +899,23 @@ struct Solver : ISolver {
     // dense-table grids: the row-dataflow kernel covers the anisotropic mode; the uniform modes of the rounding
     // iterations (include/visitors/standard_visitor.hxx:44) run on the level schedule, built on first use
     if (!is_grid) {
-      const int n = graph.pass(forward, primal, repam, labels.p, tune.level_group, num_sms, stream, err);
+      const int n = graph.pass(forward, primal, repam, send_mode == LPMP_SEND_RESIDUAL, labels.p, tune.level_group, num_sms, stream, err);
       if (n < 0) return LPMP_ERR_UNSUPPORTED;
       launches += (uint64_t)n;
       CUDA_TRY(cudaGetLastError());
-      updates += (repam == LPMP_REPAM_ANISOTROPIC ? 2 : 4) * E;
+      updates += ((repam == LPMP_REPAM_ANISOTROPIC || repam == LPMP_REPAM_ANISOTROPIC2) ? 2 : 4) * E;
       if (primal) labels_valid = true;
       return LPMP_OK;
     }
     const bool dense_wf = schedule == LPMP_SCHEDULE_WAVEFRONT && pw == LPMP_PAIRWISE_DENSE;
-    if (dense_wf && repam != LPMP_REPAM_ANISOTROPIC && !levels_built) {
-      if (striped) { err = "stripes support the anisotropic reparametrization only"; return LPMP_ERR_UNSUPPORTED; }
+    // the wavefront kernels implement the shared send with the anisotropic / uniform / damped weights; Anisotropic2 weights and
+    // residual sends run on the level schedule of the same node records, built on first use
+    const bool off_wavefront = repam == LPMP_REPAM_ANISOTROPIC2 || (send_mode == LPMP_SEND_RESIDUAL && !primal);
+    if (((dense_wf && repam != LPMP_REPAM_ANISOTROPIC) || (schedule == LPMP_SCHEDULE_WAVEFRONT && off_wavefront)) && !levels_built) {
+      if (striped) { err = "stripes support the anisotropic reparametrization with shared sends only"; return LPMP_ERR_UNSUPPORTED; }
       if (int r = build_grid_levels()) return r;
     }
-    if (schedule == LPMP_SCHEDULE_LEVELS || (dense_wf && repam != LPMP_REPAM_ANISOTROPIC)) {
+    if (schedule == LPMP_SCHEDULE_LEVELS || (dense_wf && repam != LPMP_REPAM_ANISOTROPIC) || off_wavefront) {
       // lanes per node: the update of a node is a chain of dependent gathers (incidence -> edge -> vectors / table), so the
       // level kernel is bound by the number of nodes in flight; fewer lanes per node = more nodes per SM ("level_group")
       int G = group_size_for(L);
@@ -922,7 +935,7 @@ struct Solver : ISolver {
         A.st = store();
         A.nodes = level_nodes.p + level_off[lv]; A.num_nodes = (uint32_t)cnt;
         A.inc_off = inc_off.p; A.inc_edge = inc_edge.p; A.inc_flags = inc_flags.p; A.labels = labels.p;
-        A.L = L; A.pw = pw; A.repam = repam; A.forward = forward ? 1 : 0; A.primal = primal ? 1 : 0;
+        A.L = L; A.pw = pw; A.repam = repam; A.forward = forward ? 1 : 0; A.primal = primal ? 1 : 0; A.residual = send_mode == LPMP_SEND_RESIDUAL ? 1 : 0;
         const int ctas = (int)std::min<uint64_t>((cnt + groups - 1) / groups, (uint64_t)num_sms * 8);
         level_update_kernel<Real><<<ctas, threads, (size_t)groups * per_group, stream>>>(A, G);
         ++launches;
@@ -1004,7 +1017,7 @@ struct Solver : ISolver {
       CUDA_TRY(launch_wavefront<Real>(ksel == 8 ? maps8 : maps4, A, pw, L, tl_hops(), ksel, tune, num_sms, stream));
       ++launches;
     }
-    updates += (repam == LPMP_REPAM_ANISOTROPIC ? 2 : 4) * E;
+    updates += ((repam == LPMP_REPAM_ANISOTROPIC || repam == LPMP_REPAM_ANISOTROPIC2) ? 2 : 4) * E;
     if (primal) labels_valid = true;
     return LPMP_OK;
   }
@@ -1510,6 +1523,7 @@ int lpmp_finalize(lpmp_solver* h) { return S(h)->finalize(); }
 int lpmp_begin(lpmp_solver* h) { return S(h)->begin(); }
 int lpmp_end(lpmp_solver* h) { return S(h)->synchronize(); }
 int lpmp_set_reparametrization(lpmp_solver* h, int mode) { return S(h)->set_reparametrization(mode); }
+int lpmp_set_send_mode(lpmp_solver* h, int mode) { return S(h)->set_send_mode(mode); }
 int lpmp_compute_pass(lpmp_solver* h, uint64_t) { if (int r = S(h)->pass(true, false)) return r; return S(h)->pass(false, false); }
 int lpmp_compute_forward_pass(lpmp_solver* h) { return S(h)->pass(true, false); }
 int lpmp_compute_backward_pass(lpmp_solver* h) { return S(h)->pass(false, false); }

@@ -284,7 +284,7 @@ struct GraphEngine {
     A.desc = desc.p; A.vec = vec.p; A.tab = tab.p; A.inc_off = inc_off.p; A.oth_off = oth_off.p; A.flags = flags.p; A.oth_node = oth_node.p; A.node_of = node_of.p;
     A.voff = mixed ? voff.p : nullptr; A.toff = mixed ? toff.p : nullptr; A.lab_k = mixed ? lab_k.p : nullptr; A.lab_oth = mixed ? lab_oth.p : nullptr;
     A.labels = labels; A.partial = partial;
-    A.first = 0; A.count = (uint32_t)N; A.L = L; A.P = P; A.pw = pw; A.repam = 0; A.forward = 1; A.primal = 0;
+    A.first = 0; A.count = (uint32_t)N; A.L = L; A.P = P; A.pw = pw; A.repam = 0; A.forward = 1; A.primal = 0; A.residual = 0;
     return A;
   }
 
@@ -308,9 +308,9 @@ struct GraphEngine {
 
   // one pass = the levels in order (forward) or reverse order (backward); returns the number of kernels launched, < 0 on error
   int ctas_per_sm = 0;   // fast kernel: CTAs per SM of a launch ("graph_ctas_per_sm"; 0 = default)
-  int pass(bool forward, bool primal, int repam, uint32_t* labels, int level_group, int num_sms, cudaStream_t stream, std::string& err) const {
+  int pass(bool forward, bool primal, int repam, bool residual, uint32_t* labels, int level_group, int num_sms, cudaStream_t stream, std::string& err) const {
     GraphArgs<Real> A = args(labels, nullptr);
-    A.repam = repam; A.forward = forward ? 1 : 0; A.primal = primal ? 1 : 0;
+    A.repam = repam; A.forward = forward ? 1 : 0; A.primal = primal ? 1 : 0; A.residual = residual ? 1 : 0;
     int G = 0, threads = 0;
     size_t smem = 0;
     if (!generic_shape(level_group, &G, &threads, &smem)) { err = "label count too large for the level kernel"; return -1; }

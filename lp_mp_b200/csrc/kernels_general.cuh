@@ -76,6 +76,7 @@ struct LevelArgs {
   uint32_t* labels;         // [N]
   uint32_t L;
   int pw, repam, forward, primal;
+  int residual;             // update_factor_residual instead of UpdateFactor in the plain passes
 };
 
 // One node update = receive, (argmin), snapshot, send.  Shared memory per group: th[L], t[L], oth[L], hs[L].
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(256) level_update_kernel(LevelArgs<Real> A, in
   Real* t = th + L;
   Real* oth = t + L;
   Real* hs = oth + L;
-  const bool aniso = A.repam == LPMP_REPAM_ANISOTROPIC;
+  const bool aniso = A.repam == LPMP_REPAM_ANISOTROPIC || A.repam == LPMP_REPAM_ANISOTROPIC2;
 
   for (uint32_t k = blockIdx.x * groups_per_cta + g; k < A.num_nodes; k += gridDim.x * groups_per_cta) {
     const uint32_t i = A.nodes[k];
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(256) level_update_kernel(LevelArgs<Real> A, in
     if (k1 > k0) {
       const uint32_t deg = n_in + n_out;
       double wd;
-      if (aniso) wd = 1.0 / (double)(n_in > n_out ? n_in : n_out);          // include/LP_MP.h:1397
+      if (A.repam == LPMP_REPAM_ANISOTROPIC) wd = 1.0 / (double)(n_in > n_out ? n_in : n_out);   // include/LP_MP.h:1397
+      else if (A.repam == LPMP_REPAM_ANISOTROPIC2) wd = 1.0 / (double)(A.forward ? n_out : n_in);   // :1134
       else if (A.repam == LPMP_REPAM_UNIFORM) wd = 1.0 / (double)deg;         // :1437, leave_weight 0
       else wd = 1.0 / (double)(deg + 1);                                      // :1437, leave_weight 1
       const Real w = (Real)wd;
@@ -147,6 +149,23 @@ __global__ void __launch_bounds__(256) level_update_kernel(LevelArgs<Real> A, in
           const Real d = w * t[x];
           own[x] = own[x] + d;  // RepamRight(+) first, :501-503
           th[x] = th[x] - d;    // RepamLeft(-)
+        }
+      }
+      if (A.residual && !A.primal) {   // send_messages_residual (include/factors_messages.hxx:2957-3007)
+        Real r = Real(0);
+        for (uint64_t q = k0; q < k1; ++q) {
+          const uint32_t e = A.inc_edge[q];
+          const uint32_t fl = A.inc_flags[q];
+          const uint32_t side = fl & 1u, later = (fl >> 1) & 1u;
+          const bool is_later = A.forward ? later : !later;
+          if (aniso && !is_later) continue;
+          r = r + w;
+          Real* own = side == 0 ? A.st.a(e) : A.st.b(e);
+          for (uint32_t x = gl; x < L; x += G) {
+            const Real d = r * th[x];
+            own[x] = own[x] + d;
+            th[x] = th[x] - d;
+          }
         }
       }
     }

@@ -41,6 +41,7 @@ struct GraphArgs {
   uint32_t first, count;      // nodes [first, first + count) (schedule order)
   uint32_t L, P;              // label count (the largest one when mixed), parameters per incidence (uniform L)
   int pw, repam, forward, primal;
+  int residual;               // update_factor_residual (include/factors_messages.hxx:2270-2279) instead of UpdateFactor in the plain passes
 };
 
 // ---- fast path: one label count L = LT (power of two <= 32), dense tables, at most DMAX incident edges ---------------------------
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
   const int x = threadIdx.x % LT;
   const unsigned lane = threadIdx.x & 31;
   const unsigned gmask = (LT == 32 ? 0xffffffffu : ((1u << LT) - 1u)) << (lane & ~(unsigned)(LT - 1));
-  const bool aniso = A.repam == LPMP_REPAM_ANISOTROPIC;
+  const bool aniso = A.repam == LPMP_REPAM_ANISOTROPIC || A.repam == LPMP_REPAM_ANISOTROPIC2;
   const Real INF = RealTraits<Real>::inf();
   double acc = 0.0;
   static_assert(DMAX == 4, "the node descriptor holds four slots");
@@ -151,7 +152,8 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
       }
       if (deg > 0) {
         double wd;
-        if (aniso) wd = 1.0 / (double)(n_in > n_out ? n_in : n_out);                     // include/LP_MP.h:1397
+        if (A.repam == LPMP_REPAM_ANISOTROPIC) wd = 1.0 / (double)(n_in > n_out ? n_in : n_out);   // include/LP_MP.h:1397
+        else if (A.repam == LPMP_REPAM_ANISOTROPIC2) wd = 1.0 / (double)(A.forward ? n_out : n_in);   // :1134
         else if (A.repam == LPMP_REPAM_UNIFORM) wd = 1.0 / (double)(n_in + n_out);       // :1437, leave_weight 0
         else wd = 1.0 / (double)(n_in + n_out + 1);                                      // :1437, leave_weight 1
         const Real w = (Real)wd;
@@ -164,6 +166,20 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
           if (s < (int)deg && (!aniso || is_later)) {
             own[s] = own[s] + d;  // RepamRight(+) first, :501-503
             th = th - d;          // RepamLeft(-)
+          }
+        }
+        if (A.residual && !A.primal) {   // send_messages_residual (:2957-3007): the same messages again, cumulative weight, live theta
+          Real r = Real(0);
+#pragma unroll
+          for (int s = 0; s < DMAX; ++s) {
+            const bool later = (fl[s] >> 1) & 1u;
+            const bool is_later = A.forward ? later : !later;
+            if (s < (int)deg && (!aniso || is_later)) {
+              r = r + w;
+              const Real dr = r * th;
+              own[s] = own[s] + dr;
+              th = th - dr;
+            }
           }
         }
       }
@@ -211,7 +227,7 @@ __global__ void __launch_bounds__(256) graph_node_generic_kernel(const GraphArgs
   Real* th = smem + (size_t)g * 3 * A.L;
   Real* oth = th + A.L;
   Real* hs = oth + A.L;
-  const bool aniso = A.repam == LPMP_REPAM_ANISOTROPIC;
+  const bool aniso = A.repam == LPMP_REPAM_ANISOTROPIC || A.repam == LPMP_REPAM_ANISOTROPIC2;
   const bool mixed = A.voff != nullptr;
   const Real INF = RealTraits<Real>::inf();
   double acc = 0.0;
@@ -269,7 +285,8 @@ __global__ void __launch_bounds__(256) graph_node_generic_kernel(const GraphArgs
     if (q1 > q0) {
       const uint32_t deg = n_in + n_out;
       double wd;
-      if (aniso) wd = 1.0 / (double)(n_in > n_out ? n_in : n_out);          // include/LP_MP.h:1397
+      if (A.repam == LPMP_REPAM_ANISOTROPIC) wd = 1.0 / (double)(n_in > n_out ? n_in : n_out);   // include/LP_MP.h:1397
+      else if (A.repam == LPMP_REPAM_ANISOTROPIC2) wd = 1.0 / (double)(A.forward ? n_out : n_in);   // :1134
       else if (A.repam == LPMP_REPAM_UNIFORM) wd = 1.0 / (double)deg;         // :1437, leave_weight 0
       else wd = 1.0 / (double)(deg + 1);                                      // :1437, leave_weight 1
       const Real w = (Real)wd;
@@ -284,6 +301,21 @@ __global__ void __launch_bounds__(256) graph_node_generic_kernel(const GraphArgs
           const Real d = w * hs[x];
           own[x] = own[x] + d;  // RepamRight(+) first, :501-503
           th[x] = th[x] - d;    // RepamLeft(-)
+        }
+      }
+      if (A.residual && !A.primal) {   // send_messages_residual (:2957-3007)
+        Real r = Real(0);
+        for (uint32_t q = q0; q < q1; ++q) {
+          const bool later = (A.flags[q] >> 1) & 1u;
+          const bool is_later = A.forward ? later : !later;
+          if (aniso && !is_later) continue;
+          r = r + w;
+          Real* own = rec + (uint64_t)(1 + q - q0) * Lk;
+          for (uint32_t x = gl; x < Lk; x += G) {
+            const Real d = r * th[x];
+            own[x] = own[x] + d;
+            th[x] = th[x] - d;
+          }
         }
       }
     }

@@ -246,6 +246,10 @@ class LP:
     def set_reparametrization(self, mode):
         self._ck(self.api.set_reparametrization(self.h, K.REPAM[mode] if isinstance(mode, str) else int(mode)))
 
+    def set_send_mode(self, mode):
+        """--reparametrizationType of the reference LP: "shared" (default) or "residual" (include/LP_MP.h:704-722)"""
+        self._ck(self.api.set_send_mode(self.h, K.SEND_MODE[mode] if isinstance(mode, str) else int(mode)))
+
     def ComputePass(self, iteration=0):
         self._ck(self.api.compute_pass(self.h, int(iteration)))
 

@@ -56,7 +56,7 @@ struct Oracle : OracleBase {
   uint32_t L = 0;
   int pw = -1;
   bool finalized = false, force_dense = false;
-  int repam = -1, edge_order = LPMP_EDGE_ORDER_LIFO;
+  int repam = -1, edge_order = LPMP_EDGE_ORDER_LIFO, send_mode = LPMP_SEND_SHARED;
   double constant = 0.0;
   bool labels_valid = false;
   uint32_t gridH = 0, gridW = 0;
@@ -139,10 +139,11 @@ struct Oracle : OracleBase {
     }
   }
 
-  Real omega(uint64_t i) const {
+  Real omega(uint64_t i, bool forward) const {
     const uint32_t deg = n_in[i] + n_out[i];
     double w;
     if (repam == LPMP_REPAM_ANISOTROPIC) w = 1.0 / double(std::max(n_in[i], n_out[i]));  // include/LP_MP.h:1397
+    else if (repam == LPMP_REPAM_ANISOTROPIC2) w = 1.0 / double(forward ? n_out[i] : n_in[i]);   // :1134 (no_send_messages_later)
     else if (repam == LPMP_REPAM_UNIFORM) w = 1.0 / double(deg);                            // :1437 leave_weight 0
     else w = 1.0 / double(deg + 1);                                                          // :1437 leave_weight 1
     return Real(w);
@@ -155,7 +156,7 @@ struct Oracle : OracleBase {
     Real* th = &theta[to(i)];
     Real* h = h_.data();
     const uint32_t L = Ln(i);   // (shadows the LP-wide count: everything below is per variable)
-    const bool aniso = repam == LPMP_REPAM_ANISOTROPIC;
+    const bool aniso = repam == LPMP_REPAM_ANISOTROPIC || repam == LPMP_REPAM_ANISOTROPIC2;
     for (uint64_t k = k0; k < k1; ++k) {  // ReceiveMessages, :2440-2471
       const Incidence& c = inc[k];
       const bool earlier = forward ? !c.later : c.later;
@@ -175,7 +176,7 @@ struct Oracle : OracleBase {
       labels[i] = arg;
     }
     if (k0 == k1) return;
-    const Real w = omega(i);
+    const Real w = omega(i, forward);
     Real* t = t_.data();
     for (uint32_t x = 0; x < L; ++x) t[x] = th[x];  // tmp_factor snapshot, :2801-2805
     for (uint64_t k = k0; k < k1; ++k) {             // CallSendMessages, :2698-2744
@@ -189,6 +190,22 @@ struct Oracle : OracleBase {
         th[x] -= d;   // RepamLeft(-)
       }
       ++message_updates;
+    }
+    // (rounding passes go through UpdateFactorPrimal, which always sends in shared mode: include/LP_MP.h:1592-1602)
+    if (send_mode == LPMP_SEND_RESIDUAL && !primal) {   // send_messages_residual, :2957-3007: the same messages again, cumulative weight, live theta
+      Real residual_omega = Real(0);
+      for (uint64_t k = k0; k < k1; ++k) {
+        const Incidence& c = inc[k];
+        const bool later = forward ? c.later : !c.later;
+        if (aniso && !later) continue;
+        residual_omega += w;
+        Real* own = c.side == 0 ? &a[ao(c.edge)] : &b[bo(c.edge)];
+        for (uint32_t x = 0; x < L; ++x) {
+          const Real d = residual_omega * th[x];
+          own[x] += d;
+          th[x] -= d;
+        }
+      }
     }
   }
 
@@ -543,8 +560,16 @@ int LPMP_FN(begin)(lpmp_solver* h) { return DISPATCH(H(h), ([&] { if (int r = ne
 int LPMP_FN(end)(lpmp_solver* h) { return DISPATCH(H(h), need_final(o)); }
 int LPMP_FN(set_reparametrization)(lpmp_solver* h, int mode) {
   return DISPATCH(H(h), ([&] {
-    if (mode < 0 || mode > 2) { o.err = "reparametrization mode unknown"; return int(LPMP_ERR_INVALID); }
+    if (mode < 0 || mode > 3) { o.err = "reparametrization mode unknown"; return int(LPMP_ERR_INVALID); }
     o.repam = mode;
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(set_send_mode)(lpmp_solver* h, int mode) {
+  return DISPATCH(H(h), ([&] {
+    if (mode == LPMP_SEND_ADAPTIVE) { o.err = "adaptive sending needs send_message_to_right_improvement of the marginalisation message (absent from the reference snapshot)"; return int(LPMP_ERR_UNSUPPORTED); }
+    if (mode != LPMP_SEND_SHARED && mode != LPMP_SEND_RESIDUAL) { o.err = "send mode unknown"; return int(LPMP_ERR_INVALID); }
+    o.send_mode = mode;
     return int(LPMP_OK);
   })());
 }

@@ -268,11 +268,12 @@ void lpmp_ref_add_to_constant(void* hv, double x) { static_cast<RefHandle*>(hv)-
 
 void lpmp_ref_begin(void* hv) { static_cast<RefHandle*>(hv)->solver->GetLP().Begin(); }
 
-// 0 anisotropic, 1 uniform, 2 damped_uniform
+// 0 anisotropic, 1 uniform, 2 damped_uniform, 3 anisotropic2
 void lpmp_ref_set_reparametrization(void* hv, int mode) {
   const LPReparametrizationMode m = mode == 0 ? LPReparametrizationMode::Anisotropic
                                    : mode == 1 ? LPReparametrizationMode::Uniform
-                                               : LPReparametrizationMode::DampedUniform;
+                                   : mode == 2 ? LPReparametrizationMode::DampedUniform
+                                               : LPReparametrizationMode::Anisotropic2;
   static_cast<RefHandle*>(hv)->solver->GetLP().set_reparametrization(m);
 }
 

@@ -86,7 +86,7 @@ def _pd(x):
 class RefLP:
     """The reference's own LP<FMC>/Solver (oracle/ref_driver.cpp) with the method names of lp_mp_b200.LP."""
 
-    MODES = {"anisotropic": 0, "uniform": 1, "damped_uniform": 2}
+    MODES = {"anisotropic": 0, "uniform": 1, "damped_uniform": 2, "anisotropic2": 3}
 
     def __init__(self, lib, options=()):
         self.lib = lib

@@ -173,3 +173,48 @@ def test_reference_solver_drives_lp_cuda(options, shape):
     assert same_state(ref, cu)
     # the archive of the binding is the reference's archive
     assert cu.save_dual() == ref.save_dual()
+
+
+# ---- Anisotropic2 weights and residual sends ------------------------------------------------------------------------
+ALL_MODES = ["anisotropic", "anisotropic2", "uniform", "damped_uniform"]
+
+
+@pytest.mark.parametrize("send", ["shared", "residual"])
+@pytest.mark.parametrize("mode", ALL_MODES)
+@pytest.mark.parametrize("shape", ["mixed", "graph8", "graph5_potts", "grid_levels", "grid_wavefront", "grid_dense"])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_send_variants_on_device(dtype, send, mode, shape):
+    """every reparametrisation mode x {shared, residual} on the register kernel (graph8), the generic kernel (mixed counts, Potts),
+    and grids (level schedule; grids built for the wavefront kernels switch to it for Anisotropic2 / residual): bit-identical to
+    the oracle, which tests/test_send_modes.py pins against the reference core"""
+    from test_send_modes import lockstep
+    def make(lp):
+        rng = np.random.default_rng(41)
+        if shape == "mixed":
+            build(lp, *mixed_instance(3, n=50, m=110))
+        elif shape == "graph8":
+            ei, ej = grid_edges(7, 9)
+            lp.add_unaries(rng.random((63, 8))); lp.add_pairwise_dense(ei, ej, rng.random((len(ei), 8, 8)) - 0.2)
+        elif shape == "graph5_potts":
+            ei, ej = grid_edges(6, 5)
+            lp.add_unaries(rng.random((30, 5))); lp.add_pairwise_potts(ei, ej, rng.uniform(-0.4, 1.0, len(ei)))
+        elif shape == "grid_levels":
+            lp.grid_create(7, 6, 5, "potts"); lp.grid_fill_synthetic(3, -0.2, 1.0)
+        elif shape == "grid_wavefront":
+            lp.grid_create(19, 21, 16, "trunclin"); lp.grid_fill_synthetic(3, 0.25, 1.0)
+        else:
+            lp.grid_create(6, 9, 16, "dense"); lp.grid_fill_synthetic(3, 0.0, 1.0)
+        lp.finalize(); lp.Begin(); lp.set_send_mode(send)
+        return lp
+    lockstep(make(oracle_lp(dtype)), [make(cuda_lp(dtype))], mode, iters=3)
+
+
+def test_reference_solver_drives_lp_cuda_with_residual_sends():
+    theta, edges, tables = mixed_instance(19, n=30, m=66)
+    options = ["--maxIter", "17", "--reparametrizationType", "residual", "--standardReparametrization", "anisotropic2", "-v", "0"]
+    ref, cu = adapter_pair(theta, edges, tables, options)
+    r, c = ref.solve(), cu.solve()
+    assert np.array_equal(r["flags"], c["flags"]) and np.allclose(c["lb"], r["lb"], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(ref.labeling(), cu.labeling()) and same_state(ref, cu)
+    with pytest.raises(lp_mp_b200.LpmpError):
+        cuda_lp("f64").set_send_mode("adaptive")
