@@ -104,7 +104,13 @@ public:
   }
   void ForwardPassFactorRelation(factor* f1, factor* f2) { AddFactorRelation(f1, f2); }
   void BackwardPassFactorRelation(factor* f1, factor* f2) { AddFactorRelation(f2, f1); }
-  void put_in_same_partition(factor* f1, factor* f2) { partition_graph_.push_back({f1, f2}); }   // include/LP_MP.h:465
+  // include/LP_MP.h:465.  Only updated factors (unaries) make up a partition; a pairwise factor stands for the union of its variables
+  void put_in_same_partition(factor* f1, factor* f2) {
+    auto var = [&](factor* f) { return f->kind == factor::unary ? f->index : ei_[f->index]; };
+    for (factor* f : {f1, f2}) if (f->kind == factor::pairwise) partition_pairs_.push_back({ei_[f->index], ej_[f->index]});
+    partition_pairs_.push_back({var(f1), var(f2)});
+    if (h_) push_partition_pairs();
+  }
   void add_to_constant(const REAL x) { if (h_) ck(lpmp_add_to_constant(h_, x)); else constant_ += x; }   // :462
 
   INDEX GetNumberOfFactors() const { return factors_.size(); }
@@ -114,10 +120,12 @@ public:
   // ---- the LP_TYPE surface ---------------------------------------------------------------------------------------------------
   void Begin() {   // include/LP_MP.h:704-728
     const std::string& t = reparametrization_type_arg_.getValue();
-    if (t != "shared" && t != "residual") throw std::runtime_error("LP_cuda: reparametrizationType " + t + " is not available on the device (shared | residual)");
+    if (t == "adaptive") throw std::runtime_error("LP_cuda: reparametrizationType adaptive is not available on the device (see lpmp_set_send_mode)");
+    if (t != "shared" && t != "residual" && t != "partition" && t != "overlapping_partition") throw std::runtime_error("reparametrizationType " + t + " unknown");
     if (!h_) upload();
     ck(lpmp_begin(h_));
     ck(lpmp_set_send_mode(h_, t == "residual" ? LPMP_SEND_RESIDUAL : LPMP_SEND_SHARED));
+    staged_ = t == "partition" ? 1 : (t == "overlapping_partition" ? 2 : 0);
   }
   void End() { ck(lpmp_end(h_)); }
   void set_reparametrization(const LPReparametrizationMode m) {   // include/config.hxx:72
@@ -131,7 +139,11 @@ public:
     }
     ck(lpmp_set_reparametrization(need()->h_, mode));
   }
-  void ComputePass(const INDEX iteration) { ck(lpmp_compute_pass(need()->h_, iteration)); }                                  // :869-887
+  void ComputePass(const INDEX iteration) {                                                                                 // :869-887
+    need();
+    if (staged_) ck(lpmp_compute_partition_pass(h_, inner_iteration_number_arg_.getValue(), staged_ == 2));
+    if (staged_ != 1) ck(lpmp_compute_pass(h_, iteration));
+  }
   void ComputeForwardPass() { ck(lpmp_compute_forward_pass(need()->h_)); }                                                   // :889-900
   void ComputeBackwardPass() { ck(lpmp_compute_backward_pass(need()->h_)); }                                                 // :902-911
   void ComputeForwardPassAndPrimal(const INDEX iteration) { ck(lpmp_compute_forward_pass_and_primal(need()->h_, iteration)); }   // :913-922
@@ -194,7 +206,16 @@ private:
     }
     if (constant_ != 0.0) ck(lpmp_add_to_constant(h_, constant_));
     ck(lpmp_finalize(h_));
+    push_partition_pairs();
     theta_.clear(); theta_.shrink_to_fit(); tables_.clear(); tables_.shrink_to_fit();
+  }
+
+  void push_partition_pairs() {
+    if (partition_pairs_.empty()) return;
+    std::vector<uint64_t> a, b;
+    for (const auto& p : partition_pairs_) { a.push_back(p[0]); b.push_back(p[1]); }
+    ck(lpmp_put_in_same_partition(h_, a.size(), a.data(), b.data()));
+    partition_pairs_.clear();
   }
 
   TCLAP::ValueArg<std::string> reparametrization_type_arg_;
@@ -209,7 +230,8 @@ private:
   std::vector<double> theta_, tables_;       // host staging until Begin()
   std::vector<INDEX> ei_, ej_;
   std::vector<unsigned char> reversed_;
-  std::vector<std::array<factor*, 2>> partition_graph_;
+  std::vector<std::array<INDEX, 2>> partition_pairs_;
+  int staged_ = 0;   // 1: partition, 2: overlapping_partition (--reparametrizationType)
   bool custom_relations_ = false;
   REAL constant_ = 0.0;
 };

@@ -185,6 +185,24 @@ int LPMP_FN(compute_forward_pass)(lpmp_solver* h);                   /* :889-900
 int LPMP_FN(compute_backward_pass)(lpmp_solver* h);                  /* :902-911 */
 int LPMP_FN(compute_forward_pass_and_primal)(lpmp_solver* h, uint64_t iteration);  /* :913-922 */
 int LPMP_FN(compute_backward_pass_and_primal)(lpmp_solver* h, uint64_t iteration); /* :924-933 */
+/* Staged optimisation (--reparametrizationType partition | overlapping_partition, include/LP_MP.h:463-465,869-887,1716-2051).
+ * put_in_same_partition joins the partitions of variables i[k] and j[k] (LP::put_in_same_partition on the two unary factors; only
+ * updated factors, i.e. unaries, make up a partition; a variable never mentioned is a partition of its own).  Partitions are ordered
+ * as construct_factor_partition orders them (by the root of the reference's union-find, include/union_find.hxx:36-50), the variables
+ * of a partition by their rank.
+ * compute_partition_pass == LP::compute_partition_pass(inner_iterations) (overlapping == 0: per partition `inner_iterations` forward +
+ * backward sweeps over the partition alone, then one sweep pushing into the next partition; then the same from the last partition
+ * back) or LP::compute_overlapping_partition_pass (overlapping != 0: the sweeps run over pairs of neighbouring partitions).  A sweep
+ * over a subset S follows ComputeAnisotropicWeights on S (include/LP_MP.h:1230-1415): a variable receives on the edges to variables
+ * of S before it and -- unless it is the first of S -- on its edges leaving S, sends on the edges to variables of S after it with
+ * weight 1 / max(#those, #its other edges).  LP::ComputePass in partition mode is this call; in overlapping_partition mode this call
+ * followed by a forward and a backward pass.  General graphs (add_unaries / add_pairwise_*); a grid is partitioned by building it
+ * through those calls.
+ * NOTE the reference sorts the factors of a partition with a comparator that compares an element with itself (include/LP_MP.h:1776):
+ * partitions of at most 16 factors keep their insertion order (== rank order for the default ranks), larger ones come out in an
+ * order that is an artefact of std::sort.  This library always uses the rank order. */
+int LPMP_FN(put_in_same_partition)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j);
+int LPMP_FN(compute_partition_pass)(lpmp_solver* h, uint64_t inner_iterations, int overlapping);
 int LPMP_FN(lower_bound)(lpmp_solver* h, double* out);               /* LP::LowerBound, :1507-1518 */
 int LPMP_FN(evaluate_primal)(lpmp_solver* h, double* out);           /* LP::EvaluatePrimal, :1520-1536 (+inf if inconsistent) */
 int LPMP_FN(check_primal_consistency)(lpmp_solver* h, int* out);     /* LP::CheckPrimalConsistency, :1066-1082 */

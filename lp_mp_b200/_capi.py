@@ -71,6 +71,8 @@ SIGNATURES = {
     "compute_backward_pass": [_vp],
     "compute_forward_pass_and_primal": [_vp, _u64],
     "compute_backward_pass_and_primal": [_vp, _u64],
+    "put_in_same_partition": [_vp, _u64, _pu64, _pu64],
+    "compute_partition_pass": [_vp, _u64, _i],
     "lower_bound": [_vp, _pd],
     "evaluate_primal": [_vp, _pd],
     "check_primal_consistency": [_vp, C.POINTER(_i)],

@@ -299,6 +299,8 @@ struct ISolver {
   virtual int set_reparametrization(int mode) = 0;
   virtual int set_send_mode(int mode) = 0;
   virtual int pass(bool forward, bool primal) = 0;
+  virtual int put_in_same_partition(uint64_t m, const uint64_t* i, const uint64_t* j) = 0;
+  virtual int partition_pass(uint64_t inner, int overlapping) = 0;
   virtual int lower_bound(double* out) = 0;
   virtual int evaluate_primal(double* out) = 0;
   virtual int check_primal_consistency(int* out) = 0;
@@ -1022,6 +1024,27 @@ struct Solver : ISolver {
     return LPMP_OK;
   }
 
+  // LP::put_in_same_partition / compute_partition_pass / compute_overlapping_partition_pass (include/LP_MP.h:463-465,1961-2070)
+  int put_in_same_partition(uint64_t m, const uint64_t* i, const uint64_t* j) override {
+    if (is_grid) { err = "partition passes run on the general-graph layout: build the grid through add_unaries / add_pairwise_*"; return LPMP_ERR_UNSUPPORTED; }
+    for (uint64_t k = 0; k < m; ++k) if (i[k] >= N || j[k] >= N) { err = "variable out of range"; return LPMP_ERR_INVALID; }
+    for (uint64_t k = 0; k < m; ++k) graph.partition_graph.push_back({i[k], j[k]});
+    graph.partition_valid = false;
+    return LPMP_OK;
+  }
+  int partition_pass(uint64_t inner, int overlapping) override {
+    if (int r = need_final()) return r;
+    if (is_grid) { err = "partition passes run on the general-graph layout: build the grid through add_unaries / add_pairwise_*"; return LPMP_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(device));
+    fused_lb_valid = false;
+    int launched = 0;
+    const int r = graph.partition_pass(inner, overlapping != 0, tune.level_group, num_sms, stream, err, &launched);
+    launches += (uint64_t)launched;
+    if (r) return r;
+    CUDA_TRY(cudaGetLastError());
+    return LPMP_OK;
+  }
+
   template <typename Topo>
   BoundArgs<Real, Topo> bound_args(Topo topo) {
     BoundArgs<Real, Topo> A;
@@ -1529,6 +1552,8 @@ int lpmp_compute_forward_pass(lpmp_solver* h) { return S(h)->pass(true, false); 
 int lpmp_compute_backward_pass(lpmp_solver* h) { return S(h)->pass(false, false); }
 int lpmp_compute_forward_pass_and_primal(lpmp_solver* h, uint64_t) { return S(h)->pass(true, true); }
 int lpmp_compute_backward_pass_and_primal(lpmp_solver* h, uint64_t) { return S(h)->pass(false, true); }
+int lpmp_put_in_same_partition(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j) { return S(h)->put_in_same_partition(m, i, j); }
+int lpmp_compute_partition_pass(lpmp_solver* h, uint64_t inner, int overlapping) { return S(h)->partition_pass(inner, overlapping); }
 int lpmp_lower_bound(lpmp_solver* h, double* out) { return S(h)->lower_bound(out); }
 int lpmp_evaluate_primal(lpmp_solver* h, double* out) { return S(h)->evaluate_primal(out); }
 int lpmp_check_primal_consistency(lpmp_solver* h, int* out) { return S(h)->check_primal_consistency(out); }

@@ -4,6 +4,8 @@
 #pragma once
 #include <algorithm>
 #include <numeric>
+#include <array>
+#include <map>
 #include <string>
 #include <thread>
 #include <vector>
@@ -19,6 +21,8 @@
 #endif
 
 namespace lpmp {
+
+#define LPMP_G_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(_e); return LPMP_ERR_CUDA; } } while (0)
 
 // construction on the device (one label count per LP): receiver-oriented parameters of incidence q from the edge-ordered host
 // arrays (dense: transposed for the second variable), and theta into the node records
@@ -76,6 +80,19 @@ struct GraphEngine {
   std::vector<uint64_t> level_off;          // nodes of level l: [level_off[l], level_off[l+1]) in schedule order
   std::vector<uint64_t> level_fast;         // ... of which [level_off[l], level_fast[l]) qualify for the fast kernel
   bool fast_ok = false;
+  // staged optimisation (partition passes): host copies of the incidence structure, the partitions and the planned sweeps
+  std::vector<uint32_t> k_of, h_inc, h_oth;             // schedule position of node i; inc_off / oth_node by schedule position
+  std::vector<uint64_t> rank_order;                     // nodes in rank order
+  std::vector<std::array<uint64_t, 2>> partition_graph;
+  std::vector<std::vector<uint64_t>> parts;
+  bool partition_valid = false;
+  struct Plan {
+    Buffer<uint32_t> node, base;
+    Buffer<uint8_t> code;
+    Buffer<Real> w;
+    std::vector<uint64_t> level_off;
+  };
+  std::map<std::pair<int, size_t>, Plan> plans;         // (kind, partition) -> sweep; kinds: 0 forward, 1 backward, 2 push to i+1, 3 push to i-1
 
   uint32_t Ln(uint64_t i) const { return mixed ? Lv[i] : L; }
   size_t device_bytes() const {
@@ -153,7 +170,8 @@ struct GraphEngine {
     level_fast.assign((size_t)max_level + 1, 0);
     for (uint64_t i = 0; i < N; ++i) { ++level_off[level[i] + 1]; if (is_fast(i)) ++level_fast[level[i]]; }
     for (size_t l = 0; l + 1 < level_off.size(); ++l) level_off[l + 1] += level_off[l];
-    std::vector<uint32_t> node_of_k(N), k_of(N);
+    std::vector<uint32_t> node_of_k(N);
+    k_of.assign(N, 0);
     {
       std::vector<uint64_t> pos_fast(level_off.begin(), level_off.end() - 1), pos_slow(max_level + 1);
       for (size_t l = 0; l <= max_level; ++l) { pos_slow[l] = level_off[l] + level_fast[l]; level_fast[l] += level_off[l]; }
@@ -163,6 +181,7 @@ struct GraphEngine {
         node_of_k[k] = (uint32_t)i; k_of[i] = (uint32_t)k;
       }
     }
+    rank_order = order;
     LPMP_TICK("order");
     // records
     std::vector<uint32_t> h_inc_off(N + 1, 0), h_voff, h_lab_k;
@@ -226,7 +245,6 @@ struct GraphEngine {
       }
     }
     LPMP_TICK("tab");
-#define LPMP_G_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(_e); return LPMP_ERR_CUDA; } } while (0)
     LPMP_G_TRY(put(inc_off, h_inc_off, stream));
     LPMP_G_TRY(put(oth_off, h_oth_off, stream));
     LPMP_G_TRY(put(oth_node, h_oth_node, stream));
@@ -263,6 +281,7 @@ struct GraphEngine {
       }
       LPMP_G_TRY(put(desc, h_desc, stream));
     }
+    h_inc = h_inc_off; h_oth = h_oth_node;
     if (mixed) {
       h_voff.resize(N + 1); h_lab_k.resize(N); h_lab_oth.resize(Q);
       for (uint64_t k = 0; k <= N; ++k) h_voff[k] = (uint32_t)rec_off[k];
@@ -279,12 +298,138 @@ struct GraphEngine {
     return LPMP_OK;
   }
 
+  // ---- staged optimisation: LP::construct_factor_partition / compute_partition_pass / compute_overlapping_partition_pass
+  // (/root/reference/include/LP_MP.h:1716-2051) ------------------------------------------------------------------------------------
+  void construct_partition() {
+    if (partition_valid) return;
+    partition_valid = true;
+    plans.clear();
+    // the reference's union-find (include/union_find.hxx:22-50): union by size, the root of x's set wins ties; partitions in the
+    // order of their roots (:70-92)
+    std::vector<uint64_t> id(N), sz(N, 1);
+    std::iota(id.begin(), id.end(), uint64_t(0));
+    auto find = [&](uint64_t p) { uint64_t root = p; while (root != id[root]) root = id[root]; while (p != root) { const uint64_t nx = id[p]; id[p] = root; p = nx; } return root; };
+    for (const auto& pr : partition_graph) {
+      const uint64_t i = find(pr[0]), j = find(pr[1]);
+      if (i == j) continue;
+      if (sz[i] < sz[j]) { id[i] = j; sz[j] += sz[i]; } else { id[j] = i; sz[i] += sz[j]; }
+    }
+    std::vector<uint64_t> part_of_root(N, ~uint64_t(0));
+    uint64_t np = 0;
+    for (uint64_t d = 0; d < N; ++d) if (find(d) == d) part_of_root[d] = np++;
+    parts.assign(np, {});
+    for (uint64_t t = 0; t < N; ++t) parts[part_of_root[find(rank_order[t])]].push_back(rank_order[t]);
+  }
+
+  // the sweep over `seq`: per node the receive / send code of every incidence and the send weight (ComputeAnisotropicWeights on a
+  // subsequence, include/LP_MP.h:1230-1415: receive from list members before this node and -- unless it is the first of the list --
+  // from outside the list; send to list members after it, weight 1 / max(#sends, #other messages)), grouped into the level sets of
+  // the dependencies inside the list
+  int build_plan(const std::vector<uint64_t>& seq, Plan& pl, cudaStream_t stream, std::string& err) {
+    const uint64_t NONE = ~uint64_t(0);
+    std::vector<uint64_t> pos(N, NONE);
+    for (uint64_t p = 0; p < seq.size(); ++p) pos[seq[p]] = p;
+    std::vector<uint32_t> level(seq.size(), 0);
+    uint32_t max_level = 0;
+    for (uint64_t p = 0; p < seq.size(); ++p) {
+      const uint32_t k = k_of[seq[p]];
+      uint32_t lv = 0;
+      for (uint32_t q = h_inc[k]; q < h_inc[k + 1]; ++q) { const uint64_t po = pos[h_oth[q]]; if (po != NONE && po < p) lv = std::max(lv, level[po] + 1); }
+      level[p] = lv;
+      max_level = std::max(max_level, lv);
+    }
+    pl.level_off.assign((size_t)max_level + 2, 0);
+    for (uint64_t p = 0; p < seq.size(); ++p) ++pl.level_off[level[p] + 1];
+    for (size_t l = 0; l + 1 < pl.level_off.size(); ++l) pl.level_off[l + 1] += pl.level_off[l];
+    std::vector<uint64_t> slot(pl.level_off.begin(), pl.level_off.end() - 1);
+    std::vector<uint32_t> h_node(seq.size()), h_base(seq.size());
+    std::vector<Real> h_w(seq.size());
+    std::vector<uint8_t> h_code;
+    for (uint64_t p = 0; p < seq.size(); ++p) {
+      const uint32_t k = k_of[seq[p]];
+      const uint64_t t = slot[level[p]]++;
+      h_node[t] = k;
+      h_base[t] = (uint32_t)h_code.size();
+      uint32_t n_send = 0;
+      for (uint32_t q = h_inc[k]; q < h_inc[k + 1]; ++q) {
+        const uint64_t po = pos[h_oth[q]];
+        const bool recv = po != NONE ? po < p : p > 0, send = po != NONE && po > p;
+        n_send += send ? 1u : 0u;
+        h_code.push_back((uint8_t)((recv ? 1u : 0u) | (send ? 2u : 0u)));
+      }
+      const uint32_t deg = h_inc[k + 1] - h_inc[k];
+      h_w[t] = n_send ? (Real)(1.0 / (double)std::max(n_send, deg - n_send)) : Real(0);
+    }
+    LPMP_G_TRY(put(pl.node, h_node, stream));
+    LPMP_G_TRY(put(pl.base, h_base, stream));
+    LPMP_G_TRY(put(pl.code, h_code, stream));
+    LPMP_G_TRY(put(pl.w, h_w, stream));
+    LPMP_G_TRY(cudaStreamSynchronize(stream));
+    return LPMP_OK;
+  }
+  int run_plan(int kind, size_t i, int level_group, int num_sms, cudaStream_t stream, std::string& err, int* launched) {
+    auto it = plans.find({kind, i});
+    if (it == plans.end()) {
+      std::vector<uint64_t> seq;
+      if (kind == 0) seq = parts[i];
+      else if (kind == 1) seq.assign(parts[i].rbegin(), parts[i].rend());
+      else { const auto& other = parts[kind == 2 ? i + 1 : i - 1]; seq = parts[i]; seq.insert(seq.end(), other.rbegin(), other.rend()); }
+      it = plans.emplace(std::piecewise_construct, std::forward_as_tuple(kind, i), std::forward_as_tuple()).first;
+      if (int r = build_plan(seq, it->second, stream, err)) return r;
+    }
+    const Plan& pl = it->second;
+    GraphArgs<Real> A = args(nullptr, nullptr);
+    A.plan_node = pl.node.p; A.plan_base = pl.base.p; A.plan_code = pl.code.p; A.plan_w = pl.w.p;
+    int G = 0, threads = 0;
+    size_t smem = 0;
+    if (!generic_shape(level_group, &G, &threads, &smem)) { err = "label count too large for the level kernel"; return LPMP_ERR_UNSUPPORTED; }
+    const uint64_t groups = threads / G;
+    for (size_t lv = 0; lv + 1 < pl.level_off.size(); ++lv) {
+      const uint64_t n = pl.level_off[lv + 1] - pl.level_off[lv];
+      if (!n) continue;
+      A.first = (uint32_t)pl.level_off[lv]; A.count = (uint32_t)n;
+      graph_node_generic_kernel<Real, 2><<<(int)std::min<uint64_t>((n + groups - 1) / groups, (uint64_t)num_sms * 8), threads, smem, stream>>>(A, G);
+      ++*launched;
+    }
+    return LPMP_OK;
+  }
+  int partition_pass(uint64_t no_passes, bool overlapping, int level_group, int num_sms, cudaStream_t stream, std::string& err, int* launched) {
+    construct_partition();
+    const size_t np = parts.size();
+    auto run = [&](int kind, size_t i) { return run_plan(kind, i, level_group, num_sms, stream, err, launched); };
+#define LPMP_RUN(kind, i) do { if (int _r = run(kind, i)) return _r; } while (0)
+    if (!overlapping) {   // compute_partition_pass, include/LP_MP.h:1961-1996
+      for (size_t i = 0; i < np; ++i) {
+        for (uint64_t it = 0; it < no_passes; ++it) { LPMP_RUN(0, i); LPMP_RUN(1, i); }
+        if (i + 1 < np) LPMP_RUN(2, i);
+      }
+      for (size_t ri = 0; ri < np; ++ri) {
+        const size_t i = np - ri - 1;
+        for (uint64_t it = 0; it < no_passes; ++it) { LPMP_RUN(0, i); LPMP_RUN(1, i); }
+        if (i != 0) LPMP_RUN(3, i);
+      }
+    } else {              // compute_overlapping_partition_pass, :2050-2070: f_forward(i) = push to i+1 of i, f_backward(i) = push to i of i+1
+      for (size_t i = 0; i + 1 < np; ++i) {
+        for (uint64_t it = 0; it < no_passes; ++it) { LPMP_RUN(2, i); LPMP_RUN(3, i + 1); }
+        LPMP_RUN(2, i);
+      }
+      for (size_t ri = 1; ri < np; ++ri) {
+        const size_t i = np - ri - 1;
+        for (uint64_t it = 0; it < no_passes; ++it) { LPMP_RUN(3, i + 1); LPMP_RUN(2, i); }
+        LPMP_RUN(3, i + 1);
+      }
+    }
+#undef LPMP_RUN
+    return LPMP_OK;
+  }
+
   GraphArgs<Real> args(uint32_t* labels, double* partial) const {
     GraphArgs<Real> A;
     A.desc = desc.p; A.vec = vec.p; A.tab = tab.p; A.inc_off = inc_off.p; A.oth_off = oth_off.p; A.flags = flags.p; A.oth_node = oth_node.p; A.node_of = node_of.p;
     A.voff = mixed ? voff.p : nullptr; A.toff = mixed ? toff.p : nullptr; A.lab_k = mixed ? lab_k.p : nullptr; A.lab_oth = mixed ? lab_oth.p : nullptr;
     A.labels = labels; A.partial = partial;
     A.first = 0; A.count = (uint32_t)N; A.L = L; A.P = P; A.pw = pw; A.repam = 0; A.forward = 1; A.primal = 0; A.residual = 0;
+    A.plan_node = nullptr; A.plan_base = nullptr; A.plan_code = nullptr; A.plan_w = nullptr;
     return A;
   }
 

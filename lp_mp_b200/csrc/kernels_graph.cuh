@@ -42,6 +42,12 @@ struct GraphArgs {
   uint32_t L, P;              // label count (the largest one when mixed), parameters per incidence (uniform L)
   int pw, repam, forward, primal;
   int residual;               // update_factor_residual (include/factors_messages.hxx:2270-2279) instead of UpdateFactor in the plain passes
+  // sweep over a subsequence of the nodes (partition passes, MODE 2 of the generic kernel): the t-th node of the launch is plan_node[t],
+  // its incidences carry plan_code[plan_base[t] + slot] (bit 0 receive, bit 1 send), every send has weight plan_w[t]
+  const uint32_t* plan_node;
+  const uint32_t* plan_base;
+  const uint8_t* plan_code;
+  const Real* plan_w;
 };
 
 // ---- fast path: one label count L = LT (power of two <= 32), dense tables, at most DMAX incident edges ---------------------------
@@ -216,7 +222,8 @@ __device__ __forceinline__ void graph_min_plus(int pw, const Real* __restrict__ 
 
 // ---- generic path: any label count (also mixed), any pairwise family, any degree -----------------------------------------------
 // One sub-warp group of G lanes per node, vectors staged in shared memory (per group: th[L], oth[L], hs[L]).
-// MODE 0: node update; MODE 1: lower-bound terms.
+// MODE 0: node update; MODE 1: lower-bound terms; MODE 2: node update of a planned sweep (weights and masks of
+// ComputeAnisotropicWeights on a subsequence, /root/reference/include/LP_MP.h:1230-1415, evaluated on the host).
 template <typename Real, int MODE>
 __global__ void __launch_bounds__(256) graph_node_generic_kernel(const GraphArgs<Real> A, int G) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -232,7 +239,8 @@ __global__ void __launch_bounds__(256) graph_node_generic_kernel(const GraphArgs
   const Real INF = RealTraits<Real>::inf();
   double acc = 0.0;
   for (uint32_t kk = blockIdx.x * groups_per_cta + g; kk < A.count; kk += gridDim.x * groups_per_cta) {
-    const uint32_t k = A.first + kk;
+    const uint32_t k = MODE == 2 ? A.plan_node[A.first + kk] : A.first + kk;
+    const uint8_t* code = MODE == 2 ? A.plan_code + A.plan_base[A.first + kk] : nullptr;
     const uint32_t q0 = A.inc_off[k], q1 = A.inc_off[k + 1];
     const uint32_t Lk = mixed ? A.lab_k[k] : A.L;
     Real* rec = A.vec + (mixed ? (uint64_t)A.voff[k] : ((uint64_t)k + q0) * A.L);
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(256) graph_node_generic_kernel(const GraphArgs
       const bool later = (fl >> 1) & 1u;
       if (later) ++n_out; else ++n_in;
       const bool earlier = A.forward ? !later : later;
-      if (MODE == 1 ? (fl & 1u) != 0u : (aniso && !earlier)) continue;
+      if (MODE == 2 ? (code[q - q0] & 1u) == 0u : (MODE == 1 ? (fl & 1u) != 0u : (aniso && !earlier))) continue;
       Real* own = rec + (uint64_t)(1 + q - q0) * Lk;
       const Real* other = A.vec + A.oth_off[q];
       const uint32_t Lo = mixed ? A.lab_oth[q] : A.L;
@@ -289,13 +297,13 @@ __global__ void __launch_bounds__(256) graph_node_generic_kernel(const GraphArgs
       else if (A.repam == LPMP_REPAM_ANISOTROPIC2) wd = 1.0 / (double)(A.forward ? n_out : n_in);   // :1134
       else if (A.repam == LPMP_REPAM_UNIFORM) wd = 1.0 / (double)deg;         // :1437, leave_weight 0
       else wd = 1.0 / (double)(deg + 1);                                      // :1437, leave_weight 1
-      const Real w = (Real)wd;
+      const Real w = MODE == 2 ? A.plan_w[A.first + kk] : (Real)wd;
       for (uint32_t x = gl; x < Lk; x += G) hs[x] = th[x];  // tmp_factor snapshot, :2801-2805 (each lane reads back its own labels)
       // CallSendMessages (:2698-2744)
       for (uint32_t q = q0; q < q1; ++q) {
         const bool later = (A.flags[q] >> 1) & 1u;
         const bool is_later = A.forward ? later : !later;
-        if (aniso && !is_later) continue;
+        if (MODE == 2 ? (code[q - q0] & 2u) == 0u : (aniso && !is_later)) continue;
         Real* own = rec + (uint64_t)(1 + q - q0) * Lk;
         for (uint32_t x = gl; x < Lk; x += G) {
           const Real d = w * hs[x];
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(256) graph_node_generic_kernel(const GraphArgs
           th[x] = th[x] - d;    // RepamLeft(-)
         }
       }
-      if (A.residual && !A.primal) {   // send_messages_residual (:2957-3007)
+      if (MODE != 2 && A.residual && !A.primal) {   // send_messages_residual (:2957-3007)
         Real r = Real(0);
         for (uint32_t q = q0; q < q1; ++q) {
           const bool later = (A.flags[q] >> 1) & 1u;

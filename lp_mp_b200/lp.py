@@ -250,6 +250,16 @@ class LP:
         """--reparametrizationType of the reference LP: "shared" (default) or "residual" (include/LP_MP.h:704-722)"""
         self._ck(self.api.set_send_mode(self.h, K.SEND_MODE[mode] if isinstance(mode, str) else int(mode)))
 
+    def put_in_same_partition(self, i, j):
+        """LP::put_in_same_partition on the unary factors of variables i[k], j[k] (include/LP_MP.h:465)"""
+        self._flush_pending()
+        i, j = self._edges(np.atleast_1d(i), np.atleast_1d(j))
+        self._ck(self.api.put_in_same_partition(self.h, len(i), _pu64(i), _pu64(j)))
+
+    def compute_partition_pass(self, inner_iterations=5, overlapping=False):
+        """LP::compute_partition_pass / compute_overlapping_partition_pass (include/LP_MP.h:1961-2051)"""
+        self._ck(self.api.compute_partition_pass(self.h, int(inner_iterations), 1 if overlapping else 0))
+
     def ComputePass(self, iteration=0):
         self._ck(self.api.compute_pass(self.h, int(iteration)))
 

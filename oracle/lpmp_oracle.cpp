@@ -209,6 +209,116 @@ struct Oracle : OracleBase {
     }
   }
 
+  // ---- staged optimisation: LP::put_in_same_partition / construct_factor_partition / compute_partition_pass /
+  // compute_overlapping_partition_pass (include/LP_MP.h:463-465,1716-2051) ---------------------------------------------------------
+  std::vector<std::array<uint64_t, 2>> partition_graph;
+  std::vector<std::vector<uint64_t>> parts;   // variables of every partition in rank order, partitions in the reference's order
+  bool partition_valid = false;
+
+  void construct_partition() {
+    if (partition_valid) return;
+    partition_valid = true;
+    // the reference's union-find (include/union_find.hxx:22-50): union by size, the root of x's set wins ties
+    std::vector<uint64_t> id(N), sz(N, 1);
+    std::iota(id.begin(), id.end(), uint64_t(0));
+    auto find = [&](uint64_t p) { uint64_t root = p; while (root != id[root]) root = id[root]; while (p != root) { const uint64_t nx = id[p]; id[p] = root; p = nx; } return root; };
+    for (const auto& pr : partition_graph) {
+      const uint64_t i = find(pr[0]), j = find(pr[1]);
+      if (i == j) continue;
+      if (sz[i] < sz[j]) { id[i] = j; sz[j] += sz[i]; } else { id[j] = i; sz[i] += sz[j]; }
+    }
+    // partitions in the order of their roots (get_contiguous_ids, :70-92: unaries keep their relative order among all factors)
+    std::vector<uint64_t> part_of_root(N, ~uint64_t(0));
+    uint64_t np = 0;
+    for (uint64_t d = 0; d < N; ++d) if (find(d) == d) part_of_root[d] = np++;
+    parts.assign(np, {});
+    for (uint64_t k = 0; k < N; ++k) parts[part_of_root[find(order[k])]].push_back(order[k]);   // rank order inside a partition
+  }
+
+  // one sweep over the subsequence `seq` with the weights / receive masks ComputeAnisotropicWeights derives for it
+  // (include/LP_MP.h:1230-1415 with the pairwise factors outside the iterated list, :1262-1301,1319-1345)
+  std::vector<uint64_t> pos_;
+  void sequence_pass(const std::vector<uint64_t>& seq) {
+    const uint64_t NONE = ~uint64_t(0);
+    pos_.assign(N, NONE);
+    for (uint64_t p = 0; p < seq.size(); ++p) pos_[seq[p]] = p;
+    Real* h = h_.data();
+    Real* t = t_.data();
+    for (uint64_t p = 0; p < seq.size(); ++p) {
+      const uint64_t i = seq[p];
+      const uint64_t k0 = inc_off[i], k1 = inc_off[i + 1];
+      if (k0 == k1) continue;
+      Real* th = &theta[to(i)];
+      const uint32_t Li = Ln(i);
+      uint32_t n_send = 0;
+      auto other_of = [&](const Incidence& c) { return c.side == 0 ? ej[c.edge] : ei[c.edge]; };
+      // receive: the other variable is in the list and before this one; or it is outside the list and this is not the first of the list
+      for (uint64_t k = k0; k < k1; ++k) {
+        const Incidence& c = inc[k];
+        const uint64_t po = pos_[other_of(c)];
+        if (po != NONE && po > p) ++n_send;
+        if (!(po != NONE ? po < p : p > 0)) continue;
+        min_plus(c.edge, c.side, h);
+        Real* own = c.side == 0 ? &a[ao(c.edge)] : &b[bo(c.edge)];
+        for (uint32_t x = 0; x < Li; ++x) {
+          const Real m = h[x] + own[x];
+          th[x] += m;
+          own[x] -= m;
+        }
+        ++message_updates;
+      }
+      if (n_send == 0) continue;
+      const uint32_t deg = uint32_t(k1 - k0);
+      const Real w = Real(1.0 / double(std::max(n_send, deg - n_send)));   // srmp_weight, :1386 (no receiving factor is in the list)
+      for (uint32_t x = 0; x < Li; ++x) t[x] = th[x];
+      for (uint64_t k = k0; k < k1; ++k) {
+        const Incidence& c = inc[k];
+        const uint64_t po = pos_[other_of(c)];
+        if (!(po != NONE && po > p)) continue;
+        Real* own = c.side == 0 ? &a[ao(c.edge)] : &b[bo(c.edge)];
+        for (uint32_t x = 0; x < Li; ++x) {
+          const Real d = w * t[x];
+          own[x] += d;
+          th[x] -= d;
+        }
+        ++message_updates;
+      }
+    }
+  }
+  static std::vector<uint64_t> concat_reversed(const std::vector<uint64_t>& first, const std::vector<uint64_t>& second) {
+    std::vector<uint64_t> f(first);
+    f.insert(f.end(), second.rbegin(), second.rend());
+    return f;
+  }
+  void partition_pass(uint64_t no_passes, bool overlapping) {
+    construct_partition();
+    const size_t np = parts.size();
+    auto reversed = [](const std::vector<uint64_t>& v) { return std::vector<uint64_t>(v.rbegin(), v.rend()); };
+    if (!overlapping) {   // compute_partition_pass, :1961-1996
+      for (size_t i = 0; i < np; ++i) {
+        for (uint64_t it = 0; it < no_passes; ++it) { sequence_pass(parts[i]); sequence_pass(reversed(parts[i])); }
+        if (i + 1 < np) sequence_pass(concat_reversed(parts[i], parts[i + 1]));
+      }
+      for (size_t ri = 0; ri < np; ++ri) {
+        const size_t i = np - ri - 1;
+        for (uint64_t it = 0; it < no_passes; ++it) { sequence_pass(parts[i]); sequence_pass(reversed(parts[i])); }
+        if (i != 0) sequence_pass(concat_reversed(parts[i], parts[i - 1]));
+      }
+    } else {              // compute_overlapping_partition_pass, :2050-2070
+      for (size_t i = 0; i + 1 < np; ++i) {
+        const auto f_forward = concat_reversed(parts[i], parts[i + 1]), f_backward = concat_reversed(parts[i + 1], parts[i]);
+        for (uint64_t it = 0; it < no_passes; ++it) { sequence_pass(f_forward); sequence_pass(f_backward); }
+        sequence_pass(f_forward);
+      }
+      for (size_t ri = 1; ri < np; ++ri) {
+        const size_t i = np - ri - 1;
+        const auto f_forward = concat_reversed(parts[i], parts[i + 1]), f_backward = concat_reversed(parts[i + 1], parts[i]);
+        for (uint64_t it = 0; it < no_passes; ++it) { sequence_pass(f_backward); sequence_pass(f_forward); }
+        sequence_pass(f_backward);
+      }
+    }
+  }
+
   void pass(bool forward, bool primal) {
     if (forward) for (uint64_t k = 0; k < N; ++k) update_node(order[k], true, primal);
     else for (uint64_t k = N; k-- > 0;) update_node(order[k], false, primal);
@@ -580,6 +690,17 @@ int LPMP_FN(compute_forward_pass)(lpmp_solver* h) { return DISPATCH(H(h), ([&] {
 int LPMP_FN(compute_backward_pass)(lpmp_solver* h) { return DISPATCH(H(h), ([&] { if (int r = need_repam(o)) return r; o.pass(false, false); return int(LPMP_OK); })()); }
 int LPMP_FN(compute_forward_pass_and_primal)(lpmp_solver* h, uint64_t) { return DISPATCH(H(h), ([&] { if (int r = need_repam(o)) return r; o.pass(true, true); return int(LPMP_OK); })()); }
 int LPMP_FN(compute_backward_pass_and_primal)(lpmp_solver* h, uint64_t) { return DISPATCH(H(h), ([&] { if (int r = need_repam(o)) return r; o.pass(false, true); return int(LPMP_OK); })()); }
+int LPMP_FN(put_in_same_partition)(lpmp_solver* h, uint64_t m, const uint64_t* i, const uint64_t* j) {
+  return DISPATCH(H(h), ([&] {
+    for (uint64_t k = 0; k < m; ++k) if (i[k] >= o.N || j[k] >= o.N) { o.err = "variable out of range"; return int(LPMP_ERR_INVALID); }
+    for (uint64_t k = 0; k < m; ++k) o.partition_graph.push_back({i[k], j[k]});
+    o.partition_valid = false;
+    return int(LPMP_OK);
+  })());
+}
+int LPMP_FN(compute_partition_pass)(lpmp_solver* h, uint64_t inner, int overlapping) {
+  return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; o.partition_pass(inner, overlapping != 0); return int(LPMP_OK); })());
+}
 int LPMP_FN(lower_bound)(lpmp_solver* h, double* out) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; *out = o.lower_bound(); return int(LPMP_OK); })()); }
 int LPMP_FN(evaluate_primal)(lpmp_solver* h, double* out) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; *out = o.evaluate_primal(); return int(LPMP_OK); })()); }
 int LPMP_FN(check_primal_consistency)(lpmp_solver* h, int* out) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; *out = 1; return int(LPMP_OK); })()); }

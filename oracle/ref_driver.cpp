@@ -264,6 +264,12 @@ int64_t lpmp_ref_add_pairwise(void* hv, uint64_t i, uint64_t j, const double* ta
 #endif
 }
 
+// LP::put_in_same_partition on the unary factors of variables i and j (include/LP_MP.h:465)
+void lpmp_ref_put_in_same_partition(void* hv, uint64_t i, uint64_t j) {
+  auto* h = static_cast<RefHandle*>(hv);
+  h->solver->GetLP().put_in_same_partition(h->unaries[i], h->unaries[j]);
+}
+
 void lpmp_ref_add_to_constant(void* hv, double x) { static_cast<RefHandle*>(hv)->solver->GetLP().add_to_constant(x); }
 
 void lpmp_ref_begin(void* hv) { static_cast<RefHandle*>(hv)->solver->GetLP().Begin(); }

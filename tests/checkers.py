@@ -69,6 +69,7 @@ def ref_library(fifo=False, cuda_adapter=False):
         "lpmp_ref_unary_lower_bound": ([u64, pd], d),
         "lpmp_ref_pairwise_min_marginal": ([u64, u64, pd, pd, pd, C.c_int, pd, pd], None),
         "lpmp_ref_solve": ([vp, pd, pd, C.POINTER(C.c_int32), u64, pd, pd, pd], u64),
+        "lpmp_ref_put_in_same_partition": ([vp, u64, u64], None),
         "lpmp_ref_dual_size": ([vp], u64),
         "lpmp_ref_save_dual": ([vp, vp], None),
         "lpmp_ref_load_dual": ([vp, vp], None),
@@ -115,6 +116,10 @@ class RefLP:
         self.E += 1
         self.edges = getattr(self, "edges", []) + [(i, j)]
         return r
+
+    def put_in_same_partition(self, i, j):
+        for a, b in zip(np.atleast_1d(i), np.atleast_1d(j)):
+            self.lib.lpmp_ref_put_in_same_partition(self.h, int(a), int(b))
 
     def Begin(self): self.lib.lpmp_ref_begin(self.h)
     def End(self): pass

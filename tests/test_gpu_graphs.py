@@ -218,3 +218,78 @@ def test_reference_solver_drives_lp_cuda_with_residual_sends():
     assert np.array_equal(ref.labeling(), cu.labeling()) and same_state(ref, cu)
     with pytest.raises(lp_mp_b200.LpmpError):
         cuda_lp("f64").set_send_mode("adaptive")
+
+
+# ---- staged optimisation: partition / overlapping-partition passes --------------------------------------------------
+def _row_pair_partitions(H, W):
+    """put_in_same_partition calls that make every pair of grid rows one partition"""
+    pi, pj = [], []
+    for r in range(H):
+        for c in range(W):
+            n = r * W + c
+            if c + 1 < W:
+                pi.append(n); pj.append(n + 1)
+            if r % 2 == 0 and r + 1 < H:
+                pi.append(n); pj.append(n + W)
+    return pi, pj
+
+
+@pytest.mark.parametrize("overlapping", [False, True])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_partition_passes_on_device(dtype, overlapping):
+    """LP::compute_partition_pass / compute_overlapping_partition_pass (include/LP_MP.h:1961-2070): bit-identical to the oracle, which
+    tests/test_partition_passes.py pins against the reference core"""
+    rng = np.random.default_rng(5)
+    H, W, L = 8, 7, 8
+    ei, ej = grid_edges(H, W)
+    theta, tables = rng.random((H * W, L)), rng.random((len(ei), L, L)) - 0.3
+    pi, pj = _row_pair_partitions(H, W)
+    lps = [oracle_lp(dtype), cuda_lp(dtype)]
+    for lp in lps:
+        lp.add_unaries(theta); lp.add_pairwise_dense(ei, ej, tables)
+        lp.put_in_same_partition(pi, pj)
+        lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+    o, c = lps
+    prev = c.LowerBound()
+    for it in range(3):
+        for lp in lps:
+            lp.compute_partition_pass(2, overlapping)
+            if overlapping:
+                lp.ComputeForwardPass(); lp.ComputeBackwardPass()
+        assert same_state(o, c), it
+        lb = c.LowerBound()
+        assert np.isclose(lb, o.LowerBound(), rtol=1e-12 if dtype == "f64" else 1e-6) and lb >= prev - 1e-6 * abs(prev)
+        prev = lb
+    # changing the partition afterwards rebuilds the sweeps
+    for lp in lps:
+        lp.put_in_same_partition([0], [H * W - 1])
+        lp.compute_partition_pass(1, overlapping)
+    assert same_state(o, c)
+
+
+def test_partition_passes_mixed_labels_against_the_reference_core(ref_lib):
+    theta, edges, tables = mixed_instance(13, n=36, m=80)
+    pi = [k for k in range(35) if k % 6 != 5]
+    pj = [k + 1 for k in pi]   # six partitions of six consecutive variables
+    ref = RefLP(ref_lib, ["-v", "0", "--reparametrizationType", "partition", "--innerIteration", "3"])
+    c = cuda_lp("f64")
+    build(ref, theta, edges, tables); build(c, theta, edges, tables)
+    ref.put_in_same_partition(pi, pj); c.put_in_same_partition(pi, pj)
+    ref.Begin(); c.Begin(); ref.set_reparametrization("anisotropic"); c.set_reparametrization("anisotropic")
+    for it in range(3):
+        ref.ComputePass(it); c.compute_partition_pass(3, False)
+        assert same_state(ref, c) and np.isclose(c.LowerBound(), ref.LowerBound(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["partition", "overlapping_partition"])
+def test_reference_solver_drives_lp_cuda_in_partition_mode(kind):
+    """--reparametrizationType partition / overlapping_partition: Solver::Solve() over LP_cuda == over the reference's LP<FMC>"""
+    theta, edges, tables = mixed_instance(29, n=30, m=64)
+    options = ["--maxIter", "9", "--reparametrizationType", kind, "--innerIteration", "2", "--roundingReparametrization", "anisotropic", "-v", "0"]
+    ref, cu = adapter_pair(theta, edges, tables, options)
+    pi = [k for k in range(29) if k % 5 != 4]
+    pj = [k + 1 for k in pi]
+    ref.put_in_same_partition(pi, pj); cu.put_in_same_partition(pi, pj)
+    r, c = ref.solve(), cu.solve()
+    assert np.array_equal(r["flags"], c["flags"]) and np.allclose(c["lb"], r["lb"], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(ref.labeling(), cu.labeling()) and same_state(ref, cu)
