@@ -409,7 +409,7 @@ def run_graph(args, name, rank, world, local_rank, dist, with_e2e=True):
     achieved = bytes_pass / mean_pass_s / 1e9
     levels = int(stats["num_levels"])
     per_pass_launches = stats.get("pass_launches", levels)
-    roofline = {"bound": "hbm", "kernel": stats.get("pass_kernel", f"level_update_kernel ({levels} launches = one pass: one per colour class)"),
+    roofline = {"bound": "hbm", "kernel": stats.get("pass_kernel", f"graph_node_kernel ({levels} launches = one pass: one per colour class; node-record layout)"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                 "traffic": imported_traffic(f"{name}_{dtype}"), "traffic_source": "imported from profiles/traffic.json (ncu --set full capture), not measured in this run",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_pass / max(1, per_pass_launches),
@@ -683,6 +683,27 @@ def run_grid(args, name, rank, world, local_rank, dist, dtype=None, with_e2e=Tru
     }
 
 
+def default_solve(name, max_iter, local_rank):
+    """A full Solve() with the reference's default control law (MpRoundingSolver + StandardVisitor defaults: rounding iterations with
+    damped-uniform weights every 5th iteration, include/visitors/standard_visitor.hxx:32-44; include/solver.hxx:230-257,381-400)
+    through the host mirror lp_mp_b200/solver.py: wall clock from Begin() to the end of Solve(), potentials already in HBM."""
+    import lp_mp_b200
+    from lp_mp_b200 import MpRoundingSolver, StandardVisitor
+    H, W, L, pairwise, lo, hi, desc = WORKLOADS[name]
+    lp = lp_mp_b200.LP(dtype="f32", device=local_rank).grid_create(H, W, L, pairwise)
+    lp.grid_fill_synthetic(SEED, lo, hi)
+    lp.finalize()
+    s = MpRoundingSolver(lp, StandardVisitor(maxIter=max_iter))
+    t0 = time.perf_counter()
+    s.Solve()
+    lp.synchronize()
+    dt = time.perf_counter() - t0
+    return {"workload": f"{name}: {desc}", "control_law": "StandardVisitor defaults (primalComputationInterval 5, damped_uniform rounding)", "maxIter": max_iter,
+            "seconds": dt, "ms_per_iteration": 1e3 * dt / max_iter, "value": 4.0 * edges_of(H, W) * max_iter / dt, "unit": UNIT,
+            "lower_bound": s.lower_bound(), "primal": s.primal_cost(),
+            "note": "rounding iterations run the uniform-mode kernels (4 message updates per edge and pass, slower schedule): DESIGN.md 8"}
+
+
 def compact(block):
     """an extra workload's block inside the headline line"""
     keep = ("value", "unit", "ms_per_step", "dtype", "roofline", "e2e", "gpu_launches", "time_to_bound", "cpu_baseline")
@@ -772,6 +793,10 @@ def main():
             extras["C3_f64"] = compact(run_grid(args, "C3", 0, 1, local_rank, None, dtype="f64", with_e2e=False, with_ttb=False))
         except Exception as exc:
             extras["C3_f64"] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            extras["C2_default_solve"] = default_solve("C2", 100, local_rank)
+        except Exception as exc:
+            extras["C2_default_solve"] = {"error": f"{type(exc).__name__}: {exc}"}
         args.tune = saved
         out["workloads"] = extras
 

@@ -264,6 +264,16 @@ int64_t lpmp_ref_add_pairwise(void* hv, uint64_t i, uint64_t j, const double* ta
 #endif
 }
 
+#ifdef LPMP_DRIVE_LP_CUDA
+// re-orient edge e = (i, j): AddFactorRelation(u_j, p), AddFactorRelation(p, u_i) (include/LP_MP.h:697-702)
+void lpmp_ref_reverse_edge(void* hv, uint64_t e) {
+  auto* h = static_cast<RefHandle*>(hv);
+  auto& lp = h->solver->GetLP();
+  lp.AddFactorRelation(h->unaries[h->edges[e][1]], h->pairwise[e]);
+  lp.AddFactorRelation(h->pairwise[e], h->unaries[h->edges[e][0]]);
+}
+#endif
+
 // LP::put_in_same_partition on the unary factors of variables i and j (include/LP_MP.h:465)
 void lpmp_ref_put_in_same_partition(void* hv, uint64_t i, uint64_t j) {
   auto* h = static_cast<RefHandle*>(hv);

@@ -293,3 +293,35 @@ def test_reference_solver_drives_lp_cuda_in_partition_mode(kind):
     r, c = ref.solve(), cu.solve()
     assert np.array_equal(r["flags"], c["flags"]) and np.allclose(c["lb"], r["lb"], rtol=1e-12, atol=1e-12)
     assert np.array_equal(ref.labeling(), cu.labeling()) and same_state(ref, cu)
+
+
+def test_lp_cuda_factor_relations_reorient_edges():
+    """LP_cuda::AddFactorRelation(u_j, p), (p, u_i) turns edge (i, j) around: same dual trajectory as the reference core built with
+    the edge given as (j, i) and the transposed table (the per-node message order differs, so bounds agree to round-off, not bits)"""
+    import ctypes as C
+    lib_ref, lib_cuda = ref_library(), ref_library(cuda_adapter=True)
+    if lib_ref is None or lib_cuda is None:
+        pytest.skip("oracle/_ref not built")
+    lib_cuda.lpmp_ref_reverse_edge.argtypes = [C.c_void_p, C.c_uint64]
+    lib_cuda.lpmp_ref_reverse_edge.restype = None
+    rng = np.random.default_rng(6)
+    ei, ej = grid_edges(5, 6)
+    edges = list(zip(ei.tolist(), ej.tolist()))
+    theta, tables = list(rng.random((30, 4))), list(rng.random((len(edges), 4, 4)) - 0.3)
+    flip = [e for e, (i, j) in enumerate(edges) if j == i + 1]   # all horizontal edges point left: still a DAG
+    ref, cu = RefLP(lib_ref, ["-v", "0"]), RefLP(lib_cuda, ["-v", "0"])
+    for t in theta:
+        ref.AddUnaryFactor(t); cu.AddUnaryFactor(t)
+    for e, ((i, j), t) in enumerate(zip(edges, tables)):
+        cu.AddPairwiseFactor(i, j, t)
+        if e in flip:
+            ref.AddPairwiseFactor(j, i, np.ascontiguousarray(t.T))
+            lib_cuda.lpmp_ref_reverse_edge(cu.h, e)
+        else:
+            ref.AddPairwiseFactor(i, j, t)
+    ref.Begin(); cu.Begin()
+    ref.set_reparametrization("anisotropic"); cu.set_reparametrization("anisotropic")
+    for it in range(6):
+        ref.ComputePass(it); cu.ComputePass(it)
+        assert np.isclose(cu.LowerBound(), ref.LowerBound(), rtol=1e-11), it
+    assert np.allclose(ref.unaries(), cu.unaries(), atol=1e-10)
