@@ -242,6 +242,16 @@ int LPMP_FN(stream)(lpmp_solver* h, void** out);
 int LPMP_FN(minmarginal_dense)(int dtype, uint64_t n, uint32_t L1, uint32_t L2, const double* tables, const double* msg1, const double* msg2, int side, double* out, double* lb);
 int LPMP_FN(minmarginal_potts)(int dtype, uint64_t n, uint32_t L, const double* lambda, const double* msg1, const double* msg2, int side, double* out, double* lb);
 int LPMP_FN(minmarginal_trunclin)(int dtype, uint64_t n, uint32_t L, const double* slope, const double* trunc, const double* msg1, const double* msg2, int side, double* out, double* lb);
+/* n independent FactorContainer::UpdateFactor[Primal] calls (include/factors_messages.hxx:2256-2261,2332-2373) on unary factors with
+ * `deg` incident pairwise factors each, run by the SAME kernels the passes of general graphs launch (kernels_graph.cuh: the register
+ * kernel for dense tables with L in {4, 8, 16} and deg <= 4, the generic kernel otherwise): ReceiveMessages with the receive mask of
+ * the mode -> first minimiser -> SendMessages with the mode's weight.  later[k][s] != 0: the other variable of message s comes later
+ * in the forward order; `forward` selects the pass direction (a backward pass receives from the later ones).  theta [n][L]; own
+ * [n][deg][L] = the node's side of its edges, in its message order; other [n][deg][L] = the other side; params [n][deg][P] in
+ * receiver orientation (dense: params[x_own][y_other]).  Outputs: theta_out, own_out (same shapes), label [n]. */
+int LPMP_FN(node_update)(int dtype, uint64_t n, uint32_t L, uint32_t deg, int pairwise_type, int repam, int forward, const uint8_t* later,
+                         const double* theta, const double* own, const double* other, const double* params, double* theta_out, double* own_out,
+                         uint32_t* label);
 /* n unary factors: lb[k] = min theta_k (vector::min, include/vector.hxx:289-313), arg[k] = first minimiser */
 int LPMP_FN(unary_min)(int dtype, uint64_t n, uint32_t L, const double* theta, double* lb, uint32_t* arg);
 

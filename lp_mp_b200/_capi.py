@@ -94,6 +94,7 @@ SIGNATURES = {
     "minmarginal_dense": [_i, _u64, _u32, _u32, _pd, _pd, _pd, _i, _pd, _pd],
     "minmarginal_potts": [_i, _u64, _u32, _pd, _pd, _pd, _i, _pd, _pd],
     "minmarginal_trunclin": [_i, _u64, _u32, _pd, _pd, _pd, _pd, _i, _pd, _pd],
+    "node_update": [_i, _u64, _u32, _u32, _i, _i, _i, C.POINTER(C.c_uint8), _pd, _pd, _pd, _pd, _pd, _pd, _pu32],
     "unary_min": [_i, _u64, _u32, _pd, _pd, _pu32],
 }
 _RESTYPE = {"last_error": C.c_char_p}

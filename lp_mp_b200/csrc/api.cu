@@ -1433,6 +1433,73 @@ static int run_minmarginal(int pw, uint64_t n, uint32_t L1, uint32_t L2, const d
   return cudaGetLastError() == cudaSuccess ? LPMP_OK : LPMP_ERR_CUDA;
 }
 
+// n star-shaped node updates through the kernels of the general-graph passes (kernels_graph.cuh): records [theta | own...] followed by
+// the other sides, one descriptor per node, one launch
+template <typename Real>
+static int run_node_update(uint64_t n, uint32_t L, uint32_t deg, int pw, int repam, int forward, const uint8_t* later, const double* theta, const double* own,
+                           const double* other, const double* params, double* theta_out, double* own_out, uint32_t* label) {
+  if (n == 0) return LPMP_OK;
+  const uint32_t P = pairwise_param_count(pw, L);
+  const uint64_t rec = (uint64_t)(1 + deg) * L, Q = n * deg;
+  if ((n * rec + Q * L) >= (1ull << 32)) return LPMP_ERR_UNSUPPORTED;
+  std::vector<Real> h_vec(n * rec + Q * L), h_tab(std::max<uint64_t>(1, Q * P));
+  std::vector<uint32_t> h_inc(n + 1), h_oth(std::max<uint64_t>(1, Q)), h_node(n);
+  std::vector<uint8_t> h_flags(std::max<uint64_t>(1, Q));
+  std::vector<uint4> h_desc(2 * n);
+  for (uint64_t k = 0; k < n; ++k) {
+    h_inc[k] = (uint32_t)(k * deg); h_node[k] = (uint32_t)k;
+    for (uint32_t x = 0; x < L; ++x) h_vec[k * rec + x] = (Real)theta[k * L + x];
+    uint32_t m[4] = {0, 0, 0, 0};
+    for (uint32_t s = 0; s < deg; ++s) {
+      const uint64_t q = k * deg + s;
+      for (uint32_t x = 0; x < L; ++x) { h_vec[k * rec + (1 + s) * L + x] = (Real)own[q * L + x]; h_vec[n * rec + q * L + x] = (Real)other[q * L + x]; }
+      h_oth[q] = (uint32_t)(n * rec + q * L);
+      h_flags[q] = (uint8_t)((later[q] ? 1u : 0u) << 1);
+      if (s < 4) m[s] = h_oth[q] | h_flags[q];
+    }
+    h_desc[2 * k] = make_uint4((uint32_t)(k * deg), (uint32_t)k, deg, 0u);
+    h_desc[2 * k + 1] = make_uint4(m[0], m[1], m[2], m[3]);
+  }
+  h_inc[n] = (uint32_t)Q;
+  for (uint64_t t = 0; t < Q * P; ++t) h_tab[t] = (Real)params[t];
+  DeviceBuffer<Real> vec, tab;
+  DeviceBuffer<uint32_t> inc, oth, node, labels;
+  DeviceBuffer<uint8_t> flags;
+  DeviceBuffer<uint4> desc;
+  auto up = [&](auto& d, const auto& h) -> bool {
+    return d.alloc(h.size()) == cudaSuccess && cudaMemcpy(d.p, h.data(), h.size() * sizeof(h[0]), cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  if (!up(vec, h_vec) || !up(tab, h_tab) || !up(inc, h_inc) || !up(oth, h_oth) || !up(node, h_node) || !up(flags, h_flags) || !up(desc, h_desc)) return LPMP_ERR_CUDA;
+  if (labels.alloc(n) != cudaSuccess) return LPMP_ERR_CUDA;
+  GraphArgs<Real> A;
+  std::memset(&A, 0, sizeof(A));
+  A.vec = vec.p; A.tab = tab.p; A.inc_off = inc.p; A.oth_off = oth.p; A.flags = flags.p; A.oth_node = node.p; A.node_of = node.p; A.desc = desc.p;
+  A.labels = labels.p; A.first = 0; A.count = (uint32_t)n; A.L = L; A.P = P; A.pw = pw; A.repam = repam; A.forward = forward ? 1 : 0; A.primal = 1;
+  const bool fast = pw == LPMP_PAIRWISE_DENSE && deg <= 4 && (L == 4 || L == 8 || (L == 16 && sizeof(Real) == 4));
+  if (fast) {
+    const int ctas = (int)std::min<uint64_t>((n + 256 / L - 1) / (256 / L), 148 * 12);
+    if (L == 4) graph_node_kernel<Real, 4, 4, 0><<<ctas, 256>>>(A);
+    else if (L == 8) graph_node_kernel<Real, 8, 4, 0><<<ctas, 256>>>(A);
+    else if constexpr (sizeof(Real) == 4) graph_node_kernel<Real, 16, 4, 0><<<ctas, 256>>>(A);
+  } else {
+    const int G = group_size_for(L);
+    int threads = 256;
+    const size_t per_group = 3 * (size_t)L * sizeof(Real);
+    while (threads > G && (threads / G) * per_group > 48 * 1024) threads >>= 1;
+    if ((threads / G) * per_group > 48 * 1024) return LPMP_ERR_UNSUPPORTED;
+    const uint64_t groups = threads / G;
+    graph_node_generic_kernel<Real, 0><<<(int)std::min<uint64_t>((n + groups - 1) / groups, 148 * 8), threads, (threads / G) * per_group>>>(A, G);
+  }
+  if (cudaMemcpy(h_vec.data(), vec.p, n * rec * sizeof(Real), cudaMemcpyDeviceToHost) != cudaSuccess) return LPMP_ERR_CUDA;
+  for (uint64_t k = 0; k < n; ++k) {
+    for (uint32_t x = 0; x < L; ++x) theta_out[k * L + x] = (double)h_vec[k * rec + x];
+    for (uint32_t s = 0; s < deg; ++s)
+      for (uint32_t x = 0; x < L; ++x) own_out[(k * deg + s) * L + x] = (double)h_vec[k * rec + (1 + s) * L + x];
+  }
+  if (label && cudaMemcpy(label, labels.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return LPMP_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? LPMP_OK : LPMP_ERR_CUDA;
+}
+
 template <typename Real>
 static int run_unary_min(uint64_t n, uint32_t L, const double* theta, double* lb, uint32_t* arg) {
   if (n == 0) return LPMP_OK;
@@ -1581,6 +1648,14 @@ int lpmp_minmarginal_potts(int dtype, uint64_t n, uint32_t L, const double* lamb
 int lpmp_minmarginal_trunclin(int dtype, uint64_t n, uint32_t L, const double* slope, const double* trunc, const double* msg1, const double* msg2, int side, double* out, double* lb) {
   return dtype == LPMP_F32 ? run_minmarginal<float>(LPMP_PAIRWISE_TRUNCLIN, n, L, L, slope, trunc, msg1, msg2, side, out, lb)
                            : run_minmarginal<double>(LPMP_PAIRWISE_TRUNCLIN, n, L, L, slope, trunc, msg1, msg2, side, out, lb);
+}
+int lpmp_node_update(int dtype, uint64_t n, uint32_t L, uint32_t deg, int pw, int repam, int forward, const uint8_t* later, const double* theta,
+                     const double* own, const double* other, const double* params, double* theta_out, double* own_out, uint32_t* label) {
+  if (pw < 0 || pw > 2 || repam < 0 || repam > 3 || L == 0 || (dtype != LPMP_F32 && dtype != LPMP_F64)) return LPMP_ERR_INVALID;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return LPMP_ERR_CUDA;
+  return dtype == LPMP_F32 ? run_node_update<float>(n, L, deg, pw, repam, forward, later, theta, own, other, params, theta_out, own_out, label)
+                           : run_node_update<double>(n, L, deg, pw, repam, forward, later, theta, own, other, params, theta_out, own_out, label);
 }
 int lpmp_unary_min(int dtype, uint64_t n, uint32_t L, const double* theta, double* lb, uint32_t* arg) {
   return dtype == LPMP_F32 ? run_unary_min<float>(n, L, theta, lb, arg) : run_unary_min<double>(n, L, theta, lb, arg);

@@ -800,6 +800,71 @@ int minmarginal(int type, uint64_t n, uint32_t L1, uint32_t L2, const double* p0
 
 extern "C" {
 
+}  // extern "C"
+
+namespace {
+template <typename Real>
+int node_update_t(uint64_t n, uint32_t L, uint32_t deg, int pw, int repam, int forward, const uint8_t* later, const double* theta, const double* own,
+                  const double* other, const double* params, double* theta_out, double* own_out, uint32_t* label) {
+  const uint32_t P = pw == LPMP_PAIRWISE_DENSE ? L * L : (pw == LPMP_PAIRWISE_POTTS ? 1u : 2u);
+  const bool aniso = repam == LPMP_REPAM_ANISOTROPIC || repam == LPMP_REPAM_ANISOTROPIC2;
+  const Real INF = std::numeric_limits<Real>::infinity();
+  std::vector<Real> th(L), t(L), h(L), ow(size_t(deg) * L);
+  for (uint64_t k = 0; k < n; ++k) {
+    for (uint32_t x = 0; x < L; ++x) th[x] = Real(theta[k * L + x]);
+    for (uint64_t q = 0; q < uint64_t(deg) * L; ++q) ow[q] = Real(own[k * deg * L + q]);
+    uint32_t n_in = 0, n_out = 0;
+    for (uint32_t s = 0; s < deg; ++s) { if (later[k * deg + s]) ++n_out; else ++n_in; }
+    for (uint32_t s = 0; s < deg; ++s) {   // ReceiveMessages
+      const bool lat = later[k * deg + s] != 0;
+      if (aniso && !(forward ? !lat : lat)) continue;
+      const double* p = params + (k * deg + s) * P;
+      const double* ot = other + (k * deg + s) * L;
+      for (uint32_t x = 0; x < L; ++x) {
+        Real m = INF;
+        for (uint32_t y = 0; y < L; ++y) {
+          Real c;
+          if (pw == LPMP_PAIRWISE_DENSE) c = Real(p[x * L + y]);
+          else if (pw == LPMP_PAIRWISE_POTTS) c = x == y ? Real(0) : Real(p[0]);
+          else { const uint32_t d = x > y ? x - y : y - x; c = std::min(Real(Real(p[0]) * Real(d)), Real(p[1])); }
+          m = std::min(m, Real(c + Real(ot[y])));
+        }
+        h[x] = m;
+      }
+      for (uint32_t x = 0; x < L; ++x) { const Real m = h[x] + ow[s * L + x]; th[x] += m; ow[s * L + x] -= m; }
+    }
+    uint32_t arg = 0;
+    for (uint32_t x = 1; x < L; ++x) if (th[x] < th[arg]) arg = x;
+    if (label) label[k] = arg;
+    if (deg > 0) {
+      double wd;
+      if (repam == LPMP_REPAM_ANISOTROPIC) wd = 1.0 / double(std::max(n_in, n_out));
+      else if (repam == LPMP_REPAM_ANISOTROPIC2) wd = 1.0 / double(forward ? n_out : n_in);
+      else if (repam == LPMP_REPAM_UNIFORM) wd = 1.0 / double(deg);
+      else wd = 1.0 / double(deg + 1);
+      const Real w = Real(wd);
+      for (uint32_t x = 0; x < L; ++x) t[x] = th[x];
+      for (uint32_t s = 0; s < deg; ++s) {   // SendMessages
+        const bool lat = later[k * deg + s] != 0;
+        if (aniso && !(forward ? lat : !lat)) continue;
+        for (uint32_t x = 0; x < L; ++x) { const Real d = w * t[x]; ow[s * L + x] += d; th[x] -= d; }
+      }
+    }
+    for (uint32_t x = 0; x < L; ++x) theta_out[k * L + x] = double(th[x]);
+    for (uint64_t q = 0; q < uint64_t(deg) * L; ++q) own_out[k * deg * L + q] = double(ow[q]);
+  }
+  return LPMP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int LPMP_FN(node_update)(int dtype, uint64_t n, uint32_t L, uint32_t deg, int pw, int repam, int forward, const uint8_t* later, const double* theta,
+                         const double* own, const double* other, const double* params, double* theta_out, double* own_out, uint32_t* label) {
+  if (pw < 0 || pw > 2 || repam < 0 || repam > 3 || L == 0) return LPMP_ERR_INVALID;
+  return dtype == LPMP_F32 ? node_update_t<float>(n, L, deg, pw, repam, forward, later, theta, own, other, params, theta_out, own_out, label)
+                           : node_update_t<double>(n, L, deg, pw, repam, forward, later, theta, own, other, params, theta_out, own_out, label);
+}
 int LPMP_FN(minmarginal_dense)(int dtype, uint64_t n, uint32_t L1, uint32_t L2, const double* t, const double* msg1, const double* msg2, int side, double* out, double* lb) {
   return dtype == LPMP_F32 ? minmarginal<float>(LPMP_PAIRWISE_DENSE, n, L1, L2, t, nullptr, msg1, msg2, side, out, lb) : minmarginal<double>(LPMP_PAIRWISE_DENSE, n, L1, L2, t, nullptr, msg1, msg2, side, out, lb);
 }

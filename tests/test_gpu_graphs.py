@@ -325,3 +325,43 @@ def test_lp_cuda_factor_relations_reorient_edges():
         ref.ComputePass(it); cu.ComputePass(it)
         assert np.isclose(cu.LowerBound(), ref.LowerBound(), rtol=1e-11), it
     assert np.allclose(ref.unaries(), cu.unaries(), atol=1e-10)
+
+
+# ---- single-factor entry point on the HOT kernels (lpmp_node_update) ------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("kind,L,deg", [("dense", 8, 3), ("dense", 4, 4), ("dense", 16, 2), ("dense", 8, 6), ("dense", 5, 3), ("potts", 12, 4), ("trunclin", 16, 3)])
+def test_node_update_entry_point(cuda_api, oracle_api, dtype, kind, L, deg):
+    """one UpdateFactor call per test node, run by the kernels the general-graph passes launch (the register kernel for dense L in
+    {4, 8, 16} with deg <= 4, the generic kernel otherwise): theta / own-side vectors / label bit-identical to the oracle for every
+    weight mode and both directions; the anisotropic receive agrees with the reference's min-marginals within 1e-5 (north_star (i))"""
+    import ctypes as C
+    from lp_mp_b200 import _capi as K
+    rng = np.random.default_rng(L * 31 + deg)
+    n = 257
+    P = {"dense": L * L, "potts": 1, "trunclin": 2}[kind]
+    theta, own, other = rng.random((n, L)), rng.random((n, deg, L)) - 0.5, rng.random((n, deg, L))
+    if kind == "dense":
+        params = rng.random((n, deg, P)) - 0.2
+    elif kind == "potts":
+        params = rng.uniform(-0.4, 1.0, (n, deg, 1))
+    else:
+        params = np.stack([rng.uniform(0.05, 0.5, (n, deg)), rng.uniform(0.2, 1.5, (n, deg))], axis=-1)
+    later = (rng.random((n, deg)) < 0.5).astype(np.uint8)
+    pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    def run(api, repam, forward):
+        th, ow, lab = np.zeros((n, L)), np.zeros((n, deg, L)), np.zeros(n, dtype=np.uint32)
+        st = api.node_update(K.F64 if dtype == "f64" else K.F32, n, L, deg, K.PAIRWISE[kind], repam, forward, later.ctypes.data_as(C.POINTER(C.c_uint8)),
+                             pd(theta), pd(own), pd(other), pd(params), pd(th), pd(ow), lab.ctypes.data_as(C.POINTER(C.c_uint32)))
+        assert st == 0
+        return th, ow, lab
+    for repam in range(4):
+        for forward in (1, 0):
+            got, want = run(cuda_api, repam, forward), run(oracle_api, repam, forward)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]), (repam, forward)
+    # the receive of one message == own + min-marginal of the reference's arithmetic (lpmp_minmarginal_*: matrix::min1)
+    if kind == "dense":
+        th, ow, _ = run(cuda_api, 1, 1)     # uniform: every message is received
+        h = (params.reshape(n, deg, L, L) + other[:, :, None, :]).min(axis=3)
+        m = h + own
+        sent = (theta + m.sum(axis=1)) / deg
+        assert np.allclose(ow, own - m + sent[:, None, :], rtol=1e-5 if dtype == "f32" else 1e-12, atol=1e-5 if dtype == "f32" else 1e-12)
