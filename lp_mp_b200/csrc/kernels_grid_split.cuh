@@ -163,7 +163,9 @@ __device__ __forceinline__ Real both_halves_min(Real v) {
 // earlier in the pass, its side b is the vector this step min-marginalises), and h(x) = min_y [c(x,y) + b(y)] is in registers: the
 // node's term min theta_i and the two edge terms min_x [a(x) + h(x)] cost three group minima per step, off the dependency chain, and
 // a pass leaves one double per grid row in A.lb_rows -- the separate sweep over all records (kernels_grid_bound.cuh) disappears.
-template <typename Real, int PW, int L, int WIN, bool FWD, bool LBF = false>
+// PRM: rounding passes (LP::ComputePassAndPrimal, include/LP_MP.h:1592-1602) on the fast steps: the first minimiser of theta after
+// the receives (include/factors_messages.hxx:2363,2382-2389) is worked out after the stores of the step, off the dependency chain.
+template <typename Real, int PW, int L, int WIN, bool FWD, bool LBF = false, bool PRM = false>
 __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_split_kernel(const GridArgs<Real> A) {
   static_assert(!(LBF && FWD), "the fused bound belongs to the backward pass");
   using Cfg = SplitCfg<Real, PW, L>;
@@ -433,6 +435,19 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
         const Real go = __shfl_xor_sync(FULL, ge, 16);
         lb_acc += ((double)gt + (double)ge) + (double)go;
       };
+      // PRM: label of the node of step s from theta after the receives (both halves hold it; the lower half's ballot decides)
+      auto write_label = [&](const Real (&tv)[LPL], const int s) {
+        Real lm = tv[0];
+#pragma unroll
+        for (int k = 1; k < LPL; ++k) lm = rmin(lm, tv[k]);
+        const Real g = half_min<Real>(lm);
+        const unsigned il = (unsigned)__ffs((int)(__ballot_sync(FULL, lm == g) & 0xffffu)) - 1u;
+        int kf = 0;
+#pragma unroll
+        for (int k = LPL - 1; k >= 0; --k) if (tv[k] == g) kf = k;
+        const int k1 = __shfl_sync(FULL, kf, (int)il);
+        if (lane == 0) A.labels[(uint64_t)r * W + (fwd ? (uint32_t)s : W - 1 - (uint32_t)s)] = il * LPL + (unsigned)k1;
+      };
       wait_chunk(0);
 
       // ---- single steps: kind 0: general (any column, rounding, corner weights); 1: weight 1/2, any column (existence of the row
@@ -484,6 +499,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
           // missing edges: the left column and the first row have all-zero in-side slots and parameters, so their receives are
           // exact no-ops; the last row / column has no out_col / out_row edge (select)
           const bool or_on = KIND == 2 || has_or;
+          Real tv[LPL];
 #pragma unroll
           for (int k = 0; k < LPL; ++k) {
             const Real v = (th[k] + (self_first ? m[k] : mo[k])) + (self_first ? mo[k] : m[k]);
@@ -491,7 +507,9 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
             const Real d_oc = out_col_exists ? d : Real(0), d_or = or_on ? d : Real(0);
             oo[k] = oo[k] + (hi ? d_oc : d_or);
             th[k] = (v - d_oc) - d_or;
+            tv[k] = v;
           }
+          if constexpr (PRM) write_label(tv, s);
           if constexpr (LBF) lb_terms(th, oi, h, true);
         } else {
           const bool has_ic = in_col_exists, has_oc = out_col_exists;
@@ -603,7 +621,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
           }
 #pragma unroll
           for (int k = 0; k < LPL; ++k) oth[k] = hi ? pv[k] : oth[k];
-          Real h[LPL], m[LPL], mo[LPL];
+          Real h[LPL], m[LPL], mo[LPL], tv[LPL];
           split_min_plus<Real, PW, LPL, WIN>(par, oth, h);
 #pragma unroll
           for (int k = 0; k < LPL; ++k) { m[k] = h[k] + oi[k]; oi[k] = oi[k] - m[k]; }
@@ -616,6 +634,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
             const Real d_oc = out_col_exists ? d : Real(0);
             oo[k] = oo[k] + (hi ? d_oc : d);
             th[k] = (v - d_oc) - d;
+            tv[k] = v;
           }
           sts_n_if(out_ring, Rout + (uint32_t)jj * LB, oo);   // hand-off first: the warp below is waiting for it
           st_cluster_n_if(out_dsm, Rdsm + (uint32_t)jj * LB, oo);
@@ -625,6 +644,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
           sts_n_if(true, Tout + ro, oo);
 #pragma unroll
           for (int k = 0; k < LPL; ++k) oth[k] = oo[k];
+          if constexpr (PRM) write_label(tv, s0 + jj);         // after the stores: nothing of the chain waits for the label
           if constexpr (LBF) lb_terms(th, oi, h, true);       // after the stores: nothing of the chain waits for these minima
         }
         publish(s0 + K);
@@ -632,7 +652,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
 
       // general steps for the whole band: rounding, tiny grids; for the first / last column of the first / last grid row (corner
       // weights); everything else runs the edge / steady steps
-      const bool all_general = A.primal != 0 || (int)W < 4 || (H < 2 && !(A.in_halo || A.out_halo));
+      const bool all_general = (!PRM && A.primal != 0) || (int)W < 4 || (H < 2 && !(A.in_halo || A.out_halo));
       const bool corner_row = (u == 0 && !A.in_halo) || (u + 1 == (int)H && !A.out_halo);
       int s = 0;
       if (all_general) {

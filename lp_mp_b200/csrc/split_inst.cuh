@@ -12,12 +12,14 @@ static cudaError_t launch_split_one(const CUtensorMap* maps, const GridArgs<Real
     return cudaErrorInvalidValue;
   } else {
     if (args.forward && args.lb_rows) return cudaErrorInvalidValue;   // the fused bound belongs to the backward pass
-    const int variant = args.forward ? 1 : (args.lb_rows ? 2 : 0);
-    auto kernel = args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true, false>
-                               : (args.lb_rows ? wavefront_split_kernel<Real, PW, L, WIN, false, true> : wavefront_split_kernel<Real, PW, L, WIN, false, false>);
+    if (args.primal && args.lb_rows) return cudaErrorInvalidValue;    // rounding passes leave the bound to the sweep
+    const int variant = args.primal ? (args.forward ? 3 : 4) : (args.forward ? 1 : (args.lb_rows ? 2 : 0));
+    auto kernel = args.primal ? (args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true, false, true> : wavefront_split_kernel<Real, PW, L, WIN, false, false, true>)
+                  : args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true, false, false>
+                                 : (args.lb_rows ? wavefront_split_kernel<Real, PW, L, WIN, false, true, false> : wavefront_split_kernel<Real, PW, L, WIN, false, false, false>);
     int dev = 0;
     cudaGetDevice(&dev);
-    static bool configured[64][3] = {};
+    static bool configured[64][5] = {};
     if (!configured[dev & 63][variant]) {
       cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
       if (e != cudaSuccess) return e;
