@@ -1475,6 +1475,7 @@ static int run_node_update(uint64_t n, uint32_t L, uint32_t deg, int pw, int rep
   std::memset(&A, 0, sizeof(A));
   A.vec = vec.p; A.tab = tab.p; A.inc_off = inc.p; A.oth_off = oth.p; A.flags = flags.p; A.oth_node = node.p; A.node_of = node.p; A.desc = desc.p;
   A.labels = labels.p; A.first = 0; A.count = (uint32_t)n; A.L = L; A.P = P; A.pw = pw; A.repam = repam; A.forward = forward ? 1 : 0; A.primal = 1;
+  for (int t = 1; t < 8; ++t) A.wtab[t] = (Real)(1.0 / (double)t);
   const bool fast = pw == LPMP_PAIRWISE_DENSE && deg <= 4 && (L == 4 || L == 8 || (L == 16 && sizeof(Real) == 4));
   if (fast) {
     const int ctas = (int)std::min<uint64_t>((n + 256 / L - 1) / (256 / L), 148 * 12);

@@ -430,6 +430,8 @@ struct GraphEngine {
     A.labels = labels; A.partial = partial;
     A.first = 0; A.count = (uint32_t)N; A.L = L; A.P = P; A.pw = pw; A.repam = 0; A.forward = 1; A.primal = 0; A.residual = 0;
     A.plan_node = nullptr; A.plan_base = nullptr; A.plan_code = nullptr; A.plan_w = nullptr;
+    A.wtab[0] = Real(0);
+    for (int n = 1; n < 8; ++n) A.wtab[n] = (Real)(1.0 / (double)n);
     return A;
   }
 

@@ -44,6 +44,8 @@ struct GraphArgs {
   int residual;               // update_factor_residual (include/factors_messages.hxx:2270-2279) instead of UpdateFactor in the plain passes
   // sweep over a subsequence of the nodes (partition passes, MODE 2 of the generic kernel): the t-th node of the launch is plan_node[t],
   // its incidences carry plan_code[plan_base[t] + slot] (bit 0 receive, bit 1 send), every send has weight plan_w[t]
+  Real wtab[8];               // wtab[n] = (Real)(1.0 / (double)n), wtab[0] = 0: the send weights of the register kernel (n <= 5) without a
+                              // double-precision division per node
   const uint32_t* plan_node;
   const uint32_t* plan_base;
   const uint8_t* plan_code;
@@ -56,30 +58,34 @@ struct GraphArgs {
 // MODE 0: node update; MODE 1: lower-bound terms (read only).
 template <typename Real, int LT, int DMAX, int MODE>
 __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_node_kernel(const GraphArgs<Real> A) {
+  static_assert(DMAX == 4, "the node descriptor holds four slots");
   constexpr int NPC = 256 / LT;   // nodes per CTA
+  constexpr unsigned FULLW = 0xffffffffu;
   const int x = threadIdx.x % LT;
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned gmask = (LT == 32 ? 0xffffffffu : ((1u << LT) - 1u)) << (lane & ~(unsigned)(LT - 1));
   const bool aniso = A.repam == LPMP_REPAM_ANISOTROPIC || A.repam == LPMP_REPAM_ANISOTROPIC2;
   const Real INF = RealTraits<Real>::inf();
   double acc = 0.0;
-  static_assert(DMAX == 4, "the node descriptor holds four slots");
-  // a group serves several nodes in turn; the descriptor of the next one is fetched while this one is processed, so the dependent
-  // chain per node is one round trip (descriptor -> record / tables / neighbour vectors)
+  // The loop is uniform over the CTA (a group without a node runs it with degree 0), so every shuffle is a full-warp shuffle with
+  // width LT -- no convergence bookkeeping around the sub-warp groups.  A group serves several nodes in turn; the descriptor of the
+  // next one is fetched while this one is processed: the dependent chain per node is one round trip (descriptor -> record /
+  // tables / neighbour vectors).
+  const uint32_t stride = gridDim.x * NPC;
   uint32_t kk = blockIdx.x * NPC + threadIdx.x / LT;
   uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
   if (kk < A.count) { n0 = __ldg(A.desc + 2 * (uint64_t)(A.first + kk)); n1 = __ldg(A.desc + 2 * (uint64_t)(A.first + kk) + 1); }
-  for (; kk < A.count; kk += gridDim.x * NPC) {
+  for (uint32_t base = blockIdx.x * NPC; base < A.count; base += stride, kk += stride) {
+    const bool valid = kk < A.count;
     const uint32_t k = A.first + kk;
     const uint4 d0 = n0, d1 = n1;
-    if (kk + gridDim.x * NPC < A.count) {
-      n0 = __ldg(A.desc + 2 * (uint64_t)(k + gridDim.x * NPC));
-      n1 = __ldg(A.desc + 2 * (uint64_t)(k + gridDim.x * NPC) + 1);
+    n0 = make_uint4(0, 0, 0, 0); n1 = n0;
+    if (kk + stride < A.count) {
+      n0 = __ldg(A.desc + 2 * (uint64_t)(k + stride));
+      n1 = __ldg(A.desc + 2 * (uint64_t)(k + stride) + 1);
     }
-    const uint32_t q0 = d0.x, deg = d0.z;
+    const uint32_t q0 = d0.x, deg = valid ? d0.z : 0u;
     const uint32_t meta[DMAX] = {d1.x, d1.y, d1.z, d1.w};
     Real* rec = A.vec + ((uint64_t)k + q0) * LT;
-    Real th = rec[x];
+    Real th = valid ? rec[x] : Real(0);
     Real own[DMAX], oth[DMAX], row[DMAX][LT];   // oth: label x of the neighbour's vector (the group shuffles it around)
     uint32_t fl[DMAX];
     bool recv[DMAX];
@@ -97,6 +103,8 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
     for (int s = 0; s < DMAX; ++s) {
       own[s] = s < (int)deg ? rec[(1 + s) * LT + x] : Real(0);
       oth[s] = Real(0);
+#pragma unroll
+      for (int y = 0; y < LT; ++y) row[s][y] = Real(0);
       if (recv[s]) {
         oth[s] = A.vec[(meta[s] & ~3u) + x];
         const Real* t = A.tab + ((uint64_t)(q0 + s) * LT + x) * LT;
@@ -115,22 +123,31 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
         }
       }
     }
+    // h_s(x) = min_y [ c_s(x,y) + other_s(y) ] for the slots some group of the warp receives on (warp-uniform branch)
+    Real hm[DMAX];
+#pragma unroll
+    for (int s = 0; s < DMAX; ++s) {
+      hm[s] = INF;
+      if (__any_sync(FULLW, recv[s])) {
+#pragma unroll
+        for (int y = 0; y < LT; ++y) hm[s] = rmin(hm[s], Real(row[s][y] + __shfl_sync(FULLW, oth[s], y, LT)));
+      }
+    }
     if constexpr (MODE == 1) {
       // LP::LowerBound (include/LP_MP.h:1507-1518): min theta_i + sum over the edges whose first variable this node is of
       // min_x [a(x) + min_y (c(x,y) + b(y))]
-      Real m = th;
-      for (int o = LT >> 1; o > 0; o >>= 1) m = rmin(m, __shfl_xor_sync(gmask, m, o));
-      double term = (double)m;
+      Real m = valid ? th : INF;
+#pragma unroll
+      for (int o = LT >> 1; o > 0; o >>= 1) m = rmin(m, __shfl_xor_sync(FULLW, m, o));
+      double term = valid ? (double)m : 0.0;
 #pragma unroll
       for (int s = 0; s < DMAX; ++s) {
-        Real h = INF;
-        if (recv[s]) {
+        if (__any_sync(FULLW, recv[s])) {
+          Real h = recv[s] ? Real(hm[s] + own[s]) : INF;
 #pragma unroll
-          for (int y = 0; y < LT; ++y) h = rmin(h, Real(row[s][y] + __shfl_sync(gmask, oth[s], y, LT)));
-          h = Real(h + own[s]);
+          for (int o = LT >> 1; o > 0; o >>= 1) h = rmin(h, __shfl_xor_sync(FULLW, h, o));
+          if (recv[s]) term += (double)h;
         }
-        for (int o = LT >> 1; o > 0; o >>= 1) h = rmin(h, __shfl_xor_sync(gmask, h, o));
-        if (recv[s]) term += (double)h;
       }
       if (x == 0) acc += term;
     } else {
@@ -138,10 +155,7 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
 #pragma unroll
       for (int s = 0; s < DMAX; ++s) {
         if (recv[s]) {
-          Real h = INF;
-#pragma unroll
-          for (int y = 0; y < LT; ++y) h = rmin(h, Real(row[s][y] + __shfl_sync(gmask, oth[s], y, LT)));
-          const Real m = h + own[s];
+          const Real m = hm[s] + own[s];
           th = th + m;          // RepamLeft(+)   :498-500
           own[s] = own[s] - m;  // RepamRight(-)
         }
@@ -149,20 +163,21 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
       if (A.primal) {   // MaximizePotentialAndComputePrimal: first minimum
         Real v = th;
         uint32_t idx = (uint32_t)x;
+#pragma unroll
         for (int o = LT >> 1; o > 0; o >>= 1) {
-          const Real ov = __shfl_xor_sync(gmask, v, o);
-          const uint32_t oi = __shfl_xor_sync(gmask, idx, o);
+          const Real ov = __shfl_xor_sync(FULLW, v, o);
+          const uint32_t oi = __shfl_xor_sync(FULLW, idx, o);
           if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
         }
-        if (x == 0) A.labels[d0.y] = idx;
+        if (valid && x == 0) A.labels[d0.y] = idx;
       }
       if (deg > 0) {
-        double wd;
-        if (A.repam == LPMP_REPAM_ANISOTROPIC) wd = 1.0 / (double)(n_in > n_out ? n_in : n_out);   // include/LP_MP.h:1397
-        else if (A.repam == LPMP_REPAM_ANISOTROPIC2) wd = 1.0 / (double)(A.forward ? n_out : n_in);   // :1134
-        else if (A.repam == LPMP_REPAM_UNIFORM) wd = 1.0 / (double)(n_in + n_out);       // :1437, leave_weight 0
-        else wd = 1.0 / (double)(n_in + n_out + 1);                                      // :1437, leave_weight 1
-        const Real w = (Real)wd;
+        uint32_t nw;
+        if (A.repam == LPMP_REPAM_ANISOTROPIC) nw = n_in > n_out ? n_in : n_out;         // include/LP_MP.h:1397
+        else if (A.repam == LPMP_REPAM_ANISOTROPIC2) nw = A.forward ? n_out : n_in;      // :1134
+        else if (A.repam == LPMP_REPAM_UNIFORM) nw = n_in + n_out;                       // :1437, leave_weight 0
+        else nw = n_in + n_out + 1;                                                      // :1437, leave_weight 1
+        const Real w = A.wtab[nw & 7u];   // (deg <= DMAX = 4: nw <= 5)
         const Real d = w * th;   // tmp_factor snapshot (:2801-2805): every send uses the theta left by the receives
         // CallSendMessages (:2698-2744)
 #pragma unroll
@@ -189,7 +204,7 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
           }
         }
       }
-      rec[x] = th;
+      if (valid) rec[x] = th;
 #pragma unroll
       for (int s = 0; s < DMAX; ++s) if (s < (int)deg) rec[(1 + s) * LT + x] = own[s];
     }
