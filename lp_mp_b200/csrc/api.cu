@@ -498,6 +498,7 @@ struct Solver : ISolver {
     else if (k == "wavefront_cluster") tune.cluster = value;
     else if (k == "level_group") tune.level_group = value;
     else if (k == "graph_ctas_per_sm") graph.ctas_per_sm = value;
+    else if (k == "graph_fused_bound") graph.fused_bound_enabled = value != 0;
     else if (k == "wavefront_rows") tune.rows = value;
     else if (k == "wavefront_split") tune.split = value;
     else if (k == "wavefront_fused_bound") tune.fused_bound = value;
@@ -901,8 +902,10 @@ struct Solver : ISolver {
     // dense-table grids: the row-dataflow kernel covers the anisotropic mode; the uniform modes of the rounding
     // iterations (include/visitors/standard_visitor.hxx:44) run on the level schedule, built on first use
     if (!is_grid) {
-      const int n = graph.pass(forward, primal, repam, send_mode == LPMP_SEND_RESIDUAL, labels.p, tune.level_group, num_sms, stream, err);
+      bool fused = false;
+      const int n = graph.pass(forward, primal, repam, send_mode == LPMP_SEND_RESIDUAL, labels.p, tune.level_group, num_sms, stream, err, &fused);
       if (n < 0) return LPMP_ERR_UNSUPPORTED;
+      fused_lb_valid = fused;
       launches += (uint64_t)n;
       CUDA_TRY(cudaGetLastError());
       updates += ((repam == LPMP_REPAM_ANISOTROPIC || repam == LPMP_REPAM_ANISOTROPIC2) ? 2 : 4) * E;
@@ -1083,6 +1086,16 @@ struct Solver : ISolver {
 
   int bound_launch(const Real* below_b, double add, double* out, bool to_device = false) {
     CUDA_TRY(cudaSetDevice(device));
+    if (!is_grid && fused_lb_valid) {   // the last (anisotropic backward) pass left the bound terms: one wide deterministic sum
+      double* dst = to_device ? out : result.p;
+      wide_sum_kernel<<<1, 1024, 0, stream>>>(graph.fused_partial.p, (uint32_t)graph.fused_used, add, dst);
+      ++launches;
+      CUDA_TRY(cudaGetLastError());
+      if (to_device) return LPMP_OK;
+      CUDA_TRY(cudaMemcpyAsync(out, result.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      return LPMP_OK;
+    }
     if (!is_grid) {
       int used = 0;
       const int n = graph.bound(partial.p, &used, tune.level_group, num_sms, stream, err);

@@ -80,6 +80,9 @@ struct GraphEngine {
   std::vector<uint64_t> level_off;          // nodes of level l: [level_off[l], level_off[l+1]) in schedule order
   std::vector<uint64_t> level_fast;         // ... of which [level_off[l], level_fast[l]) qualify for the fast kernel
   bool fast_ok = false;
+  // the fast part of a level, sorted by (n_in, n_out): ranges of nodes with the same number of earlier / later neighbours
+  struct Segment { uint64_t first, count; uint32_t n_in, n_out; };
+  std::vector<std::vector<Segment>> segments;
   // staged optimisation (partition passes): host copies of the incidence structure, the partitions and the planned sweeps
   std::vector<uint32_t> k_of, h_inc, h_oth;             // schedule position of node i; inc_off / oth_node by schedule position
   std::vector<uint64_t> rank_order;                     // nodes in rank order
@@ -164,8 +167,15 @@ struct GraphEngine {
     }
     LPMP_TICK("levels");
     fast_ok = !mixed && pw == LPMP_PAIRWISE_DENSE && (L == 4 || L == 8 || (L == 16 && sizeof(Real) == 4));
-    // schedule order: level by level; inside a level the nodes of the fast kernel first, each part in rank order
+    // schedule order: level by level; inside a level the nodes of the fast kernel first, sorted by their (earlier, later) neighbour
+    // counts (the register kernel is launched per range with the instance sized for its receives), each range in rank order
     auto is_fast = [&](uint64_t i) { return fast_ok && off[i + 1] - off[i] <= (uint64_t)kDmax; };
+    auto bucket_of = [&](uint64_t i) {   // n_in * (kDmax + 1) + n_out
+      uint32_t n_in = 0, n_out = 0;
+      for (uint64_t q = off[i]; q < off[i + 1]; ++q) { if (inc[q].later) ++n_out; else ++n_in; }
+      return n_in * (uint32_t)(kDmax + 1) + n_out;
+    };
+    constexpr uint32_t kBuckets = (kDmax + 1) * (kDmax + 1);
     level_off.assign((size_t)max_level + 2, 0);
     level_fast.assign((size_t)max_level + 1, 0);
     for (uint64_t i = 0; i < N; ++i) { ++level_off[level[i] + 1]; if (is_fast(i)) ++level_fast[level[i]]; }
@@ -173,11 +183,23 @@ struct GraphEngine {
     std::vector<uint32_t> node_of_k(N);
     k_of.assign(N, 0);
     {
-      std::vector<uint64_t> pos_fast(level_off.begin(), level_off.end() - 1), pos_slow(max_level + 1);
-      for (size_t l = 0; l <= max_level; ++l) { pos_slow[l] = level_off[l] + level_fast[l]; level_fast[l] += level_off[l]; }
+      // counting sort of the fast nodes of every level by bucket (stable in rank order)
+      std::vector<uint64_t> cnt((size_t)(max_level + 1) * kBuckets, 0), pos_slow(max_level + 1);
+      for (uint64_t i = 0; i < N; ++i) if (is_fast(i)) ++cnt[(size_t)level[i] * kBuckets + bucket_of(i)];
+      segments.assign((size_t)max_level + 1, {});
+      for (size_t l = 0; l <= max_level; ++l) {
+        uint64_t p = level_off[l];
+        for (uint32_t b = 0; b < kBuckets; ++b) {
+          const uint64_t c = cnt[l * kBuckets + b];
+          cnt[l * kBuckets + b] = p;   // becomes the write position of the bucket
+          if (c) segments[l].push_back({p, c, b / (uint32_t)(kDmax + 1), b % (uint32_t)(kDmax + 1)});
+          p += c;
+        }
+        pos_slow[l] = level_off[l] + level_fast[l]; level_fast[l] += level_off[l];
+      }
       for (uint64_t t = 0; t < N; ++t) {
         const uint64_t i = order[t];
-        const uint64_t k = is_fast(i) ? pos_fast[level[i]]++ : pos_slow[level[i]]++;
+        const uint64_t k = is_fast(i) ? cnt[(size_t)level[i] * kBuckets + bucket_of(i)]++ : pos_slow[level[i]]++;
         node_of_k[k] = (uint32_t)i; k_of[i] = (uint32_t)k;
       }
     }
@@ -435,11 +457,38 @@ struct GraphEngine {
     return A;
   }
 
-  template <int MODE>
+  template <int MODE, int R = kDmax, bool LBF = false>
   void launch_fast(const GraphArgs<Real>& A, int ctas, cudaStream_t stream) const {
-    if (L == 4) graph_node_kernel<Real, 4, kDmax, MODE><<<ctas, 256, 0, stream>>>(A);
-    else if (L == 8) graph_node_kernel<Real, 8, kDmax, MODE><<<ctas, 256, 0, stream>>>(A);
-    else if constexpr (sizeof(Real) == 4) graph_node_kernel<Real, 16, kDmax, MODE><<<ctas, 256, 0, stream>>>(A);
+    if (L == 4) graph_node_kernel<Real, 4, kDmax, MODE, R, LBF><<<ctas, 256, 0, stream>>>(A);
+    else if (L == 8) graph_node_kernel<Real, 8, kDmax, MODE, R, LBF><<<ctas, 256, 0, stream>>>(A);
+    else if constexpr (sizeof(Real) == 4) graph_node_kernel<Real, 16, kDmax, MODE, R, LBF><<<ctas, 256, 0, stream>>>(A);
+  }
+  int update_ctas(uint64_t count, int r, int num_sms) const {
+    const uint64_t npc = 256 / L;
+    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (r == 0 ? 32 : (r == 1 ? 24 : 12));
+    return (int)std::min<uint64_t>((count + npc - 1) / npc, (uint64_t)num_sms * per_sm);
+  }
+  // node update of [first, first + count) by the instance with registers for `r` receives per node; `lb`: also the bound terms
+  // (one partial sum per CTA at A.partial)
+  template <bool LBF>
+  void launch_update(GraphArgs<Real>& A, uint64_t first, uint64_t count, int r, int ctas, cudaStream_t stream) const {
+    A.first = (uint32_t)first; A.count = (uint32_t)count;
+    switch (r) {
+      case 0: launch_fast<0, 0, LBF>(A, ctas, stream); break;
+      case 1: launch_fast<0, 1, LBF>(A, ctas, stream); break;
+      case 2: launch_fast<0, 2, LBF>(A, ctas, stream); break;
+      case 3: launch_fast<0, 3, LBF>(A, ctas, stream); break;
+      default: launch_fast<0, 4, LBF>(A, ctas, stream); break;
+    }
+  }
+  // LP::LowerBound accumulated by the last anisotropic backward pass: fused_partial[0 .. fused_used)
+  mutable Buffer<double> fused_partial;
+  mutable int fused_used = 0;
+  bool fused_bound_enabled = true;
+  bool all_fast() const {
+    if (!fast_ok) return false;
+    for (size_t lv = 0; lv + 1 < level_off.size(); ++lv) if (level_fast[lv] != level_off[lv + 1]) return false;
+    return true;
   }
   // lanes per node / threads per CTA / shared memory of the generic kernel
   bool generic_shape(int level_group, int* G, int* threads, size_t* smem) const {
@@ -455,22 +504,52 @@ struct GraphEngine {
 
   // one pass = the levels in order (forward) or reverse order (backward); returns the number of kernels launched, < 0 on error
   int ctas_per_sm = 0;   // fast kernel: CTAs per SM of a launch ("graph_ctas_per_sm"; 0 = default)
-  int pass(bool forward, bool primal, int repam, bool residual, uint32_t* labels, int level_group, int num_sms, cudaStream_t stream, std::string& err) const {
+  int pass(bool forward, bool primal, int repam, bool residual, uint32_t* labels, int level_group, int num_sms, cudaStream_t stream, std::string& err,
+           bool* fused) const {
     GraphArgs<Real> A = args(labels, nullptr);
     A.repam = repam; A.forward = forward ? 1 : 0; A.primal = primal ? 1 : 0; A.residual = residual ? 1 : 0;
     int G = 0, threads = 0;
     size_t smem = 0;
     if (!generic_shape(level_group, &G, &threads, &smem)) { err = "label count too large for the level kernel"; return -1; }
     const size_t nlev = level_off.size() - 1;
+    const bool aniso = repam == LPMP_REPAM_ANISOTROPIC || repam == LPMP_REPAM_ANISOTROPIC2;
+    // the launches of the fast part: consecutive ranges that need the same instance go out as one launch
+    struct Launch { size_t lv; uint64_t first, count; int r, ctas; };
+    std::vector<Launch> fast_launches;
+    size_t slots = 0;
+    for (size_t lv = 0; lv < nlev; ++lv) {
+      uint64_t first = 0, count = 0;
+      int cur = -1;
+      auto flush = [&] { if (count) { const int c = update_ctas(count, cur, num_sms); fast_launches.push_back({lv, first, count, cur, c}); slots += (size_t)c; count = 0; } };
+      for (const Segment& sg : segments[lv]) {
+        const int r = (int)(aniso ? (forward ? sg.n_in : sg.n_out) : sg.n_in + sg.n_out);
+        if (r != cur) flush();
+        if (!count) first = sg.first;
+        cur = r; count += sg.count;
+      }
+      flush();
+    }
+    *fused = fused_bound_enabled && !forward && !primal && aniso && all_fast();
+    if (*fused) {
+      if (fused_partial.n < slots && fused_partial.alloc(slots) != cudaSuccess) { err = "out of device memory (fused bound)"; return -1; }
+      fused_used = 0;
+    }
     int launched = 0;
     for (size_t t = 0; t < nlev; ++t) {
       const size_t lv = forward ? t : nlev - 1 - t;
       const uint64_t n_fast = level_fast[lv] - level_off[lv], n_slow = level_off[lv + 1] - level_fast[lv];
       if (n_fast) {
-        A.first = (uint32_t)level_off[lv]; A.count = (uint32_t)n_fast;
-        const uint64_t npc = 256 / L;
-        launch_fast<0>(A, (int)std::min<uint64_t>((n_fast + npc - 1) / npc, (uint64_t)num_sms * (ctas_per_sm > 0 ? ctas_per_sm : 12)), stream);
-        ++launched;
+        for (const Launch& ln : fast_launches) {
+          if (ln.lv != lv) continue;
+          if (*fused) {
+            A.partial = fused_partial.p + fused_used;
+            fused_used += ln.ctas;
+            launch_update<true>(A, ln.first, ln.count, ln.r, ln.ctas, stream);
+          } else {
+            launch_update<false>(A, ln.first, ln.count, ln.r, ln.ctas, stream);
+          }
+          ++launched;
+        }
       }
       if (n_slow) {
         A.first = (uint32_t)level_fast[lv]; A.count = (uint32_t)n_slow;

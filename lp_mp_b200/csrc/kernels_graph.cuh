@@ -56,8 +56,15 @@ struct GraphArgs {
 // LT lanes per node, lane x owns label x of every vector of the record and row x of every table: the min-plus of a receive is LT
 // shuffles, adds and mins, no shared memory.  All loads of a node are issued before the first use.
 // MODE 0: node update; MODE 1: lower-bound terms (read only).
-template <typename Real, int LT, int DMAX, int MODE>
-__global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_node_kernel(const GraphArgs<Real> A) {
+// R = the largest number of edges a node of this launch receives on.  What bounds the light launches (few receives per node) is the
+// number of bytes in flight per SM, i.e. the number of resident threads: the host sorts the nodes of a level by their in / out
+// counts and launches each range with the instance that holds registers for exactly its receives (R = 0: ~30 registers, full
+// occupancy; R = 4: ~62).
+// LBF (anisotropic backward passes): LP::LowerBound accumulated on the fly -- in a backward pass a node is the last writer of its theta
+// and of its side of the edges it receives on (their other side was finished by the later endpoint earlier in the pass), and h(x)
+// is in registers: min theta + sum over the received edges of min_x [own(x) + h(x)]; every edge is received exactly once per pass.
+template <typename Real, int LT, int DMAX, int MODE, int R = DMAX, bool LBF = false>
+__global__ void __launch_bounds__(256, (R == 0 ? 8 : (R == 1 ? 6 : (LT * sizeof(Real) <= 32 ? 3 : 1)))) graph_node_kernel(const GraphArgs<Real> A) {
   static_assert(DMAX == 4, "the node descriptor holds four slots");
   constexpr int NPC = 256 / LT;   // nodes per CTA
   constexpr unsigned FULLW = 0xffffffffu;
@@ -86,10 +93,12 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
     const uint32_t meta[DMAX] = {d1.x, d1.y, d1.z, d1.w};
     Real* rec = A.vec + ((uint64_t)k + q0) * LT;
     Real th = valid ? rec[x] : Real(0);
-    Real own[DMAX], oth[DMAX], row[DMAX][LT];   // oth: label x of the neighbour's vector (the group shuffles it around)
+    Real own[DMAX];
     uint32_t fl[DMAX];
     bool recv[DMAX];
+    int ord[DMAX];              // the how-manieth received edge slot s is
     uint32_t n_in = 0, n_out = 0;
+    int n_recv = 0;
 #pragma unroll
     for (int s = 0; s < DMAX; ++s) {
       fl[s] = meta[s] & 3u;
@@ -97,42 +106,61 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
       if (s < (int)deg) { if (later) ++n_out; else ++n_in; }
       const bool earlier = A.forward ? !later : later;
       // MODE 1: every edge once, at its first variable
-      recv[s] = s < (int)deg && (MODE == 1 ? (fl[s] & 1u) == 0u : (!aniso || earlier));
+      recv[s] = s < (int)deg && (MODE == 1 ? (fl[s] & 1u) == 0u : (!aniso || earlier)) && n_recv < R;
+      ord[s] = n_recv;
+      n_recv += recv[s] ? 1 : 0;
     }
 #pragma unroll
-    for (int s = 0; s < DMAX; ++s) {
-      own[s] = s < (int)deg ? rec[(1 + s) * LT + x] : Real(0);
-      oth[s] = Real(0);
+    for (int s = 0; s < DMAX; ++s) own[s] = s < (int)deg ? rec[(1 + s) * LT + x] : Real(0);
+    // the j-th received edge: label x of the neighbour's vector (the group shuffles it around) and row x of its table
+    Real hm[R > 0 ? R : 1];
+    if constexpr (R > 0) {
+      Real oth[R], row[R][LT];
 #pragma unroll
-      for (int y = 0; y < LT; ++y) row[s][y] = Real(0);
-      if (recv[s]) {
-        oth[s] = A.vec[(meta[s] & ~3u) + x];
-        const Real* t = A.tab + ((uint64_t)(q0 + s) * LT + x) * LT;
-        if constexpr (sizeof(Real) == 4 && LT % 4 == 0) {
+      for (int j = 0; j < R; ++j) {
+        int sj = 0;
+        uint32_t mj = 0;
 #pragma unroll
-          for (int y = 0; y < LT; y += 4) {
-            const float4 tv = __ldg(reinterpret_cast<const float4*>(t + y));
-            row[s][y] = tv.x; row[s][y + 1] = tv.y; row[s][y + 2] = tv.z; row[s][y + 3] = tv.w;
-          }
-        } else {
+        for (int s = 0; s < DMAX; ++s) if (recv[s] && ord[s] == j) { sj = s; mj = meta[s]; }
+        oth[j] = Real(0);
 #pragma unroll
-          for (int y = 0; y < LT; y += 2) {
-            const double2 tv = __ldg(reinterpret_cast<const double2*>(t + y));
-            row[s][y] = tv.x; row[s][y + 1] = tv.y;
+        for (int y = 0; y < LT; ++y) row[j][y] = Real(0);
+        if (j < n_recv) {
+          oth[j] = A.vec[(mj & ~3u) + x];
+          const Real* t = A.tab + ((uint64_t)(q0 + sj) * LT + x) * LT;
+          if constexpr (sizeof(Real) == 4 && LT % 4 == 0) {
+#pragma unroll
+            for (int y = 0; y < LT; y += 4) {
+              const float4 tv = __ldg(reinterpret_cast<const float4*>(t + y));
+              row[j][y] = tv.x; row[j][y + 1] = tv.y; row[j][y + 2] = tv.z; row[j][y + 3] = tv.w;
+            }
+          } else {
+#pragma unroll
+            for (int y = 0; y < LT; y += 2) {
+              const double2 tv = __ldg(reinterpret_cast<const double2*>(t + y));
+              row[j][y] = tv.x; row[j][y + 1] = tv.y;
+            }
           }
         }
       }
-    }
-    // h_s(x) = min_y [ c_s(x,y) + other_s(y) ] for the slots some group of the warp receives on (warp-uniform branch)
-    Real hm[DMAX];
+      // h_j(x) = min_y [ c_j(x,y) + other_j(y) ] for the ordinals some group of the warp receives on (warp-uniform branch)
 #pragma unroll
-    for (int s = 0; s < DMAX; ++s) {
-      hm[s] = INF;
-      if (__any_sync(FULLW, recv[s])) {
+      for (int j = 0; j < R; ++j) {
+        hm[j] = INF;
+        if (__any_sync(FULLW, j < n_recv)) {
 #pragma unroll
-        for (int y = 0; y < LT; ++y) hm[s] = rmin(hm[s], Real(row[s][y] + __shfl_sync(FULLW, oth[s], y, LT)));
+          for (int y = 0; y < LT; ++y) hm[j] = rmin(hm[j], Real(row[j][y] + __shfl_sync(FULLW, oth[j], y, LT)));
+        }
       }
+    } else {
+      hm[0] = INF;
     }
+    auto h_of = [&](const int s) {   // min-marginal of slot s (static selects over the ordinals)
+      Real h = hm[0];
+#pragma unroll
+      for (int j = 1; j < R; ++j) h = ord[s] == j ? hm[j] : h;
+      return h;
+    };
     if constexpr (MODE == 1) {
       // LP::LowerBound (include/LP_MP.h:1507-1518): min theta_i + sum over the edges whose first variable this node is of
       // min_x [a(x) + min_y (c(x,y) + b(y))]
@@ -143,7 +171,7 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
 #pragma unroll
       for (int s = 0; s < DMAX; ++s) {
         if (__any_sync(FULLW, recv[s])) {
-          Real h = recv[s] ? Real(hm[s] + own[s]) : INF;
+          Real h = recv[s] ? Real(h_of(s) + own[s]) : INF;
 #pragma unroll
           for (int o = LT >> 1; o > 0; o >>= 1) h = rmin(h, __shfl_xor_sync(FULLW, h, o));
           if (recv[s]) term += (double)h;
@@ -155,7 +183,7 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
 #pragma unroll
       for (int s = 0; s < DMAX; ++s) {
         if (recv[s]) {
-          const Real m = hm[s] + own[s];
+          const Real m = h_of(s) + own[s];
           th = th + m;          // RepamLeft(+)   :498-500
           own[s] = own[s] - m;  // RepamRight(-)
         }
@@ -207,9 +235,25 @@ __global__ void __launch_bounds__(256, (LT * sizeof(Real) <= 32 ? 3 : 1)) graph_
       if (valid) rec[x] = th;
 #pragma unroll
       for (int s = 0; s < DMAX; ++s) if (s < (int)deg) rec[(1 + s) * LT + x] = own[s];
+      if constexpr (LBF) {   // after the stores
+        Real m = valid ? th : INF;
+#pragma unroll
+        for (int o = LT >> 1; o > 0; o >>= 1) m = rmin(m, __shfl_xor_sync(FULLW, m, o));
+        double term = valid ? (double)m : 0.0;
+#pragma unroll
+        for (int s = 0; s < DMAX; ++s) {
+          if (__any_sync(FULLW, recv[s])) {
+            Real h = recv[s] ? Real(h_of(s) + own[s]) : INF;
+#pragma unroll
+            for (int o = LT >> 1; o > 0; o >>= 1) h = rmin(h, __shfl_xor_sync(FULLW, h, o));
+            if (recv[s]) term += (double)h;
+          }
+        }
+        if (x == 0) acc += term;
+      }
     }
   }
-  if constexpr (MODE == 1) {
+  if constexpr (MODE == 1 || LBF) {
     const double sum = block_sum(acc);
     if (threadIdx.x == 0) A.partial[blockIdx.x] = sum;
   }
@@ -376,6 +420,14 @@ __global__ void __launch_bounds__(256) graph_primal_kernel(const GraphArgs<Real>
   }
   const double s = block_sum(acc);
   if (threadIdx.x == 0) A.partial[blockIdx.x] = s;
+}
+
+// deterministic sum of many partial sums (fused bound of a pass: one slot per CTA of every launch): one CTA, fixed strides, fixed tree
+__global__ void __launch_bounds__(1024) wide_sum_kernel(const double* __restrict__ partial, uint32_t n, double constant, double* out) {
+  double v = 0.0;
+  for (uint32_t k = threadIdx.x; k < n; k += 1024) v += partial[k];
+  const double s = block_sum(v);
+  if (threadIdx.x == 0) *out = constant + s;
 }
 
 // CheckPrimalConsistency with one label count per variable: labels that are unset or out of range

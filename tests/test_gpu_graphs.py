@@ -365,3 +365,41 @@ def test_node_update_entry_point(cuda_api, oracle_api, dtype, kind, L, deg):
         m = h + own
         sent = (theta + m.sum(axis=1)) / deg
         assert np.allclose(ow, own - m + sent[:, None, :], rtol=1e-5 if dtype == "f32" else 1e-12, atol=1e-5 if dtype == "f32" else 1e-12)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_graph_fused_bound_equals_the_sweep(dtype):
+    """anisotropic backward passes of the register kernel leave LP::LowerBound behind (one wide sum instead of a sweep over all
+    records); any other pass or state change falls back to the sweep"""
+    rng = np.random.default_rng(77)
+    n, L = 500, 8
+    perm = rng.permutation(n)
+    edges = sorted({(min(i, (i + 1) % n), max(i, (i + 1) % n)) for i in range(n)} | {(min(int(perm[k]), int(perm[k + 1])), max(int(perm[k]), int(perm[k + 1]))) for k in range(0, n, 2)})
+    ei, ej = np.array([e[0] for e in edges], dtype=np.uint64), np.array([e[1] for e in edges], dtype=np.uint64)
+    theta, tables = rng.random((n, L)), rng.random((len(edges), L, L)) - 0.2
+    lps = []
+    for fused in (1, 0):
+        lp = cuda_lp(dtype)
+        lp.set_tuning(graph_fused_bound=fused)
+        lp.add_unaries(theta); lp.add_pairwise_dense(ei, ej, tables)
+        colour, nc = lp.greedy_colouring(ei, ej)
+        lp.set_node_ranks(colour.astype(np.uint64) * n + np.arange(n, dtype=np.uint64))
+        lp.finalize(); lp.Begin(); lp.set_reparametrization("anisotropic")
+        lps.append(lp)
+    f, s = lps
+    for it in range(3):
+        f.ComputePass(it); s.ComputePass(it)
+        before = f.stats()["kernel_launches"]
+        lb = f.LowerBound()
+        assert f.stats()["kernel_launches"] - before == 1, "one wide sum, no sweep"
+        assert np.isclose(lb, s.LowerBound(), rtol=1e-13 if dtype == "f64" else 1e-6)
+        assert same_state(f, s)
+    f.ComputeForwardPass(); s.ComputeForwardPass()          # a forward pass invalidates the terms
+    assert np.isclose(f.LowerBound(), s.LowerBound(), rtol=1e-13 if dtype == "f64" else 1e-6)
+    f.ComputeBackwardPass(); s.ComputeBackwardPass()
+    th = f.unaries(); th[0, 0] += 1.0
+    f.set_unaries(th); s.set_unaries(th)                      # ... and so does a state change
+    assert np.isclose(f.LowerBound(), s.LowerBound(), rtol=1e-13 if dtype == "f64" else 1e-6)
+    f.set_reparametrization("uniform"); s.set_reparametrization("uniform")
+    f.ComputePass(9); s.ComputePass(9)
+    assert np.isclose(f.LowerBound(), s.LowerBound(), rtol=1e-13 if dtype == "f64" else 1e-6) and same_state(f, s)
