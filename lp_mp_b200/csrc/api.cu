@@ -990,7 +990,10 @@ struct Solver : ISolver {
         A.num_bands = (gridH + (uint32_t)kSplitBandRows - 1) / (uint32_t)kSplitBandRows;
         // backward passes accumulate LP::LowerBound on the fly where the pass is bandwidth-bound (more bands than SMs: the three
         // extra group minima per step hide under the memory traffic); latency-bound grids keep the separate 0.1 ms sweep
-        const bool fuse = !forward && !primal && (tune.fused_bound > 0 || (tune.fused_bound < 0 && A.num_bands > (uint32_t)num_sms));
+        // (a latency-bound launch pays ~0.05 us per chain step for the three extra group minima -- measured on C2 -- against a sweep
+        // that streams every record once)
+        const double sweep_us = (double)N * REC() * sizeof(Real) / 6.5e6, chain_us = 0.05 * ((double)gridH + gridW);
+        const bool fuse = !forward && !primal && (tune.fused_bound > 0 || (tune.fused_bound < 0 && (A.num_bands > (uint32_t)num_sms || sweep_us > chain_us)));
         if (fuse) A.lb_rows = lb_rows.p;
         const cudaError_t le = pw == LPMP_PAIRWISE_POTTS ? launch_split<Real, LPMP_PAIRWISE_POTTS>(maps_split, A, L, rows_win, tune, num_sms, stream)
                                                          : launch_split<Real, LPMP_PAIRWISE_TRUNCLIN>(maps_split, A, L, rows_win, tune, num_sms, stream);

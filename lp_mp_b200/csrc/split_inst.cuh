@@ -51,6 +51,13 @@ static cudaError_t launch_split_one(const CUtensorMap* maps, const GridArgs<Real
         if (clusters > max_clusters) clusters = max_clusters;
         if (clusters * cs > num_sms) clusters = num_sms / cs;
         if (tune.max_ctas > 0 && clusters * cs > tune.max_ctas) clusters = tune.max_ctas / cs;
+        // a latency-bound launch (every band could have its own SM) whose bands do not all fit with this cluster size: band
+        // `resident` can only start when the CTA of band 0 has finished its W columns, long after the chain has reached it when
+        // the grid is much wider than resident * 8 rows (1024 x 4096 stripes: 120 of 128 bands resident with clusters of 8 cost
+        // 0.7 ms per pass) -- take the next smaller cluster size, which co-schedules more CTAs
+        const int resident = clusters * cs;
+        if (tune.cluster <= 0 && cs > 2 && (int)args.num_bands <= num_sms && resident < (int)args.num_bands &&
+            (long long)args.W > 2LL * resident * kSplitBandRows) { (void)cudaGetLastError(); continue; }
         if (clusters >= 1) { ctas = clusters * cs; break; }
       }
       (void)cudaGetLastError();
