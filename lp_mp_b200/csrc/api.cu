@@ -1017,7 +1017,7 @@ struct Solver : ISolver {
       }
       // tile width: 8 columns unless the bands outnumber the resident warps and the narrow tile doubles residency
       int ksel = shape.default_k();
-      if (repam == LPMP_REPAM_ANISOTROPIC && shape.fits8 && shape.fits4) {
+      if (shape.fits8 && shape.fits4) {
         const uint64_t resident8 = (uint64_t)num_sms * std::max<size_t>(1, (227 * 1024) / (shape.smem8 + 1024));
         if (A.num_bands > resident8) ksel = 4;
         if (tune.tile_cols == 4 || tune.tile_cols == 8) ksel = tune.tile_cols;

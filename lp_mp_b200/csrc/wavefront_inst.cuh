@@ -8,7 +8,7 @@ template <typename Real, int PW, int L, int HOPS, bool ANISO, int KSEL>
 static cudaError_t launch_one(const CUtensorMap* maps, const GridArgs<Real>& args, const WavefrontTuning& tune, int num_sms, cudaStream_t stream) {
   using Cfg = WavefrontCfg<Real, PW, L, KSEL>;
   // the narrow tile exists for the anisotropic kernels, and for the uniform ones only where the wide tile does not fit
-  constexpr bool EXISTS = Cfg::FITS && (KSEL == 8 || ANISO || !WavefrontCfg<Real, PW, L, 8>::FITS);
+  constexpr bool EXISTS = Cfg::FITS;
   if constexpr (!EXISTS) {
     return cudaErrorInvalidValue;
   } else {
