@@ -142,6 +142,21 @@ __device__ __forceinline__ void sts_n_if(bool on, uint32_t a, const float (&v)[1
 __device__ __forceinline__ void sts_n_if(bool on, uint32_t a, const float (&v)[2]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.volatile.shared.v2.f32 [%0], {%1,%2}; }" ::"r"(a), "f"(v[0]), "f"(v[1]), "r"((uint32_t)on) : "memory"); }
 __device__ __forceinline__ void sts_n_if(bool on, uint32_t a, const double (&v)[1]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.volatile.shared.f64 [%0], %1; }" ::"r"(a), "d"(v[0]), "r"((uint32_t)on) : "memory"); }
 __device__ __forceinline__ void sts_n_if(bool on, uint32_t a, const double (&v)[2]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.volatile.shared.v2.f64 [%0], {%1,%2}; }" ::"r"(a), "d"(v[0]), "d"(v[1]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void sts_n(uint32_t a, const float (&v)[1]) { asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(a), "f"(v[0]) : "memory"); }
+__device__ __forceinline__ void sts_n(uint32_t a, const float (&v)[2]) { asm volatile("st.volatile.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v[0]), "f"(v[1]) : "memory"); }
+__device__ __forceinline__ void sts_n(uint32_t a, const double (&v)[1]) { asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(a), "d"(v[0]) : "memory"); }
+__device__ __forceinline__ void sts_n(uint32_t a, const double (&v)[2]) { asm volatile("st.volatile.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(v[0]), "d"(v[1]) : "memory"); }
+// generic address of a shared::cluster address (a ring of the next CTA of the cluster): one generic store then serves both kinds
+// of hand-off that leave the CTA -- distributed shared memory and the L2 / peer-memory slots
+__device__ __forceinline__ void* sp_generic_of_cluster(uint32_t a) {
+  uint64_t g;
+  asm volatile("{ .reg .u64 t; cvt.u64.u32 t, %1; cvta.shared::cluster.u64 %0, t; }" : "=l"(g) : "r"(a));
+  return reinterpret_cast<void*>(g);
+}
+__device__ __forceinline__ void st_generic_n_if(bool on, float* p, const float (&v)[1]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.relaxed.sys.f32 [%0], %1; }" ::"l"(p), "f"(v[0]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void st_generic_n_if(bool on, float* p, const float (&v)[2]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.relaxed.sys.v2.f32 [%0], {%1,%2}; }" ::"l"(p), "f"(v[0]), "f"(v[1]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void st_generic_n_if(bool on, double* p, const double (&v)[1]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.relaxed.sys.f64 [%0], %1; }" ::"l"(p), "d"(v[0]), "r"((uint32_t)on) : "memory"); }
+__device__ __forceinline__ void st_generic_n_if(bool on, double* p, const double (&v)[2]) { asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.relaxed.sys.v2.f64 [%0], {%1,%2}; }" ::"l"(p), "d"(v[0]), "d"(v[1]), "r"((uint32_t)on) : "memory"); }
 __device__ __forceinline__ void stg_n_relaxed_if(bool on, float* p, const float (&v)[1]) { stg1_relaxed_if(on, p, v[0]); }
 __device__ __forceinline__ void stg_n_relaxed_if(bool on, double* p, const double (&v)[1]) { stg1_relaxed_if(on, p, v[0]); }
 __device__ __forceinline__ void stg_n_relaxed_if(bool on, float* p, const float (&v)[2]) {
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
         }
         open = open && j_store < nchunks;
         if (__any_sync(FULL, moved)) spins = 0;
-        else { __nanosleep(100); if (timed_out(spins, 1u << 26)) break; }
+        else { __nanosleep((A.lean_flags & 8) ? 1000 : 100); if (timed_out(spins, 1u << 26)) break; }
       }
       if (mine) tma_wait_read<0>();   // every tile of this band has left shared memory before the rings are reused
       __syncwarp();
@@ -322,7 +337,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
             for (int q = q_in + g; q < limit; q += TG) sts4(ring + (((uint32_t)(q + qoff) & (uint32_t)(RING - 1)) * L + (uint32_t)(gl * 4)) * S, zero);
             q_in = limit;
             spins = 0;
-          } else { __nanosleep(200); if (timed_out(spins, 1u << 26)) break; }
+          } else { __nanosleep((A.lean_flags & 16) ? 2000 : 200); if (timed_out(spins, 1u << 26)) break; }
         }
       } else {
         const Real* const hand_in = (kb == 0 ? A.in_boundary : A.handoff + (uint64_t)kb * W * L) + gl * 4;
@@ -578,16 +593,26 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
       };
 
       // ---- steady steps, one tile of 8 columns at a time: every address is a per-tile base + an immediate ----
-      auto do_tile = [&](const int j) {
+      // Specialised by where the column vector goes (RINGOUT: the next warp's ring, the 7 upper rows of a band; otherwise ONE generic
+      // store into the next CTA's ring / the L2 slots / the neighbouring stripe) and by LAST (the tile ends with the last column):
+      // an in-order warp pays ~4.4 cycles per instruction of the step (profiles/r02_step_microbench.txt), so the step carries no
+      // predicate it does not need -- theta, the sentinel and both record vectors are stored by both half-warps (same words, same
+      // values), the two min-marginals reach both halves in the order of the additions by two indexed shuffles (no selects).
+      const int src_first = (lane & 15) | (recv_row_first ? 0 : 16);
+      Real* const out_gen = to_next_cta ? reinterpret_cast<Real*>(sp_generic_of_cluster(ring_dsm)) : out_ptr;
+      const bool out_gen_on = out_dsm || out_glob;
+      auto do_tile = [&](auto last_tag, auto ring_tag, const int j) {
+        constexpr bool LAST = decltype(last_tag)::value;     // the tile ends with the last column of the row (no edge to a next column)
+        constexpr bool RINGOUT = decltype(ring_tag)::value;  // the row below is the next warp of this CTA
         wait_chunk(j);
         const int s0 = (j << LOGK) - qoff;                  // step (= virtual column) at which the row enters tile j
         const uint32_t slot = (cbase + (uint32_t)j) & (NSLOT - 1);
         const uint32_t toff = slot * SLOT_REC_B + (fwd ? 0u : (uint32_t)(K - 1) * REC_B);
         const uint32_t Tth = f_th + toff, Tin = f_in + toff, Tout = f_out + toff;
         const uint32_t Tpar = f_par + slot * SLOT_PAR_B + (fwd ? 0u : (uint32_t)(K - 1) * PREC_B);
-        const uint32_t c0 = ((uint32_t)(j << LOGK) & (uint32_t)(RING - 1)) * LB;
-        const uint32_t Rin = ring_in + c0, Rout = ring_out + c0, Rdsm = ring_dsm + c0;
-        Real* const Gout = out_ptr + (int64_t)s0 * L;
+        const uint32_t cq = (uint32_t)(j << LOGK) & (uint32_t)(RING - 1);
+        const uint32_t Rin = ring_in + cq * LB, Rout = ring_out + cq * LB;
+        Real* const Gout = out_gen + (to_next_cta ? (int64_t)cq * L : (int64_t)s0 * L);
         if (warp_out_ring && s0 + K - 1 >= free_upto) {     // room in the next warp's ring for the whole tile (warp-uniform, rare)
           unsigned spins = 0;
           do {
@@ -617,31 +642,31 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
             Real sent[LPL];
 #pragma unroll
             for (int k = 0; k < LPL; ++k) sent[k] = sentinel<Real>();
-            sts_n_if(hi, rin, sent);                        // the slot is free again
+            sts_n(rin, sent);                               // the slot is free again (both halves: same words)
           }
 #pragma unroll
           for (int k = 0; k < LPL; ++k) oth[k] = hi ? pv[k] : oth[k];
-          Real h[LPL], m[LPL], mo[LPL], tv[LPL];
+          Real h[LPL], m[LPL], tv[LPL];
           split_min_plus<Real, PW, LPL, WIN>(par, oth, h);
 #pragma unroll
           for (int k = 0; k < LPL; ++k) { m[k] = h[k] + oi[k]; oi[k] = oi[k] - m[k]; }
 #pragma unroll
-          for (int k = 0; k < LPL; ++k) mo[k] = __shfl_xor_sync(FULL, m[k], 16);
-#pragma unroll
           for (int k = 0; k < LPL; ++k) {
-            const Real v = (th[k] + (self_first ? m[k] : mo[k])) + (self_first ? mo[k] : m[k]);
+            const Real m1 = __shfl_sync(FULL, m[k], src_first), m2 = __shfl_sync(FULL, m[k], src_first ^ 16);
+            const Real v = (th[k] + m1) + m2;
             const Real d = w_fast * v;
-            const Real d_oc = out_col_exists ? d : Real(0);
-            oo[k] = oo[k] + (hi ? d_oc : d);
-            th[k] = (v - d_oc) - d;
+            const Real d_oc = (RINGOUT || out_col_exists) ? d : Real(0), d_or = (LAST && jj == K - 1) ? Real(0) : d;
+            if (RINGOUT && !(LAST && jj == K - 1)) oo[k] = oo[k] + d;   // (folded after unrolling)
+            else oo[k] = oo[k] + (hi ? d_oc : d_or);
+            th[k] = (v - d_oc) - d_or;
             tv[k] = v;
           }
-          sts_n_if(out_ring, Rout + (uint32_t)jj * LB, oo);   // hand-off first: the warp below is waiting for it
-          st_cluster_n_if(out_dsm, Rdsm + (uint32_t)jj * LB, oo);
-          stg_n_relaxed_if(out_glob, Gout + jj * L, oo);
-          sts_n_if(!hi, Tth + ro, th);
-          sts_n_if(true, Tin + ro, oi);
-          sts_n_if(true, Tout + ro, oo);
+          // hand-off first: the row below is waiting for it
+          if constexpr (RINGOUT) sts_n_if(hi, Rout + (uint32_t)jj * LB, oo);
+          else st_generic_n_if(out_gen_on, Gout + jj * L, oo);
+          sts_n(Tth + ro, th);                              // (both halves hold theta)
+          sts_n(Tin + ro, oi);
+          sts_n(Tout + ro, oo);
 #pragma unroll
           for (int k = 0; k < LPL; ++k) oth[k] = oo[k];
           if constexpr (PRM) write_label(tv, s0 + jj);         // after the stores: nothing of the chain waits for the label
@@ -650,29 +675,49 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
         publish(s0 + K);
       };
 
-      // general steps for the whole band: rounding, tiny grids; for the first / last column of the first / last grid row (corner
-      // weights); everything else runs the edge / steady steps
+      // Step kinds along the row.  With in-/out-edge counts (n_in, n_out) the weight is 1 / max(n_in, n_out) = 1/2 everywhere except at
+      // column 0 of a row without a lower neighbour and at the last column of a row without an upper or a lower neighbour (general
+      // step); everything else runs the fast steps, whole tiles of them through do_tile -- INCLUDING the tile of column 0 (its
+      // missing row edge is an exact no-op, see above) and the tile of the last column (LAST), so that for W % 8 == 0 a row is
+      // tiles only: the skew between consecutive rows is then the hand-off latency of a tile step (~150 ns) instead of that of a
+      // single step (~235 ns; scripts/trace_rows.py), and a pass costs W * S + H * skew.
       const bool all_general = (!PRM && A.primal != 0) || (int)W < 4 || (H < 2 && !(A.in_halo || A.out_halo));
       const bool corner_row = (u == 0 && !A.in_halo) || (u + 1 == (int)H && !A.out_halo);
+      const bool first_fast = !all_general && out_col_exists, last_fast = !all_general && !corner_row;
+      const int s_lo = first_fast ? 0 : 1, s_hi = last_fast ? (int)W - 1 : (int)W - 2;   // fast steps: s_lo .. s_hi
+      const int j0 = all_general ? 1 : (s_lo + qoff + K - 1) >> LOGK, j1 = all_general ? 0 : ((s_hi + 1 + qoff) >> LOGK) - 1;   // whole tiles of fast steps
+      const bool ring_row = !grid_last_row && w + 1 < NW;   // the row below is the next warp of this CTA
+      const bool mark = A.trace_steps && lane == 0 && u < 4096;   // debug: row timeline (scripts/trace_rows.py)
+      bool marked = false;
+      if (mark) A.trace_steps[4096 + u] = globaltimer_ns();
       int s = 0;
-      if (all_general) {
-        for (; s < nsteps; ++s) do_step(std::integral_constant<int, 0>{}, s);
-      } else {
-        if (corner_row) do_step(std::integral_constant<int, 0>{}, s); else do_step(std::integral_constant<int, 1>{}, s);
-        ++s;
-        const int s_last = (int)W - 2;                      // interior columns: 1 .. W - 2
-        const int j0 = (1 + qoff + K - 1) >> LOGK, j1 = ((s_last + 1 + qoff) >> LOGK) - 1;   // whole tiles j0 .. j1 of interior columns
-        if (j1 >= j0) {
-          for (; s < (j0 << LOGK) - qoff; ++s) do_step(std::integral_constant<int, 2>{}, s);
 #pragma unroll 1
-          for (int j = j0; j <= j1; ++j) do_tile(j);
-          s = ((j1 + 1) << LOGK) - qoff;
+      while (s < nsteps) {
+        const int sp = s + qoff;
+        if ((sp & (K - 1)) == 0 && (sp >> LOGK) >= j0 && (sp >> LOGK) <= j1) {
+          int j = sp >> LOGK;
+          const int j_plain = ((j1 + 1) << LOGK) - qoff == nsteps ? j1 - 1 : j1;   // the tile of the last column is its own instance
+          if (ring_row) {
+#pragma unroll 1
+            for (; j <= j_plain; ++j) do_tile(std::false_type{}, std::true_type{}, j);
+            if (j <= j1) do_tile(std::true_type{}, std::true_type{}, j++);
+          } else {
+#pragma unroll 1
+            for (; j <= j_plain; ++j) do_tile(std::false_type{}, std::false_type{}, j);
+            if (j <= j1) do_tile(std::true_type{}, std::false_type{}, j++);
+          }
+          s = (j << LOGK) - qoff;
+        } else {
+          const int kind = all_general ? 0 : s == 0 ? (first_fast ? 1 : 0) : s + 1 == nsteps ? (last_fast ? 1 : 0) : 2;
+          if (kind == 0) do_step(std::integral_constant<int, 0>{}, s);
+          else if (kind == 1) do_step(std::integral_constant<int, 1>{}, s);
+          else do_step(std::integral_constant<int, 2>{}, s);
+          ++s;
         }
-#pragma unroll 1
-        for (; s <= s_last; ++s) do_step(std::integral_constant<int, 2>{}, s);
-        if (corner_row) do_step(std::integral_constant<int, 0>{}, s); else do_step(std::integral_constant<int, 1>{}, s);
+        if (mark && !marked) { A.trace_steps[u] = globaltimer_ns(); marked = true; }   // column 0 (or the tile of column 0) handed on
       }
       if constexpr (LBF) { if (lane == 0) A.lb_rows[r] = lb_acc; }
+      if (mark) A.trace_steps[3 * 4096 + u] = globaltimer_ns();    // debug: row finished
     }
     // ---- end of the band: every ring is drained and re-armed, every tile has left shared memory ----
 #pragma unroll
