@@ -501,6 +501,7 @@ struct Solver : ISolver {
     else if (k == "graph_fused_bound") graph.fused_bound_enabled = value != 0;
     else if (k == "wavefront_rows") tune.rows = value;
     else if (k == "wavefront_split") tune.split = value;
+    else if (k == "wavefront_split_uni") tune.split_uni = value;
     else if (k == "wavefront_fused_bound") tune.fused_bound = value;
     else if (k == "wavefront_trace") want_trace = value;
     else { err = "unknown tuning key " + k; return LPMP_ERR_INVALID; }
@@ -1003,6 +1004,20 @@ struct Solver : ISolver {
         if (primal) labels_valid = true;
         fused_lb_valid = fuse;
         fused_lb_open_below = fuse && has_below;
+        return LPMP_OK;
+      }
+      // the uniform / damped-uniform modes (the rounding iterations of the default control law, include/visitors/standard_visitor.hxx:44)
+      // on the split kernel: rows of whole tiles only
+      const bool uni_mode = repam == LPMP_REPAM_UNIFORM || repam == LPMP_REPAM_DAMPED_UNIFORM;
+      if (split_ok && uni_mode && !striped && rows_win >= 0 && (pw == LPMP_PAIRWISE_POTTS || L == 16) && use_split() && tune.split_uni != 0 &&
+          gridW % 8 == 0 && gridW >= 16 && split_uni_supported<Real>(pw, L)) {
+        A.num_bands = (gridH + (uint32_t)kSplitBandRows - 1) / (uint32_t)kSplitBandRows;
+        const cudaError_t le = pw == LPMP_PAIRWISE_POTTS ? launch_split_uni<Real, LPMP_PAIRWISE_POTTS>(maps_split, A, L, rows_win, tune, num_sms, stream)
+                                                         : launch_split_uni<Real, LPMP_PAIRWISE_TRUNCLIN>(maps_split, A, L, rows_win, tune, num_sms, stream);
+        CUDA_TRY(le);
+        ++launches;
+        updates += 4 * E;
+        if (primal) labels_valid = true;
         return LPMP_OK;
       }
       if (rows_ok && repam == LPMP_REPAM_ANISOTROPIC && rows_win >= 0 && use_rows()) {

@@ -24,7 +24,9 @@
 
 namespace lpmp {
 
-template <typename Real, int PW, int L>
+// UNI: the instance for the uniform / damped-uniform modes (a node also receives from -- and sends to -- its two LATER neighbours):
+// one more ring of tiles holds the records of the first row of the next band (whose in-side vectors the band's last row reads).
+template <typename Real, int PW, int L, bool UNI = false>
 struct SplitCfg {
   static constexpr int LPL = L / 16;                       // labels per lane (16 lanes per edge)
   static constexpr int NW = 8;                             // compute warps = rows per CTA
@@ -35,15 +37,17 @@ struct SplitCfg {
   static constexpr int SLOT_REC = K * REC, SLOT_PAR = K * PREC;   // reals per tile (one row)
   static constexpr int RING = 32;                          // columns per hand-off ring (power of two)
   static constexpr size_t SLOT_BYTES = (size_t)(SLOT_REC + SLOT_PAR) * sizeof(Real);
-  static constexpr size_t CTRL_OFF = 512;                  // [0,512) mbarriers, [512,640) band queue {super-band, iteration + 1} x 16,
-  static constexpr size_t CTR_OFF = 640;                   // [640,1024) step counters: +4 w: compute warp w, +64: warp 0 of the next CTA of the cluster
+  static constexpr size_t SLOT_REC_BYTES = (size_t)SLOT_REC * sizeof(Real);
+  static constexpr size_t CTRL_OFF = 640;                  // [0,640) mbarriers ([NW + 1][NSLOT]), [640,768) band queue {super-band, iteration + 1} x 16,
+  static constexpr size_t CTR_OFF = 768;                   // [768,1024) step counters: +4 w: compute warp w, +64: warp 0 of the next CTA of the cluster
   static constexpr size_t RINGS_OFF = 1024;
   static constexpr size_t TILES_OFF = (RINGS_OFF + (size_t)NW * RING * L * sizeof(Real) + 127) / 128 * 128;
-  static constexpr int NSLOT = TILES_OFF + 8 * NW * SLOT_BYTES <= 216 * 1024 ? 8 : 4;   // tiles per ring (power of two)
+  static constexpr int NSLOT = TILES_OFF + 8 * NW * SLOT_BYTES + (UNI ? 8 * SLOT_REC_BYTES : 0) <= 216 * 1024 ? 8 : 4;   // tiles per ring (power of two)
   static constexpr size_t WARP_TILE_BYTES = (size_t)NSLOT * SLOT_BYTES;
-  static constexpr size_t SMEM = TILES_OFF + NW * WARP_TILE_BYTES;
+  static constexpr size_t HALO_OFF = TILES_OFF + NW * WARP_TILE_BYTES;          // UNI: [NSLOT] record tiles of the row below the band
+  static constexpr size_t SMEM = HALO_OFF + (UNI ? (size_t)NSLOT * SLOT_REC_BYTES : 0);
   static constexpr int THREADS = 32 * (NW + 2);
-  static constexpr bool FITS = (L == 16 || L == 32) && SMEM <= 220 * 1024 && NW * NSLOT * 8 <= 512 && (PW == LPMP_PAIRWISE_POTTS || LPL == 1);
+  static constexpr bool FITS = (L == 16 || L == 32) && SMEM <= (UNI ? 226 : 220) * 1024 && (NW + 1) * NSLOT * 8 <= 640 && (PW == LPMP_PAIRWISE_POTTS || LPL == 1);
 };
 
 // ---- thread-block cluster / distributed shared memory primitives ----
@@ -180,10 +184,11 @@ __device__ __forceinline__ Real both_halves_min(Real v) {
 // a pass leaves one double per grid row in A.lb_rows -- the separate sweep over all records (kernels_grid_bound.cuh) disappears.
 // PRM: rounding passes (LP::ComputePassAndPrimal, include/LP_MP.h:1592-1602) on the fast steps: the first minimiser of theta after
 // the receives (include/factors_messages.hxx:2363,2382-2389) is worked out after the stores of the step, off the dependency chain.
-template <typename Real, int PW, int L, int WIN, bool FWD, bool LBF = false, bool PRM = false>
-__global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_split_kernel(const GridArgs<Real> A) {
+template <typename Real, int PW, int L, int WIN, bool FWD, bool LBF = false, bool PRM = false, bool UNI = false>
+__global__ void __launch_bounds__(SplitCfg<Real, PW, L, UNI>::THREADS, 1) wavefront_split_kernel(const GridArgs<Real> A) {
   static_assert(!(LBF && FWD), "the fused bound belongs to the backward pass");
-  using Cfg = SplitCfg<Real, PW, L>;
+  static_assert(!(LBF && UNI), "the fused bound needs the anisotropic backward pass (every edge final after its later node)");
+  using Cfg = SplitCfg<Real, PW, L, UNI>;
   constexpr int LPL = Cfg::LPL, NW = Cfg::NW, T = Cfg::T, K = Cfg::K, LOGK = Cfg::LOGK, P = Cfg::P, REC = Cfg::REC, PREC = Cfg::PREC, NSLOT = Cfg::NSLOT, RING = Cfg::RING;
   constexpr uint32_t S = (uint32_t)sizeof(Real);
   constexpr uint32_t REC_B = REC * S, PREC_B = PREC * S, SLOT_REC_B = Cfg::SLOT_REC * S, SLOT_PAR_B = Cfg::SLOT_PAR * S, LB = L * S;
@@ -208,13 +213,13 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
   // ring slot of a column: its tile-space index q' = q + qoff modulo RING (tiles and ring slots wrap together)
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NW * NSLOT; ++i) mbar_init(bars + 8 * i, 1);
+    for (int i = 0; i < (NW + 1) * NSLOT; ++i) mbar_init(bars + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
     Real* rg = reinterpret_cast<Real*>(smem_raw + Cfg::RINGS_OFF);
     for (int i = (int)threadIdx.x; i < NW * RING * L; i += Cfg::THREADS) rg[i] = sentinel<Real>();
-    if (threadIdx.x < 128) reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::CTRL_OFF)[threadIdx.x] = 0u;
+    if (threadIdx.x < (Cfg::RINGS_OFF - Cfg::CTRL_OFF) / 4) reinterpret_cast<volatile uint32_t*>(smem_raw + Cfg::CTRL_OFF)[threadIdx.x] = 0u;   // band queue + step counters
   }
   // CTAs of a thread-block cluster work on CONSECUTIVE bands (rank r on band sb * csize + r): the last row of band r hands its
   // vectors straight into ring 0 of rank r + 1 through distributed shared memory (~0.2 us instead of ~0.8 us through the L2
@@ -239,6 +244,8 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
   uint32_t chunk_base[NW];                // per compute warp: tiles of earlier bands (slot / mbarrier-phase sequence continues)
 #pragma unroll
   for (int w = 0; w < NW; ++w) chunk_base[w] = 0;
+  uint32_t chunk_base_halo = 0;           // UNI: ... and of the ring of the row below the band
+  const uint32_t halo_tiles = smem_base + (uint32_t)Cfg::HALO_OFF;
 
   for (uint32_t iter = 0;; ++iter) {
     // rank 0 claims the next super-band and publishes it to every CTA of the cluster (a rank is at most csize - 1 iterations behind)
@@ -267,13 +274,17 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
       // LANE w serves compute warp w (its own ring of NSLOT tiles, its own bulk groups): the bookkeeping of all rings is one SIMT
       // instruction stream -- a single thread serving every ring in turn was the bottleneck of the whole CTA (profiles/r02_split_tilewarp.txt)
       constexpr int DROP = NSLOT >= 8 ? 2 : 1;   // tiles of look-ahead given up so that a load never waits for the store just issued
+      // UNI: lane NW serves the ring of the row below the band (records only, loads only; a slot is free again when the band's last
+      // row -- its only reader -- has left the tile)
+      const bool halo_lane = UNI && lane == NW;
       const int w = lane < NW ? lane : NW - 1;
-      bool open = lane < NW && warp_live(kb, w);
-      uint32_t cb = 0;
+      bool open = (lane < NW && warp_live(kb, w)) || (halo_lane && warp_live(kb, NW));
+      uint32_t cb = halo_lane ? chunk_base_halo : 0u;
 #pragma unroll
-      for (int k = 0; k < NW; ++k) cb = k == w ? chunk_base[k] : cb;
-      const int row0 = (int)((fwd ? kb : (unsigned)nb - 1u - kb) * T) + (fwd ? w : NW - 1 - w);
-      const uint32_t rec_ring = tiles + (uint32_t)w * (uint32_t)Cfg::WARP_TILE_BYTES, par_ring = rec_ring + NSLOT * SLOT_REC_B;
+      for (int k = 0; k < NW; ++k) cb = (k == w && !halo_lane) ? chunk_base[k] : cb;
+      const int wr = halo_lane ? NW : w;       // row of the band this lane moves
+      const int row0 = (int)((fwd ? kb : (unsigned)nb - 1u - kb) * T) + (fwd ? wr : NW - 1 - wr);
+      const uint32_t rec_ring = halo_lane ? halo_tiles : tiles + (uint32_t)w * (uint32_t)Cfg::WARP_TILE_BYTES, par_ring = rec_ring + NSLOT * SLOT_REC_B;
       const uint32_t ctr_w = ctrs + 4 * (uint32_t)w;
       const bool mine = open;
       int j_load = 0, j_store = 0;
@@ -284,7 +295,8 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
         const int c = (int)(lds_volatile_u32(ctr_w) - step_base);
         int need = (j_store + 1) * K - qoff;
         if (need > nsteps) need = nsteps;
-        if (open && c >= need) {
+        if (open && halo_lane && c >= need) { ++j_store; moved = true; }   // (nothing to store: the reader has left the tile)
+        if (open && !halo_lane && c >= need) {
           const uint32_t slot = (cb + (uint32_t)j_store) & (NSLOT - 1);
           const int col0 = fwd ? j_store * K : (nchunks - 1 - j_store) * K;
           const uint32_t ncols = (uint32_t)((int)W - col0 < K ? (int)W - col0 : K);   // a tile is one contiguous run of records
@@ -296,14 +308,14 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
         // ---- loads: into a slot whose previous tile has left shared memory (never the slot of the store just issued) ----
         if (open && j_load < nchunks && j_load < j_store + NSLOT - DROP) {
           const uint32_t slot = (cb + (uint32_t)j_load) & (NSLOT - 1);
-          if (j_load >= NSLOT) tma_wait_read<DROP>();   // at least DROP younger stores of this lane were committed after the one that read the slot
+          if (j_load >= NSLOT && !halo_lane) tma_wait_read<DROP>();   // at least DROP younger stores of this lane were committed after the one that read the slot
           const int col0 = fwd ? j_load * K : (nchunks - 1 - j_load) * K;
-          const uint32_t bar = bars + 8 * ((uint32_t)w * NSLOT + slot);
+          const uint32_t bar = bars + 8 * ((uint32_t)wr * NSLOT + slot);
           const uint32_t ncols = (uint32_t)((int)W - col0 < K ? (int)W - col0 : K);
           const uint64_t node0 = (uint64_t)row0 * W + (uint32_t)col0;
-          mbar_expect_tx(bar, ncols * (REC_B + PREC_B));
+          mbar_expect_tx(bar, ncols * (REC_B + (halo_lane ? 0u : PREC_B)));
           bulk_load_1d(rec_ring + slot * SLOT_REC_B, A.rec + node0 * REC, ncols * REC_B, bar);
-          bulk_load_1d(par_ring + slot * SLOT_PAR_B, A.par + node0 * PREC, ncols * PREC_B, bar);
+          if (!halo_lane) bulk_load_1d(par_ring + slot * SLOT_PAR_B, A.par + node0 * PREC, ncols * PREC_B, bar);
           ++j_load;
           moved = true;
         }
@@ -463,6 +475,153 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
         const int k1 = __shfl_sync(FULL, kf, (int)il);
         if (lane == 0) A.labels[(uint64_t)r * W + (fwd ? (uint32_t)s : W - 1 - (uint32_t)s)] = il * LPL + (unsigned)k1;
       };
+      if constexpr (UNI) {
+        // ============ uniform / damped-uniform modes (include/LP_MP.h:1420-1449, full receive mask): a node receives from all four
+        // neighbours and sends to all four with weight 1 / deg (1 / (deg + 1)).  The two LATER neighbours have not been updated in
+        // this pass: their in-side vectors are read from shared memory -- the next column of this row's own tile, and the same
+        // column of the tile of the row below (the next warp's ring; the halo ring for the band's last row) -- and their
+        // min-marginals are off the dependency chain.  Host contract: W % 8 == 0, W >= 16, no stripes; every row is tiles only:
+        // FIRST / LAST mark the tiles of column 0 / W - 1 (no row edge on that side: nothing is sent there, one edge less in deg).
+        const bool has_ic = in_col_exists, has_oc = out_col_exists;
+        const int damp = A.repam == LPMP_REPAM_DAMPED_UNIFORM ? 1 : 0;
+        const int deg_int = 2 + (int)has_ic + (int)has_oc;
+        const Real w_int = (Real)(1.0 / (double)(deg_int + damp)), w_edge = (Real)(1.0 / (double)(deg_int - 1 + damp));
+        // order of the additions into theta (message order of the node, grid coordinates: LIFO D, R, L, U; FIFO R, D, U, L): the
+        // pair of the later edges first in a forward pass, the pair of the earlier edges first in a backward pass; inside a pair
+        // the row edge first iff ... (earlier pair: recv_row_first; later pair: the opposite)
+        const int srcB1 = (lane & 15) | (recv_row_first ? 0 : 16), srcA1 = (lane & 15) | (recv_row_first ? 16 : 0);
+        constexpr uint32_t p_out_row = (fwd ? PAR_R : PAR_L) * P * S, p_out_col = (fwd ? PAR_D : PAR_U) * P * S;
+        const uint32_t f_parA = par_ring + (hi ? p_out_col : p_out_row);
+        // the row below: the next warp's ring of tiles, or the halo ring
+        const bool below_halo = w + 1 == NW;
+        uint32_t cb_below = chunk_base_halo;
+#pragma unroll
+        for (int k = 1; k < NW; ++k) cb_below = (k == w + 1) ? chunk_base[k] : cb_below;
+        const uint32_t below_ring = below_halo ? halo_tiles : tiles + (uint32_t)(w + 1) * (uint32_t)Cfg::WARP_TILE_BYTES;
+        const uint32_t below_bars = bars + 8 * (uint32_t)(w + 1) * NSLOT;
+        auto wait_below = [&](int j) {
+          const uint32_t n = cb_below + (uint32_t)j;
+          const uint32_t bar = below_bars + 8 * (n & (NSLOT - 1));
+          const uint32_t parity = (n / NSLOT) & 1u;
+          unsigned spins = 0;
+          while (!mbar_try_wait(bar, parity)) { if (timed_out(spins, 1u << 24)) break; }
+        };
+        Real* const out_gen = to_next_cta ? reinterpret_cast<Real*>(sp_generic_of_cluster(ring_dsm)) : out_ptr;
+        const bool out_gen_on = out_dsm || out_glob;
+        const bool ring_row = !grid_last_row && w + 1 < NW;
+
+        auto uni_tile = [&](auto first_tag, auto last_tag, auto ring_tag, const int j) {
+          constexpr bool FIRST = decltype(first_tag)::value, LAST = decltype(last_tag)::value, RINGOUT = decltype(ring_tag)::value;
+          wait_chunk(j);
+          if (!LAST) wait_chunk(j + 1);                     // the right neighbour of the tile's last column
+          if (has_oc) wait_below(j);
+          const int s0 = j << LOGK;
+          const uint32_t slot = (cbase + (uint32_t)j) & (NSLOT - 1), slot_n = (cbase + (uint32_t)j + 1u) & (NSLOT - 1);
+          const uint32_t col_first = fwd ? 0u : (uint32_t)(K - 1) * REC_B;   // first column of a tile in processing order
+          const uint32_t toff = slot * SLOT_REC_B + col_first;
+          const uint32_t Tth = f_th + toff, Tin = f_in + toff, Tout = f_out + toff;
+          const uint32_t poff = slot * SLOT_PAR_B + (fwd ? 0u : (uint32_t)(K - 1) * PREC_B);
+          const uint32_t TparB = f_par + poff, TparA = f_parA + poff;
+          // the later neighbour's in-side vector: lower half: the next column of this row (own tile; the next tile for the last
+          // column), upper half: the same column of the row below
+          const uint32_t slot_b = (cb_below + (uint32_t)j) & (NSLOT - 1);
+          const uint32_t own_next = rec_ring + (uint32_t)xl * S + o_in_row;
+          const uint32_t below = (has_oc ? below_ring + slot_b * SLOT_REC_B : rec_ring + slot * SLOT_REC_B) + (uint32_t)xl * S + o_in_col + col_first;
+          const uint32_t Tlat = hi ? below : own_next + toff + (fwd ? REC_B : 0u - REC_B);
+          const uint32_t Tlat_last = hi ? below + (fwd ? (uint32_t)(K - 1) * REC_B : 0u - (uint32_t)(K - 1) * REC_B)
+                                        : own_next + (LAST ? toff : slot_n * SLOT_REC_B + col_first);
+          const uint32_t cq = (uint32_t)(j << LOGK) & (uint32_t)(RING - 1);
+          const uint32_t Rin = ring_in + cq * LB, Rout = ring_out + cq * LB;
+          Real* const Gout = out_gen + (to_next_cta ? (int64_t)cq * L : (int64_t)s0 * L);
+          if (warp_out_ring && s0 + K - 1 >= free_upto) {   // room in the next warp's ring for the whole tile (warp-uniform, rare)
+            unsigned spins = 0;
+            do {
+              free_upto = (int)(lds_volatile_u32(ctr_next) - step_base) + RING;
+            } while (s0 + K - 1 >= free_upto && !timed_out(spins, 1u << 27));
+          }
+#pragma unroll
+          for (int jj = 0; jj < K; ++jj) {
+            constexpr int SG = fwd ? 1 : -1;
+            const bool e_ir = !(FIRST && jj == 0), e_or = !(LAST && jj == K - 1);   // (folded after unrolling)
+            const uint32_t ro = (uint32_t)(SG * jj * (int)REC_B), po = (uint32_t)(SG * jj * (int)PREC_B);
+            const uint32_t rin = Rin + (uint32_t)jj * LB;
+            Real pv[LPL], parB[P], parA[P], th[LPL], oi[LPL], oo[LPL], ot[LPL];
+            lds_n_volatile<Real, LPL>(pv, rin);             // the polled slot: every lane reads the words of its labels (no vote)
+            lds_par<Real, P>(parB, TparB + po);
+            lds_par<Real, P>(parA, TparA + po);
+            lds_n<Real, LPL>(ot, jj + 1 < K ? Tlat + ro : Tlat_last);
+            lds_n<Real, LPL>(th, Tth + ro);
+            lds_n<Real, LPL>(oi, Tin + ro);
+            lds_n<Real, LPL>(oo, Tout + ro);
+            // later edges first: nothing of this depends on the row above or on the previous column
+            const bool e_A = hi ? has_oc : e_or;
+#pragma unroll
+            for (int k = 0; k < LPL; ++k) ot[k] = e_A ? ot[k] : Real(0);
+#pragma unroll
+            for (int p = 0; p < P; ++p) parA[p] = e_A ? parA[p] : Real(0);
+            Real hA[LPL], mA[LPL];
+            split_min_plus<Real, PW, LPL, WIN>(parA, ot, hA);
+#pragma unroll
+            for (int k = 0; k < LPL; ++k) { mA[k] = e_A ? Real(hA[k] + oo[k]) : Real(0); oo[k] = e_A ? Real(oo[k] - mA[k]) : oo[k]; }
+            if (is_sentinel(pv[0]) || is_sentinel(pv[LPL - 1])) {
+              unsigned spins = 0;
+              do { lds_n_volatile<Real, LPL>(pv, rin); } while ((is_sentinel(pv[0]) || is_sentinel(pv[LPL - 1])) && ((++spins & 0xffffu) != 0 || !wait_expired(A.control, t_launch)));
+              if (is_sentinel(pv[0]) || is_sentinel(pv[LPL - 1])) {
+#pragma unroll
+                for (int k = 0; k < LPL; ++k) pv[k] = Real(0);
+              }
+            }
+            {
+              Real sent[LPL];
+#pragma unroll
+              for (int k = 0; k < LPL; ++k) sent[k] = sentinel<Real>();
+              sts_n(rin, sent);                             // the slot is free again (both halves: same words)
+            }
+#pragma unroll
+            for (int k = 0; k < LPL; ++k) oth[k] = hi ? pv[k] : oth[k];
+            Real hB[LPL], mB[LPL], tv[LPL];
+            split_min_plus<Real, PW, LPL, WIN>(parB, oth, hB);
+#pragma unroll
+            for (int k = 0; k < LPL; ++k) { mB[k] = hB[k] + oi[k]; oi[k] = oi[k] - mB[k]; }
+            const Real wq = e_ir && e_or ? w_int : w_edge;
+#pragma unroll
+            for (int k = 0; k < LPL; ++k) {
+              const Real a1 = __shfl_sync(FULL, mA[k], srcA1), a2 = __shfl_sync(FULL, mA[k], srcA1 ^ 16);
+              const Real b1 = __shfl_sync(FULL, mB[k], srcB1), b2 = __shfl_sync(FULL, mB[k], srcB1 ^ 16);
+              const Real v = fwd ? Real(Real(Real(th[k] + a1) + a2) + b1) + b2 : Real(Real(Real(th[k] + b1) + b2) + a1) + a2;
+              const Real d = wq * v;
+              const Real d_ir = e_ir ? d : Real(0), d_or = e_or ? d : Real(0);
+              const Real d_ic = has_ic ? d : Real(0), d_oc = (RINGOUT || has_oc) ? d : Real(0);
+              oi[k] = oi[k] + (hi ? d_ic : d_ir);
+              oo[k] = oo[k] + (hi ? d_oc : d_or);
+              th[k] = Real(Real(Real(v - d_ir) - d_or) - d_ic) - d_oc;
+              tv[k] = v;
+            }
+            // hand-off first: the row below is waiting for it
+            if constexpr (RINGOUT) sts_n_if(hi, Rout + (uint32_t)jj * LB, oo);
+            else st_generic_n_if(out_gen_on, Gout + jj * L, oo);
+            sts_n(Tth + ro, th);                            // (both halves hold theta)
+            sts_n(Tin + ro, oi);
+            sts_n(Tout + ro, oo);
+#pragma unroll
+            for (int k = 0; k < LPL; ++k) oth[k] = oo[k];
+            if constexpr (PRM) write_label(tv, s0 + jj);       // after the stores: nothing of the chain waits for the label
+          }
+          publish(s0 + K);
+        };
+        const int j_last = nchunks - 1;
+        if (ring_row) {
+          uni_tile(std::true_type{}, std::false_type{}, std::true_type{}, 0);
+#pragma unroll 1
+          for (int j = 1; j < j_last; ++j) uni_tile(std::false_type{}, std::false_type{}, std::true_type{}, j);
+          uni_tile(std::false_type{}, std::true_type{}, std::true_type{}, j_last);
+        } else {
+          uni_tile(std::true_type{}, std::false_type{}, std::false_type{}, 0);
+#pragma unroll 1
+          for (int j = 1; j < j_last; ++j) uni_tile(std::false_type{}, std::false_type{}, std::false_type{}, j);
+          uni_tile(std::false_type{}, std::true_type{}, std::false_type{}, j_last);
+        }
+      } else {
       wait_chunk(0);
 
       // ---- single steps: kind 0: general (any column, rounding, corner weights); 1: weight 1/2, any column (existence of the row
@@ -718,10 +877,12 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L>::THREADS, 1) wavefront_s
       }
       if constexpr (LBF) { if (lane == 0) A.lb_rows[r] = lb_acc; }
       if (mark) A.trace_steps[3 * 4096 + u] = globaltimer_ns();    // debug: row finished
+      }
     }
     // ---- end of the band: every ring is drained and re-armed, every tile has left shared memory ----
 #pragma unroll
     for (int w = 0; w < NW; ++w) if (warp_live(kb, w)) chunk_base[w] += (uint32_t)nchunks;
+    if (UNI && warp_live(kb, NW)) chunk_base_halo += (uint32_t)nchunks;
     step_base += (uint32_t)nsteps;
     __syncthreads();
   }

@@ -1,5 +1,5 @@
-// Included by split_inst_*.cu with LPMP_INST_REAL and LPMP_INST_PW defined: instances of wavefront_split_kernel
-// (kernels_grid_split.cuh) and their launcher.
+// Included by split_inst_*.cu / split_uni_inst_*.cu with LPMP_INST_REAL and LPMP_INST_PW defined: instances of wavefront_split_kernel
+// (kernels_grid_split.cuh) and their launcher; with LPMP_INST_UNI the instances for the uniform / damped-uniform modes.
 #include "wavefront_launch.h"
 #include "kernels_grid_split.cuh"
 
@@ -7,16 +7,27 @@ namespace lpmp {
 
 template <typename Real, int PW, int L, int WIN>
 static cudaError_t launch_split_one(const CUtensorMap* maps, const GridArgs<Real>& args, const WavefrontTuning& tune, int num_sms, cudaStream_t stream) {
+#ifdef LPMP_INST_UNI
+  using Cfg = SplitCfg<Real, PW, L, true>;
+#else
   using Cfg = SplitCfg<Real, PW, L>;
+#endif
   if constexpr (!Cfg::FITS) {
     return cudaErrorInvalidValue;
   } else {
+#ifdef LPMP_INST_UNI
+    if (args.lb_rows || args.in_halo || args.out_halo || args.W % Cfg::K != 0 || args.W < 2 * Cfg::K) return cudaErrorInvalidValue;
+    const int variant = (args.primal ? 2 : 0) + (args.forward ? 1 : 0);
+    auto kernel = args.primal ? (args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true, false, true, true> : wavefront_split_kernel<Real, PW, L, WIN, false, false, true, true>)
+                              : (args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true, false, false, true> : wavefront_split_kernel<Real, PW, L, WIN, false, false, false, true>);
+#else
     if (args.forward && args.lb_rows) return cudaErrorInvalidValue;   // the fused bound belongs to the backward pass
     if (args.primal && args.lb_rows) return cudaErrorInvalidValue;    // rounding passes leave the bound to the sweep
     const int variant = args.primal ? (args.forward ? 3 : 4) : (args.forward ? 1 : (args.lb_rows ? 2 : 0));
     auto kernel = args.primal ? (args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true, false, true> : wavefront_split_kernel<Real, PW, L, WIN, false, false, true>)
                   : args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true, false, false>
                                  : (args.lb_rows ? wavefront_split_kernel<Real, PW, L, WIN, false, true, false> : wavefront_split_kernel<Real, PW, L, WIN, false, false, false>);
+#endif
     int dev = 0;
     cudaGetDevice(&dev);
     static bool configured[64][5] = {};
@@ -85,8 +96,16 @@ static cudaError_t launch_split_win(const CUtensorMap* maps, const GridArgs<Real
   }
 }
 
+#ifdef LPMP_INST_UNI
+#define LPMP_SPLIT_LAUNCH launch_split_uni
+#define LPMP_SPLIT_FITS split_uni_fits
+#else
+#define LPMP_SPLIT_LAUNCH launch_split
+#define LPMP_SPLIT_FITS split_fits
+#endif
+
 template <typename Real, int PW>
-cudaError_t launch_split(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int win, const WavefrontTuning& tune, int num_sms, cudaStream_t stream) {
+cudaError_t LPMP_SPLIT_LAUNCH(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int win, const WavefrontTuning& tune, int num_sms, cudaStream_t stream) {
   switch (L) {
     case 16: return launch_split_win<Real, PW, 16>(maps, args, win, tune, num_sms, stream);
     case 32: return launch_split_win<Real, PW, 32>(maps, args, win, tune, num_sms, stream);
@@ -95,15 +114,23 @@ cudaError_t launch_split(const CUtensorMap* maps, const GridArgs<Real>& args, ui
 }
 
 template <typename Real, int PW>
-bool split_fits(uint32_t L) {
+bool LPMP_SPLIT_FITS(uint32_t L) {
+#ifdef LPMP_INST_UNI
+  switch (L) {
+    case 16: return SplitCfg<Real, PW, 16, true>::FITS;
+    case 32: return SplitCfg<Real, PW, 32, true>::FITS;
+    default: return false;
+  }
+#else
   switch (L) {
     case 16: return SplitCfg<Real, PW, 16>::FITS;
     case 32: return SplitCfg<Real, PW, 32>::FITS;
     default: return false;
   }
+#endif
 }
 
-template cudaError_t launch_split<LPMP_INST_REAL, LPMP_INST_PW>(const CUtensorMap*, const GridArgs<LPMP_INST_REAL>&, uint32_t, int, const WavefrontTuning&, int, cudaStream_t);
-template bool split_fits<LPMP_INST_REAL, LPMP_INST_PW>(uint32_t);
+template cudaError_t LPMP_SPLIT_LAUNCH<LPMP_INST_REAL, LPMP_INST_PW>(const CUtensorMap*, const GridArgs<LPMP_INST_REAL>&, uint32_t, int, const WavefrontTuning&, int, cudaStream_t);
+template bool LPMP_SPLIT_FITS<LPMP_INST_REAL, LPMP_INST_PW>(uint32_t);
 
 }  // namespace lpmp

@@ -1,0 +1,4 @@
+#define LPMP_INST_REAL float
+#define LPMP_INST_PW LPMP_PAIRWISE_TRUNCLIN
+#define LPMP_INST_UNI 1
+#include "split_inst.cuh"

@@ -21,6 +21,7 @@ struct WavefrontTuning {
                         // memory); 0 = automatic (8), 1 = no clusters
   int level_group = 0;  // level kernel: lanes per node (power of two below the default pow2 >= L); 0 = default
   int warps_per_cta = 0;  // consecutive bands per CTA (<= 8 and what the shared memory holds); 0 or 1 = one band per CTA
+  int split_uni = -1;   // ... and its instances for the uniform / damped-uniform modes: 0 off (one-warp kernel), otherwise on where they apply
   int split = -1;       // edge-split variant for the anisotropic passes (kernels_grid_split.cuh: one row per warp): 1 on, 0 off, -1 automatic
   int fused_bound = -1; // split variant, backward passes: accumulate LP::LowerBound on the fly: 1 on, 0 off, -1 automatic (bandwidth-bound grids)
   int rows = -1;        // one-label-per-lane variant for the anisotropic passes (kernels_grid_rows.cuh): 1 on, 0 off, -1 automatic
@@ -92,6 +93,17 @@ inline bool split_supported(int pw, uint32_t L) {
 }
 template <typename Real, int PW>
 cudaError_t launch_split(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int win, const WavefrontTuning& tune, int num_sms, cudaStream_t stream);
+
+// ... and its instances for the uniform / damped-uniform modes (grids with W % 8 == 0, W >= 16, no stripes)
+template <typename Real, int PW> bool split_uni_fits(uint32_t L);
+template <typename Real>
+inline bool split_uni_supported(int pw, uint32_t L) {
+  if (pw == LPMP_PAIRWISE_POTTS) return split_uni_fits<Real, LPMP_PAIRWISE_POTTS>(L);
+  if (pw == LPMP_PAIRWISE_TRUNCLIN) return split_uni_fits<Real, LPMP_PAIRWISE_TRUNCLIN>(L);
+  return false;
+}
+template <typename Real, int PW>
+cudaError_t launch_split_uni(const CUtensorMap* maps, const GridArgs<Real>& args, uint32_t L, int win, const WavefrontTuning& tune, int num_sms, cudaStream_t stream);
 
 // dense-table grids (kernels_grid_dense.cuh): anisotropic passes for L in {16, 32, 64}
 template <typename Real>

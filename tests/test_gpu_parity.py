@@ -261,6 +261,36 @@ def test_wavefront_bit_parity(dtype, mode, kind, L):
     run_lockstep(lps, mode, iters=3, lb_rtol=LB_RTOL[dtype])
 
 
+@pytest.mark.parametrize("mode", ["uniform", "damped_uniform"])
+@pytest.mark.parametrize("edge_order", ["lifo", "fifo"])
+@pytest.mark.parametrize("kind,L,dtype", [("potts", 16, "f32"), ("potts", 32, "f32"), ("trunclin", 16, "f32"), ("potts", 16, "f64")])
+def test_split_kernel_uniform_modes_bit_parity(mode, edge_order, kind, L, dtype):
+    """the uniform / damped-uniform instances of the split wavefront kernel (grids with W % 8 == 0: rows of whole tiles, the later
+    neighbours' vectors read from the next warp's tiles / the halo ring): bit parity with the oracle, rounding passes included;
+    bands that do not divide H, a single band, one row, several bands per CTA, clusters of 1 / 2 CTAs"""
+    for (H, W), tuning in (((37, 32), {}), ((8, 16), {}), ((1, 24), {}), ((9, 40), dict(wavefront_cluster=1)),
+                           ((70, 48), dict(wavefront_max_ctas=2)), ((45, 64), dict(wavefront_cluster=2, wavefront_max_ctas=4))):
+        lps = grid_pair(dtype, H, W, L, kind, seed=H + W + L, edge_order=edge_order, **tuning)
+        run_lockstep(lps, mode, iters=3, lb_rtol=LB_RTOL[dtype])
+        assert lps[1].stats()["kernel_launches"] <= 40, "pass kernels (8 launches + bound / primal sweeps), not the level schedule"
+
+
+def test_split_kernel_uniform_modes_match_the_one_warp_kernel():
+    """same state from the split instances and from the one-warp wavefront kernel (wavefront_split_uni=0) on a larger grid"""
+    rng = np.random.default_rng(5)
+    H, W, L = 130, 256, 16
+    theta = rng.random((H, W, L))
+    hz = np.stack([rng.uniform(0.05, 0.5, size=(H, W - 1)), rng.uniform(0.2, 1.5, size=(H, W - 1))], axis=-1)
+    vt = np.stack([rng.uniform(0.05, 0.5, size=(H - 1, W)), rng.uniform(0.2, 1.5, size=(H - 1, W))], axis=-1)
+    lps = []
+    for uni in (0, -1):
+        lp = cuda_lp("f32").grid_create(H, W, L, "trunclin")
+        lp.grid_set_unaries(theta); lp.grid_set_pairwise(hz, vt)
+        lp.set_tuning(wavefront_split_uni=uni)
+        lps.append(lp)
+    run_lockstep(lps, "damped_uniform", iters=3, lb_rtol=1e-6)
+
+
 @pytest.mark.parametrize("H,W", [(1, 1), (1, 9), (9, 1), (2, 2), (3, 50), (50, 3), (33, 33), (64, 17)])
 def test_wavefront_ragged_shapes(H, W):
     """bands that do not divide H, grids narrower than a band, single rows / columns"""
