@@ -275,6 +275,17 @@ def test_split_kernel_uniform_modes_bit_parity(mode, edge_order, kind, L, dtype)
         assert lps[1].stats()["kernel_launches"] <= 40, "pass kernels (8 launches + bound / primal sweeps), not the level schedule"
 
 
+@pytest.mark.parametrize("kind,L,dtype", [("potts", 16, "f32"), ("potts", 32, "f32"), ("trunclin", 16, "f32"), ("trunclin", 16, "f64")])
+def test_split_kernel_rows_of_whole_tiles(kind, L, dtype):
+    """anisotropic passes on grids with W % 8 == 0: a row is tiles only (the tiles of column 0 and of the last column run the fast
+    steps, hand-off by one generic store for the last row of a band); both message orders, rounding passes included"""
+    for (H, W), tuning in (((37, 32), {}), ((8, 16), {}), ((1, 24), {}), ((9, 40), dict(wavefront_cluster=1)), ((2, 8), {}),
+                           ((70, 48), dict(wavefront_max_ctas=2)), ((45, 64), dict(wavefront_cluster=2, wavefront_max_ctas=4))):
+        for edge_order in ("lifo", "fifo"):
+            lps = grid_pair(dtype, H, W, L, kind, seed=H + W + L, edge_order=edge_order, **tuning)
+            run_lockstep(lps, "anisotropic", iters=3, lb_rtol=LB_RTOL[dtype])
+
+
 def test_split_kernel_uniform_modes_match_the_one_warp_kernel():
     """same state from the split instances and from the one-warp wavefront kernel (wavefront_split_uni=0) on a larger grid"""
     rng = np.random.default_rng(5)
