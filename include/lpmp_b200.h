@@ -103,7 +103,10 @@ int LPMP_FN(set_schedule)(lpmp_solver* h, int schedule);
  * "wavefront_ctas_per_sm", "wavefront_tile_cols" (8 or 4 columns per TMA tile), "wavefront_warps_per_cta" (consecutive
  * bands per CTA with the hand-off between them in shared memory; default 1), "wavefront_lean" (anisotropic passes: 1 = compute
  * warp + two data-mover warps per band, 0 = one warp does everything; default automatic), "wavefront_cluster" (CTAs per
- * thread-block cluster of the lean variant: consecutive bands hand off through distributed shared memory; 1 = none, default 8), "wavefront_trace" (see get_trace).
+ * thread-block cluster of the lean variant: consecutive bands hand off through distributed shared memory; 1 = none, default 8), "wavefront_trace" (see get_trace),
+ * "wavefront_rows" / "wavefront_split" (1 / 0: force / forbid the one-label-per-lane and the one-row-per-warp kernels; default automatic),
+ * "wavefront_split_uni" (0: uniform / damped-uniform passes on the one-warp kernel instead of the split kernel's instances),
+ * "wavefront_fused_bound" (backward passes accumulate LowerBound: 1 / 0 / automatic).
  * Before finalize. */
 int LPMP_FN(set_tuning)(lpmp_solver* h, const char* key, int value);
 /* Deterministic greedy colouring in node order (host utility, no handle state): colour[i] = smallest colour
