@@ -128,8 +128,9 @@ int LPMP_FN(grid_fill_synthetic)(lpmp_solver* h, uint64_t seed, double p_lo, dou
 /* Row-stripe partition (multi-GPU): declare that this grid is rows [row0, row0+H) of a taller grid with
  * H_total rows (call before grid_fill_synthetic / finalize).  A stripe owns its nodes, its horizontal and inner
  * vertical edges and, for the vertical edges crossing a stripe boundary, the message vector on ITS side (bU of its
- * first row, aD of its last row) plus a copy of their parameters.  Stripes run the wavefront schedule in the
- * anisotropic mode only.
+ * first row, aD of its last row) plus a copy of their parameters.  Stripes run the wavefront schedule: the
+ * anisotropic mode, and (Potts / truncated-linear grids) the uniform and damped-uniform modes of the rounding iterations
+ * (include/visitors/standard_visitor.hxx:44).
  *
  * A pass consumes the neighbouring stripe's outgoing vectors from an "in" buffer of W*L reals (storage dtype) per
  * boundary: in(0 = top) feeds the forward pass, in(1 = bottom) the backward pass.  Slots carry their own validity (a
@@ -140,7 +141,10 @@ int LPMP_FN(grid_fill_synthetic)(lpmp_solver* h, uint64_t seed, double p_lo, dou
  *   - exact pipelined: lpmp_grid_set_peer_boundary hands the pass kernel the neighbour's in_buf (peer-mapped
  *     pointer, same node: lpmp_ipc_export / lpmp_ipc_open); the last band of this stripe then stores each
  *     outgoing vector straight into it over NVLink while the neighbour's first band polls -- results are
- *     bit-identical to the unstriped LP. */
+ *     bit-identical to the unstriped LP.
+ * Uniform modes: a node also receives from its two NOT yet processed neighbours, so a forward pass additionally consumes in(1)
+ * (the lower stripe's bU vectors as they were BEFORE the pass) and a backward pass in(0) (the upper stripe's aD vectors): every
+ * stripe delivers that side with lpmp_grid_push_boundary before launching its pass, in both couplings. */
 int LPMP_FN(grid_set_stripe)(lpmp_solver* h, uint32_t row0, uint32_t H_total);
 /* parameters of the boundary-crossing vertical edges, [W][P] each (NULL where there is no neighbour) */
 int LPMP_FN(grid_set_boundary_pairwise)(lpmp_solver* h, const void* top, const void* bottom, int src_dtype);

@@ -964,7 +964,8 @@ struct Solver : ISolver {
       ++launches;
       fused_lb_valid = !forward;
     } else {
-      if (striped && repam != LPMP_REPAM_ANISOTROPIC) { err = "stripes support the anisotropic reparametrization only"; return LPMP_ERR_UNSUPPORTED; }
+      const bool uni_mode = repam == LPMP_REPAM_UNIFORM || repam == LPMP_REPAM_DAMPED_UNIFORM;
+      if (striped && !uni_mode && repam != LPMP_REPAM_ANISOTROPIC) { err = "stripes support the anisotropic, uniform and damped-uniform reparametrizations"; return LPMP_ERR_UNSUPPORTED; }
       GridArgs<Real> A;
       A.H = gridH; A.W = gridW;
       A.num_bands = (gridH + shape.T - 1) / shape.T;
@@ -978,6 +979,9 @@ struct Solver : ISolver {
       A.control = control.p; A.handoff = handoff.p;
       A.in_boundary = forward ? in_top.p : in_bot.p;
       A.out_boundary = forward ? peer_bot : peer_top;
+      // uniform modes on a stripe: the last virtual row also receives from the neighbouring stripe's first virtual row, whose
+      // in-side vectors (state of the previous pass) are delivered into the OTHER in-buffer before the pass (lpmp_grid_push_boundary)
+      A.later_boundary = (uni_mode && A.out_halo) ? (forward ? in_bot.p : in_top.p) : nullptr;
       A.labels = labels.p;
       A.lb_rows = nullptr;
       A.rec = rec.p; A.par = par.p;
@@ -1008,7 +1012,6 @@ struct Solver : ISolver {
       }
       // the uniform / damped-uniform modes (the rounding iterations of the default control law, include/visitors/standard_visitor.hxx:44)
       // on the split kernel: rows of whole tiles only
-      const bool uni_mode = repam == LPMP_REPAM_UNIFORM || repam == LPMP_REPAM_DAMPED_UNIFORM;
       if (split_ok && uni_mode && !striped && rows_win >= 0 && (pw == LPMP_PAIRWISE_POTTS || L == 16) && use_split() && tune.split_uni != 0 &&
           gridW % 8 == 0 && gridW >= 16 && split_uni_supported<Real>(pw, L)) {
         A.num_bands = (gridH + (uint32_t)kSplitBandRows - 1) / (uint32_t)kSplitBandRows;

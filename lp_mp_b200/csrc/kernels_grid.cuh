@@ -63,6 +63,9 @@ struct GridArgs {
   Real* in_boundary;        // [W][L] boundary 0 when in_halo: the neighbouring stripe's outgoing vectors (same protocol)
   Real* out_boundary;       // [W][L] where the last band delivers its outgoing vectors when out_halo (the neighbour's
                             // in_boundary, possibly peer memory), or null: not delivered
+  Real* later_boundary;     // [W][L] uniform modes on a stripe with out_halo: the in-side vectors of the NOT yet processed
+                            // neighbouring stripe's first virtual row (state of the previous pass, delivered before the pass;
+                            // same slot protocol: the last virtual row of the last band consumes them), or null
   uint32_t* labels;         // [H*W]
   double* lb_rows;          // [H] or null; split variant, backward pass: LP::LowerBound terms of every grid row, accumulated on the fly
   Real* rec;                // node records [H][W][5][L] (the split variant moves whole-row tile runs with 1-D bulk copies, no tensor map)
@@ -513,6 +516,15 @@ __global__ void __launch_bounds__(RINGS ? 32 * WavefrontCfg<Real, PW, L, KSEL>::
 #pragma unroll
     for (int k = 0; k < 4; ++k) { carry_row[k] = Real(0); carry_col[k] = Real(0); }
     int next_store = 0;
+    // uniform modes on a stripe: the row below the last virtual row lives on the neighbouring device; its in-side vectors
+    // (previous pass) wait in `later_boundary`, read one step ahead
+    const bool later_band = !ANISO && last_band && A.out_halo && A.later_boundary != nullptr;   // warp-uniform
+    const bool later_poller = later_band && lane_used && t == (int)H - 1 - (int)kb * T + roff;
+    const Real* const later_in = A.later_boundary + gl * 4;
+    Real later_pf[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) later_pf[k] = Real(0);
+    if constexpr (!ANISO) ld_relaxed_if<HAND_BYTES>(later_poller, later_pf, later_in);
 
     wait_chunk(0);
     if (!ANISO && nchunks > 1) wait_chunk(1);   // uniform modes: the out_row neighbour may sit in the next tile
@@ -697,6 +709,31 @@ __global__ void __launch_bounds__(RINGS ? 32 * WavefrontCfg<Real, PW, L, KSEL>::
           const uint32_t rec_q1 = rec_lane + (((uint32_t)qq1 >> LOGK) & (NSLOT - 1)) * SLOT_REC_B + (((uint32_t)qq1 & (K - 1)) ^ (uint32_t)kxor) * REC_B;
           lds4(oth_or, rec_q1 + o_in_row);
           lds4(oth_oc, (uint32_t)((int)rec + below) + o_in_col);
+          if (later_band) {
+            const bool lpoll = later_poller && q >= 0 && q < (int)W;
+            const Real* const lslot = later_in + (int64_t)q * L;
+            bool lmiss = lpoll && (is_sentinel(later_pf[0]) || is_sentinel(later_pf[1]) || is_sentinel(later_pf[2]) || is_sentinel(later_pf[3]));
+            if (__any_sync(FULL, lmiss)) {     // warp-uniform wait, bounded like the hand-off poll
+              unsigned spins = 0;
+              do {
+                ld_relaxed_if<HAND_BYTES>(lmiss, later_pf, lslot);
+                lmiss = lpoll && (is_sentinel(later_pf[0]) || is_sentinel(later_pf[1]) || is_sentinel(later_pf[2]) || is_sentinel(later_pf[3]));
+                if ((++spins & 0x3ffu) == 0) {
+                  if (spins > (1u << 22)) atomicExch(A.control + 1, 1u);
+                  if (*reinterpret_cast<volatile unsigned int*>(A.control + 1) != 0u) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) later_pf[k] = Real(0);
+                    lmiss = false;
+                  }
+                }
+              } while (__any_sync(FULL, lmiss));
+            }
+            Real sent[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { if (lpoll) oth_oc[k] = later_pf[k]; sent[k] = sentinel<Real>(); }
+            st_relaxed_if<HAND_BYTES>(lpoll, const_cast<Real*>(lslot), sent);        // free for the delivery of the next pass
+            ld_relaxed_if<HAND_BYTES>(lpoll && q + 1 < (int)W, later_pf, lslot + L);
+          }
           lds_par<Real, P>(par_or, par + p_out_row);
           lds_par<Real, P>(par_oc, par + p_out_col);
           marginal2(has_or, par_or, oth_or, own_or, m_or, has_oc, par_oc, oth_oc, own_oc, m_oc);

@@ -26,8 +26,12 @@ The lower bound / primal cost of the LP is the NCCL all-reduce of the stripes' p
 the library's stream and read back with ONE stream-ordered copy into pinned memory (LP::LowerBound,
 include/LP_MP.h:1507-1518; LP::EvaluatePrimal, :1520-1536).
 
-Only the anisotropic (SRMP) reparametrisation runs on stripes (rounding included: ``ComputeForwardPassAndPrimal``);
-the uniform modes need the not-yet-processed neighbour's vectors as well and raise ``LpmpError`` here.
+Uniform / damped-uniform passes (the rounding iterations of the default control law,
+include/visitors/standard_visitor.hxx:44): a node also receives from its two not-yet-processed neighbours, so the last
+virtual row of a stripe needs the neighbouring stripe's in-side vectors as they were before the pass.  Every rank delivers
+them (same push, into the neighbour's OTHER in-buffer) before it launches its pass, in every coupling; with the pipelined
+coupling the result stays bit-identical to the unstriped LP.  Potts / truncated-linear grids only (dense-table stripes
+are anisotropic-only and raise ``LpmpError``).
 """
 from __future__ import annotations
 
@@ -123,6 +127,7 @@ class StripedLP:
         self._peer = {}            # which -> mapped pointer of the neighbour's in-buffer across boundary `which`
         self._ipc_opened = []
         self._setup_done = False
+        self._uni = False          # current reparametrisation is uniform / damped-uniform
 
     # ---- construction -----------------------------------------------------------------------------------------
     @classmethod
@@ -209,11 +214,20 @@ class StripedLP:
 
     # ---- halo delivery before a pass -------------------------------------------------------------------------------
     def _deliver(self, send_which: int):
-        """my vectors of boundary ``send_which`` into the in-buffer of the neighbour across it (the forward pass consumes the
-        upper neighbour's last-row vectors, the backward pass the lower neighbour's first-row vectors)"""
-        if self.world == 1 or self.coupling == "pipelined":
+        """what the neighbours need from me before a pass.  ``send_which`` is the boundary whose vectors the pass of the
+        neighbour across it CARRIES on (forward: BOTTOM, the lower neighbour continues from my last row; backward: TOP); the
+        pipelined coupling delivers those from inside the pass kernel.  Uniform modes: the neighbour across the OTHER boundary
+        processes its last virtual row before I touch mine and receives from it -- my vectors there, as they are now, go out
+        in every coupling."""
+        if self.world == 1:
             return
-        if self.coupling == "halo":
+        if self._uni:
+            self._deliver_one(TOP if send_which == BOTTOM else BOTTOM, force_push=self.coupling == "pipelined")
+        if self.coupling != "pipelined":
+            self._deliver_one(send_which)
+
+    def _deliver_one(self, send_which: int, force_push: bool = False):
+        if self.coupling == "halo" or force_push:
             if send_which in self._peer:
                 self.lp.grid_push_boundary(send_which, self._peer[send_which])
             return
@@ -233,12 +247,19 @@ class StripedLP:
     def End(self):
         self.lp.End()
 
+    UNIFORM_MODES = True
+
     def set_reparametrization(self, mode):
-        if self.world > 1 and mode not in ("anisotropic", 0):
+        uni = mode in ("uniform", "damped_uniform", 1, 2)
+        if self.world > 1 and not uni and mode not in ("anisotropic", 0):
             from ._capi import LpmpError
-            raise LpmpError("unsupported: row stripes run the anisotropic reparametrization only "
+            raise LpmpError("unsupported: row stripes run the anisotropic, uniform and damped_uniform reparametrizations")
+        if self.world > 1 and uni and getattr(self.lp, "pairwise", None) == "dense":
+            from ._capi import LpmpError
+            raise LpmpError("unsupported: dense-table stripes run the anisotropic reparametrization only "
                             "(use roundingReparametrization='anisotropic' with StandardVisitor)")
         self.lp.set_reparametrization(mode)
+        self._uni = uni
 
     def ComputeForwardPass(self):
         self._deliver(BOTTOM)

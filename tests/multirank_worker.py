@@ -10,7 +10,8 @@ include/solver.hxx:321-340,387-397):
              StripedLP.LowerBound / EvaluatePrimal equal to the unstriped values, labeling() gathers the full labeling
   halo       per-pass halo through peer memory: bound == sum of the ranks' partial bounds computed independently (host path),
              monotone, below the exact bound; halo_nccl gives bit-identical stripes
-  solver     MpRoundingSolver + StandardVisitor on a StripedLP (pipelined) == the same solver on the unstriped LP
+  solver     MpRoundingSolver + StandardVisitor on a StripedLP (pipelined) == the same solver on the unstriped LP, with the
+             anisotropic rounding mode and with the default law (damped_uniform rounding); the default law on the halo coupling
 """
 import os
 import sys
@@ -97,6 +98,17 @@ def case_pipelined(rank, world, dist, device):
             assert slp.CheckPrimalConsistency()
             assert np.isclose(slp.EvaluatePrimal(), full.EvaluatePrimal(), rtol=LB_RTOL[dtype])
             assert np.array_equal(slp.lp.unaries(), my_rows(full.unaries(), slp, W))
+        # uniform modes (rounding iterations of the default control law): still bit-identical with the exact coupling
+        for mode in ("damped_uniform", "uniform"):
+            full.set_reparametrization(mode); slp.set_reparametrization(mode)
+            for it in range(2):
+                full.ComputePass(it); slp.ComputePass(it)
+                slp.synchronize()
+                assert np.array_equal(slp.lp.unaries(), my_rows(full.unaries(), slp, W)), f"{mode}: theta differs after iteration {it}"
+                assert np.isclose(slp.LowerBound(), full.LowerBound(), rtol=LB_RTOL[dtype])
+            full.ComputeBackwardPassAndPrimal(2); slp.ComputeBackwardPassAndPrimal(2)
+            assert np.array_equal(slp.labeling(), full.labeling()), f"{mode}: gathered labeling differs"
+            assert np.isclose(slp.EvaluatePrimal(), full.EvaluatePrimal(), rtol=LB_RTOL[dtype])
         slp.close()
         dist.barrier()
 
@@ -167,17 +179,27 @@ def case_solver(rank, world, dist, device):
         assert np.isclose(la, lb, rtol=1e-12) and (ua == ub or np.isclose(ua, ub, rtol=1e-12)), (la, lb, ua, ub)
     assert np.array_equal(a.solution_, b.solution_)
     assert np.isclose(a.lower_bound(), b.lower_bound(), rtol=1e-12) and np.isclose(a.primal_cost(), b.primal_cost(), rtol=1e-12)
-    # the default control law asks for damped_uniform on rounding iterations: not available on stripes -> a clear error
-    from lp_mp_b200._capi import LpmpError
-    try:
-        MpRoundingSolver(slp, StandardVisitor(maxIter=3)).Solve()
-    except LpmpError as e:
-        assert "anisotropic" in str(e)
-    else:
-        if not getattr(slp, "UNIFORM_MODES", False):
-            raise AssertionError("damped_uniform on stripes neither ran nor raised")
     slp.close()
-    dist.barrier()
+    # the DEFAULT control law (rounding in damped_uniform, include/visitors/standard_visitor.hxx:44) on stripes: identical trajectory
+    # with the exact coupling; with the per-pass halo a valid bound below the best primal
+    for dtype, kind, L, lo, hi, H, W in (("f64", "potts", 8, 0.1, 1.0, 16 * world + 2, 24), ("f32", "trunclin", 16, 0.25, 1.0, 24 * world, 64)):
+        full = full_lp(dtype, H, W, L, kind, lo, hi, device)
+        slp = striped(dtype, H, W, L, kind, lo, hi, rank, world, dist, device, "pipelined")
+        a = MpRoundingSolver(full, StandardVisitor(maxIter=12)); a.Solve()
+        b = MpRoundingSolver(slp, StandardVisitor(maxIter=12)); b.Solve()
+        assert len(a.history) == len(b.history)
+        for (la, ua, _), (lb, ub, _) in zip(a.history, b.history):
+            assert np.isclose(la, lb, rtol=LB_RTOL[dtype]) and (ua == ub or np.isclose(ua, ub, rtol=LB_RTOL[dtype])), (la, lb, ua, ub)
+        assert np.array_equal(a.solution_, b.solution_)
+        slp.close()
+        hlp = striped(dtype, H, W, L, kind, lo, hi, rank, world, dist, device, "halo")
+        c = MpRoundingSolver(hlp, StandardVisitor(maxIter=12)); c.Solve()
+        assert np.isfinite(c.primal_cost()) and c.lower_bound() <= c.primal_cost() + 1e-6 * abs(c.primal_cost())
+        assert abs(c.lower_bound() - a.lower_bound()) <= 0.05 * abs(a.lower_bound()), (c.lower_bound(), a.lower_bound())
+        if rank == 0:
+            print(f"default Solve on {world} stripes [{kind},{dtype}]: exact {a.lower_bound():.6f}/{a.primal_cost():.6f} halo {c.lower_bound():.6f}/{c.primal_cost():.6f}", flush=True)
+        hlp.close()
+        dist.barrier()
 
 
 def main():

@@ -619,6 +619,82 @@ def test_stripes_pipelined_are_bit_identical_to_the_unstriped_lp(dtype, kind, L,
     assert np.array_equal(fa[keep], ta) and np.array_equal(fb[keep], tb)
 
 
+@pytest.mark.parametrize("mode", ["uniform", "damped_uniform"])
+@pytest.mark.parametrize("dtype,kind,L,lo,hi,H,cut,W", [("f64", "trunclin", 16, 0.25, 1.0, 70, 30, 45), ("f32", "potts", 32, 0.1, 1.0, 41, 17, 39),
+                                                        ("f64", "potts", 8, 0.1, 1.0, 33, 16, 20), ("f32", "trunclin", 16, 0.25, 1.0, 19, 8, 64),
+                                                        ("f32", "potts", 16, -0.3, 1.0, 12, 11, 24)])
+def test_stripes_uniform_modes_pipelined_are_bit_identical_to_the_unstriped_lp(mode, dtype, kind, L, lo, hi, H, cut, W):
+    """uniform / damped-uniform passes on stripes (the rounding iterations of the default control law,
+    include/visitors/standard_visitor.hxx:44): the last virtual row of a stripe also receives from the other stripe's first
+    virtual row, whose vectors -- as they were before the pass -- are pushed into the OTHER in-buffer before the pass."""
+    full, (top, bot) = _stripe_pair(dtype, H, cut, W, L, kind, lo, hi)
+    bot_in_top, top_in_bot = bot.grid_boundary_ptrs(0)[0], top.grid_boundary_ptrs(1)[0]
+    top.grid_set_peer_boundary(1, bot_in_top)
+    bot.grid_set_peer_boundary(0, top_in_bot)
+    for lp in (full, top, bot):
+        lp.set_reparametrization(mode)
+
+    def both(fwd, primal, it):
+        name = "Compute" + ("Forward" if fwd else "Backward") + "Pass" + ("AndPrimal" if primal else "")
+        args = (it,) if primal else ()
+        getattr(full, name)(*args)
+        if fwd:
+            bot.grid_push_boundary(0, top_in_bot)      # bU of the lower stripe's first row, state before the pass
+            getattr(top, name)(*args); getattr(bot, name)(*args)
+        else:
+            top.grid_push_boundary(1, bot_in_top)      # aD of the upper stripe's last row
+            getattr(bot, name)(*args); getattr(top, name)(*args)
+        top.synchronize(); bot.synchronize()
+
+    for it in range(3):
+        for fwd in (True, False):
+            both(fwd, False, it)
+            assert np.array_equal(np.concatenate([top.unaries(), bot.unaries()]), full.unaries()), f"theta differs after pass {it} fwd={fwd}"
+        assert np.isclose(_striped_bound((top, bot)), full.LowerBound(), rtol=LB_RTOL[dtype])
+    # anisotropic passes in between (the default law alternates), then a rounding iteration in the uniform mode
+    for lp in (full, top, bot):
+        lp.set_reparametrization("anisotropic")
+    full.ComputePass(3)
+    top.ComputeForwardPass(); bot.ComputeForwardPass(); bot.ComputeBackwardPass(); top.ComputeBackwardPass()
+    top.synchronize(); bot.synchronize()
+    for lp in (full, top, bot):
+        lp.set_reparametrization(mode)
+    for fwd in (True, False):
+        both(fwd, True, 4)
+        assert np.array_equal(np.concatenate([top.labeling(), bot.labeling()]), full.labeling()), "labeling differs"
+        assert np.array_equal(np.concatenate([top.unaries(), bot.unaries()]), full.unaries())
+    assert np.isclose(_striped_bound((top, bot)), full.LowerBound(), rtol=LB_RTOL[dtype])
+
+
+def test_stripes_uniform_modes_per_pass_halo():
+    """block-Jacobi coupling in the damped-uniform mode: both boundaries of every stripe are pushed before a pass.  Both endpoints
+    of a boundary edge receive from it on the state of the previous pass, so the bound is that of a valid reparametrisation (below
+    every primal cost) but not necessarily monotone; it stays close to the exact run's"""
+    H, cut, W, L = 96, 48, 64, 16
+    full, (top, bot) = _stripe_pair("f64", H, cut, W, L, "trunclin", 0.25, 1.0)
+    bot_in_top, top_in_bot = bot.grid_boundary_ptrs(0)[0], top.grid_boundary_ptrs(1)[0]
+    for lp in (full, top, bot):
+        lp.set_reparametrization("damped_uniform")
+    prev = _striped_bound((top, bot))
+    for it in range(10):
+        full.ComputePass(it)
+        for fwd in (True, False):
+            top.grid_push_boundary(1, bot_in_top); bot.grid_push_boundary(0, top_in_bot)
+            if fwd:
+                top.ComputeForwardPass(); bot.ComputeForwardPass()
+            else:
+                bot.ComputeBackwardPass(); top.ComputeBackwardPass()
+        top.synchronize(); bot.synchronize()
+        prev = _striped_bound((top, bot))
+        assert abs(prev - full.LowerBound()) <= 2e-2 * abs(prev), (it, prev, full.LowerBound())
+    full.ComputeForwardPassAndPrimal(10)
+    top.grid_push_boundary(1, bot_in_top); bot.grid_push_boundary(0, top_in_bot)
+    top.ComputeForwardPassAndPrimal(10); bot.ComputeForwardPassAndPrimal(10)
+    top.synchronize(); bot.synchronize()
+    assert prev <= full.EvaluatePrimal() + 1e-9
+    assert np.mean(np.concatenate([top.labeling(), bot.labeling()]) == full.labeling()) > 0.9
+
+
 def test_stripes_per_pass_halo_is_monotone_and_close():
     """block-Jacobi coupling: each stripe sweeps with the neighbour's vectors of the previous pass.  Valid
     reparametrisation (monotone bound, below the exact one or equal) with a slightly weaker fixed point."""

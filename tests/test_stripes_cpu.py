@@ -115,6 +115,8 @@ class HostStripe:
     def _pass(self, which_in, primal):
         buf = self.in_buf[which_in]
         self.seen.append(None if buf is None else float(buf[0]))
+        other = self.in_buf[1 - which_in]
+        self.seen_later = None if other is None else float(other[0])
         self.passes += 1
         self.labelled |= primal
 
@@ -165,9 +167,21 @@ def _striped_worker(rank, world, port, out):
         lab = slp.labeling()
         ok &= lab.shape == (H * W,) and all((lab[plan.rows(r)[0] * W:(plan.rows(r)[0] + plan.rows(r)[1]) * W] == r).all() for r in range(world))
         ok &= slp.GetNumberOfFactors() == H * W + H * (W - 1) + (H - 1) * W
-        # the reference control law drives a StripedLP (Solver::Solve, include/solver.hxx:230-257)
-        s = MpRoundingSolver(slp, StandardVisitor(maxIter=4, roundingReparametrization="anisotropic"))
-        ok &= bool(s.Solve()) and len(s.history) >= 1 and getattr(lp, "ended", False) and s.solution_ is not None
+        # uniform modes: the pass also consumes the NOT yet processed neighbour's vectors across the other boundary, as they are
+        # before the pass (3 passes so far on every rank)
+        slp.set_reparametrization("damped_uniform")
+        slp.ComputeForwardPass()
+        ok &= lp.seen[-1] == (None if rank == 0 else 1000.0 * (rank - 1) + 100.0 + 3.0)
+        ok &= lp.seen_later == (None if rank == world - 1 else 1000.0 * (rank + 1) + 3.0)
+        slp.ComputeBackwardPass()
+        ok &= lp.seen[-1] == (None if rank == world - 1 else 1000.0 * (rank + 1) + 4.0)
+        ok &= lp.seen_later == (None if rank == 0 else 1000.0 * (rank - 1) + 100.0 + 4.0)
+        # the reference control law drives a StripedLP (Solver::Solve, include/solver.hxx:230-257), rounding in its default mode
+        # (damped_uniform, include/visitors/standard_visitor.hxx:44) and in the anisotropic one
+        for opts in (dict(maxIter=4), dict(maxIter=4, roundingReparametrization="anisotropic")):
+            lp.ended = False
+            s = MpRoundingSolver(slp, StandardVisitor(**opts))
+            ok &= bool(s.Solve()) and len(s.history) >= 1 and lp.ended and s.solution_ is not None
         out[rank] = int(ok)
     finally:
         dist.destroy_process_group()
