@@ -704,6 +704,39 @@ def default_solve(name, max_iter, local_rank):
             "note": "rounding iterations run the uniform-mode kernels (4 message updates per edge and pass, slower schedule): DESIGN.md 8"}
 
 
+def default_solve_on_stripes(args, name, rank, world, local_rank, dist, max_iter):
+    """The same full Solve() on the row stripes of `name` over all ranks (--default-solve, N > 1): the rounding iterations run the
+    uniform-mode passes on stripes (every rank first delivers the vectors its neighbours' last virtual rows receive from).  Wall
+    clock from Begin() to the end of Solve(), max over ranks, potentials already in HBM."""
+    import torch
+    from lp_mp_b200 import MpRoundingSolver, StandardVisitor
+    from lp_mp_b200.stripes import StripedLP
+    H, W, L, pairwise, lo, hi, desc = WORKLOADS[name]
+    out = {}
+    for coupling in (args.coupling,) if args.coupling == "pipelined" else (args.coupling, "pipelined"):
+        slp = StripedLP.make(H, W, L, pairwise, rank, world, dist=dist, dtype=args.dtype, device=local_rank, coupling=coupling)
+        slp.lp.grid_fill_synthetic(SEED, lo, hi)
+        slp.finalize()
+        s = MpRoundingSolver(slp, StandardVisitor(maxIter=max_iter))
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        s.Solve()
+        slp.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0, dist, world)
+        out[coupling] = {"seconds": dt, "ms_per_iteration": 1e3 * dt / max_iter, "value": 4.0 * edges_of(H, W) * max_iter / dt, "unit": UNIT,
+                         "lower_bound": s.lower_bound(), "primal": s.primal_cost()}
+        slp.close()
+        dist.barrier()
+    if rank == 0:
+        # the unstriped run of the same law on rank 0's GPU: what the stripes' bounds are checked against
+        one = default_solve(name, max_iter, local_rank)
+        out["one_gpu"] = {k: one[k] for k in ("seconds", "ms_per_iteration", "value", "unit", "lower_bound", "primal")}
+    dist.barrier()
+    out.update({"workload": f"{name}: {desc}; {world} row stripes", "maxIter": max_iter,
+                "control_law": "StandardVisitor defaults (primalComputationInterval 5, damped_uniform rounding)"})
+    return out
+
+
 def compact(block):
     """an extra workload's block inside the headline line"""
     keep = ("value", "unit", "ms_per_step", "dtype", "roofline", "e2e", "gpu_launches", "time_to_bound", "cpu_baseline")
@@ -733,6 +766,8 @@ def main():
     ap.add_argument("--tune", default="", help="comma separated key=value launch-shape knobs, e.g. wavefront_tile_cols=4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the blocks of the other workloads")
+    ap.add_argument("--default-solve", type=int, default=0, metavar="MAXITER",
+                    help="N > 1, grid workloads: add a full default-law Solve() of MAXITER iterations on the stripes (and on one GPU) to the line")
     ap.add_argument("--crop", type=int, default=0, help="reference arm: side of the top-left crop (default: full C1/C2, 256 else)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -799,6 +834,11 @@ def main():
             extras["C2_default_solve"] = {"error": f"{type(exc).__name__}: {exc}"}
         args.tune = saved
         out["workloads"] = extras
+
+    if world > 1 and args.default_solve > 0 and args.workload in WORKLOADS and WORKLOADS[args.workload][3] != "dense":
+        blk = default_solve_on_stripes(args, args.workload, rank, world, local_rank, dist, args.default_solve)
+        if rank == 0:
+            out["default_solve_on_stripes"] = blk
 
     if rank == 0:
         print(json.dumps(out), flush=True)

@@ -171,8 +171,11 @@ int LPMP_FN(grid_get_boundary_labels)(lpmp_solver* h, int which, uint32_t* dst_d
 /* per-pass halo without a host round trip: store this stripe's side of boundary `which` (0: bU of the first row, 1: aD of the
  * last row) into the neighbour's in-buffer (peer-mapped pointer from lpmp_ipc_open, or a pointer of the same process).  The push
  * obeys the slot protocol -- a slot is only written once the consumer of the previous pass has re-armed it -- so pushes and passes
- * of neighbouring stripes order themselves through the data, with no collective and no host synchronisation */
-int LPMP_FN(grid_push_boundary)(lpmp_solver* h, int which, void* peer_in_buf);
+ * of neighbouring stripes order themselves through the data, with no collective and no host synchronisation.
+ * Layout of an in-buffer: slot q holds the vector of the q-th column IN THE PROCESSING ORDER of the pass that consumes it (the
+ * pass kernels deliver and poll that way): column q for a forward pass, column W - 1 - q for a backward pass.  `backward` != 0
+ * says the neighbour's next pass is a backward pass. */
+int LPMP_FN(grid_push_boundary)(lpmp_solver* h, int which, void* peer_in_buf, int backward);
 /* cudaIpc wrappers (64-byte handles) so that a host language without CUDA bindings can exchange in_buf pointers */
 int LPMP_FN(ipc_export)(const void* devptr, void* handle64);
 int LPMP_FN(ipc_open)(const void* handle64, void** devptr);

@@ -57,7 +57,7 @@ SIGNATURES = {
     "grid_lower_bound_partial_device": [_vp, _vp, _vp],
     "grid_evaluate_primal_partial_device": [_vp, _vp, _vp, _vp],
     "grid_get_boundary_labels": [_vp, _i, _vp],
-    "grid_push_boundary": [_vp, _i, _vp],
+    "grid_push_boundary": [_vp, _i, _vp, _i],
     "ipc_export": [_vp, _vp],
     "ipc_open": [_vp, C.POINTER(_vp)],
     "ipc_close": [_vp],

@@ -292,7 +292,7 @@ struct ISolver {
   virtual int grid_lower_bound_partial(const void* below_b, double* out) = 0;
   virtual int grid_lower_bound_partial_device(const void* below_b, double* d_out) = 0;
   virtual int grid_evaluate_primal_partial_device(const void* below_b, const uint32_t* below_labels, double* d_out) = 0;
-  virtual int grid_push_boundary(int which, void* peer_in_buf) = 0;
+  virtual int grid_push_boundary(int which, void* peer_in_buf, int backward) = 0;
   virtual int grid_get_boundary_labels(int which, uint32_t* dst_dev) = 0;
   virtual int finalize() = 0;
   virtual int begin() = 0;
@@ -347,7 +347,10 @@ struct Solver : ISolver {
   uint32_t Ln(uint64_t i) const { return mixed() ? h_counts[i] : L; }
   GraphEngine<Real, DeviceBuffer> graph;   // general graphs: node-record layout + per-level kernels (graph_engine.cuh)
   // device state.  General graphs: theta[N][L], a[E][L], b[E][L], params[E][P].  Grids: rec[N][5][L], par[N][4][P].
-  DeviceBuffer<Real> theta, a, b, params, rec, par;
+  DeviceBuffer<Real> theta, a, b, params, rec_alloc, par;
+  // grids: the node records sit between two GHOST rows (row -1 and row H; zero unless the stripe's uniform-mode passes park the
+  // neighbouring stripe's boundary vectors there, later_gather_kernel): `rec` is the view of rows 0 .. H-1
+  struct RecView { Real* p = nullptr; size_t n = 0; size_t bytes() const { return n * sizeof(Real); } } rec;
   DeviceBuffer<Real> tab;    // dense grids: table planes tabH [H][W][L*L] then tabV [H+1][W][L*L] (kernels_grid_dense.cuh)
   DeviceBuffer<double> lb_rows;   // dense grids: per-row bound terms produced by the last backward pass
   bool fused_lb_valid = false;    // lb_rows describes the current state (no state change since that pass)
@@ -521,8 +524,10 @@ struct Solver : ISolver {
     note_run(0, 0, N);
     note_run(1, 0, E);
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(rec.alloc(N * REC()));
-    CUDA_TRY(cudaMemsetAsync(rec.p, 0, rec.bytes(), stream));
+    const uint64_t ghost = (((uint64_t)W * REC() + 63) / 64) * 64;   // one row of records, rounded to 256 / 512 bytes
+    CUDA_TRY(rec_alloc.alloc(N * REC() + 2 * ghost));
+    CUDA_TRY(cudaMemsetAsync(rec_alloc.p, 0, rec_alloc.bytes(), stream));
+    rec.p = rec_alloc.p + ghost; rec.n = N * REC();
     if (pw == LPMP_PAIRWISE_DENSE) {
       CUDA_TRY(tab.alloc((2 * N + W) * (uint64_t)P()));
       CUDA_TRY(cudaMemsetAsync(tab.p, 0, tab.bytes(), stream));
@@ -1012,9 +1017,17 @@ struct Solver : ISolver {
       }
       // the uniform / damped-uniform modes (the rounding iterations of the default control law, include/visitors/standard_visitor.hxx:44)
       // on the split kernel: rows of whole tiles only
-      if (split_ok && uni_mode && !striped && rows_win >= 0 && (pw == LPMP_PAIRWISE_POTTS || L == 16) && use_split() && tune.split_uni != 0 &&
-          gridW % 8 == 0 && gridW >= 16 && split_uni_supported<Real>(pw, L)) {
+      if (split_ok && uni_mode && (!striped || gridH % (uint32_t)kSplitBandRows == 0) && rows_win >= 0 && (pw == LPMP_PAIRWISE_POTTS || L == 16) && use_split() &&
+          tune.split_uni != 0 && gridW % 8 == 0 && gridW >= 16 && split_uni_supported<Real>(pw, L)) {
         A.num_bands = (gridH + (uint32_t)kSplitBandRows - 1) / (uint32_t)kSplitBandRows;
+        if (A.later_boundary != nullptr) {
+          // stripe (whole bands only): the not yet processed neighbouring stripe's vectors go from the in-buffer into the ghost row
+          // next to the stripe's last virtual row, where the tile warp loads them like the row below any other band
+          Real* const ghost = forward ? rec.p + (uint64_t)gridH * gridW * REC() + (uint64_t)REC_BU * L : rec.p - (uint64_t)gridW * REC() + (uint64_t)REC_AD * L;
+          later_gather_kernel<Real><<<grid_for((uint64_t)gridW * L, 256, 148 * 4), 256, 0, stream>>>(ghost, A.later_boundary, gridW, L, REC(), control.p, !forward);
+          ++launches;
+          CUDA_TRY(cudaGetLastError());
+        }
         const cudaError_t le = pw == LPMP_PAIRWISE_POTTS ? launch_split_uni<Real, LPMP_PAIRWISE_POTTS>(maps_split, A, L, rows_win, tune, num_sms, stream)
                                                          : launch_split_uni<Real, LPMP_PAIRWISE_TRUNCLIN>(maps_split, A, L, rows_win, tune, num_sms, stream);
         CUDA_TRY(le);
@@ -1216,13 +1229,14 @@ struct Solver : ISolver {
     return bound_launch(row0 + gridH < H_total ? static_cast<const Real*>(below_b) : nullptr, row0 == 0 ? constant : 0.0, d_out, true);
   }
   // per-pass halo through peer memory: own side of a stripe boundary (0: bU of the first row, 1: aD of the last row) into the
-  // neighbour's in-buffer (slot protocol, see push_boundary_kernel); enqueued on the handle's stream
-  int grid_push_boundary(int which, void* peer_in_buf) override {
+  // neighbour's in-buffer (slot protocol, see push_boundary_kernel); enqueued on the handle's stream.  The pass kernels index an
+  // in-buffer by the column's position in processing order, so vectors consumed by a BACKWARD pass are stored right to left
+  int grid_push_boundary(int which, void* peer_in_buf, int backward) override {
     if (!is_grid || !finalized) return bad_state("grid_push_boundary: need a finalized grid");
     if (!peer_in_buf) { err = "null destination"; return LPMP_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(device));
     const Real* src = which == 0 ? rec.p + (uint64_t)REC_BU * L : rec.p + (uint64_t)(gridH - 1) * gridW * REC() + (uint64_t)REC_AD * L;
-    push_boundary_kernel<Real><<<grid_for((uint64_t)gridW * L, 256, 148 * 4), 256, 0, stream>>>(static_cast<Real*>(peer_in_buf), src, gridW, L, REC(), control.p);
+    push_boundary_kernel<Real><<<grid_for((uint64_t)gridW * L, 256, 148 * 4), 256, 0, stream>>>(static_cast<Real*>(peer_in_buf), src, gridW, L, REC(), control.p, backward != 0);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     return LPMP_OK;
@@ -1404,7 +1418,7 @@ struct Solver : ISolver {
     else out->num_levels = level_off.empty() ? 0 : level_off.size() - 1;
     out->kernel_launches = launches;
     out->message_updates = updates;
-    out->device_bytes = graph.device_bytes() + theta.bytes() + a.bytes() + b.bytes() + params.bytes() + rec.bytes() + par.bytes() + tab.bytes() + labels.bytes() + inc_off.bytes() +
+    out->device_bytes = graph.device_bytes() + theta.bytes() + a.bytes() + b.bytes() + params.bytes() + rec_alloc.bytes() + par.bytes() + tab.bytes() + labels.bytes() + inc_off.bytes() +
                         inc_edge.bytes() + inc_flags.bytes() + level_nodes.bytes() + d_ei.bytes() + d_ej.bytes() + control.bytes() + handoff.bytes() +
                         in_top.bytes() + in_bot.bytes();
     out->algorithmic_bytes_per_pass = (double)sizeof(Real) * (2.0 * (double)N * L + (double)E * ((double)P() + 5.0 * L));
@@ -1626,7 +1640,7 @@ int lpmp_grid_get_boundary_vectors(lpmp_solver* h, int which, void* dst_dev) { r
 int lpmp_grid_lower_bound_partial(lpmp_solver* h, const void* below_b, double* out) { return S(h)->grid_lower_bound_partial(below_b, out); }
 int lpmp_grid_lower_bound_partial_device(lpmp_solver* h, const void* below_b, double* d_out) { return S(h)->grid_lower_bound_partial_device(below_b, d_out); }
 int lpmp_grid_evaluate_primal_partial_device(lpmp_solver* h, const void* below_b, const uint32_t* below_labels, double* d_out) { return S(h)->grid_evaluate_primal_partial_device(below_b, below_labels, d_out); }
-int lpmp_grid_push_boundary(lpmp_solver* h, int which, void* peer_in_buf) { return S(h)->grid_push_boundary(which, peer_in_buf); }
+int lpmp_grid_push_boundary(lpmp_solver* h, int which, void* peer_in_buf, int backward) { return S(h)->grid_push_boundary(which, peer_in_buf, backward); }
 int lpmp_grid_get_boundary_labels(lpmp_solver* h, int which, uint32_t* dst_dev) { return S(h)->grid_get_boundary_labels(which, dst_dev); }
 
 int lpmp_ipc_export(const void* devptr, void* handle64) {

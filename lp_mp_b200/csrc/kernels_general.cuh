@@ -248,12 +248,14 @@ __global__ void __launch_bounds__(256) primal_cost_kernel(BoundArgs<Real, Topo> 
 // the sentinel again (the consumer of the previous pass has taken its vector), so consecutive pushes can never overtake the
 // consumer.  One thread per real; bounded wait (sticky abort flag in control[1]).
 template <typename Real>
-__global__ void push_boundary_kernel(Real* dst, const Real* __restrict__ src, uint32_t W, uint32_t L, uint64_t src_stride, unsigned int* control) {
+__global__ void push_boundary_kernel(Real* dst, const Real* __restrict__ src, uint32_t W, uint32_t L, uint64_t src_stride, unsigned int* control, bool reverse) {
   const uint64_t total = (uint64_t)W * L;
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (uint64_t)gridDim.x * blockDim.x) {
-    const Real v = src[(k / L) * src_stride + (k % L)];
+    // slot k = (q, x) of the in-buffer: q counts columns in the PROCESSING order of the consuming pass (backward: q = W - 1 - c)
+    const uint64_t c = reverse ? (uint64_t)W - 1 - k / L : k / L;
+    const Real v = src[c * src_stride + (k % L)];
     unsigned spins = 0;
     for (;;) {
       Real cur;
@@ -271,6 +273,37 @@ __global__ void push_boundary_kernel(Real* dst, const Real* __restrict__ src, ui
     }
     if constexpr (sizeof(Real) == 4) asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst + k), "f"(v) : "memory");
     else asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + k), "d"(v) : "memory");
+  }
+}
+
+// Uniform-mode passes of a stripe on the split kernel: the vectors the neighbouring stripe pushed into in-buffer `in` ([W][L], slot
+// protocol) are parked in the stripe's ghost row -- dst[c * dst_stride + x], the in-side slot of the records of row H (forward) or
+// row -1 (backward) -- where the pass kernel's tile warp finds them like any other row below a band.  Waits for every slot
+// (the push is issued before the neighbour's pass, so this never waits on a pass), re-arms it; bounded wait.
+template <typename Real>
+__global__ void later_gather_kernel(Real* __restrict__ dst, Real* in, uint32_t W, uint32_t L, uint64_t dst_stride, unsigned int* control, bool reverse) {
+  const uint64_t total = (uint64_t)W * L;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (uint64_t)gridDim.x * blockDim.x) {
+    Real cur;
+    unsigned spins = 0;
+    for (;;) {
+      if constexpr (sizeof(Real) == 4) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(cur) : "l"(in + k) : "memory");
+      else asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(cur) : "l"(in + k) : "memory");
+      bool empty;
+      if constexpr (sizeof(Real) == 4) empty = __float_as_uint(cur) == 0xffffffffu;
+      else empty = __double_as_longlong(cur) == -1ll;
+      if (!empty) break;
+      if ((++spins & 0xffu) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 4000000000ull) { if (control) atomicExch(control + 1, 1u); cur = Real(0); break; }
+      }
+    }
+    dst[(reverse ? (uint64_t)W - 1 - k / L : k / L) * dst_stride + (k % L)] = cur;   // in-buffers are in processing order, records in column order
+    if constexpr (sizeof(Real) == 4) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(in + k), "r"(0xffffffffu) : "memory");
+    else asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(in + k), "l"(-1ll) : "memory");
   }
 }
 

@@ -240,6 +240,12 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L, UNI>::THREADS, 1) wavefr
     return kb < A.num_bands && u >= 0 && u < (int)H;
   };
 
+  // UNI: is there a row below virtual band kb whose records the halo ring holds?  Inside the grid, or -- stripes (whole bands only,
+  // A.later_boundary set by the host) -- the ghost row next to the stripe's last virtual row (later_gather_kernel filled it)
+  auto halo_live = [&](unsigned kb) {
+    return warp_live(kb, NW) || (A.later_boundary != nullptr && kb + 1u == A.num_bands && (int)kb * T + NW - roff == (int)H);
+  };
+
   uint32_t step_base = 0;                 // steps of earlier bands: the published step counters are monotone
   uint32_t chunk_base[NW];                // per compute warp: tiles of earlier bands (slot / mbarrier-phase sequence continues)
 #pragma unroll
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L, UNI>::THREADS, 1) wavefr
       // row -- its only reader -- has left the tile)
       const bool halo_lane = UNI && lane == NW;
       const int w = lane < NW ? lane : NW - 1;
-      bool open = (lane < NW && warp_live(kb, w)) || (halo_lane && warp_live(kb, NW));
+      bool open = (lane < NW && warp_live(kb, w)) || (halo_lane && halo_live(kb));
       uint32_t cb = halo_lane ? chunk_base_halo : 0u;
 #pragma unroll
       for (int k = 0; k < NW; ++k) cb = (k == w && !halo_lane) ? chunk_base[k] : cb;
@@ -480,7 +486,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L, UNI>::THREADS, 1) wavefr
         // neighbours and sends to all four with weight 1 / deg (1 / (deg + 1)).  The two LATER neighbours have not been updated in
         // this pass: their in-side vectors are read from shared memory -- the next column of this row's own tile, and the same
         // column of the tile of the row below (the next warp's ring; the halo ring for the band's last row) -- and their
-        // min-marginals are off the dependency chain.  Host contract: W % 8 == 0, W >= 16, no stripes; every row is tiles only:
+        // min-marginals are off the dependency chain.  Host contract: W % 8 == 0, W >= 16, stripes of whole bands; every row is tiles only:
         // FIRST / LAST mark the tiles of column 0 / W - 1 (no row edge on that side: nothing is sent there, one edge less in deg).
         const bool has_ic = in_col_exists, has_oc = out_col_exists;
         const int damp = A.repam == LPMP_REPAM_DAMPED_UNIFORM ? 1 : 0;
@@ -882,7 +888,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L, UNI>::THREADS, 1) wavefr
     // ---- end of the band: every ring is drained and re-armed, every tile has left shared memory ----
 #pragma unroll
     for (int w = 0; w < NW; ++w) if (warp_live(kb, w)) chunk_base[w] += (uint32_t)nchunks;
-    if (UNI && warp_live(kb, NW)) chunk_base_halo += (uint32_t)nchunks;
+    if (UNI && halo_live(kb)) chunk_base_halo += (uint32_t)nchunks;
     step_base += (uint32_t)nsteps;
     __syncthreads();
   }

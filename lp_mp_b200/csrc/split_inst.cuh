@@ -16,7 +16,10 @@ static cudaError_t launch_split_one(const CUtensorMap* maps, const GridArgs<Real
     return cudaErrorInvalidValue;
   } else {
 #ifdef LPMP_INST_UNI
-    if (args.lb_rows || args.in_halo || args.out_halo || args.W % Cfg::K != 0 || args.W < 2 * Cfg::K) return cudaErrorInvalidValue;
+    if (args.lb_rows || args.W % Cfg::K != 0 || args.W < 2 * Cfg::K) return cudaErrorInvalidValue;
+    // stripes: whole bands only, and the ghost row next to the last virtual row holds the neighbouring stripe's vectors
+    if ((args.in_halo || args.out_halo) && args.H % Cfg::T != 0) return cudaErrorInvalidValue;
+    if (args.out_halo && args.later_boundary == nullptr) return cudaErrorInvalidValue;
     const int variant = (args.primal ? 2 : 0) + (args.forward ? 1 : 0);
     auto kernel = args.primal ? (args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true, false, true, true> : wavefront_split_kernel<Real, PW, L, WIN, false, false, true, true>)
                               : (args.forward ? wavefront_split_kernel<Real, PW, L, WIN, true, false, false, true> : wavefront_split_kernel<Real, PW, L, WIN, false, false, false, true>);

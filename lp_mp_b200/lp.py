@@ -225,8 +225,9 @@ class LP:
     def grid_get_boundary_labels(self, which, dst_ptr):
         self._ck(self.api.grid_get_boundary_labels(self.h, int(which), C.c_void_p(dst_ptr)))
 
-    def grid_push_boundary(self, which, peer_ptr):
-        self._ck(self.api.grid_push_boundary(self.h, int(which), C.c_void_p(peer_ptr)))
+    def grid_push_boundary(self, which, peer_ptr, backward):
+        """``backward``: the pass of the neighbour that consumes the vectors is a backward pass (slots right to left)"""
+        self._ck(self.api.grid_push_boundary(self.h, int(which), C.c_void_p(peer_ptr), int(bool(backward))))
 
     def finalize(self):
         self._flush_pending()

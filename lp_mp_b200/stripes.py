@@ -15,7 +15,8 @@ still runs the groups sequentially.  Here a grid of ``H_total`` rows is cut into
     Before a pass every rank stores the current vectors of its boundary row into the in-buffer of the neighbour that will
     consume them -- one small kernel writing through NVLink peer memory (``lpmp_grid_push_boundary``).  The in-buffer
     slots carry their own validity (sentinel protocol of the pass kernels), so pushes and passes of neighbouring stripes
-    order themselves through the data: no collective, no host synchronisation on the data path.  All stripes sweep
+    order themselves through the data: no collective, no host synchronisation on the data path (slot q = the q-th column
+    in the processing order of the consuming pass, i.e. right to left for a backward pass).  All stripes sweep
     concurrently, each using the neighbour's state of the previous pass: always a valid reparametrisation (monotone
     lower bound), but a different fixed point than the sequential order (hard part 2).
 
@@ -221,15 +222,18 @@ class StripedLP:
         in every coupling."""
         if self.world == 1:
             return
+        backward = send_which == TOP      # the pass about to run, here and on the neighbours
         if self._uni:
-            self._deliver_one(TOP if send_which == BOTTOM else BOTTOM, force_push=self.coupling == "pipelined")
+            self._deliver_one(TOP if send_which == BOTTOM else BOTTOM, backward, force_push=self.coupling == "pipelined")
         if self.coupling != "pipelined":
-            self._deliver_one(send_which)
+            self._deliver_one(send_which, backward)
 
-    def _deliver_one(self, send_which: int, force_push: bool = False):
+    def _deliver_one(self, send_which: int, backward: bool, force_push: bool = False):
+        """in-buffer slots are in the processing order of the consuming pass: right to left for a backward pass
+        (include/lpmp_b200.h, lpmp_grid_push_boundary)"""
         if self.coupling == "halo" or force_push:
             if send_which in self._peer:
-                self.lp.grid_push_boundary(send_which, self._peer[send_which])
+                self.lp.grid_push_boundary(send_which, self._peer[send_which], backward)
             return
         recv_which = TOP if send_which == BOTTOM else BOTTOM
         with self._stream_ctx():
@@ -237,6 +241,8 @@ class StripedLP:
             if send_which in self._stage:
                 self.lp.grid_get_boundary_vectors(send_which, self._stage[send_which].data_ptr())
                 send = self._stage[send_which]
+                if backward:
+                    send = send.view(-1, self.lp.L).flip(0).contiguous().view(-1)
             recv = self._in[recv_which][1] if recv_which in self._in else None
             neighbour_exchange(self.dist, self.rank, self.world, send_which, send, recv)
 

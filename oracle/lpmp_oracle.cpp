@@ -659,7 +659,7 @@ int LPMP_FN(grid_lower_bound_partial)(lpmp_solver* h, const void*, double*) { GE
 int LPMP_FN(grid_lower_bound_partial_device)(lpmp_solver* h, const void*, double*) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
 int LPMP_FN(grid_evaluate_primal_partial_device)(lpmp_solver* h, const void*, const uint32_t*, double*) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
 int LPMP_FN(grid_get_boundary_labels)(lpmp_solver* h, int, uint32_t*) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
-int LPMP_FN(grid_push_boundary)(lpmp_solver* h, int, void*) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
+int LPMP_FN(grid_push_boundary)(lpmp_solver* h, int, void*, int) { GET_ERR(H(h)) = "stripes: device only"; return LPMP_ERR_UNSUPPORTED; }
 int LPMP_FN(get_trace)(lpmp_solver*, uint64_t*, uint64_t) { return LPMP_ERR_UNSUPPORTED; }
 int LPMP_FN(ipc_export)(const void*, void*) { return LPMP_ERR_UNSUPPORTED; }
 int LPMP_FN(ipc_open)(const void*, void**) { return LPMP_ERR_UNSUPPORTED; }

@@ -15,9 +15,9 @@ in_top, in_bot = lp.grid_boundary_ptrs(0)[0], lp.grid_boundary_ptrs(1)[0]
 stream = torch.cuda.ExternalStream(lp.stream())
 def run(fwd, uni, primal):
     # carried side: what the neighbour's last virtual row would hand over; later side (uniform modes): its first virtual row's vectors
-    lp.grid_push_boundary(1 if fwd else 0, in_top if fwd else in_bot)
+    lp.grid_push_boundary(1 if fwd else 0, in_top if fwd else in_bot, not fwd)
     if uni:
-        lp.grid_push_boundary(0 if fwd else 1, in_bot if fwd else in_top)
+        lp.grid_push_boundary(0 if fwd else 1, in_bot if fwd else in_top, not fwd)
     name = "Compute" + ("Forward" if fwd else "Backward") + "Pass" + ("AndPrimal" if primal else "")
     getattr(lp, name)(*((1,) if primal else ()))
 def timed(fn, n=3):

@@ -622,7 +622,10 @@ def test_stripes_pipelined_are_bit_identical_to_the_unstriped_lp(dtype, kind, L,
 @pytest.mark.parametrize("mode", ["uniform", "damped_uniform"])
 @pytest.mark.parametrize("dtype,kind,L,lo,hi,H,cut,W", [("f64", "trunclin", 16, 0.25, 1.0, 70, 30, 45), ("f32", "potts", 32, 0.1, 1.0, 41, 17, 39),
                                                         ("f64", "potts", 8, 0.1, 1.0, 33, 16, 20), ("f32", "trunclin", 16, 0.25, 1.0, 19, 8, 64),
-                                                        ("f32", "potts", 16, -0.3, 1.0, 12, 11, 24)])
+                                                        ("f32", "potts", 16, -0.3, 1.0, 12, 11, 24),
+                                                        # stripes of whole bands of 8 rows, W % 8 == 0: the split kernel's uniform instances
+                                                        ("f32", "potts", 32, 0.1, 1.0, 48, 16, 40), ("f32", "trunclin", 16, 0.25, 1.0, 40, 24, 64),
+                                                        ("f64", "trunclin", 16, 0.25, 1.0, 32, 16, 32), ("f32", "potts", 16, 0.1, 1.0, 16, 8, 16)])
 def test_stripes_uniform_modes_pipelined_are_bit_identical_to_the_unstriped_lp(mode, dtype, kind, L, lo, hi, H, cut, W):
     """uniform / damped-uniform passes on stripes (the rounding iterations of the default control law,
     include/visitors/standard_visitor.hxx:44): the last virtual row of a stripe also receives from the other stripe's first
@@ -639,10 +642,10 @@ def test_stripes_uniform_modes_pipelined_are_bit_identical_to_the_unstriped_lp(m
         args = (it,) if primal else ()
         getattr(full, name)(*args)
         if fwd:
-            bot.grid_push_boundary(0, top_in_bot)      # bU of the lower stripe's first row, state before the pass
+            bot.grid_push_boundary(0, top_in_bot, False)      # bU of the lower stripe's first row, state before the pass
             getattr(top, name)(*args); getattr(bot, name)(*args)
         else:
-            top.grid_push_boundary(1, bot_in_top)      # aD of the upper stripe's last row
+            top.grid_push_boundary(1, bot_in_top, True)       # aD of the upper stripe's last row (backward pass: slots right to left)
             getattr(bot, name)(*args); getattr(top, name)(*args)
         top.synchronize(); bot.synchronize()
 
@@ -651,6 +654,12 @@ def test_stripes_uniform_modes_pipelined_are_bit_identical_to_the_unstriped_lp(m
             both(fwd, False, it)
             assert np.array_equal(np.concatenate([top.unaries(), bot.unaries()]), full.unaries()), f"theta differs after pass {it} fwd={fwd}"
         assert np.isclose(_striped_bound((top, bot)), full.LowerBound(), rtol=LB_RTOL[dtype])
+    if dtype == "f32" and W % 8 == 0 and W >= 16 and cut % 8 == 0 and (H - cut) % 8 == 0 and (kind == "potts" or L == 16) and L in (16, 32):
+        # the split instances ran: a forward pass of the upper stripe is the gather of the lower stripe's vectors + the pass kernel
+        n0 = top.stats()["kernel_launches"]
+        both(True, False, 3)
+        assert top.stats()["kernel_launches"] - n0 == 2
+        assert np.array_equal(np.concatenate([top.unaries(), bot.unaries()]), full.unaries())
     # anisotropic passes in between (the default law alternates), then a rounding iteration in the uniform mode
     for lp in (full, top, bot):
         lp.set_reparametrization("anisotropic")
@@ -679,7 +688,7 @@ def test_stripes_uniform_modes_per_pass_halo():
     for it in range(10):
         full.ComputePass(it)
         for fwd in (True, False):
-            top.grid_push_boundary(1, bot_in_top); bot.grid_push_boundary(0, top_in_bot)
+            top.grid_push_boundary(1, bot_in_top, not fwd); bot.grid_push_boundary(0, top_in_bot, not fwd)
             if fwd:
                 top.ComputeForwardPass(); bot.ComputeForwardPass()
             else:
@@ -688,7 +697,7 @@ def test_stripes_uniform_modes_per_pass_halo():
         prev = _striped_bound((top, bot))
         assert abs(prev - full.LowerBound()) <= 2e-2 * abs(prev), (it, prev, full.LowerBound())
     full.ComputeForwardPassAndPrimal(10)
-    top.grid_push_boundary(1, bot_in_top); bot.grid_push_boundary(0, top_in_bot)
+    top.grid_push_boundary(1, bot_in_top, False); bot.grid_push_boundary(0, top_in_bot, False)
     top.ComputeForwardPassAndPrimal(10); bot.ComputeForwardPassAndPrimal(10)
     top.synchronize(); bot.synchronize()
     assert prev <= full.EvaluatePrimal() + 1e-9
@@ -704,10 +713,10 @@ def test_stripes_per_pass_halo_is_monotone_and_close():
     assert np.isclose(prev, full.LowerBound(), rtol=1e-12)
     for it in range(20):
         full.ComputePass(it)
-        top.grid_get_boundary_vectors(1, bot.grid_boundary_ptrs(0)[0]); top.synchronize()
+        top.grid_push_boundary(1, bot.grid_boundary_ptrs(0)[0], False); top.synchronize()
         top.ComputeForwardPass(); bot.ComputeForwardPass()
         top.synchronize(); bot.synchronize()
-        bot.grid_get_boundary_vectors(0, top.grid_boundary_ptrs(1)[0]); bot.synchronize()
+        bot.grid_push_boundary(0, top.grid_boundary_ptrs(1)[0], True); bot.synchronize()
         bot.ComputeBackwardPass(); top.ComputeBackwardPass()
         top.synchronize(); bot.synchronize()
         lb = _striped_bound((top, bot))
@@ -716,6 +725,26 @@ def test_stripes_per_pass_halo_is_monotone_and_close():
     exact = full.LowerBound()
     assert prev <= exact + 1e-9 * abs(exact)
     assert abs(prev - exact) <= 5e-3 * abs(exact), (prev, exact)
+
+
+@pytest.mark.parametrize("dtype,kind,L,lo,hi,H,cut,W", [("f64", "trunclin", 16, 0.25, 1.0, 37, 16, 29), ("f32", "potts", 32, 0.1, 1.0, 48, 16, 40),
+                                                        ("f32", "potts", 8, -0.3, 1.0, 21, 9, 17), ("f32", "trunclin", 16, 0.25, 1.0, 40, 24, 64)])
+def test_stripes_push_after_the_neighbours_pass_is_exact(dtype, kind, L, lo, hi, H, cut, W):
+    """the push of the per-pass halo coupling delivers what the pipelined coupling delivers (slot q = q-th column in processing
+    order: right to left for a backward pass): pushed AFTER the neighbour's pass has finished, the stripes reproduce the unstriped
+    LP bit for bit.  (Pushed before it -- the coupling proper -- the same vectors arrive one pass late.)"""
+    full, (top, bot) = _stripe_pair(dtype, H, cut, W, L, kind, lo, hi)
+    bot_in_top, top_in_bot = bot.grid_boundary_ptrs(0)[0], top.grid_boundary_ptrs(1)[0]
+    for it in range(3):
+        full.ComputeForwardPass()
+        top.ComputeForwardPass(); top.grid_push_boundary(1, bot_in_top, False); top.synchronize()
+        bot.ComputeForwardPass(); bot.synchronize()
+        assert np.array_equal(np.concatenate([top.unaries(), bot.unaries()]), full.unaries()), f"theta differs after forward pass {it}"
+        full.ComputeBackwardPass()
+        bot.ComputeBackwardPass(); bot.grid_push_boundary(0, top_in_bot, True); bot.synchronize()
+        top.ComputeBackwardPass(); top.synchronize()
+        assert np.array_equal(np.concatenate([top.unaries(), bot.unaries()]), full.unaries()), f"theta differs after backward pass {it}"
+        assert np.isclose(_striped_bound((top, bot)), full.LowerBound(), rtol=LB_RTOL[dtype])
 
 
 # ---- solver loop: reference control law driving the device ---------------------------------------------------------

@@ -90,8 +90,9 @@ class HostStripe:
         self.passes, self.seen, self.labelled, self.repam = 0, [], False, None
         self.finalized = False
 
-    def _vec(self, which):      # my side of boundary `which` after `passes` passes
-        return np.full(self.grid_shape[1] * self.L, 1000.0 * self.rank + 100.0 * which + self.passes)
+    def _vec(self, which):      # my side of boundary `which` after `passes` passes; + 0.25 * column
+        W, L = self.grid_shape[1], self.L
+        return 1000.0 * self.rank + 100.0 * which + self.passes + 0.25 * np.repeat(np.arange(W, dtype=np.float64), L)
 
     def finalize(self): self.finalized = True
     def Begin(self): pass
@@ -153,14 +154,14 @@ def _striped_worker(rank, world, port, out):
         slp = StripedLP(lp, plan, rank, dist, coupling="halo_nccl", device="cpu").finalize()
         ok = True
         # bound: sum over ranks of (rank + 1) + first entry of the lower neighbour's TOP vector (none for the last rank)
-        want = sum(r + 1 for r in range(world)) + sum(1000.0 * (r + 1) + 0.0 for r in range(world - 1))
+        want = sum(r + 1 for r in range(world)) + sum(1000.0 * (r + 1) + 0.25 for r in range(world - 1))   # (mean of 0.25 * column, W = 3)
         ok &= slp.LowerBound() == want
         ok &= slp.EvaluatePrimal() == float("inf") and not slp.CheckPrimalConsistency()
         slp.set_reparametrization("anisotropic")
         slp.ComputeForwardPass()     # consumes the upper neighbour's BOTTOM vector of pass count 0
         ok &= lp.seen[-1] == (None if rank == 0 else 1000.0 * (rank - 1) + 100.0)
-        slp.ComputeBackwardPass()    # consumes the lower neighbour's TOP vector after its one pass
-        ok &= lp.seen[-1] == (None if rank == world - 1 else 1000.0 * (rank + 1) + 1.0)
+        slp.ComputeBackwardPass()    # consumes the lower neighbour's TOP vector after its one pass, slots right to left: slot 0 = column W - 1
+        ok &= lp.seen[-1] == (None if rank == world - 1 else 1000.0 * (rank + 1) + 1.0 + 0.25 * (W - 1))
         slp.ComputeForwardPassAndPrimal(1)
         ok &= slp.CheckPrimalConsistency()
         ok &= slp.EvaluatePrimal() == sum(7.0 * (r + 1) for r in range(world)) + sum(10.0 * (r + 1) for r in range(world - 1))
@@ -174,8 +175,8 @@ def _striped_worker(rank, world, port, out):
         ok &= lp.seen[-1] == (None if rank == 0 else 1000.0 * (rank - 1) + 100.0 + 3.0)
         ok &= lp.seen_later == (None if rank == world - 1 else 1000.0 * (rank + 1) + 3.0)
         slp.ComputeBackwardPass()
-        ok &= lp.seen[-1] == (None if rank == world - 1 else 1000.0 * (rank + 1) + 4.0)
-        ok &= lp.seen_later == (None if rank == 0 else 1000.0 * (rank - 1) + 100.0 + 4.0)
+        ok &= lp.seen[-1] == (None if rank == world - 1 else 1000.0 * (rank + 1) + 4.0 + 0.25 * (W - 1))
+        ok &= lp.seen_later == (None if rank == 0 else 1000.0 * (rank - 1) + 100.0 + 4.0 + 0.25 * (W - 1))
         # the reference control law drives a StripedLP (Solver::Solve, include/solver.hxx:230-257), rounding in its default mode
         # (damped_uniform, include/visitors/standard_visitor.hxx:44) and in the anisotropic one
         for opts in (dict(maxIter=4), dict(maxIter=4, roundingReparametrization="anisotropic")):
