@@ -222,6 +222,11 @@ int LPMP_FN(num_messages)(const lpmp_solver* h, uint64_t* out);      /* LP::GetN
 
 /* ---- state access (serialize_dual / serialize_primal equivalents, include/serialization.hxx:228-426) -- */
 int LPMP_FN(get_labeling)(lpmp_solver* h, uint32_t* out /* [N] */);
+/* Solver::RegisterPrimal (include/solver.hxx:321-340) keeps the best labeling seen so far: keep_labeling copies the current one
+ * aside ON THE DEVICE (stream-ordered, no host synchronisation -- a rounding iteration never waits for N labels to travel),
+ * get_kept_labeling downloads that copy */
+int LPMP_FN(keep_labeling)(lpmp_solver* h);
+int LPMP_FN(get_kept_labeling)(lpmp_solver* h, uint32_t* out /* [N] */);
 int LPMP_FN(get_unaries)(lpmp_solver* h, double* theta /* [N][L] */);
 int LPMP_FN(get_messages)(lpmp_solver* h, double* a /* [E][L] */, double* b /* [E][L] */); /* edge insertion order */
 int LPMP_FN(set_messages)(lpmp_solver* h, const double* a, const double* b);

@@ -80,6 +80,8 @@ SIGNATURES = {
     "num_factors": [_vp, _pu64],
     "num_messages": [_vp, _pu64],
     "get_labeling": [_vp, _pu32],
+    "keep_labeling": [_vp],
+    "get_kept_labeling": [_vp, _pu32],
     "get_unaries": [_vp, _pd],
     "get_messages": [_vp, _pd, _pd],
     "set_messages": [_vp, _pd, _pd],

@@ -307,6 +307,8 @@ struct ISolver {
   virtual int add_to_constant(double x) = 0;
   virtual int counts(uint64_t* factors, uint64_t* messages) = 0;
   virtual int get_labeling(uint32_t* out) = 0;
+  virtual int keep_labeling() = 0;
+  virtual int get_kept_labeling(uint32_t* out) = 0;
   virtual int get_unaries(double* th) = 0;
   virtual int get_messages(double* a, double* b) = 0;
   virtual int set_messages(const double* a, const double* b) = 0;
@@ -359,7 +361,8 @@ struct Solver : ISolver {
   DeviceBuffer<Real> handoff, in_top, in_bot;   // band-to-band / stripe-to-stripe column vectors (sentinel protocol)
   Real* peer_top = nullptr;  // upper neighbour's in_bot (delivery target of the backward pass), or null
   Real* peer_bot = nullptr;  // lower neighbour's in_top (delivery target of the forward pass), or null
-  DeviceBuffer<uint32_t> d_ei, d_ej, inc_edge, level_nodes, labels;
+  DeviceBuffer<uint32_t> d_ei, d_ej, inc_edge, level_nodes, labels, kept_labels;
+  bool kept_valid = false;        // kept_labels holds a labeling (keep_labeling)
   DeviceBuffer<uint64_t> inc_off;
   DeviceBuffer<uint8_t> inc_flags;
   DeviceBuffer<double> partial, result;
@@ -1277,6 +1280,23 @@ struct Solver : ISolver {
     CUDA_TRY(cudaStreamSynchronize(stream));
     return check_abort();
   }
+  // Solver::RegisterPrimal keeps the best labeling seen (include/solver.hxx:321-340): a device-side copy, ordered on the handle's
+  // stream -- the rounding iterations of a solve never wait for a download of N labels
+  int keep_labeling() override {
+    if (int r = need_final()) return r;
+    if (!labels_valid) return bad_state("keep_labeling: no rounding pass has run");
+    CUDA_TRY(cudaSetDevice(device));
+    if (kept_labels.n < N) CUDA_TRY(kept_labels.alloc(N));
+    CUDA_TRY(cudaMemcpyAsync(kept_labels.p, labels.p, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+    kept_valid = true;
+    return LPMP_OK;
+  }
+  int get_kept_labeling(uint32_t* out) override {
+    if (!kept_valid) return bad_state("get_kept_labeling: nothing kept");
+    CUDA_TRY(cudaMemcpyAsync(out, kept_labels.p, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return check_abort();
+  }
   int download(std::vector<Real>& tmp, const Real* src, uint64_t n) {
     tmp.resize(n);
     CUDA_TRY(cudaMemcpyAsync(tmp.data(), src, n * sizeof(Real), cudaMemcpyDeviceToHost, stream));
@@ -1677,6 +1697,8 @@ int lpmp_add_to_constant(lpmp_solver* h, double x) { return S(h)->add_to_constan
 int lpmp_num_factors(const lpmp_solver* h, uint64_t* out) { return const_cast<ISolver*>(S(h))->counts(out, nullptr); }
 int lpmp_num_messages(const lpmp_solver* h, uint64_t* out) { return const_cast<ISolver*>(S(h))->counts(nullptr, out); }
 int lpmp_get_labeling(lpmp_solver* h, uint32_t* out) { return S(h)->get_labeling(out); }
+int lpmp_keep_labeling(lpmp_solver* h) { return S(h)->keep_labeling(); }
+int lpmp_get_kept_labeling(lpmp_solver* h, uint32_t* out) { return S(h)->get_kept_labeling(out); }
 int lpmp_get_unaries(lpmp_solver* h, double* th) { return S(h)->get_unaries(th); }
 int lpmp_get_messages(lpmp_solver* h, double* a, double* b) { return S(h)->get_messages(a, b); }
 int lpmp_set_messages(lpmp_solver* h, const double* a, const double* b) { return S(h)->set_messages(a, b); }

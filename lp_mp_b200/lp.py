@@ -310,6 +310,15 @@ class LP:
         self._ck(self.api.get_labeling(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
         return out
 
+    def keep_labeling(self):
+        """device-side copy of the current labeling (what Solver::RegisterPrimal keeps, include/solver.hxx:321-340)"""
+        self._ck(self.api.keep_labeling(self.h))
+
+    def kept_labeling(self):
+        out = np.zeros(self.N, dtype=np.uint32)
+        self._ck(self.api.get_kept_labeling(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
     def _unpack(self, packed, counts):
         """packed per-variable / per-edge vectors of a mixed-count LP -> [n][L] padded with zeros (as checkers.RefLP reports them)"""
         out = np.zeros((len(counts), self.L), dtype=np.float64)

@@ -113,12 +113,20 @@ class Solver:
         self.visitor_ = visitor or StandardVisitor()
         self.lowerBound_ = -math.inf
         self.bestPrimalCost_ = math.inf
-        self.solution_ = None
+        self._solution = None      # best labeling on the host, or None while it only exists as the LP's kept (device-side) copy
+        self._kept = False
         self.iter = 0
         self.history = []  # (lower bound, best primal, LpControl of that iteration) per visit
 
     def GetLP(self):
         return self.lp_
+
+    @property
+    def solution_(self):
+        """best labeling registered so far (Solver::solution_, include/solver.hxx:340); downloaded on first use"""
+        if self._solution is None and self._kept:
+            self._solution = self.lp_.kept_labeling()
+        return self._solution
 
     def lower_bound(self):
         return self.lowerBound_
@@ -141,6 +149,7 @@ class Solver:
             self.RegisterPrimal()
             self.lowerBound_ = self.lp_.LowerBound()
             self.visitor_.end(self.lowerBound_, self.bestPrimalCost_)
+        _ = self.solution_      # the solution outlives the LP handle
         return not c.error
 
     def Begin(self):  # :261-264
@@ -164,7 +173,11 @@ class Solver:
         cost = self.lp_.EvaluatePrimal()
         if cost < self.bestPrimalCost_ and self.lp_.CheckPrimalConsistency():
             self.bestPrimalCost_ = cost
-            self.solution_ = self.lp_.labeling()
+            if hasattr(self.lp_, "keep_labeling"):      # device-side copy: the iteration does not wait for N labels to travel
+                self.lp_.keep_labeling()
+                self._solution, self._kept = None, True
+            else:
+                self._solution = self.lp_.labeling()
 
 
 class MpRoundingSolver(Solver):

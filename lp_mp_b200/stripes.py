@@ -346,9 +346,18 @@ class StripedLP:
             res = int(t.item())      # inside the stream context: the copy is ordered after the reduction
         return bool(res)
 
+    def keep_labeling(self):
+        """every stripe keeps its part on its device (Solver::RegisterPrimal, include/solver.hxx:321-340): nothing travels"""
+        self.lp.keep_labeling()
+
+    def kept_labeling(self):
+        return self._gather_labeling(self.lp.kept_labeling())
+
     def labeling(self):
-        """the labeling of the whole grid on every rank (Solver::RegisterPrimal keeps the best one, include/solver.hxx:321-340)"""
-        mine = self.lp.labeling()
+        """the labeling of the whole grid on every rank"""
+        return self._gather_labeling(self.lp.labeling())
+
+    def _gather_labeling(self, mine):
         if self.world == 1:
             return mine
         import torch

@@ -63,7 +63,7 @@ struct Oracle : OracleBase {
   std::vector<Real> theta, a, b, params;  // params: [E][P]
   std::vector<uint64_t> ei, ej, rank, order, inc_off;
   std::vector<Incidence> inc;
-  std::vector<uint32_t> n_in, n_out, labels;
+  std::vector<uint32_t> n_in, n_out, labels, kept_labels;
   std::vector<Real> h_, t_;  // scratch
   uint64_t message_updates = 0;
   // mixed label counts (add_unaries_var): every per-variable / per-edge array is packed; L = the largest count
@@ -709,6 +709,8 @@ int LPMP_FN(num_factors)(const lpmp_solver* h, uint64_t* out) { return DISPATCH(
 int LPMP_FN(num_messages)(const lpmp_solver* h, uint64_t* out) { return DISPATCH(H(h), ([&] { *out = 2 * o.E; return int(LPMP_OK); })()); }
 
 int LPMP_FN(get_labeling)(lpmp_solver* h, uint32_t* out) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; std::copy(o.labels.begin(), o.labels.end(), out); return int(LPMP_OK); })()); }
+int LPMP_FN(keep_labeling)(lpmp_solver* h) { return DISPATCH(H(h), ([&] { if (int r = need_final(o)) return r; o.kept_labels = o.labels; return int(LPMP_OK); })()); }
+int LPMP_FN(get_kept_labeling)(lpmp_solver* h, uint32_t* out) { return DISPATCH(H(h), ([&] { std::copy(o.kept_labels.begin(), o.kept_labels.end(), out); return int(LPMP_OK); })()); }
 int LPMP_FN(get_unaries)(lpmp_solver* h, double* th) { return DISPATCH(H(h), ([&] { for (uint64_t k = 0; k < o.theta.size(); ++k) th[k] = double(o.theta[k]); return int(LPMP_OK); })()); }
 int LPMP_FN(get_messages)(lpmp_solver* h, double* a, double* b) {
   return DISPATCH(H(h), ([&] {

@@ -748,6 +748,27 @@ def test_stripes_push_after_the_neighbours_pass_is_exact(dtype, kind, L, lo, hi,
 
 
 # ---- solver loop: reference control law driving the device ---------------------------------------------------------
+def test_kept_labeling_is_a_device_side_snapshot():
+    """Solver::RegisterPrimal (include/solver.hxx:321-340) keeps the best labeling: lpmp_keep_labeling copies it aside on the device,
+    later rounding passes do not touch the copy"""
+    chain = fill(cuda_lp("f64"), "dense", np.random.default_rng(1).random((300, 4)), np.arange(299, dtype=np.uint64), np.arange(1, 300, dtype=np.uint64), 4, 4)
+    for lp in (grid_pair("f32", 40, 64, 16, "trunclin", seed=3)[1], chain):
+        if not lp.finalized:
+            lp.finalize()
+        lp.Begin(); lp.set_reparametrization("anisotropic")
+        with pytest.raises(Exception):
+            lp.keep_labeling()            # no rounding pass yet
+        lp.ComputeForwardPassAndPrimal(0)
+        first = lp.labeling()
+        lp.keep_labeling()
+        lp.set_reparametrization("damped_uniform")
+        lp.ComputeBackwardPassAndPrimal(0)
+        lp.ComputePass(1)
+        lp.ComputeForwardPassAndPrimal(2)
+        assert lp is chain or not np.array_equal(lp.labeling(), first)
+        assert np.array_equal(lp.kept_labeling(), first)
+
+
 def test_frustrated_cycle_goldens_on_device():
     """test/graphical_model.cpp:98-136 (lower bounds are goldens; see tests/test_oracle_goldens.py for the primal note)"""
     from lp_mp_b200 import MpRoundingSolver, StandardVisitor

@@ -139,6 +139,8 @@ class HostStripe:
 
     def CheckPrimalConsistency(self): return self.labelled
     def labeling(self): return np.full(self.grid_shape[0] * self.grid_shape[1], self.rank, dtype=np.uint32)
+    def keep_labeling(self): self.kept = self.passes                     # device-side copy in the product: nothing travels
+    def kept_labeling(self): return self.labeling() + 100 * self.kept    # (+ when it was kept)
 
 
 def _striped_worker(rank, world, port, out):
@@ -183,6 +185,10 @@ def _striped_worker(rank, world, port, out):
             lp.ended = False
             s = MpRoundingSolver(slp, StandardVisitor(**opts))
             ok &= bool(s.Solve()) and len(s.history) >= 1 and lp.ended and s.solution_ is not None
+            # the solution is the gather of what every stripe KEPT at the last improvement, not of the current labels
+            sol = s.solution_
+            ok &= sol.shape == (H * W,) and all((sol[plan.rows(r)[0] * W:(plan.rows(r)[0] + plan.rows(r)[1]) * W] % 100 == r).all() for r in range(world))
+            ok &= (sol // 100).min() == (sol // 100).max() == lp.kept
         out[rank] = int(ok)
     finally:
         dist.destroy_process_group()
