@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L, UNI>::THREADS, 1) wavefr
         lb_acc += ((double)gt + (double)ge) + (double)go;
       };
       // PRM: label of the node of step s from theta after the receives (both halves hold it; the lower half's ballot decides)
-      auto write_label = [&](const Real (&tv)[LPL], const int s) {
+      auto label_of = [&](const Real (&tv)[LPL]) -> unsigned {     // (the same value in every lane)
         Real lm = tv[0];
 #pragma unroll
         for (int k = 1; k < LPL; ++k) lm = rmin(lm, tv[k]);
@@ -479,7 +479,20 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L, UNI>::THREADS, 1) wavefr
 #pragma unroll
         for (int k = LPL - 1; k >= 0; --k) if (tv[k] == g) kf = k;
         const int k1 = __shfl_sync(FULL, kf, (int)il);
-        if (lane == 0) A.labels[(uint64_t)r * W + (fwd ? (uint32_t)s : W - 1 - (uint32_t)s)] = il * LPL + (unsigned)k1;
+        return il * LPL + (unsigned)k1;
+      };
+      auto write_label = [&](const Real (&tv)[LPL], const int s) {
+        const unsigned lab = label_of(tv);
+        if (lane == 0) A.labels[(uint64_t)r * W + (fwd ? (uint32_t)s : W - 1 - (uint32_t)s)] = lab;
+      };
+      // tiles: lane jj keeps the label of step s0 + jj (a select, no branch in the step); one store of K labels after the tile
+      unsigned tile_labels = 0u;
+      auto keep_label = [&](const Real (&tv)[LPL], const int jj) {
+        const unsigned lab = label_of(tv);
+        tile_labels = lane == jj ? lab : tile_labels;
+      };
+      auto write_tile_labels = [&](const int s0) {
+        if (lane < K) A.labels[(uint64_t)r * W + (fwd ? (uint32_t)(s0 + lane) : W - 1 - (uint32_t)(s0 + lane))] = tile_labels;
       };
       if constexpr (UNI) {
         // ============ uniform / damped-uniform modes (include/LP_MP.h:1420-1449, full receive mask): a node receives from all four
@@ -611,9 +624,10 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L, UNI>::THREADS, 1) wavefr
             sts_n(Tout + ro, oo);
 #pragma unroll
             for (int k = 0; k < LPL; ++k) oth[k] = oo[k];
-            if constexpr (PRM) write_label(tv, s0 + jj);       // after the stores: nothing of the chain waits for the label
+            if constexpr (PRM) keep_label(tv, jj);             // after the stores: nothing of the chain waits for the label
           }
           publish(s0 + K);
+          if constexpr (PRM) write_tile_labels(s0);
         };
         const int j_last = nchunks - 1;
         if (ring_row) {
@@ -834,10 +848,11 @@ __global__ void __launch_bounds__(SplitCfg<Real, PW, L, UNI>::THREADS, 1) wavefr
           sts_n(Tout + ro, oo);
 #pragma unroll
           for (int k = 0; k < LPL; ++k) oth[k] = oo[k];
-          if constexpr (PRM) write_label(tv, s0 + jj);         // after the stores: nothing of the chain waits for the label
+          if constexpr (PRM) keep_label(tv, jj);               // after the stores: nothing of the chain waits for the label
           if constexpr (LBF) lb_terms(th, oi, h, true);       // after the stores: nothing of the chain waits for these minima
         }
         publish(s0 + K);
+        if constexpr (PRM) write_tile_labels(s0);
       };
 
       // Step kinds along the row.  With in-/out-edge counts (n_in, n_out) the weight is 1 / max(n_in, n_out) = 1/2 everywhere except at
