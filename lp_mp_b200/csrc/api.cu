@@ -170,12 +170,13 @@ __global__ void gather_strided_kernel(Dst* __restrict__ dst, const Src* __restri
 // edge at cell (r,c) -> node (r,c) field f_first and node (r,c) + second_off field f_second
 template <typename Dst, typename Src>
 __global__ void scatter_edge_params_kernel(Dst* __restrict__ par, const Src* __restrict__ src, uint32_t rows, uint32_t cols, uint32_t W, uint32_t P,
-                                           uint32_t second_off, int f_first, int f_second) {
+                                           uint32_t second_off, int f_first, int f_second, unsigned int* neg_flag) {
   const uint64_t n = (uint64_t)rows * cols * P;
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t p = (uint32_t)(k % P);
     const uint64_t cell = k / P;
     const uint64_t node = (cell / cols) * W + (cell % cols);
+    if (neg_flag != nullptr && !(src[k] >= Src(0))) *neg_flag = 1u;   // Potts: a negative (or NaN) lambda selects the two-minima update
     const Dst v = (Dst)src[k];
     if (f_first >= 0) par[(node * PAR_EDGES + f_first) * P + p] = v;
     if (f_second >= 0) par[((node + second_off) * PAR_EDGES + f_second) * P + p] = v;
@@ -407,10 +408,6 @@ struct Solver : ISolver {
     tl_reach = std::max(tl_reach, reach);
   }
   template <typename Src>
-  void note_potts_array(const Src* p, uint64_t n_edges) {
-    for (uint64_t e = 0; e < n_edges && !potts_neg; ++e) potts_neg = !(p[e] >= Src(0));
-  }
-  template <typename Src>
   void note_trunclin_array(const Src* p, uint64_t n_edges) {
     Src ls = 0, lt = 0;
     bool have = false;
@@ -568,13 +565,21 @@ struct Solver : ISolver {
     const uint64_t n = (uint64_t)rows * cols * Pn;
     if (n == 0 || !src) return LPMP_OK;
     if (pw == LPMP_PAIRWISE_TRUNCLIN) note_trunclin_array(src, (uint64_t)rows * cols);
-    if (pw == LPMP_PAIRWISE_POTTS) note_potts_array(src, (uint64_t)rows * cols);
     DeviceBuffer<Src> tmp;
     if (int r = upload(tmp, src, n)) return r;
-    scatter_edge_params_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(par.p, tmp.p, rows, cols, gridW, Pn, second_off, f_first, f_second);
+    // Potts: the sign scan of the lambdas rides on the scatter kernel (a host loop over the 33.5 M edges of C3 costs more than their upload)
+    unsigned int* const neg_flag = pw == LPMP_PAIRWISE_POTTS && !potts_neg ? bad_count.p : nullptr;
+    if (neg_flag) CUDA_TRY(cudaMemsetAsync(neg_flag, 0, sizeof(unsigned int), stream));
+    scatter_edge_params_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(par.p, tmp.p, rows, cols, gridW, Pn, second_off, f_first, f_second, neg_flag);
     ++launches;
     CUDA_TRY(cudaGetLastError());
+    return finish_edge_plane(neg_flag);
+  }
+  int finish_edge_plane(unsigned int* neg_flag) {
+    unsigned int neg = 0;
+    if (neg_flag) CUDA_TRY(cudaMemcpyAsync(&neg, neg_flag, sizeof(neg), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
+    if (neg) potts_neg = true;
     return LPMP_OK;
   }
   Real* tabH() const { return tab.p; }
@@ -668,14 +673,14 @@ struct Solver : ISolver {
     const uint32_t Pn = P();
     const uint64_t n = (uint64_t)gridW * Pn;
     if (pw == LPMP_PAIRWISE_TRUNCLIN) note_trunclin_array(bottom, gridW);
-    if (pw == LPMP_PAIRWISE_POTTS) note_potts_array(bottom, gridW);
     DeviceBuffer<Src> tmp;
     if (int r = upload(tmp, bottom, n)) return r;
-    scatter_edge_params_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(par.p + (uint64_t)(gridH - 1) * gridW * PREC(), tmp.p, 1, gridW, gridW, Pn, 0, PAR_D, -1);
+    unsigned int* const neg_flag = pw == LPMP_PAIRWISE_POTTS && !potts_neg ? bad_count.p : nullptr;
+    if (neg_flag) CUDA_TRY(cudaMemsetAsync(neg_flag, 0, sizeof(unsigned int), stream));
+    scatter_edge_params_kernel<Real, Src><<<grid_for(n, 256), 256, 0, stream>>>(par.p + (uint64_t)(gridH - 1) * gridW * PREC(), tmp.p, 1, gridW, gridW, Pn, 0, PAR_D, -1, neg_flag);
     ++launches;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    return LPMP_OK;
+    return finish_edge_plane(neg_flag);
   }
   int grid_boundary_ptrs(int which, void** in_buf, uint64_t* bytes) override {
     if (!striped) return bad_state("grid_boundary_ptrs: not a stripe");

@@ -305,8 +305,11 @@ class LP:
         return out.value
 
     # ---- state ------------------------------------------------------------------------------------------
-    def labeling(self):
-        out = np.zeros(self.N, dtype=np.uint32)
+    def labeling(self, out=None):
+        """``out``: a contiguous uint32 array of N entries to fill (e.g. the numpy view of a pinned tensor), else a new array"""
+        if out is None:
+            out = np.empty(self.N, dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.size == self.N and out.flags["C_CONTIGUOUS"]
         self._ck(self.api.get_labeling(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
         return out
 
