@@ -588,7 +588,7 @@ def _striped_bound(stripes):
 
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
 @pytest.mark.parametrize("kind,L,lo,hi,H,cut,W", [("trunclin", 16, 0.25, 1.0, 70, 30, 45), ("potts", 32, 0.1, 1.0, 41, 17, 39),
-                                                  ("potts", 8, 0.1, 1.0, 33, 16, 20)])
+                                                  ("potts", 8, 0.1, 1.0, 33, 16, 20), ("dense", 16, 0.0, 1.0, 29, 13, 21), ("dense", 64, 0.0, 1.0, 9, 4, 12)])
 def test_stripes_pipelined_are_bit_identical_to_the_unstriped_lp(dtype, kind, L, lo, hi, H, cut, W):
     """exact coupling: the last band of the upper stripe stores its outgoing vectors straight into the lower stripe's
     in-buffer while that stripe's pass kernel polls them (on multi-GPU boxes the pointer is a cudaIpc mapping)"""
@@ -728,7 +728,8 @@ def test_stripes_per_pass_halo_is_monotone_and_close():
 
 
 @pytest.mark.parametrize("dtype,kind,L,lo,hi,H,cut,W", [("f64", "trunclin", 16, 0.25, 1.0, 37, 16, 29), ("f32", "potts", 32, 0.1, 1.0, 48, 16, 40),
-                                                        ("f32", "potts", 8, -0.3, 1.0, 21, 9, 17), ("f32", "trunclin", 16, 0.25, 1.0, 40, 24, 64)])
+                                                        ("f32", "potts", 8, -0.3, 1.0, 21, 9, 17), ("f32", "trunclin", 16, 0.25, 1.0, 40, 24, 64),
+                                                        ("f32", "dense", 16, 0.0, 1.0, 24, 11, 19), ("f64", "dense", 32, 0.0, 1.0, 10, 6, 13)])
 def test_stripes_push_after_the_neighbours_pass_is_exact(dtype, kind, L, lo, hi, H, cut, W):
     """the push of the per-pass halo coupling delivers what the pipelined coupling delivers (slot q = q-th column in processing
     order: right to left for a backward pass): pushed AFTER the neighbour's pass has finished, the stripes reproduce the unstriped
