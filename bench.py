@@ -143,6 +143,10 @@ class ClockSampler:
                 pass
             time.sleep(0.002)
 
+    def mark(self):
+        """start of the timed region: samples taken so far (warm-up) are dropped"""
+        self.rows = []
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
@@ -374,18 +378,19 @@ def run_graph(args, name, rank, world, local_rank, dist, with_e2e=True):
 
     lp, nc = build()
     stream = torch.cuda.ExternalStream(lp.stream(), device=local_rank)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()           # polling starts with the warm-up (the first NVML queries of a process are slow) ...
     for it in range(args.warmup):
         lp.ComputePass(it); lp.LowerBound()
     lp.synchronize()
     launches0 = lp.stats()["kernel_launches"]
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     pass_ev = []
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    clocks.mark()                # ... and only the samples of the timed region are kept
     ev[0].record(stream)
     lb = None
     for it in range(args.steps):
@@ -498,18 +503,19 @@ def run_grid(args, name, rank, world, local_rank, dist, dtype=None, with_e2e=Tru
     slp = fill(make())
     lp = slp.lp
     stream = torch.cuda.ExternalStream(lp.stream(), device=local_rank)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()           # polling starts with the warm-up (the first NVML queries of a process are slow) ...
     for it in range(args.warmup):
         slp.ComputePass(it); slp.LowerBound()
     slp.synchronize()
     launches0 = lp.stats()["kernel_launches"]
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     pass_ev = []
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    clocks.mark()                # ... and only the samples of the timed region are kept
     ev[0].record(stream)
     lb = None
     for it in range(args.steps):
