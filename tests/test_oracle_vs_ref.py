@@ -129,6 +129,36 @@ def test_solve_control_law(ref_lib, options):
     assert s.primal_cost() == pytest.approx(r["final_ub"], rel=1e-12)
 
 
+def test_solver_keeps_the_best_labeling():
+    """Solver::RegisterPrimal keeps the solution of the best primal cost seen (include/solver.hxx:321-340); the mirror keeps it
+    inside the LP (lpmp_keep_labeling: a device-side copy in the product) and fetches it once at the end of Solve()"""
+    rng = np.random.default_rng(3)
+    H, W, L = 7, 9, 5
+    ei, ej = grid_edges(H, W)
+    theta, tables = rng.random((H * W, L)), rng.random((len(ei), L, L))
+    seen = []
+
+    class Recording(MpRoundingSolver):
+        def RegisterPrimal(self):
+            before = self.bestPrimalCost_
+            super().RegisterPrimal()
+            if self.bestPrimalCost_ < before:
+                seen.append((self.bestPrimalCost_, self.lp_.labeling().copy()))
+
+    o = oracle_lp("f64")
+    o.add_unaries(theta); o.add_pairwise_dense(ei, ej, tables)
+    s = Recording(o, StandardVisitor(maxIter=23, primalComputationInterval=2))
+    assert s.Solve()
+    assert len(seen) >= 2, "the instance should improve its primal more than once"
+    best_cost, best_labels = seen[-1]
+    assert s.primal_cost() == best_cost
+    assert np.array_equal(s.solution_, best_labels)
+    # the kept labeling really is the best one, not the last one rounded
+    lab = s.solution_
+    cost = theta[np.arange(H * W), lab].sum() + sum(tables[e][lab[i], lab[j]] for e, (i, j) in enumerate(zip(ei, ej)))
+    assert cost == pytest.approx(best_cost, rel=1e-12)
+
+
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("kind", ["potts", "potts_neg", "trunclin"])
 def test_fast_paths_equal_dense(dtype, kind):
